@@ -1,0 +1,173 @@
+/*
+ * ksw2_b200.h -- C ABI of the B200-native batched banded-alignment engine.
+ *
+ * This is the drop-in boundary for SEDEF's one data-parallel hot path: the ksw2
+ * `ksw_extz2_sse` call made by `align_helper()` (reference src/align.cc:49-57), plus the
+ * per-alignment statistics that `Alignment::populate_nice_alignment()` (src/align.cc:274-315)
+ * and the BEDPE stat loop of `process()` (src/stats_main.cc:244-271) derive from the CIGAR.
+ *
+ * Everything here is plain C: pointers, sizes, POD structs. No torch / CUDA types.
+ * All entry points need a CUDA device; there is NO CPU fallback. A call made without a
+ * usable device returns KSW_B200_ERR_NO_DEVICE (batch API) or leaves `ez` reset and prints
+ * to stderr (ksw2-compatible single-pair API, which has no error channel).
+ */
+#ifndef KSW2_B200_H_
+#define KSW2_B200_H_
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- ksw2 call surface (reference extern/ksw2.h:6-30) ------------------------------- */
+
+#ifndef KSW_NEG_INF
+#define KSW_NEG_INF -0x40000000            /* extern/ksw2.h:6 */
+#endif
+#ifndef KSW_EZ_SCORE_ONLY
+#define KSW_EZ_SCORE_ONLY  0x01            /* extern/ksw2.h:8  : no traceback / CIGAR */
+#define KSW_EZ_RIGHT       0x02            /* extern/ksw2.h:9  : right-align gaps */
+#define KSW_EZ_GENERIC_SC  0x04            /* extern/ksw2.h:10 : full m*m matrix (NOT supported -> KSW_B200_ERR_UNSUPPORTED) */
+#define KSW_EZ_APPROX_MAX  0x08            /* extern/ksw2.h:11 : (NOT supported yet) */
+#define KSW_EZ_APPROX_DROP 0x10            /* extern/ksw2.h:12 : only meaningful with APPROX_MAX */
+#define KSW_EZ_EXTZ_ONLY   0x40            /* extern/ksw2.h:13 : always trace back from (max_t,max_q) */
+#define KSW_EZ_REV_CIGAR   0x80            /* extern/ksw2.h:14 : emit the CIGAR end->start */
+#endif
+
+#ifndef KSW2_H_
+/* Layout-identical to the reference's result record (extern/ksw2.h:22-30, 56 bytes). */
+typedef struct {
+	uint32_t max:31, zdropped:1;
+	int max_q, max_t;      /* max extension coordinate */
+	int mqe, mqe_t;        /* max score when reaching the end of query */
+	int mte, mte_q;        /* max score when reaching the end of target */
+	int score;             /* max score reaching both ends; may be KSW_NEG_INF */
+	uint32_t *cigar;       /* malloc()'d by the callee, free()'d by the caller (src/align.cc:65) */
+	int64_t m_cigar, n_cigar;
+} ksw_extz_t;
+#endif
+
+/* ---- SD statistics record ("Alignment::from_cigar" statistics) ----------------------- */
+/*
+ * All integer fields SEDEF derives from one alignment.  `a` is the query string (first
+ * argument of Alignment(fa, fb), src/align.cc:76), `b` the target.  ksw op I(1) consumes the
+ * query and is SEDEF's 'D'; ksw op D(2) consumes the target and is SEDEF's 'I'
+ * (src/align.cc:58-63).  Computed on the GPU from the CIGAR and the ORIGINAL-CASE bytes.
+ */
+typedef struct {
+	int32_t span;              /* alignment.size(): number of columns          (src/align.h:79)  */
+	int32_t gaps;              /* number of non-M CIGAR runs                   (src/align.cc:300-305) */
+	int32_t gap_bases;         /* sum of non-M run lengths                     (src/align.cc:300-305) */
+	int32_t matches;           /* gap-free columns with ceq(a,b) (N never equal) (src/align.cc:29-35,306-314) */
+	int32_t mismatches;        /* gap-free columns without ceq                 (src/align.cc:306-314) */
+	int32_t indel_a;           /* columns with a == '-'                        (src/stats_main.cc:247) */
+	int32_t indel_b;           /* columns with b == '-'                        (src/stats_main.cc:248) */
+	int32_t alnB;              /* gap-free columns                             (src/stats_main.cc:257) */
+	int32_t matchB;            /* toupper(a)==toupper(b), a not gap (N==N counts) (src/stats_main.cc:249) */
+	int32_t mismatchB;         /*                                              (src/stats_main.cc:259) */
+	int32_t transitionsB;      /*                                              (src/stats_main.cc:260-266) */
+	int32_t transversionsB;    /*                                              (src/stats_main.cc:260-266) */
+	int32_t uppercaseA;        /* non-gap, non-N, isupper(a)                   (src/stats_main.cc:250-252) */
+	int32_t uppercaseB;        /*                                              (src/stats_main.cc:253-255) */
+	int32_t uppercaseMatches;  /* equal columns with both bases upper-case     (src/stats_main.cc:267-269) */
+	int32_t reserved;          /* pad to 64 bytes; always 0 */
+} sd_stats_t;
+
+/* Floating-point BEDPE fields, derived ON THE HOST from the integers above with the same
+ * double-precision expressions as src/stats_main.cc:273-283,297-299. */
+typedef struct {
+	double fracMatch, fracMatchIndel, jcK, k2K, errorScaled, filter_score;
+	double gap_error, mismatch_error, total_error;    /* src/align.h:84-92 */
+} sd_stats_fp_t;
+void sd_stats_derive_fp(const sd_stats_t *s, sd_stats_fp_t *out);
+
+/* ---- error codes ---------------------------------------------------------------------- */
+enum {
+	KSW_B200_OK = 0,
+	KSW_B200_ERR_NO_DEVICE   = -1,   /* no CUDA device / driver: there is no CPU fallback */
+	KSW_B200_ERR_CUDA        = -2,   /* a CUDA runtime call failed (see ksw_b200_last_error) */
+	KSW_B200_ERR_DOMAIN      = -3,   /* scoring outside the int8-exact domain: mat[0]+2(q+e)+q > 127,
+	                                    mat[1] > 0, q<=0, e<=0 (reference wraps in int8) */
+	KSW_B200_ERR_UNSUPPORTED = -4,   /* flag not supported (GENERIC_SC, APPROX_MAX) */
+	KSW_B200_ERR_TOO_WIDE    = -5,   /* a pair needs more live slots per anti-diagonal than the widest kernel */
+	KSW_B200_ERR_NOMEM       = -6,   /* host or device allocation failed */
+	KSW_B200_ERR_ARG         = -7,   /* bad argument (n<0, NULL pointers, symbol >= m) */
+	KSW_B200_ERR_INEXACT     = -8    /* reserved */
+};
+const char *ksw_b200_strerror(int code);
+const char *ksw_b200_last_error(void);   /* thread-local detail string of the last failure */
+
+/* ---- context ---------------------------------------------------------------------------- */
+/* Bind the engine to `ndev` devices starting at `first_dev` (ndev<=0: all visible devices).
+ * Idempotent; the first batch call initialises lazily with (0, all).  Returns the number of
+ * devices bound or a negative error code. */
+int  ksw_b200_init(int first_dev, int ndev);
+void ksw_b200_destroy(void);
+int  ksw_b200_num_devices(void);
+/* Upper bound on rounded live slots per anti-diagonal a pair may need (SURVEY App. C:
+ * 16*n_col_, or 16*ceil(tlen/16) if smaller). */
+int  ksw_b200_max_slots(void);
+
+/* ---- single pair: identical signature and ownership to ksw_extz2_sse -------------------- */
+/* Replaces extern/ksw2.h:50 / extern/ksw2_extz2_sse.cc:23.  `km` is ignored, as in the
+ * reference build (HAVE_KALLOC undefined, extern/ksw2.h:88-96). */
+void ksw_extz2_b200(void *km, int qlen, const uint8_t *query, int tlen, const uint8_t *target,
+                    int8_t m, const int8_t *mat, int8_t q, int8_t e, int w, int zdrop, int flag,
+                    ksw_extz_t *ez);
+
+/* ---- batch ------------------------------------------------------------------------------- */
+/*
+ * n independent pairs with shared scoring parameters.  Pairs are bucketed by live-slot width
+ * and length, sharded over the bound devices by a length-balanced greedy (LPT) partition on
+ * in-band cell counts, and gathered by original index.  ez[i] is fully overwritten exactly
+ * as ksw_extz2_sse would; ez[i].cigar is malloc()'d (caller frees) unless SCORE_ONLY.
+ * stats (optional, may be NULL): per-pair SD statistics; needs q_raw/t_raw = original-case
+ * ASCII bytes of the same lengths (if NULL the encoded bytes are decoded as "ACGTN").
+ * Pairs with qlen<=0 || tlen<=0 get the reset record (extern/ksw2_extz2_sse.cc:56-57).
+ * Returns KSW_B200_OK or an error code; on error no ez[i].cigar is left allocated.
+ */
+int ksw_extz2_batch(int n, const int *qlen, const uint8_t *const *query,
+                    const int *tlen, const uint8_t *const *target,
+                    int8_t m, const int8_t *mat, int8_t q, int8_t e, int w, int zdrop, int flag,
+                    ksw_extz_t *ez, sd_stats_t *stats,
+                    const uint8_t *const *q_raw, const uint8_t *const *t_raw);
+
+/* Same, with all sequences in two flat arrays (offsets in bytes; q_raw/t_raw share the
+ * offsets).  This is the zero-gather form the align-stage driver and the Python wrapper use. */
+int ksw_extz2_batch_flat(int n, const int *qlen, const int64_t *qoff, const uint8_t *qbuf,
+                         const int *tlen, const int64_t *toff, const uint8_t *tbuf,
+                         int8_t m, const int8_t *mat, int8_t q, int8_t e, int w, int zdrop, int flag,
+                         ksw_extz_t *ez, sd_stats_t *stats,
+                         const uint8_t *q_raw_buf, const uint8_t *t_raw_buf);
+
+/* ---- resident batches (measurement + pipelined callers) -------------------------------- */
+/*
+ * A resident batch keeps the encoded inputs in HBM so that repeated runs time the device
+ * path alone.  upload = pack + H2D; run = DP + traceback + stats kernels on the device(s)
+ * (returns device time in ms measured with CUDA events on the launching streams, max over
+ * devices); fetch = D2H + gather into ez/stats.
+ */
+typedef struct ksw_b200_batch ksw_b200_batch_t;
+ksw_b200_batch_t *ksw_b200_batch_upload(int n, const int *qlen, const int64_t *qoff, const uint8_t *qbuf,
+                                        const int *tlen, const int64_t *toff, const uint8_t *tbuf,
+                                        int8_t m, const int8_t *mat, int8_t q, int8_t e,
+                                        int w, int zdrop, int flag,
+                                        const uint8_t *q_raw_buf, const uint8_t *t_raw_buf, int *err);
+int  ksw_b200_batch_run(ksw_b200_batch_t *b, float *device_ms);
+int  ksw_b200_batch_fetch(ksw_b200_batch_t *b, ksw_extz_t *ez, sd_stats_t *stats);
+/* number of kernel launches issued by the last run, and per-kernel-class device ms */
+int  ksw_b200_batch_launches(const ksw_b200_batch_t *b);
+int  ksw_b200_batch_kernel_ms(const ksw_b200_batch_t *b, float *dp_ms, float *tb_ms, float *aux_ms);
+int64_t ksw_b200_batch_cells(const ksw_b200_batch_t *b);   /* host-side in-band cell count (all diagonals) */
+void ksw_b200_batch_free(ksw_b200_batch_t *b);
+
+/* In-band DP cells of one pair if every anti-diagonal is processed
+ * (sum over r of en0-st0+1, extern/ksw2_extz2_sse.cc:105-109). */
+int64_t ksw_b200_count_cells(int qlen, int tlen, int w);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KSW2_B200_H_ */

@@ -1,0 +1,731 @@
+// engine.cu -- host side of libsedef_b200.so: the C ABI of include/ksw2_b200.h.
+//
+// Responsibilities (all host C++, no torch):
+//   * validate + plan: per pair compute the rounded live-slot width (16*n_col_ of
+//     extern/ksw2_extz2_sse.cc:74-75, or T if smaller), pick the narrowest kernel class that holds
+//     it, count in-band cells, sort each class by descending work;
+//   * shard over the bound devices with a length-balanced greedy (LPT) partition on cells;
+//   * pack sequences into one pinned arena per device ([16 zero bytes | query | pad][target | pad]),
+//     one H2D copy; optional second arena with the original-case bytes for the SD statistics;
+//   * run: per class, in waves bounded by traceback memory, launch the DP kernel (persistent
+//     grid, dynamic work queue) and the traceback+stats kernel on the device stream;
+//   * fetch: D2H of compact records + compact CIGAR arena, gather by original index into
+//     ksw_extz_t / sd_stats_t exactly as ksw_extz2_sse would have filled them.
+// There is no CPU fallback: without a device every entry point fails.
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "../../include/ksw2_b200.h"
+#include "extz_core.cuh"
+#include "extz_dp.cuh"
+#include "extz_tb.cuh"
+
+using namespace extz;
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+static int fail(int code, const std::string &msg) { g_last_error = msg; return code; }
+#define CUDA_TRY(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { \
+	return fail(KSW_B200_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)); } } while (0)
+
+extern "C" const char *ksw_b200_strerror(int code)
+{
+	switch (code) {
+	case KSW_B200_OK: return "ok";
+	case KSW_B200_ERR_NO_DEVICE: return "no usable CUDA device (this engine has no CPU fallback)";
+	case KSW_B200_ERR_CUDA: return "CUDA runtime error";
+	case KSW_B200_ERR_DOMAIN: return "scoring parameters outside the supported domain";
+	case KSW_B200_ERR_UNSUPPORTED: return "unsupported flag or alphabet (KSW_EZ_APPROX_MAX, m > 8)";
+	case KSW_B200_ERR_TOO_WIDE: return "pair needs more live slots per anti-diagonal than the widest kernel";
+	case KSW_B200_ERR_NOMEM: return "out of memory";
+	case KSW_B200_ERR_ARG: return "bad argument";
+	case KSW_B200_ERR_INEXACT: return "inexact";
+	default: return "unknown error";
+	}
+}
+extern "C" const char *ksw_b200_last_error(void) { return g_last_error.c_str(); }
+
+// ------------------------------------------------------------------------------------------------
+// kernel classes
+// ------------------------------------------------------------------------------------------------
+struct KClass { int G, S; };
+static const KClass kClasses[] = { {8, 4}, {16, 4}, {16, 8}, {32, 8}, {32, 16}, {32, 32} };
+static const int kNumClasses = sizeof(kClasses) / sizeof(kClasses[0]);
+static inline int class_ns(int c) { return kClasses[c].G * kClasses[c].S; }
+// S == 32 lanes switch whole-lane (two 16-blocks), which costs 16 slots of window (extz_dp.cuh)
+static inline int class_capacity(int c) { return kClasses[c].S > 16 ? class_ns(c) - 16 : class_ns(c); }
+
+template <int G, int S>
+static cudaError_t launch_dp_gs(const DpLaunch &L, bool cigar, bool right, int grid, cudaStream_t st)
+{
+	if (cigar) {
+		if (right) extz_dp_kernel<G, S, true, true><<<grid, 128, 0, st>>>(L);
+		else       extz_dp_kernel<G, S, true, false><<<grid, 128, 0, st>>>(L);
+	} else       extz_dp_kernel<G, S, false, false><<<grid, 128, 0, st>>>(L);
+	return cudaGetLastError();
+}
+static cudaError_t launch_dp(int c, const DpLaunch &L, bool cigar, bool right, int grid, cudaStream_t st)
+{
+	switch (c) {
+	case 0: return launch_dp_gs<8, 4>(L, cigar, right, grid, st);
+	case 1: return launch_dp_gs<16, 4>(L, cigar, right, grid, st);
+	case 2: return launch_dp_gs<16, 8>(L, cigar, right, grid, st);
+	case 3: return launch_dp_gs<32, 8>(L, cigar, right, grid, st);
+	case 4: return launch_dp_gs<32, 16>(L, cigar, right, grid, st);
+	case 5: return launch_dp_gs<32, 32>(L, cigar, right, grid, st);
+	}
+	return cudaErrorInvalidValue;
+}
+template <int G, int S>
+static int dp_occupancy_gs(bool cigar, bool right)
+{
+	int nb = 0;
+	if (cigar) {
+		if (right) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, extz_dp_kernel<G, S, true, true>, 128, 0);
+		else       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, extz_dp_kernel<G, S, true, false>, 128, 0);
+	} else       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, extz_dp_kernel<G, S, false, false>, 128, 0);
+	return nb;
+}
+static int dp_occupancy(int c, bool cigar, bool right)
+{
+	switch (c) {
+	case 0: return dp_occupancy_gs<8, 4>(cigar, right);
+	case 1: return dp_occupancy_gs<16, 4>(cigar, right);
+	case 2: return dp_occupancy_gs<16, 8>(cigar, right);
+	case 3: return dp_occupancy_gs<32, 8>(cigar, right);
+	case 4: return dp_occupancy_gs<32, 16>(cigar, right);
+	case 5: return dp_occupancy_gs<32, 32>(cigar, right);
+	}
+	return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+struct DevCtx {
+	int dev = -1;
+	int sms = 0;
+	cudaStream_t stream = nullptr;
+	size_t tb_budget = 0;          // bytes of traceback memory one wave may use
+};
+static std::mutex g_mu;
+static std::vector<DevCtx> g_devs;
+
+extern "C" int ksw_b200_init(int first_dev, int ndev)
+{
+	std::lock_guard<std::mutex> lk(g_mu);
+	int count = 0;
+	cudaError_t e = cudaGetDeviceCount(&count);
+	if (e != cudaSuccess || count <= 0)
+		return fail(KSW_B200_ERR_NO_DEVICE, std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e));
+	if (first_dev < 0) first_dev = 0;
+	if (ndev <= 0 || first_dev + ndev > count) ndev = count - first_dev;
+	if (ndev <= 0) return fail(KSW_B200_ERR_NO_DEVICE, "no device in the requested range");
+	if ((int)g_devs.size() == ndev && g_devs[0].dev == first_dev) return ndev;
+	for (auto &d : g_devs) { cudaSetDevice(d.dev); if (d.stream) cudaStreamDestroy(d.stream); }
+	g_devs.clear();
+	for (int i = 0; i < ndev; ++i) {
+		DevCtx d; d.dev = first_dev + i;
+		CUDA_TRY(cudaSetDevice(d.dev));
+		cudaDeviceProp p; CUDA_TRY(cudaGetDeviceProperties(&p, d.dev));
+		d.sms = p.multiProcessorCount;
+		CUDA_TRY(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
+		size_t fr = 0, tot = 0; CUDA_TRY(cudaMemGetInfo(&fr, &tot));
+		const char *env = getenv("KSW_B200_TB_BUDGET_MB");
+		d.tb_budget = env ? (size_t)atoll(env) << 20 : std::min<size_t>(fr / 2, (size_t)48 << 30);
+		g_devs.push_back(d);
+	}
+	return ndev;
+}
+extern "C" void ksw_b200_destroy(void)
+{
+	std::lock_guard<std::mutex> lk(g_mu);
+	for (auto &d : g_devs) { cudaSetDevice(d.dev); if (d.stream) cudaStreamDestroy(d.stream); }
+	g_devs.clear();
+}
+extern "C" int ksw_b200_num_devices(void) { return (int)g_devs.size(); }
+extern "C" int ksw_b200_max_slots(void) { return class_capacity(kNumClasses - 1); }
+
+static int ensure_init()
+{
+	if (!g_devs.empty()) return (int)g_devs.size();
+	return ksw_b200_init(0, 0);
+}
+
+// ------------------------------------------------------------------------------------------------
+// planning helpers
+// ------------------------------------------------------------------------------------------------
+extern "C" int64_t ksw_b200_count_cells(int qlen, int tlen, int w)
+{
+	if (qlen <= 0 || tlen <= 0) return 0;
+	if (w < 0) w = tlen > qlen ? tlen : qlen;
+	// closed form would need care with the >>1 rounding; the loop is O(q+t) and only runs at plan time
+	int64_t c = 0;
+	for (int r = 0; r < qlen + tlen - 1; ++r) {
+		int st = 0, en = tlen - 1;
+		if (st < r - qlen + 1) st = r - qlen + 1;
+		if (en > r) en = r;
+		if (st < ((r - w + 1) >> 1)) st = (r - w + 1) >> 1;
+		if (en > ((r + w) >> 1)) en = (r + w) >> 1;
+		if (st > en) break;
+		c += en - st + 1;
+	}
+	return c;
+}
+// cheap estimate used for load balancing only
+static inline int64_t est_cells(int qlen, int tlen, int w)
+{
+	int64_t mn = std::min(qlen, tlen);
+	int64_t width = std::min<int64_t>(mn, (int64_t)w + 1);
+	return width * ((int64_t)qlen + tlen - 1);
+}
+
+struct DevBuf {
+	void *p = nullptr; size_t cap = 0;
+	int ensure(size_t bytes) {
+		if (bytes <= cap) return 0;
+		if (p) cudaFree(p);
+		p = nullptr; cap = 0;
+		size_t want = bytes + bytes / 8 + 256;
+		if (cudaMalloc(&p, want) != cudaSuccess) { cudaGetLastError(); if (cudaMalloc(&p, bytes) != cudaSuccess) { p = nullptr; return -1; } want = bytes; }
+		cap = want; return 0;
+	}
+	void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+struct PinBuf {
+	void *p = nullptr; size_t cap = 0;
+	int ensure(size_t bytes) {
+		if (bytes <= cap) return 0;
+		if (p) cudaFreeHost(p);
+		p = nullptr; cap = 0;
+		size_t want = bytes + bytes / 8 + 256;
+		if (cudaMallocHost(&p, want) != cudaSuccess) { cudaGetLastError(); p = nullptr; return -1; }
+		cap = want; return 0;
+	}
+	void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+struct Wave { int cls; int first, count; size_t tb_bytes; };
+
+// one device's share of a batch
+struct SubBatch {
+	DevCtx *dc = nullptr;
+	std::vector<PairDesc> pairs;        // grouped by class, each class sorted by descending work
+	std::vector<Wave> waves;
+	int class_first[kNumClasses + 1] = {0};
+	size_t arena_bytes = 0;
+	PinBuf h_arena, h_raw, h_results, h_cigar, h_stats;
+	DevBuf d_arena, d_raw, d_pairs, d_results, d_tb, d_cigar, d_stats, d_misc, d_table;
+	size_t cigar_cap = 0;               // entries
+	unsigned long long cigar_used = 0;
+	cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+	float dp_ms = 0, tb_ms = 0, total_ms = 0;
+	int launches = 0;
+	void release() {
+		h_arena.release(); h_raw.release(); h_results.release(); h_cigar.release(); h_stats.release();
+		d_arena.release(); d_raw.release(); d_pairs.release(); d_results.release(); d_tb.release();
+		d_cigar.release(); d_stats.release(); d_misc.release(); d_table.release();
+		for (auto &e : ev) if (e) { cudaEventDestroy(e); e = nullptr; }
+	}
+};
+
+struct ksw_b200_batch {
+	int n = 0;
+	int8_t m = 0; int8_t q = 0, e = 0; int w = 0, zdrop = 0, flag = 0;
+	int8_t mat[64];
+	bool early_out = false;             // -min_sc > 2(q+e): every pair returns the reset record (:81)
+	bool want_stats = false, have_raw = false;
+	Scoring sc;
+	uint32_t table[kTableStride * kTableStride];
+	std::vector<SubBatch> subs;
+	std::vector<uint8_t> is_empty;      // pairs with qlen<=0 || tlen<=0 (reset record)
+	int64_t cells = 0;
+};
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+static int build_scoring(ksw_b200_batch &B)
+{
+	const int m = B.m, q = B.q, e = B.e;
+	if (m <= 0) return 0;   // every pair is reset (:57)
+	if (m > kTableStride) return fail(KSW_B200_ERR_UNSUPPORTED, "alphabet size m > 8 is not supported");
+	if (B.flag & KSW_EZ_APPROX_MAX) return fail(KSW_B200_ERR_UNSUPPORTED, "KSW_EZ_APPROX_MAX is not supported");
+	int max_sc = B.mat[0], min_sc = B.mat[1];
+	for (int t = 1; t < m * m; ++t) { max_sc = std::max<int>(max_sc, B.mat[t]); min_sc = std::min<int>(min_sc, B.mat[t]); }
+	B.early_out = (-min_sc > 2 * (q + e));                                          // :81
+	const int qe2 = (q + e) * 2;
+	auto top = [](int v) { return (uint32_t)(uint8_t)(int8_t)v << 24; };            // int8 truncation like _mm_set1_epi8
+	B.sc.q_s = top(q); B.sc.maxsc_s = top(B.mat[0] + qe2); B.sc.s0_s = top(0 + qe2);
+	B.sc.q = q; B.sc.e = e; B.sc.qe = q + e; B.sc.zdrop = B.zdrop; B.sc.flag = B.flag; B.sc.w_in = B.w;
+	for (int a = 0; a < kTableStride; ++a)
+		for (int b = 0; b < kTableStride; ++b) {
+			int s;
+			if (B.flag & KSW_EZ_GENERIC_SC) s = (a < m && b < m) ? B.mat[a * m + b] : 0;     // :141
+			else s = (a == m - 1 || b == m - 1) ? 0 : (a == b ? B.mat[0] : B.mat[1]);        // :129-136
+			B.table[a * kTableStride + b] = top((int8_t)s + (int8_t)qe2);                    // :27 z = s + qe2 (wrapping)
+		}
+	return 0;
+}
+
+// live-slot requirement of one pair
+static inline int slots_needed(int qlen, int tlen, int w)
+{
+	int T = (tlen + 15) / 16 * 16;
+	int n_col = std::min(qlen, tlen);
+	n_col = (std::min(n_col, w + 1) + 15) / 16 + 1;                                 // :74-75
+	return std::min(T, n_col * 16);
+}
+
+// ------------------------------------------------------------------------------------------------
+// upload
+// ------------------------------------------------------------------------------------------------
+extern "C" ksw_b200_batch_t *ksw_b200_batch_upload(int n, const int *qlen, const int64_t *qoff, const uint8_t *qbuf,
+                                                   const int *tlen, const int64_t *toff, const uint8_t *tbuf,
+                                                   int8_t m, const int8_t *mat, int8_t q, int8_t e,
+                                                   int w, int zdrop, int flag,
+                                                   const uint8_t *q_raw_buf, const uint8_t *t_raw_buf, int *err)
+{
+	auto bail = [&](int code) -> ksw_b200_batch_t * { if (err) *err = code; return nullptr; };
+	if (err) *err = KSW_B200_OK;
+	if (n < 0 || (n > 0 && (!qlen || !tlen || !qoff || !toff || !qbuf || !tbuf)) || (m > 0 && !mat))
+		return bail(fail(KSW_B200_ERR_ARG, "null pointer or negative count"));
+	int nd = ensure_init();
+	if (nd <= 0) return bail(nd);
+
+	ksw_b200_batch *B = new ksw_b200_batch();
+	B->n = n; B->m = m; B->q = q; B->e = e; B->w = w; B->zdrop = zdrop; B->flag = flag;
+	memset(B->mat, 0, sizeof(B->mat));
+	if (m > 0 && m <= kTableStride) memcpy(B->mat, mat, (size_t)m * m);
+	B->have_raw = q_raw_buf && t_raw_buf;
+	B->want_stats = !(flag & KSW_EZ_SCORE_ONLY) && !getenv("KSW_B200_NO_STATS");   // the fused K4 pass is on by default
+	int rc = build_scoring(*B);
+	if (rc) { delete B; return bail(rc); }
+	B->is_empty.assign(n, 0);
+	B->subs.resize(nd);
+	for (int d = 0; d < nd; ++d) B->subs[d].dc = &g_devs[d];
+
+	// ---- classify + LPT partition ----
+	struct Item { int idx; int cls; int64_t work; };
+	std::vector<Item> items; items.reserve(n);
+	for (int i = 0; i < n; ++i) {
+		if (m <= 0 || qlen[i] <= 0 || tlen[i] <= 0 || B->early_out) { B->is_empty[i] = 1; continue; }
+		int wi = w < 0 ? std::max(qlen[i], tlen[i]) : std::min(w, std::max(qlen[i], tlen[i]));
+		int need = slots_needed(qlen[i], tlen[i], wi);
+		int c = 0;
+		while (c < kNumClasses && class_capacity(c) < need) ++c;
+		if (c == kNumClasses) {
+			delete B;
+			return bail(fail(KSW_B200_ERR_TOO_WIDE, "pair " + std::to_string(i) + " needs " + std::to_string(need) +
+			                 " live slots; widest kernel holds " + std::to_string(class_capacity(kNumClasses - 1))));
+		}
+		items.push_back({i, c, est_cells(qlen[i], tlen[i], wi)});
+	}
+	std::vector<int> order(items.size());
+	std::iota(order.begin(), order.end(), 0);
+	std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return items[a].work > items[b].work; });
+	std::vector<int64_t> load(nd, 0);
+	std::vector<std::vector<int>> per_dev(nd);
+	for (int oi : order) {                                                          // greedy LPT
+		int best = 0;
+		for (int d = 1; d < nd; ++d) if (load[d] < load[best]) best = d;
+		load[best] += items[oi].work + 1;
+		per_dev[best].push_back(oi);
+	}
+
+	// ---- per device: group by class (descending work inside), pack, copy ----
+	for (int d = 0; d < nd; ++d) {
+		SubBatch &sb = B->subs[d];
+		auto &lst = per_dev[d];
+		std::stable_sort(lst.begin(), lst.end(), [&](int a, int b) { return items[a].cls < items[b].cls; });
+		size_t pos = 0;
+		sb.pairs.resize(lst.size());
+		for (int c = 0; c <= kNumClasses; ++c) {
+			int k = 0;
+			while (k < (int)lst.size() && items[lst[k]].cls < c) ++k;
+			sb.class_first[c] = k;                                                  // first pair of class >= c
+		}
+		for (size_t k = 0; k < lst.size(); ++k) {
+			const Item &it = items[lst[k]];
+			PairDesc &pd = sb.pairs[k];
+			const int i = it.idx;
+			pd.qlen = qlen[i]; pd.tlen = tlen[i];
+			pd.w = w < 0 ? std::max(qlen[i], tlen[i]) : std::min(w, std::max(qlen[i], tlen[i]));
+			pd.orig = i;
+			pd.q_off = (int64_t)(pos + kQPadL);
+			pos = align_up(pos + kQPadL + qlen[i], 16);
+			pd.t_off = (int64_t)pos;
+			pos = align_up(pos + tlen[i], 16);
+			pd.tb_off = 0;
+		}
+		sb.arena_bytes = pos + 16;
+		if (lst.empty()) continue;
+		if (cudaSetDevice(sb.dc->dev) != cudaSuccess) { delete B; return bail(fail(KSW_B200_ERR_CUDA, "cudaSetDevice")); }
+		if (sb.h_arena.ensure(sb.arena_bytes) || sb.d_arena.ensure(sb.arena_bytes) ||
+		    (B->have_raw && (sb.h_raw.ensure(sb.arena_bytes) || sb.d_raw.ensure(sb.arena_bytes)))) {
+			for (auto &s : B->subs) s.release();
+			delete B; return bail(fail(KSW_B200_ERR_NOMEM, "sequence arena allocation failed"));
+		}
+		uint8_t *ha = (uint8_t *)sb.h_arena.p, *hr = (uint8_t *)sb.h_raw.p;
+		const int64_t np = (int64_t)sb.pairs.size();
+		int bad_symbol = 0;
+#pragma omp parallel for schedule(static) reduction(| : bad_symbol)
+		for (int64_t k = 0; k < np; ++k) {
+			const PairDesc &pd = sb.pairs[k];
+			const int i = pd.orig;
+			uint8_t *qd = ha + pd.q_off, *td = ha + pd.t_off;
+			memset(qd - kQPadL, 0, kQPadL);
+			memcpy(qd, qbuf + qoff[i], pd.qlen);
+			memset(qd + pd.qlen, 0, (size_t)(pd.t_off - pd.q_off) - pd.qlen);
+			memcpy(td, tbuf + toff[i], pd.tlen);
+			memset(td + pd.tlen, 0, align_up(pd.tlen, 16) - pd.tlen);
+			uint8_t acc = 0;
+			for (int x = 0; x < pd.qlen; ++x) acc |= qd[x];
+			for (int x = 0; x < pd.tlen; ++x) acc |= td[x];
+			if (acc >= kTableStride) bad_symbol |= 1;
+			if (hr) {
+				memcpy(hr + pd.q_off, q_raw_buf + qoff[i], pd.qlen);
+				memcpy(hr + pd.t_off, t_raw_buf + toff[i], pd.tlen);
+			}
+		}
+		if (bad_symbol) {
+			for (auto &s : B->subs) s.release();
+			delete B; return bail(fail(KSW_B200_ERR_ARG, "sequence symbol >= 8"));
+		}
+		cudaStream_t st = sb.dc->stream;
+		bool ok = cudaMemcpyAsync(sb.d_arena.p, ha, sb.arena_bytes, cudaMemcpyHostToDevice, st) == cudaSuccess;
+		if (ok && hr) ok = cudaMemcpyAsync(sb.d_raw.p, hr, sb.arena_bytes, cudaMemcpyHostToDevice, st) == cudaSuccess;
+		// per-pair descriptors, results, table
+		const size_t pbytes = sb.pairs.size() * sizeof(PairDesc);
+		ok = ok && !sb.d_pairs.ensure(pbytes) && !sb.d_results.ensure(sb.pairs.size() * sizeof(PairResult)) &&
+		     !sb.d_table.ensure(sizeof(B->table)) && !sb.d_misc.ensure(4096) &&
+		     !sb.h_results.ensure(sb.pairs.size() * sizeof(PairResult));
+		if (ok) ok = cudaMemcpyAsync(sb.d_table.p, B->table, sizeof(B->table), cudaMemcpyHostToDevice, st) == cudaSuccess;
+		for (auto &e2 : sb.ev) if (ok) ok = cudaEventCreate(&e2) == cudaSuccess;
+		if (!ok) {
+			std::string msg = std::string("upload failed: ") + cudaGetErrorString(cudaGetLastError());
+			for (auto &s : B->subs) s.release();
+			delete B; return bail(fail(KSW_B200_ERR_CUDA, msg));
+		}
+	}
+	// exact cell count (for GCUPS) -- O(sum of lengths), parallel
+	{
+		int64_t cells = 0;
+		const int64_t ni = (int64_t)items.size();
+#pragma omp parallel for schedule(dynamic, 256) reduction(+ : cells)
+		for (int64_t k = 0; k < ni; ++k) {
+			int i = items[k].idx;
+			cells += ksw_b200_count_cells(qlen[i], tlen[i], w);
+		}
+		B->cells = cells;
+	}
+	for (auto &sb : B->subs) if (!sb.pairs.empty()) { cudaSetDevice(sb.dc->dev); cudaStreamSynchronize(sb.dc->stream); }
+	return B;
+}
+
+extern "C" int64_t ksw_b200_batch_cells(const ksw_b200_batch_t *b) { return b ? b->cells : 0; }
+
+// ------------------------------------------------------------------------------------------------
+// run
+// ------------------------------------------------------------------------------------------------
+static int plan_waves(ksw_b200_batch &B, SubBatch &sb, bool cigar)
+{
+	sb.waves.clear();
+	size_t max_tb = 0, max_cig = 0;
+	for (int c = 0; c < kNumClasses; ++c) {
+		int first = sb.class_first[c], last = sb.class_first[c + 1];
+		if (first >= last) continue;
+		const size_t rowB = (size_t)class_ns(c) / 2;
+		int k = first;
+		while (k < last) {
+			Wave wv{c, k, 0, 0};
+			size_t cig = 0;
+			while (k < last) {
+				PairDesc &pd = sb.pairs[k];
+				size_t bytes = cigar ? align_up(((size_t)pd.qlen + pd.tlen) * rowB, 256) : 0;
+				if (wv.count > 0 && wv.tb_bytes + bytes > sb.dc->tb_budget) break;
+				pd.tb_off = (int64_t)wv.tb_bytes;
+				wv.tb_bytes += bytes;
+				cig += (size_t)pd.qlen + pd.tlen + 2;
+				++wv.count; ++k;
+			}
+			max_tb = std::max(max_tb, wv.tb_bytes);
+			max_cig += cig;
+			sb.waves.push_back(wv);
+		}
+	}
+	if (cigar) {
+		if (sb.d_tb.ensure(max_tb + 256)) return fail(KSW_B200_ERR_NOMEM, "traceback arena allocation failed");
+		// compact CIGAR arena: offsets are int32 in PairResult
+		if (max_cig > 0x7fffffffull) max_cig = 0x7fffffffull;
+		sb.cigar_cap = max_cig;
+		if (sb.d_cigar.ensure(max_cig * 4 + 256)) return fail(KSW_B200_ERR_NOMEM, "CIGAR arena allocation failed");
+		if (B.want_stats && sb.d_stats.ensure(sb.pairs.size() * sizeof(sd_stats_t))) return fail(KSW_B200_ERR_NOMEM, "stats allocation failed");
+	}
+	return 0;
+}
+
+static int run_sub(ksw_b200_batch &B, SubBatch &sb)
+{
+	if (sb.pairs.empty()) { sb.total_ms = sb.dp_ms = sb.tb_ms = 0; sb.launches = 0; return 0; }
+	const bool cigar = !(B.flag & KSW_EZ_SCORE_ONLY);
+	const bool right = (B.flag & KSW_EZ_RIGHT) != 0;
+	CUDA_TRY(cudaSetDevice(sb.dc->dev));
+	cudaStream_t st = sb.dc->stream;
+	int rc = plan_waves(B, sb, cigar);
+	if (rc) return rc;
+	// descriptors carry tb offsets -> (re)upload
+	CUDA_TRY(cudaMemcpyAsync(sb.d_pairs.p, sb.pairs.data(), sb.pairs.size() * sizeof(PairDesc), cudaMemcpyHostToDevice, st));
+	// misc: [0..63] work counters (one per wave, reused round-robin), [64] cigar cursor (u64 at byte 512), [66] overflow
+	CUDA_TRY(cudaMemsetAsync(sb.d_misc.p, 0, 4096, st));
+	int *d_counters = (int *)sb.d_misc.p;
+	unsigned long long *d_cursor = (unsigned long long *)((char *)sb.d_misc.p + 2048);
+	int *d_overflow = (int *)((char *)sb.d_misc.p + 2048 + 64);
+	sb.launches = 0; sb.dp_ms = sb.tb_ms = 0;
+	CUDA_TRY(cudaEventRecord(sb.ev[0], st));
+	std::vector<std::pair<cudaEvent_t, cudaEvent_t>> dp_ev, tb_ev;
+	int wave_no = 0;
+	for (const Wave &wv : sb.waves) {
+		const int c = wv.cls;
+		DpLaunch L;
+		L.pairs = (const PairDesc *)sb.d_pairs.p + wv.first;
+		L.results = (PairResult *)sb.d_results.p + wv.first;
+		L.seq = (const uint8_t *)sb.d_arena.p;
+		L.tb = (uint8_t *)sb.d_tb.p;
+		L.table = (const uint32_t *)sb.d_table.p;
+		if (wave_no >= 500) return fail(KSW_B200_ERR_NOMEM, "too many waves; raise KSW_B200_TB_BUDGET_MB");
+		L.work_counter = d_counters + wave_no;
+		L.n = wv.count; L.sc = B.sc;
+		int occ = dp_occupancy(c, cigar, right);
+		if (occ <= 0) return fail(KSW_B200_ERR_CUDA, "DP kernel cannot be resident (occupancy 0)");
+		const int groups_per_block = 128 / kClasses[c].G;
+		int grid = std::min((wv.count + groups_per_block - 1) / groups_per_block, sb.dc->sms * occ);
+		cudaEvent_t a, b2, c2;
+		CUDA_TRY(cudaEventCreate(&a)); CUDA_TRY(cudaEventCreate(&b2)); CUDA_TRY(cudaEventCreate(&c2));
+		CUDA_TRY(cudaEventRecord(a, st));
+		CUDA_TRY(launch_dp(c, L, cigar, right, grid, st));
+		CUDA_TRY(cudaEventRecord(b2, st));
+		++sb.launches;
+		dp_ev.push_back({a, b2});
+		if (cigar) {
+			TbLaunch TL;
+			TL.pairs = L.pairs; TL.results = L.results; TL.tb = L.tb;
+			TL.raw = B.have_raw ? (const uint8_t *)sb.d_raw.p : nullptr;
+			TL.seq = L.seq;
+			TL.cigar_arena = (uint32_t *)sb.d_cigar.p; TL.cigar_cursor = d_cursor; TL.cigar_capacity = sb.cigar_cap;
+			TL.stats = B.want_stats ? (sd_stats_t *)sb.d_stats.p + wv.first : nullptr;
+			TL.overflow = d_overflow;
+			TL.n = wv.count; TL.NS = class_ns(c); TL.flag = B.flag;
+			int tgrid = (wv.count + 127) / 128;
+			if (B.want_stats) extz_traceback_kernel<true><<<tgrid, 128, 0, st>>>(TL);
+			else extz_traceback_kernel<false><<<tgrid, 128, 0, st>>>(TL);
+			CUDA_TRY(cudaGetLastError());
+			++sb.launches;
+		}
+		CUDA_TRY(cudaEventRecord(c2, st));
+		tb_ev.push_back({b2, c2});
+		++wave_no;
+	}
+	CUDA_TRY(cudaEventRecord(sb.ev[1], st));
+	CUDA_TRY(cudaStreamSynchronize(st));
+	CUDA_TRY(cudaEventElapsedTime(&sb.total_ms, sb.ev[0], sb.ev[1]));
+	for (auto &p : dp_ev) { float ms = 0; cudaEventElapsedTime(&ms, p.first, p.second); sb.dp_ms += ms; }
+	for (auto &p : tb_ev) { float ms = 0; cudaEventElapsedTime(&ms, p.first, p.second); sb.tb_ms += ms; }
+	for (auto &p : dp_ev) cudaEventDestroy(p.first);
+	for (auto &p : tb_ev) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+	int ovf = 0;
+	CUDA_TRY(cudaMemcpy(&ovf, d_overflow, sizeof(int), cudaMemcpyDeviceToHost));
+	CUDA_TRY(cudaMemcpy(&sb.cigar_used, d_cursor, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+	if (ovf) return fail(KSW_B200_ERR_NOMEM, "compact CIGAR arena overflow");
+	return 0;
+}
+
+extern "C" int ksw_b200_batch_run(ksw_b200_batch_t *B, float *device_ms)
+{
+	if (!B) return fail(KSW_B200_ERR_ARG, "null batch");
+	float worst = 0;
+	// waves of different devices overlap: launches are asynchronous, run_sub only blocks on its own stream
+	// (one device per process is the scaling configuration; in-process multi-device runs them back to back
+	//  on the host side but concurrently on the devices when the batch fits one wave)
+	for (auto &sb : B->subs) {
+		int rc = run_sub(*B, sb);
+		if (rc) return rc;
+		worst = std::max(worst, sb.total_ms);
+	}
+	if (device_ms) *device_ms = worst;
+	return KSW_B200_OK;
+}
+
+extern "C" int ksw_b200_batch_launches(const ksw_b200_batch_t *B)
+{
+	int n = 0;
+	if (B) for (auto &sb : B->subs) n += sb.launches;
+	return n;
+}
+extern "C" int ksw_b200_batch_kernel_ms(const ksw_b200_batch_t *B, float *dp_ms, float *tb_ms, float *aux_ms)
+{
+	if (!B) return KSW_B200_ERR_ARG;
+	float d = 0, t = 0, tot = 0;
+	for (auto &sb : B->subs) { d = std::max(d, sb.dp_ms); t = std::max(t, sb.tb_ms); tot = std::max(tot, sb.total_ms); }
+	if (dp_ms) *dp_ms = d;
+	if (tb_ms) *tb_ms = t;
+	if (aux_ms) *aux_ms = std::max(0.f, tot - d - t);
+	return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// fetch
+// ------------------------------------------------------------------------------------------------
+static void reset_ez(ksw_extz_t *ez)                                              // extern/ksw2.h:153-159
+{
+	ez->max_q = ez->max_t = ez->mqe_t = ez->mte_q = -1;
+	ez->max = 0; ez->score = ez->mqe = ez->mte = KSW_NEG_INF;
+	ez->n_cigar = 0; ez->m_cigar = 0; ez->zdropped = 0;
+	ez->cigar = 0;
+}
+
+extern "C" int ksw_b200_batch_fetch(ksw_b200_batch_t *B, ksw_extz_t *ez, sd_stats_t *stats)
+{
+	if (!B || (B->n > 0 && !ez)) return fail(KSW_B200_ERR_ARG, "null argument");
+	const bool cigar = !(B->flag & KSW_EZ_SCORE_ONLY);
+	for (int i = 0; i < B->n; ++i) reset_ez(&ez[i]);
+	if (stats) memset(stats, 0, sizeof(sd_stats_t) * (size_t)B->n);
+	int rc_all = 0;
+	for (auto &sb : B->subs) {
+		if (sb.pairs.empty()) continue;
+		CUDA_TRY(cudaSetDevice(sb.dc->dev));
+		cudaStream_t st = sb.dc->stream;
+		const size_t np = sb.pairs.size();
+		CUDA_TRY(cudaMemcpyAsync(sb.h_results.p, sb.d_results.p, np * sizeof(PairResult), cudaMemcpyDeviceToHost, st));
+		if (cigar && sb.cigar_used) {
+			if (sb.h_cigar.ensure(sb.cigar_used * 4)) return fail(KSW_B200_ERR_NOMEM, "pinned CIGAR buffer");
+			CUDA_TRY(cudaMemcpyAsync(sb.h_cigar.p, sb.d_cigar.p, sb.cigar_used * 4, cudaMemcpyDeviceToHost, st));
+		}
+		if (cigar && stats && B->want_stats) {
+			if (sb.h_stats.ensure(np * sizeof(sd_stats_t))) return fail(KSW_B200_ERR_NOMEM, "pinned stats buffer");
+			CUDA_TRY(cudaMemcpyAsync(sb.h_stats.p, sb.d_stats.p, np * sizeof(sd_stats_t), cudaMemcpyDeviceToHost, st));
+		}
+		CUDA_TRY(cudaStreamSynchronize(st));
+		const PairResult *res = (const PairResult *)sb.h_results.p;
+		const uint32_t *carena = (const uint32_t *)sb.h_cigar.p;
+		const sd_stats_t *hst = (const sd_stats_t *)sb.h_stats.p;
+		int nomem = 0;
+#pragma omp parallel for schedule(static) reduction(| : nomem)
+		for (int64_t k = 0; k < (int64_t)np; ++k) {
+			const PairResult &r = res[k];
+			ksw_extz_t *z = &ez[sb.pairs[k].orig];
+			z->max = (uint32_t)r.max; z->zdropped = (uint32_t)r.zdropped;
+			z->max_q = r.max_q; z->max_t = r.max_t; z->mqe = r.mqe; z->mqe_t = r.mqe_t;
+			z->mte = r.mte; z->mte_q = r.mte_q; z->score = r.score;
+			if (cigar && r.n_cigar > 0) {
+				int64_t cap = 4;                                                  // growth of ksw_push_cigar (extern/ksw2.h:101-105)
+				while (cap < r.n_cigar) cap <<= 1;
+				z->cigar = (uint32_t *)malloc((size_t)cap << 2);
+				if (!z->cigar) { nomem |= 1; continue; }
+				memcpy(z->cigar, carena + r.cigar_off, (size_t)r.n_cigar * 4);
+				z->n_cigar = r.n_cigar; z->m_cigar = cap;
+			}
+			if (cigar && stats && B->want_stats) stats[sb.pairs[k].orig] = hst[k];
+		}
+		if (nomem) rc_all = KSW_B200_ERR_NOMEM;
+	}
+	if (rc_all) {
+		for (int i = 0; i < B->n; ++i) { free(ez[i].cigar); ez[i].cigar = 0; ez[i].n_cigar = ez[i].m_cigar = 0; }
+		return fail(rc_all, "malloc of a CIGAR failed");
+	}
+	return KSW_B200_OK;
+}
+
+extern "C" void ksw_b200_batch_free(ksw_b200_batch_t *B)
+{
+	if (!B) return;
+	for (auto &sb : B->subs) { if (sb.dc) cudaSetDevice(sb.dc->dev); sb.release(); }
+	delete B;
+}
+
+// ------------------------------------------------------------------------------------------------
+// one-shot entry points
+// ------------------------------------------------------------------------------------------------
+extern "C" int ksw_extz2_batch_flat(int n, const int *qlen, const int64_t *qoff, const uint8_t *qbuf,
+                                    const int *tlen, const int64_t *toff, const uint8_t *tbuf,
+                                    int8_t m, const int8_t *mat, int8_t q, int8_t e, int w, int zdrop, int flag,
+                                    ksw_extz_t *ez, sd_stats_t *stats,
+                                    const uint8_t *q_raw_buf, const uint8_t *t_raw_buf)
+{
+	int err = 0;
+	ksw_b200_batch_t *B = ksw_b200_batch_upload(n, qlen, qoff, qbuf, tlen, toff, tbuf, m, mat, q, e, w, zdrop, flag,
+	                                           q_raw_buf, t_raw_buf, &err);
+	if (!B) return err;
+	int rc = ksw_b200_batch_run(B, nullptr);
+	if (rc == 0) rc = ksw_b200_batch_fetch(B, ez, stats);
+	ksw_b200_batch_free(B);
+	return rc;
+}
+
+extern "C" int ksw_extz2_batch(int n, const int *qlen, const uint8_t *const *query,
+                               const int *tlen, const uint8_t *const *target,
+                               int8_t m, const int8_t *mat, int8_t q, int8_t e, int w, int zdrop, int flag,
+                               ksw_extz_t *ez, sd_stats_t *stats,
+                               const uint8_t *const *q_raw, const uint8_t *const *t_raw)
+{
+	if (n < 0 || (n > 0 && (!qlen || !tlen || !query || !target))) return fail(KSW_B200_ERR_ARG, "null pointer or negative count");
+	// gather into flat buffers (offsets are relative to the lowest pointer would be fragile; copy instead)
+	std::vector<int64_t> qoff(n), toff(n);
+	int64_t qs = 0, ts = 0;
+	for (int i = 0; i < n; ++i) { qoff[i] = qs; toff[i] = ts; qs += std::max(0, qlen[i]); ts += std::max(0, tlen[i]); }
+	std::vector<uint8_t> qb(qs + 1), tb(ts + 1), qr, tr;
+	const bool raw = q_raw && t_raw;
+	if (raw) { qr.resize(qs + 1); tr.resize(ts + 1); }
+	for (int i = 0; i < n; ++i) {
+		if (qlen[i] > 0) { memcpy(&qb[qoff[i]], query[i], qlen[i]); if (raw) memcpy(&qr[qoff[i]], q_raw[i], qlen[i]); }
+		if (tlen[i] > 0) { memcpy(&tb[toff[i]], target[i], tlen[i]); if (raw) memcpy(&tr[toff[i]], t_raw[i], tlen[i]); }
+	}
+	return ksw_extz2_batch_flat(n, qlen, qoff.data(), qb.data(), tlen, toff.data(), tb.data(), m, mat, q, e, w, zdrop, flag,
+	                            ez, stats, raw ? qr.data() : nullptr, raw ? tr.data() : nullptr);
+}
+
+extern "C" void ksw_extz2_b200(void *km, int qlen, const uint8_t *query, int tlen, const uint8_t *target,
+                               int8_t m, const int8_t *mat, int8_t q, int8_t e, int w, int zdrop, int flag,
+                               ksw_extz_t *ez)
+{
+	(void)km;
+	reset_ez(ez);
+	if (m <= 0 || qlen <= 0 || tlen <= 0) return;                                   // :57
+	int64_t zero = 0;
+	int rc = ksw_extz2_batch_flat(1, &qlen, &zero, query, &tlen, &zero, target, m, mat, q, e, w, zdrop, flag, ez, nullptr, nullptr, nullptr);
+	if (rc) {
+		fprintf(stderr, "[ksw_extz2_b200] %s: %s\n", ksw_b200_strerror(rc), ksw_b200_last_error());
+		reset_ez(ez);
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-side floating point fields (src/stats_main.cc:273-283,297-299; src/align.h:84-92)
+// ------------------------------------------------------------------------------------------------
+extern "C" void sd_stats_derive_fp(const sd_stats_t *s, sd_stats_fp_t *o)
+{
+	o->fracMatch = double(s->matchB) / (s->alnB);
+	o->fracMatchIndel = double(s->matchB) / (s->span);
+	double jcp = double(s->mismatchB) / (s->alnB);
+	o->jcK = -0.75 * log(1.0 - 4.0 / 3 * jcp);
+	double p = double(s->transitionsB) / (s->alnB);
+	double q = double(s->transversionsB) / (s->alnB);
+	double w1 = 1.0 / (1 - 2.0 * p - q);
+	double w2 = 1.0 / (1 - 2.0 * q);
+	o->k2K = 0.5 * log(w1) + 0.25 * log(w2);
+	o->errorScaled = (s->gaps + s->mismatches) / double(s->gaps + s->mismatches + s->matches);
+	o->filter_score = 1 - o->errorScaled;
+	double tot = s->matches + s->gap_bases + s->mismatches;
+	o->gap_error = 100.0 * s->gap_bases / tot;                                       // src/common.h:99 pct()
+	o->mismatch_error = 100.0 * s->mismatches / tot;
+	o->total_error = o->mismatch_error + o->gap_error;
+}

@@ -1,0 +1,137 @@
+// extz_tb.cuh -- K3 + K4 of SURVEY.md section 2.1: device-side traceback -> CIGAR, fused with the SD
+// statistics pass (Alignment::populate_nice_alignment + the BEDPE stat loop), one THREAD per pair.
+//
+// The walk is a sequential pointer chase of <= qlen+tlen dependent 4-bit reads per pair, so it is
+// latency-bound per pair and throughput comes from having every lane of every warp on a different
+// pair (10^5 pairs in flight hide the L2/HBM latency).  The reversed CIGAR is written IN PLACE
+// over the pair's own, already consumed traceback rows (row bytes >= 4 per step, see below), so the
+// kernel needs no scratch memory; the finished CIGAR is then copied to a compact arena whose
+// cursor is a single atomicAdd per pair.
+#pragma once
+#include <cuda_runtime.h>
+#include "extz_core.cuh"
+#include "../../include/ksw2_b200.h"
+
+namespace extz {
+
+struct TbLaunch {
+	const PairDesc *pairs;
+	PairResult *results;
+	uint8_t *tb;                 // traceback arena of the wave
+	const uint8_t *raw;          // arena of ORIGINAL-CASE bytes (same offsets as the code arena) or nullptr
+	const uint8_t *seq;          // code arena (used to synthesise "ACGTN" when raw == nullptr)
+	uint32_t *cigar_arena;       // compact output
+	unsigned long long *cigar_cursor;
+	unsigned long long cigar_capacity;
+	sd_stats_t *stats;           // [n] indexed like pairs, or nullptr
+	int *overflow;               // set to 1 when the compact arena is too small
+	int n, NS, flag;
+};
+
+__device__ __forceinline__ int raw_byte(const TbLaunch &L, int64_t off, int idx)
+{
+	if (L.raw) return L.raw[off + idx];
+	int c = L.seq[off + idx];
+	return c == 0 ? 'A' : c == 1 ? 'C' : c == 2 ? 'G' : c == 3 ? 'T' : 'N';
+}
+
+template <bool kStats>
+__global__ void __launch_bounds__(128)
+extz_traceback_kernel(TbLaunch L)
+{
+	int pi = blockIdx.x * blockDim.x + threadIdx.x;
+	if (pi >= L.n) return;
+	const PairDesc pd = L.pairs[pi];
+	PairResult pr = L.results[pi];
+	const int qlen = pd.qlen, tlen = pd.tlen, w = pd.w, NS = L.NS;
+	const int T = (tlen + 15) & ~15;
+	const int rowB = NS >> 1;
+
+	StatAcc sa;
+	sa.span = sa.gap_bases = sa.matches = sa.mismatches = sa.indel_a = sa.indel_b = sa.alnB = sa.matchB = 0;
+	sa.mismatchB = sa.transitionsB = sa.transversionsB = sa.uppercaseA = sa.uppercaseB = sa.uppercaseMatches = 0;
+
+	int i0, j0; bool run = true;                                   // extern/ksw2_extz2_sse.cc:290-295
+	if (!pr.zdropped && !(L.flag & kFlagExtzOnly)) { i0 = tlen - 1; j0 = qlen - 1; }
+	else if (pr.max_t >= 0 && pr.max_q >= 0) { i0 = pr.max_t; j0 = pr.max_q; }
+	else { i0 = j0 = -1; run = false; }
+
+	uint8_t *tbp = L.tb + pd.tb_off;
+	// reversed CIGAR grows downward from the end of the rows that can be visited: entry k lives at
+	// end - 4(k+1).  After reading row r, rows >= r are dead, and k+1 <= r0 - r + 1 steps have
+	// been pushed, so the entries never reach a live row as long as rowB >= 4.
+	uint32_t *cend = (uint32_t *)(tbp + ((int64_t)(run ? i0 + j0 : 0) + 1) * rowB);
+	int64_t n = 0; int32_t gaps = 0; uint32_t last = 0;             // `last` caches cend[-n]
+	auto push = [&](uint32_t op, int len) {                         // ksw_push_cigar (extern/ksw2.h:98-111)
+		if (n == 0 || op != (last & 0xfu)) {
+			if (n) cend[-n] = last;
+			++n; last = (uint32_t)len << 4 | op;
+			if (op != 0) ++gaps;
+		} else last += (uint32_t)len << 4;
+	};
+
+	if (run) {
+		int i = i0, j = j0, state = 0;
+		while (i >= 0 && j >= 0) {                                  // extern/ksw2.h:124-144
+			int r = i + j;
+			Band b; band_of(r, qlen, tlen, w, T, false, b);
+			int force = -1;
+			if (i < b.st) force = 2;
+			if (i > b.en) force = 1;
+			uint32_t tmp = 0;
+			if (force < 0) tmp = tb_fetch(tbp, NS, r, i);
+			int hstate = (tmp & 2u) ? 2 : (int)(tmp & 1u);          // which of H/E/F gave the max
+			if (state == 0) state = hstate;
+			else if (!((tmp >> (state + 1)) & 1u)) state = 0;       // continuation bits: E -> bit2, F -> bit3
+			if (state == 0) state = hstate;
+			if (force >= 0) state = force;
+			if (state == 0) {
+				push(0, 1);
+				if (kStats) stat_match_col(sa, raw_byte(L, pd.q_off, j), raw_byte(L, pd.t_off, i));
+				--i; --j;
+			} else if (state == 1) {
+				push(2, 1);                                          // ksw D: consumes the target
+				if (kStats) stat_tonly_col(sa, raw_byte(L, pd.t_off, i));
+				--i;
+			} else {
+				push(1, 1);                                          // ksw I: consumes the query
+				if (kStats) stat_qonly_col(sa, raw_byte(L, pd.q_off, j));
+				--j;
+			}
+		}
+		if (i >= 0) {                                               // extern/ksw2.h:145
+			push(2, i + 1);
+			if (kStats) for (int k = i; k >= 0; --k) stat_tonly_col(sa, raw_byte(L, pd.t_off, k));
+		}
+		if (j >= 0) {                                               // extern/ksw2.h:146
+			push(1, j + 1);
+			if (kStats) for (int k = j; k >= 0; --k) stat_qonly_col(sa, raw_byte(L, pd.q_off, k));
+		}
+		if (n) cend[-n] = last;
+	}
+
+	// ---- copy to the compact arena: memory order [cend-n, cend) is the FORWARD cigar ----
+	unsigned long long off = 0;
+	if (n) {
+		off = atomicAdd(L.cigar_cursor, (unsigned long long)n);
+		if (off + (unsigned long long)n > L.cigar_capacity) { *L.overflow = 1; n = 0; }
+	}
+	const bool rev = (L.flag & kFlagRevCigar) != 0;
+	for (int64_t k = 0; k < n; ++k)
+		L.cigar_arena[off + k] = rev ? cend[-1 - k] : cend[-n + k];
+	pr.n_cigar = (int32_t)n;
+	pr.cigar_off = (int32_t)off;
+	L.results[pi].n_cigar = (int32_t)n;
+	L.results[pi].cigar_off = (int32_t)off;
+
+	if (kStats && L.stats) {
+		sd_stats_t s;
+		s.span = sa.span; s.gaps = gaps; s.gap_bases = sa.gap_bases; s.matches = sa.matches; s.mismatches = sa.mismatches;
+		s.indel_a = sa.indel_a; s.indel_b = sa.indel_b; s.alnB = sa.alnB; s.matchB = sa.matchB; s.mismatchB = sa.mismatchB;
+		s.transitionsB = sa.transitionsB; s.transversionsB = sa.transversionsB;
+		s.uppercaseA = sa.uppercaseA; s.uppercaseB = sa.uppercaseB; s.uppercaseMatches = sa.uppercaseMatches; s.reserved = 0;
+		L.stats[pi] = s;
+	}
+}
+
+} // namespace extz

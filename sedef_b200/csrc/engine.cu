@@ -58,54 +58,60 @@ extern "C" const char *ksw_b200_last_error(void) { return g_last_error.c_str(); 
 // ------------------------------------------------------------------------------------------------
 // kernel classes
 // ------------------------------------------------------------------------------------------------
-struct KClass { int G, S; };
-static const KClass kClasses[] = { {8, 4}, {16, 4}, {16, 8}, {32, 8}, {32, 16}, {32, 32} };
+struct KClass { int G, S; bool wide; };
+// narrow classes: G <= 32 lanes per pair, 128-thread CTAs; wide classes: one CTA of G lanes per pair
+static const KClass kClasses[] = { {8, 4, false}, {16, 4, false}, {16, 8, false}, {32, 8, false}, {32, 16, false},
+                                   {32, 32, false}, {64, 16, true}, {128, 16, true}, {256, 16, true} };
 static const int kNumClasses = sizeof(kClasses) / sizeof(kClasses[0]);
 static inline int class_ns(int c) { return kClasses[c].G * kClasses[c].S; }
 // S == 32 lanes switch whole-lane (two 16-blocks), which costs 16 slots of window (extz_dp.cuh)
 static inline int class_capacity(int c) { return kClasses[c].S > 16 ? class_ns(c) - 16 : class_ns(c); }
+static inline int class_threads(int c) { return kClasses[c].wide ? kClasses[c].G : 128; }
+static inline int class_pairs_per_block(int c) { return kClasses[c].wide ? 1 : 128 / kClasses[c].G; }
 
-template <int G, int S>
+// kernel selection: every (class, cigar, right) combination is a distinct instantiation
+template <int G, int S, bool W, bool C, bool R> struct KSel;
+template <int G, int S, bool C, bool R> struct KSel<G, S, false, C, R> { static constexpr auto fn = extz_dp_kernel<G, S, C, R>; };
+template <int G, int S, bool C, bool R> struct KSel<G, S, true, C, R> { static constexpr auto fn = extz_dp_wide_kernel<G, S, C, R>; };
+
+template <int G, int S, bool W>
 static cudaError_t launch_dp_gs(const DpLaunch &L, bool cigar, bool right, int grid, cudaStream_t st)
 {
+	constexpr int threads = W ? G : 128;
 	if (cigar) {
-		if (right) extz_dp_kernel<G, S, true, true><<<grid, 128, 0, st>>>(L);
-		else       extz_dp_kernel<G, S, true, false><<<grid, 128, 0, st>>>(L);
-	} else       extz_dp_kernel<G, S, false, false><<<grid, 128, 0, st>>>(L);
+		if (right) KSel<G, S, W, true, true>::fn<<<grid, threads, 0, st>>>(L);
+		else       KSel<G, S, W, true, false>::fn<<<grid, threads, 0, st>>>(L);
+	} else       KSel<G, S, W, false, false>::fn<<<grid, threads, 0, st>>>(L);
 	return cudaGetLastError();
 }
-static cudaError_t launch_dp(int c, const DpLaunch &L, bool cigar, bool right, int grid, cudaStream_t st)
-{
-	switch (c) {
-	case 0: return launch_dp_gs<8, 4>(L, cigar, right, grid, st);
-	case 1: return launch_dp_gs<16, 4>(L, cigar, right, grid, st);
-	case 2: return launch_dp_gs<16, 8>(L, cigar, right, grid, st);
-	case 3: return launch_dp_gs<32, 8>(L, cigar, right, grid, st);
-	case 4: return launch_dp_gs<32, 16>(L, cigar, right, grid, st);
-	case 5: return launch_dp_gs<32, 32>(L, cigar, right, grid, st);
-	}
-	return cudaErrorInvalidValue;
-}
-template <int G, int S>
+template <int G, int S, bool W>
 static int dp_occupancy_gs(bool cigar, bool right)
 {
+	constexpr int threads = W ? G : 128;
 	int nb = 0;
 	if (cigar) {
-		if (right) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, extz_dp_kernel<G, S, true, true>, 128, 0);
-		else       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, extz_dp_kernel<G, S, true, false>, 128, 0);
-	} else       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, extz_dp_kernel<G, S, false, false>, 128, 0);
+		if (right) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, KSel<G, S, W, true, true>::fn, threads, 0);
+		else       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, KSel<G, S, W, true, false>::fn, threads, 0);
+	} else       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, KSel<G, S, W, false, false>::fn, threads, 0);
 	return nb;
+}
+#define EXTZ_FOR_CLASS(c, CALL) \
+	switch (c) { \
+	case 0: return CALL(8, 4, false); case 1: return CALL(16, 4, false); case 2: return CALL(16, 8, false); \
+	case 3: return CALL(32, 8, false); case 4: return CALL(32, 16, false); case 5: return CALL(32, 32, false); \
+	case 6: return CALL(64, 16, true); case 7: return CALL(128, 16, true); case 8: return CALL(256, 16, true); }
+static cudaError_t launch_dp(int c, const DpLaunch &L, bool cigar, bool right, int grid, cudaStream_t st)
+{
+#define EXTZ_CALL(G, S, W) launch_dp_gs<G, S, W>(L, cigar, right, grid, st)
+	EXTZ_FOR_CLASS(c, EXTZ_CALL)
+#undef EXTZ_CALL
+	return cudaErrorInvalidValue;
 }
 static int dp_occupancy(int c, bool cigar, bool right)
 {
-	switch (c) {
-	case 0: return dp_occupancy_gs<8, 4>(cigar, right);
-	case 1: return dp_occupancy_gs<16, 4>(cigar, right);
-	case 2: return dp_occupancy_gs<16, 8>(cigar, right);
-	case 3: return dp_occupancy_gs<32, 8>(cigar, right);
-	case 4: return dp_occupancy_gs<32, 16>(cigar, right);
-	case 5: return dp_occupancy_gs<32, 32>(cigar, right);
-	}
+#define EXTZ_CALL(G, S, W) dp_occupancy_gs<G, S, W>(cigar, right)
+	EXTZ_FOR_CLASS(c, EXTZ_CALL)
+#undef EXTZ_CALL
 	return 0;
 }
 
@@ -507,7 +513,7 @@ static int run_sub(ksw_b200_batch &B, SubBatch &sb)
 		L.n = wv.count; L.sc = B.sc;
 		int occ = dp_occupancy(c, cigar, right);
 		if (occ <= 0) return fail(KSW_B200_ERR_CUDA, "DP kernel cannot be resident (occupancy 0)");
-		const int groups_per_block = 128 / kClasses[c].G;
+		const int groups_per_block = class_pairs_per_block(c);
 		int grid = std::min((wv.count + groups_per_block - 1) / groups_per_block, sb.dc->sms * occ);
 		cudaEvent_t a, b2, c2;
 		CUDA_TRY(cudaEventCreate(&a)); CUDA_TRY(cudaEventCreate(&b2)); CUDA_TRY(cudaEventCreate(&c2));

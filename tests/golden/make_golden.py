@@ -1,0 +1,110 @@
+"""Regenerates the golden fixtures in tests/golden/ from the REFERENCE itself.
+
+Run in the build container (needs /root/reference and `make -C oracle ref_full`):
+    python tests/golden/make_golden.py
+Outputs (committed):
+  ksw2_kat.json        the reference's only fixed test pair (python/simulations.py:6-7) through the compiled
+                       reference kernel for the parameter table of SURVEY.md Appendix B.3, plus the
+                       SEDEF-level record produced by the reference's own Alignment class
+  ksw2_golden.json     self-contained fuzz vectors: ASCII pairs + expected ksw_extz_t fields + CIGARs
+                       from oracle/_ref/libksw2_ref.so (unmodified extern/ksw2_extz2_sse.cc)
+  sd_stats_golden.json soft-masked pairs + the reference Alignment(fa, fb) CIGAR string and error counters
+                       from oracle/_ref/libsedef_ref.so (unmodified src/align.cc)
+"""
+import ctypes as C
+import json
+import os
+import re
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+import oracle  # noqa: E402
+from sedef_b200 import synth  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = "/root/reference"
+mat = synth.sedef_matrix()
+
+
+def kat_pair():
+    src = open(os.path.join(REF, "python", "simulations.py")).read()
+    m = re.findall(r"'([ACGTNacgtn]{500,})'", src)
+    return m[0], m[1]
+
+
+def sedef_ref():
+    lib = C.CDLL(os.path.join(ROOT, "oracle", "_ref", "libsedef_ref.so"))
+    lib.ref_alignment.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int] + [C.POINTER(C.c_int)] * 5
+    return lib
+
+
+def ref_alignment(lib, fa: str, fb: str):
+    buf = C.create_string_buffer(4 * (len(fa) + len(fb)) + 64)
+    v = [C.c_int(0) for _ in range(5)]
+    rc = lib.ref_alignment(fa.encode(), fb.encode(), buf, len(buf), *[C.byref(x) for x in v])
+    assert rc == 0
+    return dict(cigar=buf.value.decode(), span=v[0].value, matches=v[1].value, mismatches=v[2].value,
+                gaps=v[3].value, gap_bases=v[4].value)
+
+
+def main():
+    ref = oracle.ref()
+    slib = sedef_ref()
+    s1, s2 = kat_pair()
+    ps = synth.pairs_from_strings([(s1, s2)])
+    q, t = ps.pair(0)
+    rows = []
+    for w, zd, flag in [(-1, -1, 0), (100, -1, 0), (20, -1, 0), (10, -1, 0), (-1, -1, 0x02), (-1, -1, 0x01),
+                        (-1, -1, 0x80), (100, 50, 0), (100, 50, 0x40), (10, -1, 0x40), (10, -1, 0x42)]:
+        f, c = ref.extz2(q, t, mat, 40, 1, w, zd, flag)
+        rows.append(dict(w=w, zdrop=zd, flag=flag, fields=f, cigar=oracle.cigar_str(c)))
+    kat = dict(source="reference python/simulations.py:6-7 (seq1, seq2); outputs of the compiled reference",
+               seq1=s1, seq2=s2, scoring=dict(m=5, match=5, mismatch=-4, gapo=40, gape=1), rows=rows,
+               sedef_alignment=ref_alignment(slib, s1, s2),
+               # stat loop of src/stats_main.cc:244-283 on Alignment(seq1, seq2)
+               survey_stat_loop=dict(span=1137, indel_a=1, indel_b=19, alnB=1117, matchB=1092, mismatchB=25,
+                                     transitionsB=18, transversionsB=7, uppercaseA=355, uppercaseB=348,
+                                     uppercaseMatches=338, gaps=4, gap_bases=20,
+                                     fracMatch=0.977619, fracMatchIndel=0.960422, jcK=0.0227221, k2K=0.0227815,
+                                     filter_score=0.97413))
+    json.dump(kat, open(os.path.join(HERE, "ksw2_kat.json"), "w"), indent=1)
+
+    # ---- kernel-level golden vectors ----
+    groups = []
+    specs = [
+        ("tiny", dict(n=60, min_len=1, max_len=40, div=0.15), [(-1, -1, 0), (3, -1, 0), (8, 10, 0)]),
+        ("ragged", dict(n=40, min_len=1, max_len=400, div=0.12), [(-1, -1, 0), (20, -1, 0), (50, 100, 0), (30, 80, 0x02),
+                                                                     (30, 80, 0x01), (30, 80, 0x40), (30, 80, 0x80), (5, -1, 0)]),
+        ("divergent", dict(n=25, min_len=200, max_len=700, div=0.4, burst=60), [(16, 30, 0), (100, 200, 0), (-1, 150, 0)]),
+    ]
+    for gi, (name, kw, params) in enumerate(specs):
+        pset = synth.make_pairs_mixed(seed=4242 + gi, **kw)
+        pairs = [("".join(map(chr, pset.raw_pair(i)[0])), "".join(map(chr, pset.raw_pair(i)[1]))) for i in range(pset.n)]
+        runs = []
+        for (w, zd, flag) in params:
+            _, fr, cr = ref.batch(pset, mat, 40, 1, w, zd, flag, nthreads=4)
+            runs.append(dict(w=w, zdrop=zd, flag=flag,
+                             fields=[[f[k] for k in ("max", "zdropped", "max_q", "max_t", "mqe", "mqe_t", "mte", "mte_q", "score", "n_cigar")] for f in fr],
+                             cigars=[oracle.cigar_str(c) for c in cr]))
+        groups.append(dict(name=name, pairs=pairs, runs=runs))
+    json.dump(dict(source="oracle/_ref/libksw2_ref.so (unmodified reference extern/ksw2_extz2_sse.cc), SEDEF scoring",
+                   field_order=["max", "zdropped", "max_q", "max_t", "mqe", "mqe_t", "mte", "mte_q", "score", "n_cigar"],
+                   groups=groups), open(os.path.join(HERE, "ksw2_golden.json"), "w"))
+
+    # ---- SEDEF-level golden records from the reference's Alignment class ----
+    pset = synth.make_pairs_mixed(60, seed=777, min_len=5, max_len=500, div=0.1, n_frac=0.01)
+    recs = []
+    for i in range(pset.n):
+        fa = "".join(map(chr, pset.raw_pair(i)[0])); fb = "".join(map(chr, pset.raw_pair(i)[1]))
+        recs.append(dict(a=fa, b=fb, **ref_alignment(slib, fa, fb)))
+    json.dump(dict(source="oracle/_ref/libsedef_ref.so: reference Alignment(fa, fb) (src/align.cc:76-88,274-315)",
+                   records=recs), open(os.path.join(HERE, "sd_stats_golden.json"), "w"))
+    for f in ("ksw2_kat.json", "ksw2_golden.json", "sd_stats_golden.json"):
+        print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,219 @@
+"""GPU parity tests: the CUDA path (through the C ABI of include/ksw2_b200.h) against
+  (1) the committed golden vectors produced by the compiled reference,
+  (2) the oracle (oracle/_ref compiled reference when present, else the scalar port) on seeded inputs,
+  (3) size-independent properties at BASELINE.json's full sizes.
+Bit-exact on every integer output: score, max/end coordinates, z-drop flag, CIGAR, SD statistics."""
+import numpy as np
+import pytest
+
+import oracle
+from sedef_b200 import align, engine, synth
+from helpers import FIELD_ORDER, cigar_consistent, load_json
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def checker(built):
+    engine.init(0, 1)
+    return oracle.ref() if oracle.have_ref() else oracle.port()
+
+
+def compare(ps, mat, checker, w, zdrop, flag, use_raw=True):
+    got = engine.extz2_batch(ps, mat, 40, 1, w, zdrop, flag, use_raw=use_raw)
+    _, fr, cr = checker.batch(ps, mat, 40, 1, w, zdrop, flag, nthreads=8)
+    for i in range(ps.n):
+        assert got.fields(i) == fr[i], (i, int(ps.qlen[i]), int(ps.tlen[i]), got.fields(i), fr[i])
+        assert got.cigars[i].tolist() == cr[i], (i, int(ps.qlen[i]), int(ps.tlen[i]))
+        if not (flag & engine.KSW_EZ_SCORE_ONLY):
+            fwd = cr[i] if not (flag & engine.KSW_EZ_REV_CIGAR) else cr[i][::-1]
+            qa, ta = ps.raw_pair(i)
+            if not use_raw:
+                qa = synth.ASCII[ps.pair(i)[0]]; ta = synth.ASCII[ps.pair(i)[1]]
+            assert got.stats_dict(i) == oracle.sd_stats(fwd, qa, ta), i
+    return got
+
+
+def test_kat_table(checker, mat, golden_dir):
+    kat = load_json(golden_dir, "ksw2_kat.json")
+    ps = synth.pairs_from_strings([(kat["seq1"], kat["seq2"])])
+    q, t = ps.pair(0)
+    for row in kat["rows"]:
+        f, c = engine.extz2(q, t, mat, 40, 1, row["w"], row["zdrop"], row["flag"])       # ksw2-compatible single-pair entry
+        assert f == row["fields"], row
+        assert oracle.cigar_str(c) == row["cigar"], row
+
+
+def test_golden_vectors(checker, mat, golden_dir):
+    g = load_json(golden_dir, "ksw2_golden.json")
+    for grp in g["groups"]:
+        ps = synth.pairs_from_strings([tuple(p) for p in grp["pairs"]])
+        for run in grp["runs"]:
+            got = engine.extz2_batch(ps, mat, 40, 1, run["w"], run["zdrop"], run["flag"])
+            for i in range(ps.n):
+                f = got.fields(i)
+                assert [f[k] for k in FIELD_ORDER] == run["fields"][i], (grp["name"], run, i)
+                assert oracle.cigar_str(got.cigars[i].tolist()) == run["cigars"][i], (grp["name"], i)
+
+
+def test_sedef_alignment_mirror(checker, golden_dir):
+    """Alignment(fa, fb) mirror (sedef_b200/align.py) against the reference's own Alignment class."""
+    g = load_json(golden_dir, "sd_stats_golden.json")
+    res = align.align_pairs([(r["a"], r["b"]) for r in g["records"]])
+    for r, a in zip(g["records"], res):
+        assert a.cigar_string() == r["cigar"]
+        assert (a.span(), a.matches(), a.mismatches(), a.gaps(), a.gap_bases()) == \
+               (r["span"], r["matches"], r["mismatches"], r["gaps"], r["gap_bases"])
+    kat = load_json(golden_dir, "ksw2_kat.json")
+    a = align.align(kat["seq1"], kat["seq2"])
+    exp = kat["survey_stat_loop"]
+    for k in ("span", "indel_a", "indel_b", "alnB", "matchB", "mismatchB", "transitionsB", "transversionsB",
+              "uppercaseA", "uppercaseB", "uppercaseMatches", "gaps", "gap_bases"):
+        assert a.stats[k] == exp[k], k
+    fp = a.bedpe_fp()
+    for k in ("fracMatch", "fracMatchIndel", "jcK", "k2K", "filter_score"):
+        assert float("%.6g" % fp[k]) == exp[k]
+    assert "%.1f" % a.total_error() == "4.0"
+
+
+@pytest.mark.parametrize("w,zdrop,flag,kw", [
+    (-1, -1, 0, dict(min_len=1, max_len=40, div=0.15)),            # SEDEF's median call size (<= 32 bp)
+    (-1, -1, 0, dict(min_len=1, max_len=250, div=0.1)),
+    (-1, -1, 0, dict(min_len=200, max_len=520, div=0.1)),          # the 500x500 side extensions
+    (-1, 120, 0, dict(min_len=50, max_len=500, div=0.4)),
+    (20, -1, 0, dict(min_len=1, max_len=600, div=0.15)),
+    (50, 100, 0, dict(min_len=1, max_len=600, div=0.15)),
+    (100, -1, 0, dict(min_len=600, max_len=1300, div=0.08)),
+    (30, 80, 0x01, dict(min_len=1, max_len=600, div=0.2)),
+    (30, 80, 0x02, dict(min_len=1, max_len=600, div=0.2)),
+    (30, 80, 0x04, dict(min_len=1, max_len=600, div=0.2)),
+    (30, 80, 0x40, dict(min_len=1, max_len=600, div=0.2)),
+    (30, 80, 0x80, dict(min_len=1, max_len=600, div=0.2)),
+    (30, 80, 0xc2, dict(min_len=1, max_len=600, div=0.2)),
+    (5, -1, 0, dict(min_len=1, max_len=600, div=0.3)),
+    (3, 20, 0, dict(min_len=1, max_len=600, div=0.3)),
+    (1, -1, 0, dict(min_len=1, max_len=300, div=0.3)),
+    (0, -1, 0, dict(min_len=1, max_len=100, div=0.1)),
+    (17, 30, 0, dict(min_len=100, max_len=900, div=0.4, burst=80)),
+    (33, -1, 0x40, dict(min_len=100, max_len=900, div=0.2, burst=100)),
+])
+def test_fuzz_vs_oracle(checker, mat, w, zdrop, flag, kw):
+    ps = synth.make_pairs_mixed(250, seed=9000 + 13 * (w + 2) + flag, **kw)
+    compare(ps, mat, checker, w, zdrop, flag)
+
+
+def test_config2_shape_vs_oracle(checker, mat):
+    """BASELINE.json configs[1] shape (1 kbp pairs, w=100, 5 % divergence) at a size the oracle finishes in seconds."""
+    ps = synth.make_pairs_small(3000, length=1000, div=0.05, seed=0x5EDEF002)
+    compare(ps, mat, checker, 100, -1, 0)
+
+
+def test_config3_shape_vs_oracle(checker, mat):
+    """BASELINE.json configs[2] shape (long pairs, z-drop on, indels) scaled to the widest kernel (w=400)."""
+    ps = synth.make_pairs_large(24, min_len=3000, max_len=12000, seed=0x5EDEF003)
+    compare(ps, mat, checker, 400, 400, 0)
+    compare(ps, mat, checker, 500, 400, 0)              # the configs[2] band: 528 live slots (32 lanes x 32 slots)
+    compare(ps, mat, checker, 1200, 400, 0)             # CTA-wide banded
+
+
+def test_no_raw_bytes_decodes_codes(checker, mat):
+    ps = synth.make_pairs_mixed(100, seed=5, min_len=1, max_len=300, div=0.1)
+    compare(ps, mat, checker, -1, -1, 0, use_raw=False)
+
+
+def test_edge_cases(checker, mat):
+    pairs = [("A", "A"), ("A", "C"), ("N", "N"), ("ACGT", "A"), ("A", "ACGT"), ("NNNNNNNNNN", "ACGTACGTAC"),
+             ("acgtnACGTN" * 5, "ACGTNacgtn" * 5), ("A" * 16, "A" * 16), ("A" * 17, "A" * 15), ("C" * 15, "C" * 33),
+             ("ACGT" * 8, "TGCA" * 8), ("G" * 100, "G"), ("G", "G" * 100)]
+    ps = synth.pairs_from_strings(pairs)
+    for (w, zd, flag) in [(-1, -1, 0), (2, -1, 0), (0, -1, 0), (4, 5, 0), (-1, -1, 2)]:
+        compare(ps, mat, checker, w, zd, flag)
+
+
+def test_empty_and_degenerate_inputs(checker, mat):
+    # n = 0
+    ps0 = synth.pairs_from_strings([])
+    r0 = engine.extz2_batch(ps0, mat, 40, 1)
+    assert r0.ez.shape[0] == 0
+    # qlen == 0 or tlen == 0 -> reset record (extern/ksw2_extz2_sse.cc:56-57), others unaffected
+    ps = synth.pairs_from_strings([("ACGT", "ACGT"), ("", "ACGT"), ("ACGT", ""), ("ACGTACGT", "ACGAACGT")])
+    got = engine.extz2_batch(ps, mat, 40, 1)
+    reset = dict(max=0, zdropped=0, max_q=-1, max_t=-1, mqe=engine.KSW_NEG_INF, mqe_t=-1, mte=engine.KSW_NEG_INF,
+                 mte_q=-1, score=engine.KSW_NEG_INF, n_cigar=0)
+    assert got.fields(1) == reset and got.fields(2) == reset
+    assert got.fields(0)["score"] == 20 and got.fields(3)["score"] == 31
+    # -min_sc > 2(q+e): silent early return (extern/ksw2_extz2_sse.cc:81)
+    bad = synth.sedef_matrix(5, -100)
+    got = engine.extz2_batch(ps, bad, 40, 1)
+    assert all(got.fields(i) == reset for i in range(ps.n))
+
+
+def test_widest_pair_and_too_wide(checker, mat):
+    """1000x1000 unbanded (SEDEF's largest direct gap fill, src/align.cc:233-236) and 4 kbp unbanded pairs run on the
+    CTA-wide kernels; beyond 4096 live slots the engine refuses (no silent fallback)."""
+    ps = synth.make_pairs_small(6, length=1000, div=0.1, seed=3)
+    compare(ps, mat, checker, -1, -1, 0)
+    ps4k = synth.make_pairs_small(3, length=4000, div=0.1, seed=8)
+    ps4k.tlen[:] = np.minimum(ps4k.tlen, 4090)
+    compare(ps4k, mat, checker, -1, -1, 0)
+    big = synth.make_pairs_small(2, length=6000, div=0.05, seed=4)
+    with pytest.raises(engine.EngineError) as ei:
+        engine.extz2_batch(big, mat, 40, 1, -1, -1, 0)
+    assert ei.value.code == -5
+    with pytest.raises(engine.EngineError) as ei:
+        engine.extz2_batch(ps, mat, 40, 1, -1, -1, engine.KSW_EZ_APPROX_MAX)
+    assert ei.value.code == -4
+
+
+def test_other_scoring_parameters(checker):
+    """Scoring is not hard-wired: user-supplied --match/--mismatch/--gap-open/--gap-extend (src/align_main.cc:343-373)."""
+    ps = synth.make_pairs_mixed(150, seed=77, min_len=1, max_len=400, div=0.15)
+    for (ma, mi, go, ge) in [(1, -1, 2, 1), (2, -4, 4, 2), (5, -4, 40, 1), (10, -9, 30, 3), (5, -4, 50, 1)]:
+        m = synth.sedef_matrix(ma, mi)
+        for w in (-1, 25):
+            got = engine.extz2_batch(ps, m, go, ge, w, -1, 0)
+            _, fr, cr = checker.batch(ps, m, go, ge, w, -1, 0, nthreads=8)
+            for i in range(ps.n):
+                assert got.fields(i) == fr[i], (ma, mi, go, ge, w, i)
+                assert got.cigars[i].tolist() == cr[i]
+
+
+def test_full_size_config2_properties(checker, mat):
+    """BASELINE.json configs[1] at FULL size (100k x 1 kbp, w=100): size-independent properties for every pair
+    (CIGAR consumes both sequences, stats are consistent with the CIGAR, idempotence across runs) and the
+    oracle on a seeded sample."""
+    n = 100000
+    ps = synth.make_pairs_small(n, length=1000, div=0.05, seed=0x5EDEF002)
+    rb = engine.ResidentBatch(ps, mat, 40, 1, 100, -1, 0)
+    rb.run()
+    a = rb.fetch()
+    rb.run()
+    b = rb.fetch()
+    rb.free()
+    for k in ("max_zd", "max_q", "max_t", "mqe", "mqe_t", "mte", "mte_q", "score", "n_cigar"):
+        assert np.array_equal(a.ez[k], b.ez[k]), k                                 # idempotent
+    assert np.array_equal(a.stats, b.stats)
+    qsum = np.zeros(n, np.int64); tsum = np.zeros(n, np.int64); gaps = np.zeros(n, np.int64); gapb = np.zeros(n, np.int64)
+    for i in range(n):
+        c = a.cigars[i]
+        assert np.array_equal(c, b.cigars[i])
+        op = c & 0xF; ln = (c >> 4).astype(np.int64)
+        qsum[i] = ln[op != 2].sum(); tsum[i] = ln[op != 1].sum()
+        gaps[i] = (op != 0).sum(); gapb[i] = ln[op != 0].sum()
+    zd = (a.ez["max_zd"] >> 31).astype(bool)
+    assert not zd.any()                                                             # band 100 never breaks at 5 % / 1 bp indels
+    assert np.array_equal(qsum, ps.qlen) and np.array_equal(tsum, ps.tlen)
+    st = a.stats
+    assert np.array_equal(st["gaps"], gaps) and np.array_equal(st["gap_bases"], gapb)
+    assert np.array_equal(st["span"], st["alnB"] + st["gap_bases"])
+    assert np.array_equal(st["alnB"], st["matchB"] + st["mismatchB"])
+    assert np.array_equal(st["alnB"], st["matches"] + st["mismatches"])
+    assert np.array_equal(st["mismatchB"], st["transitionsB"] + st["transversionsB"])
+    assert np.array_equal(st["indel_a"] + st["indel_b"], st["gap_bases"])
+    assert (a.ez["score"] == a.ez["mqe"]).sum() > 0
+    sample = np.random.default_rng(5).choice(n, 1500, replace=False)
+    sub = ps.subset(sample)
+    _, fr, cr = checker.batch(sub, mat, 40, 1, 100, -1, 0, nthreads=8)
+    for k, i in enumerate(sample):
+        assert a.fields(int(i)) == fr[k], int(i)
+        assert a.cigars[int(i)].tolist() == cr[k], int(i)

@@ -1,0 +1,93 @@
+"""CPU tests: the oracle itself is pinned against the reference's golden vectors (tests/golden, generated
+from the compiled reference) and -- where oracle/_ref exists -- fuzzed against the compiled reference."""
+import numpy as np
+import pytest
+
+import oracle
+from sedef_b200 import synth
+from helpers import FIELD_ORDER, load_json, parse_cigar
+
+
+def test_struct_layout():
+    import ctypes
+    assert ctypes.sizeof(oracle.KswExtz) == 56          # sizeof(ksw_extz_t) == 56
+    assert ctypes.sizeof(oracle.SdStats) == 64
+
+
+def test_port_matches_kat(built, mat, golden_dir):
+    kat = load_json(golden_dir, "ksw2_kat.json")
+    ps = synth.pairs_from_strings([(kat["seq1"], kat["seq2"])])
+    q, t = ps.pair(0)
+    for row in kat["rows"]:
+        f, c = oracle.port().extz2(q, t, mat, 40, 1, row["w"], row["zdrop"], row["flag"])
+        assert f == row["fields"], row
+        assert oracle.cigar_str(c) == row["cigar"], row
+    # the survey's table (Appendix B.3) spot values
+    r0 = kat["rows"][0]
+    assert r0["fields"]["score"] == 5180 and r0["fields"]["mte_q"] == 1133 and r0["cigar"] == "277M3I15M1I87M1D570M15I168M"
+
+
+def test_port_matches_golden_vectors(built, mat, golden_dir):
+    g = load_json(golden_dir, "ksw2_golden.json")
+    assert g["field_order"] == FIELD_ORDER
+    n = 0
+    for grp in g["groups"]:
+        ps = synth.pairs_from_strings([tuple(p) for p in grp["pairs"]])
+        for run in grp["runs"]:
+            _, fr, cr = oracle.port().batch(ps, mat, 40, 1, run["w"], run["zdrop"], run["flag"], nthreads=2)
+            for i in range(ps.n):
+                assert [fr[i][k] for k in FIELD_ORDER] == run["fields"][i], (grp["name"], run["w"], run["flag"], i)
+                assert oracle.cigar_str(cr[i]) == run["cigars"][i], (grp["name"], run["w"], run["flag"], i)
+                n += 1
+    assert n > 500
+
+
+def test_sd_stats_port_matches_reference_alignment_class(built, mat, golden_dir):
+    g = load_json(golden_dir, "sd_stats_golden.json")
+    for rec in g["records"]:
+        ps = synth.pairs_from_strings([(rec["a"], rec["b"])])
+        q, t = ps.pair(0)
+        _, cig = oracle.port().extz2(q, t, mat, 40, 1, -1, -1, 0)
+        assert oracle.cigar_str(cig, "MDI") == rec["cigar"]            # ksw I -> 'D', ksw D -> 'I' (src/align.cc:62)
+        st = oracle.sd_stats(cig, ps.q_raw, ps.t_raw)
+        for k in ("span", "matches", "mismatches", "gaps", "gap_bases"):
+            assert st[k] == rec[k], (k, rec["cigar"])
+
+
+def test_sd_stats_port_matches_survey_stat_loop(built, mat, golden_dir):
+    kat = load_json(golden_dir, "ksw2_kat.json")
+    ps = synth.pairs_from_strings([(kat["seq1"], kat["seq2"])])
+    q, t = ps.pair(0)
+    _, cig = oracle.port().extz2(q, t, mat, 40, 1, -1, -1, 0)
+    st = oracle.sd_stats(cig, ps.q_raw, ps.t_raw)
+    exp = kat["survey_stat_loop"]
+    for k in ("span", "indel_a", "indel_b", "alnB", "matchB", "mismatchB", "transitionsB", "transversionsB",
+              "uppercaseA", "uppercaseB", "uppercaseMatches", "gaps", "gap_bases"):
+        assert st[k] == exp[k], k
+    sa = kat["sedef_alignment"]
+    assert (st["matches"], st["mismatches"]) == (sa["matches"], sa["mismatches"])
+
+
+def test_cell_count_matches_appendix_c(built):
+    # SURVEY.md Appendix C
+    assert synth.count_cells(1000, 1000, 100) == 190900
+    assert synth.count_cells(1000, 1000, -1) == 1000000
+    assert synth.count_cells(10000, 10000, 500) == 9759500
+    assert synth.count_cells(32, 32, -1) == 1024
+    lib = oracle.port().lib
+    for (q, t, w) in [(1000, 1000, 100), (7, 300, 5), (300, 7, 50), (1, 1, -1), (50, 60, 0)]:
+        assert lib.oracle_count_cells(q, t, w) == synth.count_cells(q, t, w)
+
+
+@pytest.mark.skipif(not oracle.have_ref(), reason="oracle/_ref not built (no /root/reference here)")
+@pytest.mark.parametrize("w,zdrop,flag,maxlen,div", [
+    (-1, -1, 0, 300, 0.1), (20, -1, 0, 500, 0.1), (50, 100, 0, 500, 0.15), (100, -1, 0, 900, 0.05),
+    (30, 80, 0x01, 400, 0.2), (30, 80, 0x02, 400, 0.2), (30, 80, 0x04, 400, 0.2), (30, 80, 0x08, 400, 0.2),
+    (30, 80, 0x18, 400, 0.2), (30, 80, 0x40, 400, 0.2), (30, 80, 0x80, 400, 0.2), (30, 80, 0xc2, 400, 0.2),
+    (5, -1, 0, 300, 0.3), (1, -1, 0, 100, 0.3), (0, -1, 0, 100, 0.1), (16, 30, 0, 400, 0.4)])
+def test_port_vs_compiled_reference_fuzz(built, mat, w, zdrop, flag, maxlen, div):
+    ps = synth.make_pairs_mixed(120, seed=31 * (w + 7) + flag, min_len=1, max_len=maxlen, div=div)
+    _, fr, cr = oracle.ref().batch(ps, mat, 40, 1, w, zdrop, flag, nthreads=4)
+    _, fp, cp = oracle.port().batch(ps, mat, 40, 1, w, zdrop, flag, nthreads=4)
+    assert fr == fp
+    assert cr == cp

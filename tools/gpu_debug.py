@@ -27,6 +27,11 @@ configs = [
     ("mixed", 100, dict(min_len=1, max_len=100, div=0.1), 0, -1, 0),
     ("mixed", 100, dict(min_len=300, max_len=900, div=0.1), -1, -1, 0),
     ("large", 20, dict(min_len=2000, max_len=6000), 200, 400, 0),
+    ("mixed", 24, dict(min_len=900, max_len=1400, div=0.1), -1, -1, 0),          # wide (64..128 lanes)
+    ("mixed", 12, dict(min_len=1500, max_len=3500, div=0.1), -1, -1, 0),         # wide (128..256 lanes)
+    ("large", 12, dict(min_len=4000, max_len=9000), 500, 400, 0),                # w=500: 528 slots
+    ("large", 8, dict(min_len=4000, max_len=9000), 1500, -1, 0),                 # w=1500: wide banded
+    ("mixed", 12, dict(min_len=1500, max_len=3500, div=0.3), -1, 300, 2),        # wide, z-drop, right-align
 ]
 only = [int(x) for x in sys.argv[1:]] if len(sys.argv) > 1 else None
 for ci, (gen, n, kw, w, zdrop, flag) in enumerate(configs):

@@ -29,7 +29,7 @@ extern "C" {
 #ifndef KSW_EZ_SCORE_ONLY
 #define KSW_EZ_SCORE_ONLY  0x01            /* extern/ksw2.h:8  : no traceback / CIGAR */
 #define KSW_EZ_RIGHT       0x02            /* extern/ksw2.h:9  : right-align gaps */
-#define KSW_EZ_GENERIC_SC  0x04            /* extern/ksw2.h:10 : full m*m matrix (NOT supported -> KSW_B200_ERR_UNSUPPORTED) */
+#define KSW_EZ_GENERIC_SC  0x04            /* extern/ksw2.h:10 : full m*m matrix (m <= 8) */
 #define KSW_EZ_APPROX_MAX  0x08            /* extern/ksw2.h:11 : (NOT supported yet) */
 #define KSW_EZ_APPROX_DROP 0x10            /* extern/ksw2.h:12 : only meaningful with APPROX_MAX */
 #define KSW_EZ_EXTZ_ONLY   0x40            /* extern/ksw2.h:13 : always trace back from (max_t,max_q) */
@@ -88,9 +88,9 @@ enum {
 	KSW_B200_OK = 0,
 	KSW_B200_ERR_NO_DEVICE   = -1,   /* no CUDA device / driver: there is no CPU fallback */
 	KSW_B200_ERR_CUDA        = -2,   /* a CUDA runtime call failed (see ksw_b200_last_error) */
-	KSW_B200_ERR_DOMAIN      = -3,   /* scoring outside the int8-exact domain: mat[0]+2(q+e)+q > 127,
-	                                    mat[1] > 0, q<=0, e<=0 (reference wraps in int8) */
-	KSW_B200_ERR_UNSUPPORTED = -4,   /* flag not supported (GENERIC_SC, APPROX_MAX) */
+	KSW_B200_ERR_DOMAIN      = -3,   /* reserved: the kernels reproduce the reference's int8 wrap-around, so there is
+	                                    no scoring domain restriction */
+	KSW_B200_ERR_UNSUPPORTED = -4,   /* KSW_EZ_APPROX_MAX, or an alphabet with m > 8 */
 	KSW_B200_ERR_TOO_WIDE    = -5,   /* a pair needs more live slots per anti-diagonal than the widest kernel */
 	KSW_B200_ERR_NOMEM       = -6,   /* host or device allocation failed */
 	KSW_B200_ERR_ARG         = -7,   /* bad argument (n<0, NULL pointers, symbol >= m) */
@@ -134,6 +134,9 @@ int ksw_extz2_batch(int n, const int *qlen, const uint8_t *const *query,
                     ksw_extz_t *ez, sd_stats_t *stats,
                     const uint8_t *const *q_raw, const uint8_t *const *t_raw);
 
+/* Convenience for batch callers: free() every ez[i].cigar of a result array and clear the fields. */
+void ksw_b200_free_cigars(ksw_extz_t *ez, int n);
+
 /* Same, with all sequences in two flat arrays (offsets in bytes; q_raw/t_raw share the
  * offsets).  This is the zero-gather form the align-stage driver and the Python wrapper use. */
 int ksw_extz2_batch_flat(int n, const int *qlen, const int64_t *qoff, const uint8_t *qbuf,
@@ -161,6 +164,10 @@ int  ksw_b200_batch_fetch(ksw_b200_batch_t *b, ksw_extz_t *ez, sd_stats_t *stats
 int  ksw_b200_batch_launches(const ksw_b200_batch_t *b);
 int  ksw_b200_batch_kernel_ms(const ksw_b200_batch_t *b, float *dp_ms, float *tb_ms, float *aux_ms);
 int64_t ksw_b200_batch_cells(const ksw_b200_batch_t *b);   /* host-side in-band cell count (all diagonals) */
+/* bytes copied host->device by upload(+run) and device->host by the last fetch */
+int  ksw_b200_batch_io_bytes(const ksw_b200_batch_t *b, int64_t *h2d, int64_t *d2h);
+/* the fused SD-statistics pass is on by default for CIGAR runs; 0 switches it off for this batch */
+void ksw_b200_batch_set_stats(ksw_b200_batch_t *b, int on);
 void ksw_b200_batch_free(ksw_b200_batch_t *b);
 
 /* In-band DP cells of one pair if every anti-diagonal is processed

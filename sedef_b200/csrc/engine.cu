@@ -153,8 +153,10 @@ extern "C" int ksw_b200_init(int first_dev, int ndev)
 	}
 	return ndev;
 }
+static void pool_clear();
 extern "C" void ksw_b200_destroy(void)
 {
+	pool_clear();
 	std::lock_guard<std::mutex> lk(g_mu);
 	for (auto &d : g_devs) { cudaSetDevice(d.dev); if (d.stream) cudaStreamDestroy(d.stream); }
 	g_devs.clear();
@@ -196,29 +198,63 @@ static inline int64_t est_cells(int qlen, int tlen, int w)
 	return width * ((int64_t)qlen + tlen - 1);
 }
 
+// Buffers are recycled through a small process-wide pool: cudaMalloc / cudaMallocHost of hundreds of MB cost
+// tens of milliseconds, which would dominate a one-shot ksw_extz2_batch call (the align-stage driver issues
+// one batch per wave, back to back).
+struct PoolEntry { void *p; size_t cap; int dev; bool pinned; };
+static std::mutex g_pool_mu;
+static std::vector<PoolEntry> g_pool;
+static void *pool_take(size_t bytes, int dev, bool pinned, size_t *cap_out)
+{
+	std::lock_guard<std::mutex> lk(g_pool_mu);
+	int best = -1;
+	for (int i = 0; i < (int)g_pool.size(); ++i)
+		if (g_pool[i].pinned == pinned && (pinned || g_pool[i].dev == dev) && g_pool[i].cap >= bytes &&
+		    (best < 0 || g_pool[i].cap < g_pool[best].cap)) best = i;
+	if (best < 0) return nullptr;
+	void *p = g_pool[best].p; *cap_out = g_pool[best].cap;
+	g_pool.erase(g_pool.begin() + best);
+	return p;
+}
+static void pool_give(void *p, size_t cap, int dev, bool pinned)
+{
+	std::lock_guard<std::mutex> lk(g_pool_mu);
+	g_pool.push_back({p, cap, dev, pinned});
+}
+static void pool_clear()
+{
+	std::lock_guard<std::mutex> lk(g_pool_mu);
+	for (auto &e : g_pool) { if (e.pinned) cudaFreeHost(e.p); else { cudaSetDevice(e.dev); cudaFree(e.p); } }
+	g_pool.clear();
+}
 struct DevBuf {
-	void *p = nullptr; size_t cap = 0;
+	void *p = nullptr; size_t cap = 0; int dev = 0;
 	int ensure(size_t bytes) {
 		if (bytes <= cap) return 0;
-		if (p) cudaFree(p);
-		p = nullptr; cap = 0;
+		release();
+		cudaGetDevice(&dev);
+		if ((p = pool_take(bytes, dev, false, &cap))) return 0;
 		size_t want = bytes + bytes / 8 + 256;
-		if (cudaMalloc(&p, want) != cudaSuccess) { cudaGetLastError(); if (cudaMalloc(&p, bytes) != cudaSuccess) { p = nullptr; return -1; } want = bytes; }
+		if (cudaMalloc(&p, want) != cudaSuccess) {
+			cudaGetLastError(); pool_clear();
+			if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); p = nullptr; return -1; }
+			want = bytes;
+		}
 		cap = want; return 0;
 	}
-	void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+	void release() { if (p) pool_give(p, cap, dev, false); p = nullptr; cap = 0; }
 };
 struct PinBuf {
 	void *p = nullptr; size_t cap = 0;
 	int ensure(size_t bytes) {
 		if (bytes <= cap) return 0;
-		if (p) cudaFreeHost(p);
-		p = nullptr; cap = 0;
+		release();
+		if ((p = pool_take(bytes, 0, true, &cap))) return 0;
 		size_t want = bytes + bytes / 8 + 256;
 		if (cudaMallocHost(&p, want) != cudaSuccess) { cudaGetLastError(); p = nullptr; return -1; }
 		cap = want; return 0;
 	}
-	void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+	void release() { if (p) pool_give(p, cap, 0, true); p = nullptr; cap = 0; }
 };
 
 struct Wave { int cls; int first, count; size_t tb_bytes; };
@@ -237,6 +273,7 @@ struct SubBatch {
 	cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 	float dp_ms = 0, tb_ms = 0, total_ms = 0;
 	int launches = 0;
+	size_t h2d_bytes = 0, d2h_bytes = 0;
 	void release() {
 		h_arena.release(); h_raw.release(); h_results.release(); h_cigar.release(); h_stats.release();
 		d_arena.release(); d_raw.release(); d_pairs.release(); d_results.release(); d_tb.release();
@@ -410,6 +447,7 @@ extern "C" ksw_b200_batch_t *ksw_b200_batch_upload(int n, const int *qlen, const
 		cudaStream_t st = sb.dc->stream;
 		bool ok = cudaMemcpyAsync(sb.d_arena.p, ha, sb.arena_bytes, cudaMemcpyHostToDevice, st) == cudaSuccess;
 		if (ok && hr) ok = cudaMemcpyAsync(sb.d_raw.p, hr, sb.arena_bytes, cudaMemcpyHostToDevice, st) == cudaSuccess;
+		sb.h2d_bytes = sb.arena_bytes * (hr ? 2 : 1) + sizeof(B->table);
 		// per-pair descriptors, results, table
 		const size_t pbytes = sb.pairs.size() * sizeof(PairDesc);
 		ok = ok && !sb.d_pairs.ensure(pbytes) && !sb.d_results.ensure(sb.pairs.size() * sizeof(PairResult)) &&
@@ -439,6 +477,16 @@ extern "C" ksw_b200_batch_t *ksw_b200_batch_upload(int n, const int *qlen, const
 }
 
 extern "C" int64_t ksw_b200_batch_cells(const ksw_b200_batch_t *b) { return b ? b->cells : 0; }
+extern "C" int ksw_b200_batch_io_bytes(const ksw_b200_batch_t *b, int64_t *h2d, int64_t *d2h)
+{
+	if (!b) return KSW_B200_ERR_ARG;
+	int64_t a = 0, c = 0;
+	for (auto &sb : b->subs) { a += (int64_t)sb.h2d_bytes; c += (int64_t)sb.d2h_bytes; }
+	if (h2d) *h2d = a;
+	if (d2h) *d2h = c;
+	return 0;
+}
+extern "C" void ksw_b200_batch_set_stats(ksw_b200_batch_t *b, int on) { if (b) b->want_stats = on && !(b->flag & KSW_EZ_SCORE_ONLY); }
 
 // ------------------------------------------------------------------------------------------------
 // run
@@ -491,6 +539,7 @@ static int run_sub(ksw_b200_batch &B, SubBatch &sb)
 	if (rc) return rc;
 	// descriptors carry tb offsets -> (re)upload
 	CUDA_TRY(cudaMemcpyAsync(sb.d_pairs.p, sb.pairs.data(), sb.pairs.size() * sizeof(PairDesc), cudaMemcpyHostToDevice, st));
+	sb.h2d_bytes += sb.pairs.size() * sizeof(PairDesc);
 	// misc: [0..63] work counters (one per wave, reused round-robin), [64] cigar cursor (u64 at byte 512), [66] overflow
 	CUDA_TRY(cudaMemsetAsync(sb.d_misc.p, 0, 4096, st));
 	int *d_counters = (int *)sb.d_misc.p;
@@ -621,6 +670,7 @@ extern "C" int ksw_b200_batch_fetch(ksw_b200_batch_t *B, ksw_extz_t *ez, sd_stat
 			CUDA_TRY(cudaMemcpyAsync(sb.h_stats.p, sb.d_stats.p, np * sizeof(sd_stats_t), cudaMemcpyDeviceToHost, st));
 		}
 		CUDA_TRY(cudaStreamSynchronize(st));
+		sb.d2h_bytes = np * sizeof(PairResult) + (cigar ? sb.cigar_used * 4 : 0) + ((cigar && stats && B->want_stats) ? np * sizeof(sd_stats_t) : 0);
 		const PairResult *res = (const PairResult *)sb.h_results.p;
 		const uint32_t *carena = (const uint32_t *)sb.h_cigar.p;
 		const sd_stats_t *hst = (const sd_stats_t *)sb.h_stats.p;
@@ -649,6 +699,13 @@ extern "C" int ksw_b200_batch_fetch(ksw_b200_batch_t *B, ksw_extz_t *ez, sd_stat
 		return fail(rc_all, "malloc of a CIGAR failed");
 	}
 	return KSW_B200_OK;
+}
+
+extern "C" void ksw_b200_free_cigars(ksw_extz_t *ez, int n)
+{
+	if (!ez) return;
+#pragma omp parallel for schedule(static)
+	for (int i = 0; i < n; ++i) { free(ez[i].cigar); ez[i].cigar = nullptr; ez[i].n_cigar = ez[i].m_cigar = 0; }
 }
 
 extern "C" void ksw_b200_batch_free(ksw_b200_batch_t *B)

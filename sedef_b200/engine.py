@@ -60,7 +60,8 @@ EXPORTS = ["ksw_b200_strerror", "ksw_b200_last_error", "ksw_b200_init", "ksw_b20
            "ksw_b200_num_devices", "ksw_b200_max_slots", "ksw_extz2_b200", "ksw_extz2_batch",
            "ksw_extz2_batch_flat", "ksw_b200_batch_upload", "ksw_b200_batch_run", "ksw_b200_batch_fetch",
            "ksw_b200_batch_launches", "ksw_b200_batch_kernel_ms", "ksw_b200_batch_cells",
-           "ksw_b200_batch_free", "ksw_b200_count_cells", "sd_stats_derive_fp"]
+           "ksw_b200_batch_free", "ksw_b200_count_cells", "sd_stats_derive_fp",
+           "ksw_b200_batch_io_bytes", "ksw_b200_batch_set_stats", "ksw_b200_free_cigars"]
 
 
 def load():
@@ -99,6 +100,9 @@ def load():
     lib.ksw_b200_batch_cells.argtypes = [vp]
     lib.ksw_b200_batch_cells.restype = i64
     lib.ksw_b200_batch_free.argtypes = [vp]
+    lib.ksw_b200_batch_io_bytes.argtypes = [vp, C.POINTER(i64), C.POINTER(i64)]
+    lib.ksw_b200_batch_set_stats.argtypes = [vp, i32]
+    lib.ksw_b200_free_cigars.argtypes = [vp, i32]
     lib.sd_stats_derive_fp.argtypes = [C.POINTER(SdStats), C.POINTER(SdStatsFp)]
     lib.free = C.CDLL(None).free
     lib.free.argtypes = [vp]
@@ -146,10 +150,7 @@ def _collect(lib, ez: np.ndarray, keep_cigars: bool):
         for i in range(ez.shape[0]):
             n, p = int(ez[i]["n_cigar"]), int(ez[i]["cigar"])
             cigs.append(np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint32)), shape=(n,)).copy() if n else np.zeros(0, np.uint32))
-    for p in ez["cigar"]:
-        if p:
-            lib.free(int(p))
-    ez["cigar"] = 0
+    lib.ksw_b200_free_cigars(ez.ctypes.data, ez.shape[0])
     return cigs
 
 
@@ -215,6 +216,14 @@ class ResidentBatch:
 
     def cells(self) -> int:
         return int(self.lib.ksw_b200_batch_cells(self.h))
+
+    def io_bytes(self):
+        a, b = C.c_int64(0), C.c_int64(0)
+        self.lib.ksw_b200_batch_io_bytes(self.h, C.byref(a), C.byref(b))
+        return int(a.value), int(b.value)
+
+    def set_stats(self, on: bool):
+        self.lib.ksw_b200_batch_set_stats(self.h, int(on))
 
     def fetch(self, want_stats=True, keep_cigars=True) -> BatchResult:
         ez = np.zeros(self.n, EZ_DTYPE)

@@ -410,7 +410,7 @@ extern "C" ksw_b200_batch_t *ksw_b200_batch_upload(int n, const int *qlen, const
 			pos = align_up(pos + tlen[i], 16);
 			pd.tb_off = 0;
 		}
-		sb.arena_bytes = pos + 16;
+		sb.arena_bytes = pos + 128;   // the query window may read a few bytes past the last sequence
 		if (lst.empty()) continue;
 		if (cudaSetDevice(sb.dc->dev) != cudaSuccess) { delete B; return bail(fail(KSW_B200_ERR_CUDA, "cudaSetDevice")); }
 		if (sb.h_arena.ensure(sb.arena_bytes) || sb.d_arena.ensure(sb.arena_bytes) ||

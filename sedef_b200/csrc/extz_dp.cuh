@@ -27,58 +27,99 @@ struct DpLaunch {
 
 __device__ __forceinline__ uint32_t ld_u8(const uint8_t *p) { return (uint32_t)__ldg(p); }
 
+// ---- shared-memory index of circular slot c (conflict-free 128-bit rows: quad j of every lane is contiguous) ----
+template <int G, int S>
+__device__ __forceinline__ int hidx(int c)
+{
+	const int lane = c / S, i = c % S;                       // S is a power of two
+	return (((i >> 2) * G + lane) << 2) | (i & 3);
+}
+
 // ---- per-lane state: S consecutive slots starting at t0 (circular window, slot t lives at t mod NS) ----
 template <int S>
 struct LaneState {
 	uint32_t U[S], V[S], X[S], Y[S];   // u, v, x, y of extern/ksw2_extz2_sse.cc:54, top-byte form
 	uint32_t Z[S];                      // s + 2(q+e) as last written by the score fill (persistent: stale outside the fill range)
-	uint32_t TC[S];                     // byte offset of the slot's target symbol row in the score table
+	uint32_t TW[S / 4];                 // target symbols of the lane's slots, one byte each, pre-scaled by 32 (table row offset)
+	uint32_t QW[S / 4];                 // sliding query window: byte i = 4 * query[r - (t0 + i)] (table column offset)
 	int t0;
 };
 
+// 4 * query[j], or 0 where the reference reads the zeroed tail of qr[] (j < 0, App. A.1); j may run a few bytes
+// past the query (values there are never used: the slot is below the band) but stays inside the arena
+__device__ __forceinline__ uint32_t qbyte4(const uint8_t *qseq, int j)
+{
+	return j >= -kQPadL ? ld_u8(qseq + j) << 2 : 0u;
+}
+
+// (re)load the lane's slots for the window position t0, as seen at the START of anti-diagonal r (before its shift)
 template <int S>
-__device__ __forceinline__ void lane_load_slots(LaneState<S> &ls, const uint8_t *tseq, int tlen, const Scoring &sc)
+__device__ __forceinline__ void lane_load_slots(LaneState<S> &ls, const uint8_t *tseq, int tlen, const uint8_t *qseq, int r,
+                                                const Scoring &sc)
 {
 #pragma unroll
-	for (int i = 0; i < S; ++i) {
-		ls.U[i] = ls.V[i] = ls.X[i] = ls.Y[i] = 0u; ls.Z[i] = sc.s0_s;                  // calloc'ed arrays (:83)
-		int t = ls.t0 + i;
-		ls.TC[i] = (t < tlen ? ld_u8(tseq + t) : 0u) * (kTableStride * 4);          // sf[] reads 0 beyond tlen (App. A.1)
+	for (int i = 0; i < S; ++i) { ls.U[i] = ls.V[i] = ls.X[i] = ls.Y[i] = 0u; ls.Z[i] = sc.s0_s; }   // calloc'ed arrays (:83)
+#pragma unroll
+	for (int k = 0; k < S / 4; ++k) {
+		uint32_t tw = 0, qw = 0;
+#pragma unroll
+		for (int b = 0; b < 4; ++b) {
+			const int t = ls.t0 + 4 * k + b;
+			tw |= (t < tlen ? ld_u8(tseq + t) << 5 : 0u) << (8 * b);                                 // sf[] reads 0 beyond tlen (App. A.1)
+			qw |= qbyte4(qseq, r - 1 - t) << (8 * b);
+		}
+		ls.TW[k] = tw; ls.QW[k] = qw;
 	}
 }
 
-// window slide + top-row boundary + score fill for one anti-diagonal
+// window slide + query shift + top-row boundary + score fill for one anti-diagonal
 template <int S, int NS>
 __device__ __forceinline__ void lane_prepare(LaneState<S> &ls, const Band &b, int r, const uint8_t *qseq, const uint8_t *tseq,
                                              int tlen, const uint32_t *sTable, const Scoring &sc)
 {
 	// lanes whose slots all fell below the rounded range take the slots NS further up
-	if (ls.t0 + S - 1 < b.st) { ls.t0 += NS; lane_load_slots<S>(ls, tseq, tlen, sc); }
+	if (ls.t0 + S - 1 < b.st) { ls.t0 += NS; lane_load_slots<S>(ls, tseq, tlen, qseq, r, sc); }
+	// the query slides past the slots by one per anti-diagonal: shift the byte window, inject query[r - t0]
+	{
+		const uint32_t nb = qbyte4(qseq, r - ls.t0);
+#pragma unroll
+		for (int k = S / 4 - 1; k > 0; --k) ls.QW[k] = __funnelshift_l(ls.QW[k - 1], ls.QW[k], 8);
+		ls.QW[0] = (ls.QW[0] << 8) | nb;
+	}
 	// top-row boundary (:122): y[r] = 0, u[r] = r ? q : 0 when the rounded range reaches slot r
 	if (b.en >= r) {
-		int k = r - ls.t0;
+		const int k = r - ls.t0;
+		if ((unsigned)k < (unsigned)S) {
 #pragma unroll
-		for (int i = 0; i < S; ++i) if (k == i) { ls.Y[i] = 0u; ls.U[i] = r ? sc.q_s : 0u; }
+			for (int i = 0; i < S; ++i) if (k == i) { ls.Y[i] = 0u; ls.U[i] = r ? sc.q_s : 0u; }
+		}
 	}
-	// score fill (:124-141): slots st0..fe get a fresh s, all others keep the stale one
-	const uint8_t *qp = qseq + (r - ls.t0);                      // query[r - t] for slot t = t0 + i is qp[-i]
-	const int lo = b.st0 - ls.t0, hi = b.fe - ls.t0;
+	// score fill (:124-141): slots st0..fe get a fresh s, all others keep the stale one.  Branch-free: the
+	// table offsets of 4 slots come from one packed add, the in-range mask is tested bit by bit (R2P).
+	int lo = b.st0 - ls.t0, hi = b.fe - ls.t0 + 1;
+	lo = lo < 0 ? 0 : (lo > S ? S : lo);
+	hi = hi < 0 ? 0 : (hi > S ? S : hi);
+	const uint32_t fillmask = hi > lo ? ((hi >= 32 ? 0xffffffffu : ((1u << hi) - 1u)) & ~((1u << lo) - 1u)) : 0u;
 #pragma unroll
-	for (int i = 0; i < S; ++i) {
-		if (i >= lo && i <= hi) {
-			uint32_t qc = ld_u8(qp - i);
-			ls.Z[i] = *(const uint32_t *)((const char *)sTable + ls.TC[i] + qc * 4);
+	for (int k = 0; k < S / 4; ++k) {
+		const uint32_t offs = ls.TW[k] + ls.QW[k];                 // byte b: 32*target + 4*query <= 252
+#pragma unroll
+		for (int bb = 0; bb < 4; ++bb) {
+			const int i = 4 * k + bb;
+			const uint32_t off = __byte_perm(offs, 0u, 0x4440 | bb);
+			const uint32_t zn = *(const uint32_t *)((const char *)sTable + off);
+			if (fillmask & (1u << i)) ls.Z[i] = zn;
 		}
 	}
 }
 
 // the cells of one anti-diagonal for this lane (:149-220), traceback codes, u' dump and lazy-H update (:233-255).
 // Returns the maximum of the lane's updated lazy-H entries (slot en0 was knocked out by the leader beforehand).
-template <int S, int NS, bool kCigar, bool kRight>
-__device__ __forceinline__ int32_t lane_cells(LaneState<S> &ls, const Band &b, int r, int last_st, uint32_t xin, uint32_t vin,
+template <int G, int S, bool kCigar, bool kRight>
+__device__ __forceinline__ int32_t lane_cells(LaneState<S> &ls, const Band &b, int r, int last_st, int lane, uint32_t xin, uint32_t vin,
                                               uint8_t *tbp, int32_t *H, uint32_t *Us, const Scoring &sc)
 {
-	constexpr int MASK = NS - 1;
+	constexpr int NS = G * S;
 	constexpr int NSUB = (S + 15) / 16;                 // 16-slot sub-blocks per lane (1 unless S == 32)
 	constexpr int SUBW = S < 16 ? S : 16;
 	int32_t lane_max = kNegInf;
@@ -105,7 +146,7 @@ __device__ __forceinline__ int32_t lane_cells(LaneState<S> &ls, const Band &b, i
 				if (kCigar) codes |= c << ((ii & 7) * 4);
 				if (kCigar && (ii & 7) == 0) {
 					// 8 codes = one 32-bit word; S == 4 packs 4 codes into 16 bits
-					int c0 = (ls.t0 + i) & MASK;
+					const int c0 = lane * S + i;                                   // == (t0 + i) mod NS
 					uint8_t *dst = tbp + (int64_t)r * (NS >> 1) + (c0 >> 1);
 					if (S >= 8) *(uint32_t *)dst = codes; else *(uint16_t *)dst = (uint16_t)codes;
 					codes = 0;
@@ -114,12 +155,12 @@ __device__ __forceinline__ int32_t lane_cells(LaneState<S> &ls, const Band &b, i
 #pragma unroll
 			for (int ii = 0; ii < SUBW; ii += 4) {
 				const int i = sb * 16 + ii;
-				const int c0 = (ls.t0 + i) & MASK;
-				*(uint4 *)&Us[c0] = make_uint4(ls.U[i], ls.U[i + 1], ls.U[i + 2], ls.U[i + 3]);
-				int4 h = *(int4 *)&H[c0];
+				const int h0 = (((i >> 2) * G + lane) << 2);                       // hidx of the lane's quad
+				*(uint4 *)&Us[h0] = make_uint4(ls.U[i], ls.U[i + 1], ls.U[i + 2], ls.U[i + 3]);
+				int4 h = *(int4 *)&H[h0];
 				h.x += (int32_t)(ls.V[i] >> 24); h.y += (int32_t)(ls.V[i + 1] >> 24);
 				h.z += (int32_t)(ls.V[i + 2] >> 24); h.w += (int32_t)(ls.V[i + 3] >> 24);
-				*(int4 *)&H[c0] = h;
+				*(int4 *)&H[h0] = h;
 				int32_t m01 = h.x > h.y ? h.x : h.y, m23 = h.z > h.w ? h.z : h.w;
 				int32_t m = m01 > m23 ? m01 : m23;
 				lane_max = lane_max > m ? lane_max : m;
@@ -129,16 +170,33 @@ __device__ __forceinline__ int32_t lane_cells(LaneState<S> &ls, const Band &b, i
 	return lane_max;
 }
 
-// smallest tie-break key among this lane's slots whose lazy H equals gm (slot en0 is handled by the leader)
-template <int S, int NS>
-__device__ __forceinline__ uint32_t lane_argmax_key(const LaneState<S> &ls, const Band &b, const int32_t *H, int32_t gm)
+// arg-max, fast pass: (count << 24) + sum of t over this lane's slots whose lazy H equals gm.  Exited and not yet
+// entered slots hold ~KSW_NEG_INF and can never match; slot en0 (register value = knocked-out) is added by the leader.
+template <int G, int S>
+__device__ __forceinline__ uint32_t lane_argmax_count(const LaneState<S> &ls, int lane, const int32_t *H, int32_t gm)
 {
-	constexpr int MASK = NS - 1;
+	uint32_t acc = 0;
+#pragma unroll
+	for (int j = 0; j < S / 4; ++j) {
+		const int4 h = *(const int4 *)&H[((j * G + lane) << 2)];
+		const uint32_t base = (1u << 24) + (uint32_t)(ls.t0 + 4 * j);
+		if (h.x == gm) acc += base;
+		if (h.y == gm) acc += base + 1;
+		if (h.z == gm) acc += base + 2;
+		if (h.w == gm) acc += base + 3;
+	}
+	return acc;
+}
+
+// arg-max, exact pass (only on real ties): smallest tie-break key among this lane's slots whose lazy H equals gm
+template <int G, int S>
+__device__ __forceinline__ uint32_t lane_argmax_key(const LaneState<S> &ls, const Band &b, int lane, const int32_t *H, int32_t gm)
+{
 	uint32_t key = 0xffffffffu;
 #pragma unroll
 	for (int i = 0; i < S; ++i) {
 		int t = ls.t0 + i;
-		if (t >= b.st0 && t <= b.en0 && !(t == b.en0 && b.en0 > 0) && H[t & MASK] == gm) {
+		if (t >= b.st0 && t <= b.en0 && !(t == b.en0 && b.en0 > 0) && H[(((i >> 2) * G + lane) << 2) | (i & 3)] == gm) {
 			uint32_t k = tie_key(t, b.st0, b.en0);
 			key = k < key ? k : key;
 		}
@@ -157,43 +215,50 @@ struct Leader {
 	__device__ __forceinline__ void reset() { ez_reset(ez); st0_prev = 0; exit_slot = -2; exit_H = kNegInf; Hprev_true = kNegInf; Hen0_lazy = gmax = kNegInf; }
 
 	// before the cells: remember/knock out slots that must not take part in the regular H update
-	template <int MASK>
+	template <int G, int S>
 	__device__ __forceinline__ void pre(int32_t *H, const Band &b, int r, int qe)
 	{
 		Hprev_true = kNegInf;
 		if (r == 0) return;
 		if (b.st0 > st0_prev) {                              // slot st0-1 left the band: keep its TRUE H, drop it from the max
 			int xs = b.st0 - 1;
-			exit_slot = xs; exit_H = H[xs & MASK] - qe * (r - 1);
-			H[xs & MASK] = kNegInf;
+			const int hx = hidx<G, S>(xs & (G * S - 1));
+			exit_slot = xs; exit_H = H[hx] - qe * (r - 1);
+			H[hx] = kNegInf;
 		}
 		if (b.en0 > 0) {
 			int ps = b.en0 - 1;
-			Hprev_true = (ps == exit_slot) ? exit_H : H[ps & MASK] - qe * (r - 1);
-			H[b.en0 & MASK] = kNegInf;                       // the regular update must not count for slot en0
+			Hprev_true = (ps == exit_slot) ? exit_H : H[hidx<G, S>(ps & (G * S - 1))] - qe * (r - 1);
+			H[hidx<G, S>(b.en0 & (G * S - 1))] = kNegInf;    // the regular update must not count for slot en0
 		}
 	}
 	// after the cells: H[en0] (:228 / :259), diagonal max in the lazy domain; returns need_arg
-	template <int MASK>
+	template <int G, int S>
 	__device__ __forceinline__ int mid(int32_t *H, const uint32_t *Us, const Band &b, int r, int qe, int32_t reduced_max,
 	                                   uint32_t v0_r0, int zdrop)
 	{
 		gmax = reduced_max;
 		if (r == 0) { Hen0_lazy = (int32_t)(v0_r0 >> 24) - 2 * qe; H[0] = Hen0_lazy; gmax = Hen0_lazy; }   // :259
 		else if (b.en0 > 0) {
-			Hen0_lazy = Hprev_true + (int32_t)(Us[b.en0 & MASK] >> 24) - qe + qe * r;                       // :228, true -> lazy
-			H[b.en0 & MASK] = Hen0_lazy;
+			const int he = hidx<G, S>(b.en0 & (G * S - 1));
+			Hen0_lazy = Hprev_true + (int32_t)(Us[he] >> 24) - qe + qe * r;                                  // :228, true -> lazy
+			H[he] = Hen0_lazy;
 			gmax = gmax > Hen0_lazy ? gmax : Hen0_lazy;
 		} else Hen0_lazy = H[0];                              // en0 == 0: regular update (:228 else-arm)
 		int32_t maxH_true = gmax - qe * r;
 		return (maxH_true > ez.max) || (zdrop >= 0);
+	}
+	// contribution of slot en0 to the fast arg-max pass
+	__device__ __forceinline__ uint32_t en0_count(const Band &b, int r) const
+	{
+		return 0u;   // unused: the count pass reads the final H[en0] from shared memory
 	}
 	__device__ __forceinline__ uint32_t en0_key(const Band &b, int r) const
 	{
 		return (Hen0_lazy == gmax && (r == 0 || b.en0 > 0)) ? 0u : 0xffffffffu;   // slot en0 wins every tie (:229-231)
 	}
 	// end scores, z-drop (:261-267); returns stop
-	template <int MASK>
+	template <int G, int S>
 	__device__ __forceinline__ int fin(const int32_t *H, const Band &b, int r, int qe, int max_t, int qlen, int tlen,
 	                                   int zdrop, int e)
 	{
@@ -202,7 +267,7 @@ struct Leader {
 		int32_t maxH_true = gmax - qe * r;
 		if (b.en0 == tlen - 1 && Hen0_true > ez.mte) { ez.mte = Hen0_true; ez.mte_q = r - b.en; }          // :261-262
 		if (r - b.st0 == qlen - 1) {                                                                      // :263-264
-			int32_t Hst0 = (b.st0 == b.en0) ? Hen0_true : H[b.st0 & MASK] - qe * r;
+			int32_t Hst0 = (b.st0 == b.en0) ? Hen0_true : H[hidx<G, S>(b.st0 & (G * S - 1))] - qe * r;
 			if (Hst0 > ez.mqe) { ez.mqe = Hst0; ez.mqe_t = b.st0; }
 		}
 		int stop = 0;
@@ -221,21 +286,45 @@ struct Leader {
 	}
 };
 
+// ---- group collectives (all 32 lanes of the warp execute them; groups are G-aligned lane ranges) ----
+template <int G> __device__ __forceinline__ int32_t group_max(int32_t v)
+{
+	if (G == 32) return __reduce_max_sync(0xffffffffu, v);
+#pragma unroll
+	for (int d = 1; d < G; d <<= 1) { int32_t o = __shfl_xor_sync(0xffffffffu, v, d); v = v > o ? v : o; }
+	return v;
+}
+template <int G> __device__ __forceinline__ uint32_t group_min_u(uint32_t v)
+{
+	if (G == 32) return __reduce_min_sync(0xffffffffu, v);
+#pragma unroll
+	for (int d = 1; d < G; d <<= 1) { uint32_t o = __shfl_xor_sync(0xffffffffu, v, d); v = v < o ? v : o; }
+	return v;
+}
+template <int G> __device__ __forceinline__ uint32_t group_sum_u(uint32_t v)
+{
+	if (G == 32) return __reduce_add_sync(0xffffffffu, v);
+#pragma unroll
+	for (int d = 1; d < G; d <<= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+	return v;
+}
+
 // =====================================================================================================
-// narrow kernel: G <= 32 lanes per pair
+// narrow kernel: G <= 32 lanes per pair, the 32/G pairs of a warp advance in lock-step
 // =====================================================================================================
 template <int G, int S, bool kCigar, bool kRight>
 __global__ void __launch_bounds__(128)
 extz_dp_kernel(DpLaunch L)
 {
 	constexpr int NS = G * S;
-	constexpr int MASK = NS - 1;
 	constexpr int GROUPS_PER_BLOCK = 128 / G;
-	static_assert(G <= 32 && (NS & MASK) == 0, "NS must be a power of two");
+	constexpr int PPW = 32 / G;                          // pairs per warp
+	constexpr unsigned FULL = 0xffffffffu;
+	static_assert(G <= 32 && (NS & (NS - 1)) == 0, "NS must be a power of two");
 	static_assert(S % 4 == 0 && (16 % S == 0 || S % 16 == 0), "lane slots must tile 16-slot blocks");
 
-	__shared__ int32_t sH[GROUPS_PER_BLOCK][NS];        // lazy H: H + (q+e)*r   (:222-259)
-	__shared__ uint32_t sU[GROUPS_PER_BLOCK][NS];       // u' of the current diagonal (for H[en0], :228)
+	__shared__ __align__(16) int32_t sH[GROUPS_PER_BLOCK][NS];        // lazy H: H + (q+e)*r   (:222-259)
+	__shared__ __align__(16) uint32_t sU[GROUPS_PER_BLOCK][NS];       // u' of the current diagonal (for H[en0], :228)
 	__shared__ uint32_t sTable[kTableStride * kTableStride];
 
 	for (int i = threadIdx.x; i < kTableStride * kTableStride; i += blockDim.x) sTable[i] = L.table[i];
@@ -244,7 +333,6 @@ extz_dp_kernel(DpLaunch L)
 	const int lane_w = threadIdx.x & 31;
 	const int gl = threadIdx.x % G;                                  // lane within group
 	const int gidx = threadIdx.x / G;                                // group within block
-	const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane_w & ~(G - 1)));
 	const int pred_lane = (gl + G - 1) & (G - 1);                    // circular predecessor (relative to group)
 	int32_t *H = sH[gidx];
 	uint32_t *Us = sU[gidx];
@@ -253,63 +341,80 @@ extz_dp_kernel(DpLaunch L)
 	const bool generic = (sc.flag & kFlagGenericSc) != 0;
 
 	for (;;) {
-		int pi = 0;
-		if (gl == 0) pi = atomicAdd(L.work_counter, 1);              // dynamic work queue, pairs sorted by descending work
-		pi = __shfl_sync(gmask, pi, 0, G);
-		if (pi >= L.n) break;
-		const PairDesc pd = L.pairs[pi];
+		int base = 0;
+		if (lane_w == 0) base = atomicAdd(L.work_counter, PPW);      // dynamic work queue, pairs sorted by descending work
+		base = __shfl_sync(FULL, base, 0);
+		if (base >= L.n) break;
+		const int pi = base + lane_w / G;
+		bool alive = pi < L.n;
+		const PairDesc pd = L.pairs[alive ? pi : base];
 		const int qlen = pd.qlen, tlen = pd.tlen, w = pd.w;
 		const int T = (tlen + 15) & ~15;
 		const uint8_t *qseq = L.seq + pd.q_off;                      // qseq[j], j in [-kQPadL, qlen) readable
 		const uint8_t *tseq = L.seq + pd.t_off;
 		uint8_t *tbp = kCigar ? L.tb + pd.tb_off : nullptr;
+		const int R = alive ? qlen + tlen - 1 : 0;
+		int maxR = R;
+#pragma unroll
+		for (int d = G; d < 32; d <<= 1) { int o = __shfl_xor_sync(FULL, maxR, d); maxR = maxR > o ? maxR : o; }
 
 		LaneState<S> ls;
 		ls.t0 = gl * S;
-		lane_load_slots<S>(ls, tseq, tlen, sc);
+		lane_load_slots<S>(ls, tseq, tlen, qseq, 0, sc);
 #pragma unroll
-		for (int i = 0; i < S; ++i) H[gl * S + i] = kNegInf;         // :86-89
-		__syncwarp(gmask);
+		for (int j = 0; j < S / 4; ++j) *(int4 *)&H[(j * G + gl) << 2] = make_int4(kNegInf, kNegInf, kNegInf, kNegInf);   // :86-89
+		__syncwarp();
 
 		Leader ld; ld.reset();                                       // meaningful in the leader lane only
 		int last_st = -1, n_diag = 0, zdropped_band = 0;
-		const int R = qlen + tlen - 1;
 
-		for (int r = 0; r < R; ++r) {
+		for (int r = 0; r < maxR; ++r) {
+			bool act = alive && r < R;
 			Band b;
-			if (!band_of(r, qlen, tlen, w, T, generic, b)) { zdropped_band = 1; break; }      // :110-113
+			const bool okb = band_of(r, qlen, tlen, w, T, generic, b);
+			if (act && !okb) { zdropped_band = 1; alive = false; act = false; }                // :110-113
 
-			// carry from the circular predecessor: OLD x,v of its top slot (:28-35,117-121)
-			uint32_t xin = __shfl_sync(gmask, ls.X[S - 1], pred_lane, G);
-			uint32_t vin = __shfl_sync(gmask, ls.V[S - 1], pred_lane, G);
-			lane_prepare<S, NS>(ls, b, r, qseq, tseq, tlen, sTable, sc);
-			if (gl == 0) ld.pre<MASK>(H, b, r, qe);
-			__syncwarp(gmask);
-
-			int32_t lane_max = lane_cells<S, NS, kCigar, kRight>(ls, b, r, last_st, xin, vin, tbp, H, Us, sc);
-			__syncwarp(gmask);
-
-			int32_t red = __reduce_max_sync(gmask, lane_max);
-			int need_arg = 0;
-			if (gl == 0) need_arg = ld.mid<MASK>(H, Us, b, r, qe, red, ls.V[0], sc.zdrop);
-			need_arg = __shfl_sync(gmask, need_arg, 0, G);
+			// carry from the circular predecessor: OLD x,v of its top slot (:28-35)
+			const uint32_t xin = __shfl_sync(FULL, ls.X[S - 1], pred_lane, G);
+			const uint32_t vin = __shfl_sync(FULL, ls.V[S - 1], pred_lane, G);
+			if (act) {
+				lane_prepare<S, NS>(ls, b, r, qseq, tseq, tlen, sTable, sc);
+				if (gl == 0) ld.pre<G, S>(H, b, r, qe);
+			}
+			__syncwarp();
+			int32_t lane_max = kNegInf;
+			if (act) lane_max = lane_cells<G, S, kCigar, kRight>(ls, b, r, last_st, gl, xin, vin, tbp, H, Us, sc);
+			__syncwarp();
+			const int32_t red = group_max<G>(lane_max);
+			int need = 0;
+			if (act && gl == 0) need = ld.mid<G, S>(H, Us, b, r, qe, red, ls.V[0], sc.zdrop);
+			__syncwarp();
+			need = __shfl_sync(FULL, need, 0, G);
 			int max_t = b.en0;
-			if (need_arg) {
-				int32_t gm = __shfl_sync(gmask, ld.gmax, 0, G);
-				uint32_t key = lane_argmax_key<S, NS>(ls, b, H, gm);
-				if (gl == 0) { uint32_t k0 = ld.en0_key(b, r); key = k0 < key ? k0 : key; }
-				key = __reduce_min_sync(gmask, key);
-				max_t = tie_key_slot(key, b.en0);
+			if (__any_sync(FULL, need)) {
+				const int32_t gm = __shfl_sync(FULL, ld.gmax, 0, G);
+				uint32_t cnt = 0;
+				if (need) cnt = lane_argmax_count<G, S>(ls, gl, H, gm);
+				cnt = group_sum_u<G>(cnt);
+				max_t = (int)(cnt & 0x00ffffffu);
+				const int tie = need && (cnt >> 24) != 1u;
+				if (__any_sync(FULL, tie)) {                                                      // real ties: exact 4-lane rule
+					uint32_t key = 0xffffffffu;
+					if (tie) {
+						key = lane_argmax_key<G, S>(ls, b, gl, H, gm);
+						if (gl == 0) { uint32_t k0 = ld.en0_key(b, r); key = k0 < key ? k0 : key; }
+					}
+					key = group_min_u<G>(key);
+					if (tie) max_t = tie_key_slot(key, b.en0);
+				}
 			}
 			int stop = 0;
-			if (gl == 0) stop = ld.fin<MASK>(H, b, r, qe, max_t, qlen, tlen, sc.zdrop, sc.e);
-			stop = __shfl_sync(gmask, stop, 0, G);
-			n_diag = r + 1;
-			last_st = b.st;
-			if (stop) break;
+			if (act && gl == 0) stop = ld.fin<G, S>(H, b, r, qe, max_t, qlen, tlen, sc.zdrop, sc.e);
+			stop = __shfl_sync(FULL, stop, 0, G);
+			if (act) { n_diag = r + 1; last_st = b.st; if (stop) alive = false; }
 		}
-		if (gl == 0) { if (zdropped_band) ld.ez.zdropped = 1; ld.store(&L.results[pi], n_diag); }
-		__syncwarp(gmask);
+		if (pi < L.n && gl == 0) { if (zdropped_band) ld.ez.zdropped = 1; ld.store(&L.results[pi], n_diag); }
+		__syncwarp();
 	}
 }
 
@@ -321,13 +426,12 @@ __global__ void __launch_bounds__(G)
 extz_dp_wide_kernel(DpLaunch L)
 {
 	constexpr int NS = G * S;
-	constexpr int MASK = NS - 1;
 	constexpr int NW = G / 32;
-	static_assert(G > 32 && G % 32 == 0 && (NS & MASK) == 0, "wide kernel: whole warps, NS power of two");
+	static_assert(G > 32 && G % 32 == 0 && (NS & (NS - 1)) == 0, "wide kernel: whole warps, NS power of two");
 	static_assert(S % 4 == 0 && (16 % S == 0 || S % 16 == 0), "lane slots must tile 16-slot blocks");
 
-	__shared__ int32_t H[NS];
-	__shared__ uint32_t Us[NS];
+	__shared__ __align__(16) int32_t H[NS];
+	__shared__ __align__(16) uint32_t Us[NS];
 	__shared__ uint32_t sTable[kTableStride * kTableStride];
 	__shared__ uint32_t sCarryX[NW], sCarryV[NW];       // OLD x,v of every warp's top slot
 	__shared__ int32_t sWarpMax[NW];
@@ -358,9 +462,9 @@ extz_dp_wide_kernel(DpLaunch L)
 
 		LaneState<S> ls;
 		ls.t0 = gl * S;
-		lane_load_slots<S>(ls, tseq, tlen, sc);
+		lane_load_slots<S>(ls, tseq, tlen, qseq, 0, sc);
 #pragma unroll
-		for (int i = 0; i < S; ++i) H[gl * S + i] = kNegInf;
+		for (int j = 0; j < S / 4; ++j) *(int4 *)&H[(j * G + gl) << 2] = make_int4(kNegInf, kNegInf, kNegInf, kNegInf);
 		Leader ld; ld.reset();
 		int last_st = -1, n_diag = 0, zdropped_band = 0;
 		const int R = qlen + tlen - 1;
@@ -374,12 +478,12 @@ extz_dp_wide_kernel(DpLaunch L)
 			uint32_t xin = __shfl_up_sync(0xffffffffu, ls.X[S - 1], 1);
 			uint32_t vin = __shfl_up_sync(0xffffffffu, ls.V[S - 1], 1);
 			if (lane == 31) { sCarryX[wid] = ls.X[S - 1]; sCarryV[wid] = ls.V[S - 1]; }
-			if (gl == 0) ld.pre<MASK>(H, b, r, qe);
+			if (gl == 0) ld.pre<G, S>(H, b, r, qe);
 			__syncthreads();                                                                   // A
 			// phase 2: cells
 			if (lane == 0) { int pw = (wid + NW - 1) % NW; xin = sCarryX[pw]; vin = sCarryV[pw]; }
 			lane_prepare<S, NS>(ls, b, r, qseq, tseq, tlen, sTable, sc);
-			int32_t lane_max = lane_cells<S, NS, kCigar, kRight>(ls, b, r, last_st, xin, vin, tbp, H, Us, sc);
+			int32_t lane_max = lane_cells<G, S, kCigar, kRight>(ls, b, r, last_st, gl, xin, vin, tbp, H, Us, sc);
 			int32_t wmax = __reduce_max_sync(0xffffffffu, lane_max);
 			if (lane == 0) sWarpMax[wid] = wmax;
 			__syncthreads();                                                                   // B
@@ -388,13 +492,13 @@ extz_dp_wide_kernel(DpLaunch L)
 				int32_t red = sWarpMax[0];
 #pragma unroll
 				for (int k = 1; k < NW; ++k) red = red > sWarpMax[k] ? red : sWarpMax[k];
-				int need = ld.mid<MASK>(H, Us, b, r, qe, red, ls.V[0], sc.zdrop);
+				int need = ld.mid<G, S>(H, Us, b, r, qe, red, ls.V[0], sc.zdrop);
 				sNeedArg = need; sGmax = ld.gmax;
-				if (!need) sStop = ld.fin<MASK>(H, b, r, qe, b.en0, qlen, tlen, sc.zdrop, sc.e);
+				if (!need) sStop = ld.fin<G, S>(H, b, r, qe, b.en0, qlen, tlen, sc.zdrop, sc.e);
 			}
 			__syncthreads();                                                                   // C
 			if (sNeedArg) {
-				uint32_t key = lane_argmax_key<S, NS>(ls, b, H, sGmax);
+				uint32_t key = lane_argmax_key<G, S>(ls, b, gl, H, sGmax);
 				key = __reduce_min_sync(0xffffffffu, key);
 				if (lane == 0) sWarpKey[wid] = key;
 				__syncthreads();                                                               // D
@@ -402,7 +506,7 @@ extz_dp_wide_kernel(DpLaunch L)
 					uint32_t k = ld.en0_key(b, r);
 #pragma unroll
 					for (int j = 0; j < NW; ++j) k = sWarpKey[j] < k ? sWarpKey[j] : k;
-					sStop = ld.fin<MASK>(H, b, r, qe, tie_key_slot(k, b.en0), qlen, tlen, sc.zdrop, sc.e);
+					sStop = ld.fin<G, S>(H, b, r, qe, tie_key_slot(k, b.en0), qlen, tlen, sc.zdrop, sc.e);
 				}
 				__syncthreads();                                                               // E
 			}

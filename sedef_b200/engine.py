@@ -150,7 +150,9 @@ def _collect(lib, ez: np.ndarray, keep_cigars: bool):
         for i in range(ez.shape[0]):
             n, p = int(ez[i]["n_cigar"]), int(ez[i]["cigar"])
             cigs.append(np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint32)), shape=(n,)).copy() if n else np.zeros(0, np.uint32))
-    lib.ksw_b200_free_cigars(ez.ctypes.data, ez.shape[0])
+    n_keep, m_keep = ez["n_cigar"].copy(), ez["m_cigar"].copy()
+    lib.ksw_b200_free_cigars(ez.ctypes.data, ez.shape[0])         # frees every ez[i].cigar and clears the fields
+    ez["n_cigar"], ez["m_cigar"] = n_keep, m_keep                  # keep the counts visible to the Python caller
     return cigs
 
 

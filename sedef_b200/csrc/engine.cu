@@ -60,9 +60,10 @@ extern "C" const char *ksw_b200_last_error(void) { return g_last_error.c_str(); 
 // ------------------------------------------------------------------------------------------------
 struct KClass { int G, S; bool wide; };
 // narrow classes: G <= 32 lanes per pair, 128-thread CTAs; wide classes: one CTA of G lanes per pair
-static const KClass kClasses[] = { {8, 4, false}, {16, 4, false}, {16, 8, false}, {32, 8, false}, {32, 16, false},
+static const KClass kClasses[] = { {2, 16, false}, {4, 16, false}, {8, 16, false}, {16, 16, false}, {32, 16, false},
                                    {32, 32, false}, {64, 16, true}, {128, 16, true}, {256, 16, true} };
 static const int kNumClasses = sizeof(kClasses) / sizeof(kClasses[0]);
+static const int kNumSizedClasses = kNumClasses;                        // all classes are ordered by capacity
 static inline int class_ns(int c) { return kClasses[c].G * kClasses[c].S; }
 // S == 32 lanes switch whole-lane (two 16-blocks), which costs 16 slots of window (extz_dp.cuh)
 static inline int class_capacity(int c) { return kClasses[c].S > 16 ? class_ns(c) - 16 : class_ns(c); }
@@ -97,8 +98,8 @@ static int dp_occupancy_gs(bool cigar, bool right)
 }
 #define EXTZ_FOR_CLASS(c, CALL) \
 	switch (c) { \
-	case 0: return CALL(8, 4, false); case 1: return CALL(16, 4, false); case 2: return CALL(16, 8, false); \
-	case 3: return CALL(32, 8, false); case 4: return CALL(32, 16, false); case 5: return CALL(32, 32, false); \
+	case 0: return CALL(2, 16, false); case 1: return CALL(4, 16, false); case 2: return CALL(8, 16, false); \
+	case 3: return CALL(16, 16, false); case 4: return CALL(32, 16, false); case 5: return CALL(32, 32, false); \
 	case 6: return CALL(64, 16, true); case 7: return CALL(128, 16, true); case 8: return CALL(256, 16, true); }
 static cudaError_t launch_dp(int c, const DpLaunch &L, bool cigar, bool right, int grid, cudaStream_t st)
 {
@@ -162,7 +163,7 @@ extern "C" void ksw_b200_destroy(void)
 	g_devs.clear();
 }
 extern "C" int ksw_b200_num_devices(void) { return (int)g_devs.size(); }
-extern "C" int ksw_b200_max_slots(void) { return class_capacity(kNumClasses - 1); }
+extern "C" int ksw_b200_max_slots(void) { return class_capacity(kNumSizedClasses - 1); }
 
 static int ensure_init()
 {
@@ -365,11 +366,11 @@ extern "C" ksw_b200_batch_t *ksw_b200_batch_upload(int n, const int *qlen, const
 		int wi = w < 0 ? std::max(qlen[i], tlen[i]) : std::min(w, std::max(qlen[i], tlen[i]));
 		int need = slots_needed(qlen[i], tlen[i], wi);
 		int c = 0;
-		while (c < kNumClasses && class_capacity(c) < need) ++c;
-		if (c == kNumClasses) {
+		while (c < kNumSizedClasses && class_capacity(c) < need) ++c;
+		if (c == kNumSizedClasses) {
 			delete B;
 			return bail(fail(KSW_B200_ERR_TOO_WIDE, "pair " + std::to_string(i) + " needs " + std::to_string(need) +
-			                 " live slots; widest kernel holds " + std::to_string(class_capacity(kNumClasses - 1))));
+			                 " live slots; widest kernel holds " + std::to_string(class_capacity(kNumSizedClasses - 1))));
 		}
 		items.push_back({i, c, est_cells(qlen[i], tlen[i], wi)});
 	}

@@ -26,6 +26,12 @@ struct DpLaunch {
 };
 
 __device__ __forceinline__ uint32_t ld_u8(const uint8_t *p) { return (uint32_t)__ldg(p); }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t saddr)
+{
+	uint32_t v;
+	asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));   // the table is read-only after the prologue
+	return v;
+}
 
 // ---- shared-memory index of circular slot c (conflict-free 128-bit rows: quad j of every lane is contiguous) ----
 template <int G, int S>
@@ -75,7 +81,7 @@ __device__ __forceinline__ void lane_load_slots(LaneState<S> &ls, const uint8_t 
 // window slide + query shift + top-row boundary + score fill for one anti-diagonal
 template <int S, int NS>
 __device__ __forceinline__ void lane_prepare(LaneState<S> &ls, const Band &b, int r, const uint8_t *qseq, const uint8_t *tseq,
-                                             int tlen, const uint32_t *sTable, const Scoring &sc)
+                                             int tlen, uint32_t table_saddr, const Scoring &sc)
 {
 	// lanes whose slots all fell below the rounded range take the slots NS further up
 	if (ls.t0 + S - 1 < b.st) { ls.t0 += NS; lane_load_slots<S>(ls, tseq, tlen, qseq, r, sc); }
@@ -107,7 +113,7 @@ __device__ __forceinline__ void lane_prepare(LaneState<S> &ls, const Band &b, in
 		for (int bb = 0; bb < 4; ++bb) {
 			const int i = 4 * k + bb;
 			const uint32_t off = __byte_perm(offs, 0u, 0x4440 | bb);
-			const uint32_t zn = *(const uint32_t *)((const char *)sTable + off);
+			const uint32_t zn = lds_u32(table_saddr + off);
 			if (fillmask & (1u << i)) ls.Z[i] = zn;
 		}
 	}
@@ -312,8 +318,16 @@ template <int G> __device__ __forceinline__ uint32_t group_sum_u(uint32_t v)
 // =====================================================================================================
 // narrow kernel: G <= 32 lanes per pair, the 32/G pairs of a warp advance in lock-step
 // =====================================================================================================
+// Occupancy targets found by measurement on B200 (profiles/r01_tuning.md): 16 slots per lane want 3 CTAs/SM
+// (168 registers, no spills): 341 GCUPS on config 2, against 293 (227 regs, 2 CTAs) and 335 (128 regs, spills).
+#ifndef EXTZ_MIN_BLOCKS
+#define EXTZ_MIN_BLOCKS 4
+#endif
+#ifndef EXTZ_MIN_BLOCKS16
+#define EXTZ_MIN_BLOCKS16 3
+#endif
 template <int G, int S, bool kCigar, bool kRight>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, (S <= 8 ? EXTZ_MIN_BLOCKS : (S == 16 ? EXTZ_MIN_BLOCKS16 : 1)))
 extz_dp_kernel(DpLaunch L)
 {
 	constexpr int NS = G * S;
@@ -330,6 +344,7 @@ extz_dp_kernel(DpLaunch L)
 	for (int i = threadIdx.x; i < kTableStride * kTableStride; i += blockDim.x) sTable[i] = L.table[i];
 	__syncthreads();
 
+	const uint32_t table_saddr = (uint32_t)__cvta_generic_to_shared(sTable);
 	const int lane_w = threadIdx.x & 31;
 	const int gl = threadIdx.x % G;                                  // lane within group
 	const int gidx = threadIdx.x / G;                                // group within block
@@ -378,7 +393,7 @@ extz_dp_kernel(DpLaunch L)
 			const uint32_t xin = __shfl_sync(FULL, ls.X[S - 1], pred_lane, G);
 			const uint32_t vin = __shfl_sync(FULL, ls.V[S - 1], pred_lane, G);
 			if (act) {
-				lane_prepare<S, NS>(ls, b, r, qseq, tseq, tlen, sTable, sc);
+				lane_prepare<S, NS>(ls, b, r, qseq, tseq, tlen, table_saddr, sc);
 				if (gl == 0) ld.pre<G, S>(H, b, r, qe);
 			}
 			__syncwarp();
@@ -442,6 +457,7 @@ extz_dp_wide_kernel(DpLaunch L)
 	for (int i = threadIdx.x; i < kTableStride * kTableStride; i += blockDim.x) sTable[i] = L.table[i];
 	__syncthreads();
 
+	const uint32_t table_saddr = (uint32_t)__cvta_generic_to_shared(sTable);
 	const int gl = threadIdx.x;
 	const int lane = gl & 31, wid = gl >> 5;
 	const Scoring sc = L.sc;
@@ -482,7 +498,7 @@ extz_dp_wide_kernel(DpLaunch L)
 			__syncthreads();                                                                   // A
 			// phase 2: cells
 			if (lane == 0) { int pw = (wid + NW - 1) % NW; xin = sCarryX[pw]; vin = sCarryV[pw]; }
-			lane_prepare<S, NS>(ls, b, r, qseq, tseq, tlen, sTable, sc);
+			lane_prepare<S, NS>(ls, b, r, qseq, tseq, tlen, table_saddr, sc);
 			int32_t lane_max = lane_cells<G, S, kCigar, kRight>(ls, b, r, last_st, gl, xin, vin, tbp, H, Us, sc);
 			int32_t wmax = __reduce_max_sync(0xffffffffu, lane_max);
 			if (lane == 0) sWarpMax[wid] = wmax;

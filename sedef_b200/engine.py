@@ -14,7 +14,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libsedef_b200.so")
+LIB_PATH = os.environ.get("SEDEF_B200_LIB", os.path.join(HERE, "libsedef_b200.so"))   # env override: A/B builds
 
 KSW_NEG_INF = -0x40000000
 KSW_EZ_SCORE_ONLY, KSW_EZ_RIGHT, KSW_EZ_GENERIC_SC, KSW_EZ_APPROX_MAX = 0x01, 0x02, 0x04, 0x08

@@ -134,6 +134,9 @@ int ksw_extz2_batch(int n, const int *qlen, const uint8_t *const *query,
                     ksw_extz_t *ez, sd_stats_t *stats,
                     const uint8_t *const *q_raw, const uint8_t *const *t_raw);
 
+/* H2D / D2H bytes and kernel launches of the last one-shot batch call made by this thread. */
+void ksw_b200_last_call_io(int64_t *h2d, int64_t *d2h, int *launches);
+
 /* Convenience for batch callers: free() every ez[i].cigar of a result array and clear the fields. */
 void ksw_b200_free_cigars(ksw_extz_t *ez, int n);
 
@@ -166,6 +169,8 @@ int  ksw_b200_batch_kernel_ms(const ksw_b200_batch_t *b, float *dp_ms, float *tb
 int64_t ksw_b200_batch_cells(const ksw_b200_batch_t *b);   /* host-side in-band cell count (all diagonals) */
 /* bytes copied host->device by upload(+run) and device->host by the last fetch */
 int  ksw_b200_batch_io_bytes(const ksw_b200_batch_t *b, int64_t *h2d, int64_t *d2h);
+/* host-side phase times of this batch in ms: {plan, pack, h2d wait, d2h, gather} */
+int  ksw_b200_batch_host_ms(const ksw_b200_batch_t *b, double *out5);
 /* the fused SD-statistics pass is on by default for CIGAR runs; 0 switches it off for this batch */
 void ksw_b200_batch_set_stats(ksw_b200_batch_t *b, int on);
 void ksw_b200_batch_free(ksw_b200_batch_t *b);

@@ -14,6 +14,7 @@
 // There is no CPU fallback: without a device every entry point fails.
 #include <cuda_runtime.h>
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -21,7 +22,9 @@
 #include <mutex>
 #include <numeric>
 #include <string>
+#include <thread>
 #include <vector>
+#include <condition_variable>
 
 #include "../../include/ksw2_b200.h"
 #include "extz_core.cuh"
@@ -271,15 +274,19 @@ struct SubBatch {
 	DevBuf d_arena, d_raw, d_pairs, d_results, d_tb, d_cigar, d_stats, d_misc, d_table;
 	size_t cigar_cap = 0;               // entries
 	unsigned long long cigar_used = 0;
+	cudaStream_t stream = nullptr;      // every batch owns a stream so that the H2D of one batch overlaps the kernels of another
 	cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 	float dp_ms = 0, tb_ms = 0, total_ms = 0;
 	int launches = 0;
 	size_t h2d_bytes = 0, d2h_bytes = 0;
+	std::vector<std::pair<cudaEvent_t, cudaEvent_t>> dp_ev, tb_ev;   // per-wave kernel timing events of the last launch
+	bool launched = false;
 	void release() {
 		h_arena.release(); h_raw.release(); h_results.release(); h_cigar.release(); h_stats.release();
 		d_arena.release(); d_raw.release(); d_pairs.release(); d_results.release(); d_tb.release();
 		d_cigar.release(); d_stats.release(); d_misc.release(); d_table.release();
 		for (auto &e : ev) if (e) { cudaEventDestroy(e); e = nullptr; }
+		if (stream) { cudaStreamDestroy(stream); stream = nullptr; }
 	}
 };
 
@@ -293,10 +300,13 @@ struct ksw_b200_batch {
 	uint32_t table[kTableStride * kTableStride];
 	std::vector<SubBatch> subs;
 	std::vector<uint8_t> is_empty;      // pairs with qlen<=0 || tlen<=0 (reset record)
-	int64_t cells = 0;
+	int64_t cells = -1;                 // exact in-band cell count, computed on first request
+	std::vector<int> cq, ct;            // lengths kept for the lazy cell count
+	double t_plan = 0, t_pack = 0, t_h2d = 0, t_d2h = 0, t_gather = 0;   // host-side phase times (ms)
 };
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+static inline double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 static int build_scoring(ksw_b200_batch &B)
 {
@@ -358,6 +368,7 @@ extern "C" ksw_b200_batch_t *ksw_b200_batch_upload(int n, const int *qlen, const
 	B->subs.resize(nd);
 	for (int d = 0; d < nd; ++d) B->subs[d].dc = &g_devs[d];
 
+	const double t_start = now_ms();
 	// ---- classify + LPT partition ----
 	struct Item { int idx; int cls; int64_t work; };
 	std::vector<Item> items; items.reserve(n);
@@ -386,6 +397,7 @@ extern "C" ksw_b200_batch_t *ksw_b200_batch_upload(int n, const int *qlen, const
 		per_dev[best].push_back(oi);
 	}
 
+	B->t_plan = now_ms() - t_start;
 	// ---- per device: group by class (descending work inside), pack, copy ----
 	for (int d = 0; d < nd; ++d) {
 		SubBatch &sb = B->subs[d];
@@ -419,6 +431,7 @@ extern "C" ksw_b200_batch_t *ksw_b200_batch_upload(int n, const int *qlen, const
 			for (auto &s : B->subs) s.release();
 			delete B; return bail(fail(KSW_B200_ERR_NOMEM, "sequence arena allocation failed"));
 		}
+		const double t_pack0 = now_ms();
 		uint8_t *ha = (uint8_t *)sb.h_arena.p, *hr = (uint8_t *)sb.h_raw.p;
 		const int64_t np = (int64_t)sb.pairs.size();
 		int bad_symbol = 0;
@@ -445,7 +458,9 @@ extern "C" ksw_b200_batch_t *ksw_b200_batch_upload(int n, const int *qlen, const
 			for (auto &s : B->subs) s.release();
 			delete B; return bail(fail(KSW_B200_ERR_ARG, "sequence symbol >= 8"));
 		}
-		cudaStream_t st = sb.dc->stream;
+		B->t_pack += now_ms() - t_pack0;
+		if (!sb.stream && cudaStreamCreateWithFlags(&sb.stream, cudaStreamNonBlocking) != cudaSuccess) sb.stream = nullptr;
+		cudaStream_t st = sb.stream ? sb.stream : sb.dc->stream;
 		bool ok = cudaMemcpyAsync(sb.d_arena.p, ha, sb.arena_bytes, cudaMemcpyHostToDevice, st) == cudaSuccess;
 		if (ok && hr) ok = cudaMemcpyAsync(sb.d_raw.p, hr, sb.arena_bytes, cudaMemcpyHostToDevice, st) == cudaSuccess;
 		sb.h2d_bytes = sb.arena_bytes * (hr ? 2 : 1) + sizeof(B->table);
@@ -462,22 +477,34 @@ extern "C" ksw_b200_batch_t *ksw_b200_batch_upload(int n, const int *qlen, const
 			delete B; return bail(fail(KSW_B200_ERR_CUDA, msg));
 		}
 	}
-	// exact cell count (for GCUPS) -- O(sum of lengths), parallel
+	B->cq.assign(qlen, qlen + n); B->ct.assign(tlen, tlen + n);
 	{
-		int64_t cells = 0;
-		const int64_t ni = (int64_t)items.size();
-#pragma omp parallel for schedule(dynamic, 256) reduction(+ : cells)
-		for (int64_t k = 0; k < ni; ++k) {
-			int i = items[k].idx;
-			cells += ksw_b200_count_cells(qlen[i], tlen[i], w);
-		}
-		B->cells = cells;
+		const double t0 = now_ms();
+		for (auto &sb : B->subs) if (!sb.pairs.empty()) { cudaSetDevice(sb.dc->dev); cudaStreamSynchronize(sb.stream ? sb.stream : sb.dc->stream); }
+		B->t_h2d = now_ms() - t0;
 	}
-	for (auto &sb : B->subs) if (!sb.pairs.empty()) { cudaSetDevice(sb.dc->dev); cudaStreamSynchronize(sb.dc->stream); }
 	return B;
 }
 
-extern "C" int64_t ksw_b200_batch_cells(const ksw_b200_batch_t *b) { return b ? b->cells : 0; }
+extern "C" int64_t ksw_b200_batch_cells(const ksw_b200_batch_t *cb)
+{
+	ksw_b200_batch_t *b = const_cast<ksw_b200_batch_t *>(cb);
+	if (!b) return 0;
+	if (b->cells < 0) {                                                             // exact count, O(sum of lengths), parallel
+		int64_t cells = 0;
+#pragma omp parallel for schedule(dynamic, 256) reduction(+ : cells)
+		for (int i = 0; i < b->n; ++i)
+			if (!b->is_empty[i]) cells += ksw_b200_count_cells(b->cq[i], b->ct[i], b->w);
+		b->cells = cells;
+	}
+	return b->cells;
+}
+extern "C" int ksw_b200_batch_host_ms(const ksw_b200_batch_t *b, double *out5)
+{
+	if (!b || !out5) return KSW_B200_ERR_ARG;
+	out5[0] = b->t_plan; out5[1] = b->t_pack; out5[2] = b->t_h2d; out5[3] = b->t_d2h; out5[4] = b->t_gather;
+	return 0;
+}
 extern "C" int ksw_b200_batch_io_bytes(const ksw_b200_batch_t *b, int64_t *h2d, int64_t *d2h)
 {
 	if (!b) return KSW_B200_ERR_ARG;
@@ -529,13 +556,15 @@ static int plan_waves(ksw_b200_batch &B, SubBatch &sb, bool cigar)
 	return 0;
 }
 
-static int run_sub(ksw_b200_batch &B, SubBatch &sb)
+// asynchronous part of a run: plan waves and enqueue every kernel of this device on the batch's stream
+static int launch_sub(ksw_b200_batch &B, SubBatch &sb)
 {
+	sb.launched = false;
 	if (sb.pairs.empty()) { sb.total_ms = sb.dp_ms = sb.tb_ms = 0; sb.launches = 0; return 0; }
 	const bool cigar = !(B.flag & KSW_EZ_SCORE_ONLY);
 	const bool right = (B.flag & KSW_EZ_RIGHT) != 0;
 	CUDA_TRY(cudaSetDevice(sb.dc->dev));
-	cudaStream_t st = sb.dc->stream;
+	cudaStream_t st = sb.stream ? sb.stream : sb.dc->stream;
 	int rc = plan_waves(B, sb, cigar);
 	if (rc) return rc;
 	// descriptors carry tb offsets -> (re)upload
@@ -548,7 +577,8 @@ static int run_sub(ksw_b200_batch &B, SubBatch &sb)
 	int *d_overflow = (int *)((char *)sb.d_misc.p + 2048 + 64);
 	sb.launches = 0; sb.dp_ms = sb.tb_ms = 0;
 	CUDA_TRY(cudaEventRecord(sb.ev[0], st));
-	std::vector<std::pair<cudaEvent_t, cudaEvent_t>> dp_ev, tb_ev;
+	auto &dp_ev = sb.dp_ev; auto &tb_ev = sb.tb_ev;
+	dp_ev.clear(); tb_ev.clear();
 	int wave_no = 0;
 	for (const Wave &wv : sb.waves) {
 		const int c = wv.cls;
@@ -592,12 +622,27 @@ static int run_sub(ksw_b200_batch &B, SubBatch &sb)
 		++wave_no;
 	}
 	CUDA_TRY(cudaEventRecord(sb.ev[1], st));
+	sb.launched = true;
+	return 0;
+}
+
+// blocking part: wait for the stream, read the timers, the CIGAR cursor and the overflow flag
+static int finish_sub(ksw_b200_batch &B, SubBatch &sb)
+{
+	if (!sb.launched) return 0;
+	sb.launched = false;
+	CUDA_TRY(cudaSetDevice(sb.dc->dev));
+	cudaStream_t st = sb.stream ? sb.stream : sb.dc->stream;
+	auto &dp_ev = sb.dp_ev; auto &tb_ev = sb.tb_ev;
+	unsigned long long *d_cursor = (unsigned long long *)((char *)sb.d_misc.p + 2048);
+	int *d_overflow = (int *)((char *)sb.d_misc.p + 2048 + 64);
 	CUDA_TRY(cudaStreamSynchronize(st));
 	CUDA_TRY(cudaEventElapsedTime(&sb.total_ms, sb.ev[0], sb.ev[1]));
 	for (auto &p : dp_ev) { float ms = 0; cudaEventElapsedTime(&ms, p.first, p.second); sb.dp_ms += ms; }
 	for (auto &p : tb_ev) { float ms = 0; cudaEventElapsedTime(&ms, p.first, p.second); sb.tb_ms += ms; }
 	for (auto &p : dp_ev) cudaEventDestroy(p.first);
 	for (auto &p : tb_ev) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+	dp_ev.clear(); tb_ev.clear();
 	int ovf = 0;
 	CUDA_TRY(cudaMemcpy(&ovf, d_overflow, sizeof(int), cudaMemcpyDeviceToHost));
 	CUDA_TRY(cudaMemcpy(&sb.cigar_used, d_cursor, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
@@ -612,8 +657,9 @@ extern "C" int ksw_b200_batch_run(ksw_b200_batch_t *B, float *device_ms)
 	// waves of different devices overlap: launches are asynchronous, run_sub only blocks on its own stream
 	// (one device per process is the scaling configuration; in-process multi-device runs them back to back
 	//  on the host side but concurrently on the devices when the batch fits one wave)
+	for (auto &sb : B->subs) { int rc = launch_sub(*B, sb); if (rc) return rc; }          // every device gets its work first
 	for (auto &sb : B->subs) {
-		int rc = run_sub(*B, sb);
+		int rc = finish_sub(*B, sb);
 		if (rc) return rc;
 		worst = std::max(worst, sb.total_ms);
 	}
@@ -653,14 +699,16 @@ extern "C" int ksw_b200_batch_fetch(ksw_b200_batch_t *B, ksw_extz_t *ez, sd_stat
 {
 	if (!B || (B->n > 0 && !ez)) return fail(KSW_B200_ERR_ARG, "null argument");
 	const bool cigar = !(B->flag & KSW_EZ_SCORE_ONLY);
-	for (int i = 0; i < B->n; ++i) reset_ez(&ez[i]);
+	B->t_d2h = B->t_gather = 0;
+	{ const double t0 = now_ms(); for (int i = 0; i < B->n; ++i) reset_ez(&ez[i]); B->t_gather += now_ms() - t0; }
 	if (stats) memset(stats, 0, sizeof(sd_stats_t) * (size_t)B->n);
 	int rc_all = 0;
 	for (auto &sb : B->subs) {
 		if (sb.pairs.empty()) continue;
 		CUDA_TRY(cudaSetDevice(sb.dc->dev));
-		cudaStream_t st = sb.dc->stream;
+		cudaStream_t st = sb.stream ? sb.stream : sb.dc->stream;
 		const size_t np = sb.pairs.size();
+		const double t_f0 = now_ms();
 		CUDA_TRY(cudaMemcpyAsync(sb.h_results.p, sb.d_results.p, np * sizeof(PairResult), cudaMemcpyDeviceToHost, st));
 		if (cigar && sb.cigar_used) {
 			if (sb.h_cigar.ensure(sb.cigar_used * 4)) return fail(KSW_B200_ERR_NOMEM, "pinned CIGAR buffer");
@@ -671,6 +719,8 @@ extern "C" int ksw_b200_batch_fetch(ksw_b200_batch_t *B, ksw_extz_t *ez, sd_stat
 			CUDA_TRY(cudaMemcpyAsync(sb.h_stats.p, sb.d_stats.p, np * sizeof(sd_stats_t), cudaMemcpyDeviceToHost, st));
 		}
 		CUDA_TRY(cudaStreamSynchronize(st));
+		B->t_d2h += now_ms() - t_f0;
+		const double t_g0 = now_ms();
 		sb.d2h_bytes = np * sizeof(PairResult) + (cigar ? sb.cigar_used * 4 : 0) + ((cigar && stats && B->want_stats) ? np * sizeof(sd_stats_t) : 0);
 		const PairResult *res = (const PairResult *)sb.h_results.p;
 		const uint32_t *carena = (const uint32_t *)sb.h_cigar.p;
@@ -694,6 +744,7 @@ extern "C" int ksw_b200_batch_fetch(ksw_b200_batch_t *B, ksw_extz_t *ez, sd_stat
 			if (cigar && stats && B->want_stats) stats[sb.pairs[k].orig] = hst[k];
 		}
 		if (nomem) rc_all = KSW_B200_ERR_NOMEM;
+		B->t_gather += now_ms() - t_g0;
 	}
 	if (rc_all) {
 		for (int i = 0; i < B->n; ++i) { free(ez[i].cigar); ez[i].cigar = 0; ez[i].n_cigar = ez[i].m_cigar = 0; }
@@ -719,19 +770,117 @@ extern "C" void ksw_b200_batch_free(ksw_b200_batch_t *B)
 // ------------------------------------------------------------------------------------------------
 // one-shot entry points
 // ------------------------------------------------------------------------------------------------
+extern "C" void ksw_b200_free_cigars(ksw_extz_t *ez, int n);
+// I/O accounting of the last one-shot call of this thread
+static thread_local int64_t g_last_h2d = 0, g_last_d2h = 0;
+static thread_local int g_last_launches = 0;
+extern "C" void ksw_b200_last_call_io(int64_t *h2d, int64_t *d2h, int *launches)
+{
+	if (h2d) *h2d = g_last_h2d;
+	if (d2h) *d2h = g_last_d2h;
+	if (launches) *launches = g_last_launches;
+}
+
+// One-shot batch.  Large batches are cut into chunks that flow through a two-stage software pipeline:
+// a producer thread packs chunk k+1 into pinned memory and copies it to the device (its own stream) while
+// this thread runs the kernels of chunk k and gathers its results -- H2D, kernels and D2H overlap.
 extern "C" int ksw_extz2_batch_flat(int n, const int *qlen, const int64_t *qoff, const uint8_t *qbuf,
                                     const int *tlen, const int64_t *toff, const uint8_t *tbuf,
                                     int8_t m, const int8_t *mat, int8_t q, int8_t e, int w, int zdrop, int flag,
                                     ksw_extz_t *ez, sd_stats_t *stats,
                                     const uint8_t *q_raw_buf, const uint8_t *t_raw_buf)
 {
-	int err = 0;
-	ksw_b200_batch_t *B = ksw_b200_batch_upload(n, qlen, qoff, qbuf, tlen, toff, tbuf, m, mat, q, e, w, zdrop, flag,
-	                                           q_raw_buf, t_raw_buf, &err);
-	if (!B) return err;
-	int rc = ksw_b200_batch_run(B, nullptr);
-	if (rc == 0) rc = ksw_b200_batch_fetch(B, ez, stats);
-	ksw_b200_batch_free(B);
+	g_last_h2d = g_last_d2h = 0; g_last_launches = 0;
+	if (n < 0) return fail(KSW_B200_ERR_ARG, "negative count");
+	const char *env = getenv("KSW_B200_CHUNK_PAIRS");
+	const int chunk_pairs = env ? std::max(1, atoi(env)) : 25000;
+	// chunk sizes ramp up (1 : 2 : 4 : 4 ...) so that the first H2D copy -- the only one nothing can hide -- is short
+	int nchunks = std::max(1, std::min(16, n / chunk_pairs + (n >= 2 * chunk_pairs ? 1 : 0)));
+	std::vector<int> start(nchunks + 1, 0);
+	{
+		std::vector<double> wgt(nchunks, 4.0);
+		if (nchunks >= 3) { wgt[0] = 1.0; wgt[1] = 2.0; }
+		double tot = 0; for (double x : wgt) tot += x;
+		double acc = 0;
+		for (int c = 0; c < nchunks; ++c) { acc += wgt[c]; start[c + 1] = (int)((double)n * acc / tot + 0.5); }
+		start[nchunks] = n;
+	}
+
+	auto upload_chunk = [&](int c, int *err) -> ksw_b200_batch_t * {
+		const int s0 = start[c], cnt = start[c + 1] - s0;
+		return ksw_b200_batch_upload(cnt, qlen + s0, qoff + s0, qbuf, tlen + s0, toff + s0, tbuf, m, mat, q, e, w, zdrop, flag,
+		                             q_raw_buf, t_raw_buf, err);
+	};
+	auto consume = [&](ksw_b200_batch_t *B, int c, bool launched) -> int {
+		const int s0 = start[c];
+		int rc = 0;
+		if (!launched) { if (!stats) B->want_stats = false; rc = ksw_b200_batch_run(B, nullptr); }
+		else for (auto &sb : B->subs) { rc = finish_sub(*B, sb); if (rc) break; }
+		if (rc == 0) rc = ksw_b200_batch_fetch(B, ez + s0, stats ? stats + s0 : nullptr);
+		int64_t a = 0, d = 0; ksw_b200_batch_io_bytes(B, &a, &d);
+		g_last_h2d += a; g_last_d2h += d; g_last_launches += ksw_b200_batch_launches(B);
+		ksw_b200_batch_free(B);
+		return rc;
+	};
+	if (nchunks == 1) {
+		int err = 0;
+		ksw_b200_batch_t *B = upload_chunk(0, &err);
+		if (!B) return err;
+		return consume(B, 0, false);
+	}
+	// producer / consumer over chunks, one chunk of look-ahead
+	std::mutex mu; std::condition_variable cv;
+	std::vector<ksw_b200_batch_t *> ready(nchunks, nullptr);
+	std::vector<int> errs(nchunks, 0), done(nchunks, 0);
+	int consumed = 0; bool abort_all = false;
+	std::string producer_error;
+	std::thread producer([&] {
+		for (int c = 0; c < nchunks; ++c) {
+			{
+				std::unique_lock<std::mutex> lk(mu);
+				cv.wait(lk, [&] { return abort_all || c - consumed <= 2; });       // at most two chunks ahead (bounds pinned + traceback memory)
+				if (abort_all) return;
+			}
+			int err = 0;
+			ksw_b200_batch_t *B = upload_chunk(c, &err);
+			if (B) {                                                        // enqueue the kernels right behind the H2D copy
+				if (!stats) B->want_stats = false;
+				for (auto &sb : B->subs) { err = launch_sub(*B, sb); if (err) break; }
+				if (err) { ksw_b200_batch_free(B); B = nullptr; }
+			}
+			{
+				std::lock_guard<std::mutex> lk(mu);
+				ready[c] = B; errs[c] = err; done[c] = 1;
+				if (!B) producer_error = g_last_error;
+			}
+			cv.notify_all();
+			if (!B) return;
+		}
+	});
+	int rc = 0;
+	for (int c = 0; c < nchunks && rc == 0; ++c) {
+		ksw_b200_batch_t *B = nullptr;
+		{
+			std::unique_lock<std::mutex> lk(mu);
+			cv.wait(lk, [&] { return done[c] != 0; });
+			B = ready[c];
+			if (!B) { rc = errs[c]; g_last_error = producer_error; }
+		}
+		if (B) rc = consume(B, c, true);
+		{
+			std::lock_guard<std::mutex> lk(mu);
+			consumed = c + 1;
+			if (rc) abort_all = true;
+		}
+		cv.notify_all();
+	}
+	{ std::lock_guard<std::mutex> lk(mu); abort_all = abort_all || rc != 0; }
+	cv.notify_all();
+	producer.join();
+	if (rc) {                                                           // leave nothing allocated on error
+		for (int c = 0; c < nchunks; ++c) if (ready[c] && c >= consumed) ksw_b200_batch_free(ready[c]);
+		ksw_b200_free_cigars(ez, n);
+	}
 	return rc;
 }
 

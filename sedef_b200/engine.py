@@ -61,7 +61,7 @@ EXPORTS = ["ksw_b200_strerror", "ksw_b200_last_error", "ksw_b200_init", "ksw_b20
            "ksw_extz2_batch_flat", "ksw_b200_batch_upload", "ksw_b200_batch_run", "ksw_b200_batch_fetch",
            "ksw_b200_batch_launches", "ksw_b200_batch_kernel_ms", "ksw_b200_batch_cells",
            "ksw_b200_batch_free", "ksw_b200_count_cells", "sd_stats_derive_fp",
-           "ksw_b200_batch_io_bytes", "ksw_b200_batch_set_stats", "ksw_b200_free_cigars"]
+           "ksw_b200_batch_io_bytes", "ksw_b200_batch_set_stats", "ksw_b200_free_cigars", "ksw_b200_batch_host_ms", "ksw_b200_last_call_io"]
 
 
 def load():
@@ -103,6 +103,8 @@ def load():
     lib.ksw_b200_batch_io_bytes.argtypes = [vp, C.POINTER(i64), C.POINTER(i64)]
     lib.ksw_b200_batch_set_stats.argtypes = [vp, i32]
     lib.ksw_b200_free_cigars.argtypes = [vp, i32]
+    lib.ksw_b200_batch_host_ms.argtypes = [vp, C.POINTER(C.c_double)]
+    lib.ksw_b200_last_call_io.argtypes = [C.POINTER(i64), C.POINTER(i64), C.POINTER(i32)]
     lib.sd_stats_derive_fp.argtypes = [C.POINTER(SdStats), C.POINTER(SdStatsFp)]
     lib.free = C.CDLL(None).free
     lib.free.argtypes = [vp]
@@ -176,6 +178,13 @@ def extz2_batch(ps, mat, q: int, e: int, w: int = -1, zdrop: int = -1, flag: int
     return BatchResult(ez, cigs, stats)
 
 
+def last_call_io():
+    """(h2d_bytes, d2h_bytes, kernel_launches) of the last one-shot batch call of this thread."""
+    a, b, c = C.c_int64(0), C.c_int64(0), C.c_int(0)
+    load().ksw_b200_last_call_io(C.byref(a), C.byref(b), C.byref(c))
+    return int(a.value), int(b.value), int(c.value)
+
+
 def extz2(query, target, mat, q: int, e: int, w: int = -1, zdrop: int = -1, flag: int = 0, m: int = 5):
     """Single pair through the ksw2-compatible entry point `ksw_extz2_b200` -> (fields, cigar list)."""
     lib = load()
@@ -223,6 +232,11 @@ class ResidentBatch:
         a, b = C.c_int64(0), C.c_int64(0)
         self.lib.ksw_b200_batch_io_bytes(self.h, C.byref(a), C.byref(b))
         return int(a.value), int(b.value)
+
+    def host_ms(self) -> dict:
+        a = (C.c_double * 5)()
+        self.lib.ksw_b200_batch_host_ms(self.h, a)
+        return dict(zip(("plan", "pack", "h2d", "d2h", "gather"), [float(x) for x in a]))
 
     def set_stats(self, on: bool):
         self.lib.ksw_b200_batch_set_stats(self.h, int(on))

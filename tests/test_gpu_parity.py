@@ -217,3 +217,17 @@ def test_full_size_config2_properties(checker, mat):
     for k, i in enumerate(sample):
         assert a.fields(int(i)) == fr[k], int(i)
         assert a.cigars[int(i)].tolist() == cr[k], int(i)
+
+
+def test_pipelined_one_shot_matches_oracle(checker, mat, monkeypatch):
+    """Large one-shot batches are cut into chunks that flow through the upload/launch/fetch pipeline
+    (ksw_extz2_batch_flat); force small chunks and check every pair, in original order, against the oracle."""
+    monkeypatch.setenv("KSW_B200_CHUNK_PAIRS", "700")
+    ps = synth.make_pairs_mixed(5000, seed=424242, min_len=1, max_len=260, div=0.12)
+    got = compare(ps, mat, checker, 40, 60, 0)
+    assert engine.last_call_io()[2] >= 8            # several chunks -> several kernel launches
+    monkeypatch.setenv("KSW_B200_CHUNK_PAIRS", "100000000")
+    one = engine.extz2_batch(ps, mat, 40, 1, 40, 60, 0)
+    for k in ("max_zd", "max_q", "max_t", "mqe", "mqe_t", "mte", "mte_q", "score", "n_cigar"):
+        assert np.array_equal(got.ez[k], one.ez[k]), k
+    assert np.array_equal(got.stats, one.stats)

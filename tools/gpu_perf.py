@@ -16,5 +16,19 @@ for it in range(4):
     print("run %d: %.2f ms  -> %.1f GCUPS, %.0f pairs/s  (dp %.2f tb %.2f aux %.2f ms, launches %d)" % (
         it, ms, rb.cells() / ms / 1e6, n / ms * 1e3, k["dp_ms"], k["tb_ms"], k["aux_ms"], rb.launches()))
 t0 = time.time(); res = rb.fetch(); print("fetch %.3fs" % (time.time() - t0))
-t0 = time.time(); r2 = engine.extz2_batch(ps, mat, 40, 1, w, -1, flag, keep_cigars=False); dt = time.time() - t0
+for it in range(3):
+    t0 = time.time(); b = engine.ResidentBatch(ps, mat, 40, 1, w, -1, flag); t1 = time.time(); b.run(); t2 = time.time()
+    r2 = b.fetch(keep_cigars=False); t3 = time.time(); hm = b.host_ms(); b.free(); t4 = time.time()
+    print("e2e iter %d: upload %.1f run %.1f fetch %.1f free %.1f ms | host phases %s" % (it, (t1-t0)*1e3, (t2-t1)*1e3, (t3-t2)*1e3, (t4-t3)*1e3, {k: round(v, 1) for k, v in hm.items()}))
+dt = t4 - t0
+lib = engine.load()
+ez = np.zeros(n, engine.EZ_DTYPE); st = np.zeros(n, engine.STATS_DTYPE)
+for it in range(4):
+    t0 = time.time()
+    rc = lib.ksw_extz2_batch_flat(n, ps.qlen.ctypes.data, ps.qoff.ctypes.data, ps.q.ctypes.data, ps.tlen.ctypes.data, ps.toff.ctypes.data,
+                                  ps.t.ctypes.data, 5, mat.ctypes.data, 40, 1, w, -1, flag, ez.ctypes.data, st.ctypes.data,
+                                  ps.q_raw.ctypes.data, ps.t_raw.ctypes.data)
+    t1 = time.time(); lib.ksw_b200_free_cigars(ez.ctypes.data, n); t2 = time.time()
+    print("one-shot C call %.1f ms (rc %d) + free_cigars %.1f ms; io %s" % ((t1 - t0) * 1e3, rc, (t2 - t1) * 1e3, engine.last_call_io()))
+dt = t2 - t0
 print("e2e one-shot %.3fs -> %.1f GCUPS %.0f pairs/s" % (dt, rb.cells() / dt / 1e9, n / dt))

@@ -59,7 +59,7 @@ def build(force: bool = False) -> None:
     """Compile the checkers (oracle/Makefile). `_ref/` is rebuilt only where /root/reference exists."""
     args = ["make", "-C", HERE, "-s"] + (["-B"] if force else [])
     subprocess.run(args + ["liboracle_port.so"], check=True)
-    subprocess.run(args + ["ref"], check=False)
+    subprocess.run(args + ["ref_full"], check=False)   # needs sedef_b200/libsedef_b200.so for the redirect variant
 
 
 _SIG = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int8, C.c_void_p, C.c_int8, C.c_int8,

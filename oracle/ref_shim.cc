@@ -6,6 +6,11 @@
 #include <cstring>
 #include <string>
 #include "align.h"   // /root/reference/src/align.h
+#include "chain.h"   // /root/reference/src/chain.h
+#include "hit.h"
+#include "hash.h"
+#include <memory>
+#include <sstream>
 
 extern "C" {
 // Alignment(fa, fb): reference src/align.cc:76-88 (align_dna + align_helper + populate_nice_alignment)
@@ -26,5 +31,24 @@ int ref_alignment_from_cigar(const char *fa, const char *fb, const char *cigar,
 	Alignment a{std::string(fa), std::string(fb), std::string(cigar)};
 	*span = a.span(); *matches = a.matches(); *mismatches = a.mismatches(); *gaps = a.gaps(); *gap_bases = a.gap_bases();
 	return 0;
+}
+// fast_align(query, ref, orig, k): the reference's whole per-region align path (src/chain.cc:203-268: anchors,
+// chaining, Alignment guide constructors with ksw gap fills, refine_chains with merges and +-500 bp side
+// extensions) -- i.e. every call site of the hot path, untouched.  One text line per resulting hit.
+int ref_fast_align(const char *query, const char *ref, int kmer_size, char *out, int cap)
+{
+	std::string q(query), r(ref);
+	auto qp = std::make_shared<Sequence>("QRY", q);
+	auto rp = std::make_shared<Sequence>("REF", r);
+	Hit orig{qp, 0, (int)q.size(), rp, 0, (int)r.size()};
+	std::vector<Hit> hits = fast_align(q, r, orig, kmer_size);
+	std::ostringstream os;
+	for (auto &h : hits)
+		os << h.query_start << ' ' << h.query_end << ' ' << h.ref_start << ' ' << h.ref_end << ' ' << h.aln.cigar_string() << ' '
+		   << h.aln.span() << ' ' << h.aln.matches() << ' ' << h.aln.mismatches() << ' ' << h.aln.gaps() << ' ' << h.aln.gap_bases() << '\n';
+	std::string sres = os.str();
+	if ((int)sres.size() + 1 > cap) return -1;
+	memcpy(out, sres.c_str(), sres.size() + 1);
+	return (int)hits.size();
 }
 }

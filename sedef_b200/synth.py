@@ -268,3 +268,27 @@ def count_cells(qlen: int, tlen: int, w: int) -> int:
     if bad.size:
         width = width[:bad[0]]
     return int(width.sum())
+
+
+def make_region_pair(length: int = 8000, div: float = 0.06, flank: int = 1500, seed: int = 0x5EDEF004):
+    """One candidate region pair as the align stage sees it (BASELINE.json configs[0]/[3] shape): a soft-masked
+    query region and a reference region holding a diverged copy (makeSmall substitutions/1-bp indels plus a few
+    longer indels) between unrelated flanks.  Returns (query_ascii, ref_ascii) as str."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    core = make_pairs_small(1, length=length, div=div, seed=seed, n_frac=0.0005)
+    q = core.q_raw.copy(); t = core.t_raw.copy()
+    # a few longer indels in the copy (the makeLarge idea)
+    for _ in range(3):
+        p = int(rng.integers(200, max(201, len(t) - 200)))
+        k = int(rng.integers(20, 120))
+        if rng.random() < 0.5:
+            t = np.concatenate([t[:p], t[p + k:]])
+        else:
+            ins = ASCII[rng.integers(0, 4, k)]
+            t = np.concatenate([t[:p], ins, t[p:]])
+    def flank_seq(n):
+        codes = rng.integers(0, 4, n).astype(np.uint8)
+        return _to_ascii(codes, _softmask(rng, n, mean_run=200))
+    qs = np.concatenate([flank_seq(flank), q, flank_seq(flank)])
+    ts = np.concatenate([flank_seq(flank), t, flank_seq(flank)])
+    return qs.tobytes().decode(), ts.tobytes().decode()

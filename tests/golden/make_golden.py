@@ -102,7 +102,18 @@ def main():
         recs.append(dict(a=fa, b=fb, **ref_alignment(slib, fa, fb)))
     json.dump(dict(source="oracle/_ref/libsedef_ref.so: reference Alignment(fa, fb) (src/align.cc:76-88,274-315)",
                    records=recs), open(os.path.join(HERE, "sd_stats_golden.json"), "w"))
-    for f in ("ksw2_kat.json", "ksw2_golden.json", "sd_stats_golden.json"):
+    # ---- region-level golden: the reference's whole fast_align() (every call site of the hot path) ----
+    slib.ref_fast_align.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_char_p, C.c_int]
+    regs = []
+    for (L, div, seed) in [(2500, 0.03, 11), (6000, 0.06, 12), (9000, 0.10, 13)]:
+        qs, ts = synth.make_region_pair(L, div, seed=seed)
+        buf = C.create_string_buffer(1 << 22)
+        n = slib.ref_fast_align(qs.encode(), ts.encode(), 11, buf, len(buf))
+        regs.append(dict(length=L, div=div, seed=seed, n_hits=n, hits=buf.value.decode()))
+    json.dump(dict(source="oracle/_ref/libsedef_ref.so: reference fast_align(query, ref, orig, 11) (src/chain.cc:203-268) on "
+                          "synth.make_region_pair(length, div, seed=seed); one line per hit: qs qe rs re cigar span matches mismatches gaps gap_bases",
+                   regions=regs), open(os.path.join(HERE, "fast_align_golden.json"), "w"))
+    for f in ("ksw2_kat.json", "ksw2_golden.json", "sd_stats_golden.json", "fast_align_golden.json"):
         print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")
 
 

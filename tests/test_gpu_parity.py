@@ -231,3 +231,32 @@ def test_pipelined_one_shot_matches_oracle(checker, mat, monkeypatch):
     for k in ("max_zd", "max_q", "max_t", "mqe", "mqe_t", "mte", "mte_q", "score", "n_cigar"):
         assert np.array_equal(got.ez[k], one.ez[k]), k
     assert np.array_equal(got.stats, one.stats)
+
+
+def _fast_align(libpath, q, t):
+    import ctypes as C
+    lib = C.CDLL(libpath)
+    lib.ref_fast_align.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_char_p, C.c_int]
+    buf = C.create_string_buffer(1 << 22)
+    n = lib.ref_fast_align(q.encode(), t.encode(), 11, buf, len(buf))
+    return n, buf.value.decode(), lib
+
+
+def test_reference_call_sites_with_cuda_kernel(checker, golden_dir):
+    """Drop-in check at the reference's own call sites: the UNMODIFIED reference align stage (fast_align: anchors,
+    chaining, guide constructors, refine/merge, side extensions) linked against the product library through the
+    one-line binding of INTEGRATION.md (oracle/ksw_redirect.c) must produce the same hits and CIGARs as with its
+    own SSE kernel, and as the committed golden."""
+    import os
+    ref_dir = os.path.join(os.path.dirname(oracle.__file__), "_ref")
+    sse, b200 = os.path.join(ref_dir, "libsedef_ref.so"), os.path.join(ref_dir, "libsedef_ref_b200.so")
+    if not (os.path.exists(sse) and os.path.exists(b200)):
+        pytest.skip("oracle/_ref/libsedef_ref*.so not built")
+    g = load_json(golden_dir, "fast_align_golden.json")
+    for reg in g["regions"]:
+        q, t = synth.make_region_pair(reg["length"], reg["div"], seed=reg["seed"])
+        n1, out1, _ = _fast_align(sse, q, t)
+        n2, out2, lib2 = _fast_align(b200, q, t)
+        assert lib2.ksw_redirect_calls() > 0            # the CUDA kernel really was underneath
+        assert (n1, out1) == (reg["n_hits"], reg["hits"])
+        assert (n2, out2) == (n1, out1)

@@ -91,3 +91,19 @@ def test_port_vs_compiled_reference_fuzz(built, mat, w, zdrop, flag, maxlen, div
     _, fp, cp = oracle.port().batch(ps, mat, 40, 1, w, zdrop, flag, nthreads=4)
     assert fr == fp
     assert cr == cp
+
+
+@pytest.mark.skipif(not oracle.have_ref(), reason="oracle/_ref not built")
+def test_region_golden_reproducible(built, golden_dir):
+    """tests/golden/fast_align_golden.json is what the compiled reference align stage produces here (CPU, SSE kernel)."""
+    import ctypes as C, os
+    path = os.path.join(os.path.dirname(oracle.__file__), "_ref", "libsedef_ref.so")
+    if not os.path.exists(path):
+        pytest.skip("libsedef_ref.so not built")
+    lib = C.CDLL(path)
+    lib.ref_fast_align.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_char_p, C.c_int]
+    for reg in load_json(golden_dir, "fast_align_golden.json")["regions"]:
+        q, t = synth.make_region_pair(reg["length"], reg["div"], seed=reg["seed"])
+        buf = C.create_string_buffer(1 << 22)
+        n = lib.ref_fast_align(q.encode(), t.encode(), 11, buf, len(buf))
+        assert (n, buf.value.decode()) == (reg["n_hits"], reg["hits"])

@@ -152,6 +152,8 @@ def run_ours(args):
     mat = synth.sedef_matrix()
     W, ZD, FLAG = 100, -1, 0
     engine.init(local, 1)
+    host_threads = max(1, (os.cpu_count() or 1) // max(1, world))   # torchrun exports OMP_NUM_THREADS=1; share the cores
+    engine.set_host_threads(host_threads)
     torch.cuda.set_device(local)
     ps = make_workload(args.pairs, rank)
 
@@ -197,6 +199,7 @@ def run_ours(args):
     barrier_sync(dist, local)
     e2e_ms = allreduce_max(dist, local, (time.perf_counter() - t0) * 1e3) / e2e_steps
     e2e_gcups = cells_total / (e2e_ms * 1e-3) / 1e9
+    io = (int(allreduce_sum(dist, local, float(io[0]))), int(allreduce_sum(dist, local, float(io[1]))), io[2])
     score_sum = int(res.ez["score"].astype(np.int64).sum())
 
     # ---- CPU baseline on this box (rank 0, N == 1 only) -------------------------------------------------
@@ -231,7 +234,7 @@ def run_ours(args):
             "e2e": {"value": round(e2e_gcups, 2), "unit": "GCUPS", "h2d_bytes_per_step": int(io[0]), "d2h_bytes_per_step": int(io[1]),
                     "ms_per_step": round(e2e_ms, 3), "pairs_per_s": round(pairs_total / (e2e_ms * 1e-3), 1),
                     "api": "ksw_extz2_batch_flat (one call, host buffers in, ksw_extz_t + malloc'd CIGARs + sd_stats_t out; chunked upload/launch/fetch pipeline inside)",
-                    "checksum_score_sum": score_sum},
+                    "checksum_score_sum": score_sum, "host_threads_per_rank": host_threads},
             "roofline": {"bound": "int_alu", "achieved": round(achieved_tops, 3), "peak": round(p_int, 3), "unit": "Tlane-op/s",
                          "frac": round(achieved_tops / p_int, 4), "traffic": traffic,
                          "kernel": "extz_dp_kernel<8,16,cigar,left> (8 lanes x 16 slots per pair, 4 pairs per warp)", "ops_per_cell": OPS_PER_CELL,

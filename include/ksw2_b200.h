@@ -106,6 +106,8 @@ const char *ksw_b200_last_error(void);   /* thread-local detail string of the la
 int  ksw_b200_init(int first_dev, int ndev);
 void ksw_b200_destroy(void);
 int  ksw_b200_num_devices(void);
+/* Host threads used for packing / gathering (0 = OpenMP default). */
+void ksw_b200_set_host_threads(int n);
 /* Upper bound on rounded live slots per anti-diagonal a pair may need (SURVEY App. C:
  * 16*n_col_, or 16*ceil(tlen/16) if smaller). */
 int  ksw_b200_max_slots(void);

@@ -13,6 +13,7 @@
 //     ksw_extz_t / sd_stats_t exactly as ksw_extz2_sse would have filled them.
 // There is no CPU fallback: without a device every entry point fails.
 #include <cuda_runtime.h>
+#include <omp.h>
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -130,6 +131,11 @@ struct DevCtx {
 };
 static std::mutex g_mu;
 static std::vector<DevCtx> g_devs;
+// host threads used for packing / gathering (0: OpenMP default).  Launchers such as torchrun export
+// OMP_NUM_THREADS=1, which would serialise the host side of every rank; callers can override it here.
+static int g_host_threads = 0;
+static inline int host_threads() { return g_host_threads > 0 ? g_host_threads : omp_get_max_threads(); }
+extern "C" void ksw_b200_set_host_threads(int n) { g_host_threads = n > 0 ? n : 0; }
 
 extern "C" int ksw_b200_init(int first_dev, int ndev)
 {
@@ -378,6 +384,7 @@ extern "C" ksw_b200_batch_t *ksw_b200_batch_upload(int n, const int *qlen, const
 		int need = slots_needed(qlen[i], tlen[i], wi);
 		int c = 0;
 		while (c < kNumSizedClasses && class_capacity(c) < need) ++c;
+		if (c == 5 && getenv("KSW_B200_SKIP_S32")) c = 6;                              // A/B: 32 lanes x 32 slots vs 64-lane CTA
 		if (c == kNumSizedClasses) {
 			delete B;
 			return bail(fail(KSW_B200_ERR_TOO_WIDE, "pair " + std::to_string(i) + " needs " + std::to_string(need) +
@@ -435,7 +442,7 @@ extern "C" ksw_b200_batch_t *ksw_b200_batch_upload(int n, const int *qlen, const
 		uint8_t *ha = (uint8_t *)sb.h_arena.p, *hr = (uint8_t *)sb.h_raw.p;
 		const int64_t np = (int64_t)sb.pairs.size();
 		int bad_symbol = 0;
-#pragma omp parallel for schedule(static) reduction(| : bad_symbol)
+#pragma omp parallel for num_threads(host_threads()) schedule(static) reduction(| : bad_symbol)
 		for (int64_t k = 0; k < np; ++k) {
 			const PairDesc &pd = sb.pairs[k];
 			const int i = pd.orig;
@@ -492,7 +499,7 @@ extern "C" int64_t ksw_b200_batch_cells(const ksw_b200_batch_t *cb)
 	if (!b) return 0;
 	if (b->cells < 0) {                                                             // exact count, O(sum of lengths), parallel
 		int64_t cells = 0;
-#pragma omp parallel for schedule(dynamic, 256) reduction(+ : cells)
+#pragma omp parallel for num_threads(host_threads()) schedule(dynamic, 256) reduction(+ : cells)
 		for (int i = 0; i < b->n; ++i)
 			if (!b->is_empty[i]) cells += ksw_b200_count_cells(b->cq[i], b->ct[i], b->w);
 		b->cells = cells;
@@ -726,7 +733,7 @@ extern "C" int ksw_b200_batch_fetch(ksw_b200_batch_t *B, ksw_extz_t *ez, sd_stat
 		const uint32_t *carena = (const uint32_t *)sb.h_cigar.p;
 		const sd_stats_t *hst = (const sd_stats_t *)sb.h_stats.p;
 		int nomem = 0;
-#pragma omp parallel for schedule(static) reduction(| : nomem)
+#pragma omp parallel for num_threads(host_threads()) schedule(static) reduction(| : nomem)
 		for (int64_t k = 0; k < (int64_t)np; ++k) {
 			const PairResult &r = res[k];
 			ksw_extz_t *z = &ez[sb.pairs[k].orig];
@@ -756,7 +763,7 @@ extern "C" int ksw_b200_batch_fetch(ksw_b200_batch_t *B, ksw_extz_t *ez, sd_stat
 extern "C" void ksw_b200_free_cigars(ksw_extz_t *ez, int n)
 {
 	if (!ez) return;
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for num_threads(host_threads()) schedule(static)
 	for (int i = 0; i < n; ++i) { free(ez[i].cigar); ez[i].cigar = nullptr; ez[i].n_cigar = ez[i].m_cigar = 0; }
 }
 

@@ -252,7 +252,9 @@ struct Leader {
 			gmax = gmax > Hen0_lazy ? gmax : Hen0_lazy;
 		} else Hen0_lazy = H[0];                              // en0 == 0: regular update (:228 else-arm)
 		int32_t maxH_true = gmax - qe * r;
-		return (maxH_true > ez.max) || (zdrop >= 0);
+		// ksw_apply_zdrop (extern/ksw2.h:161-177) only looks at the arg-max slot when the maximum improves, or when
+		// max - H > zdrop (+ l*e >= 0) can fire; in every other case it has no effect, so the arg-max is not needed
+		return (maxH_true > ez.max) || (zdrop >= 0 && ez.max - maxH_true > zdrop);
 	}
 	// contribution of slot en0 to the fast arg-max pass
 	__device__ __forceinline__ uint32_t en0_count(const Band &b, int r) const

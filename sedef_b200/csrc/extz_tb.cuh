@@ -14,6 +14,8 @@
 
 namespace extz {
 
+constexpr int kPrefetchRows = 16;
+
 struct TbLaunch {
 	const PairDesc *pairs;
 	PairResult *results;
@@ -74,6 +76,12 @@ extz_traceback_kernel(TbLaunch L)
 		int i = i0, j = j0, state = 0;
 		while (i >= 0 && j >= 0) {                                  // extern/ksw2.h:124-144
 			int r = i + j;
+			// the walk is a dependent chain of nibble reads; pull the rows it will need next into L2/L1 early
+			// (the column moves by at most one slot per row, so row r-16 is read within 8 bytes of the current column)
+			if (r >= kPrefetchRows) {
+				const uint8_t *pf = tbp + (int64_t)(r - kPrefetchRows) * rowB + (((i - kPrefetchRows / 2) & (NS - 1)) >> 1);
+				asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
+			}
 			Band b; band_of(r, qlen, tlen, w, T, false, b);
 			int force = -1;
 			if (i < b.st) force = 2;

@@ -61,7 +61,7 @@ EXPORTS = ["ksw_b200_strerror", "ksw_b200_last_error", "ksw_b200_init", "ksw_b20
            "ksw_extz2_batch_flat", "ksw_b200_batch_upload", "ksw_b200_batch_run", "ksw_b200_batch_fetch",
            "ksw_b200_batch_launches", "ksw_b200_batch_kernel_ms", "ksw_b200_batch_cells",
            "ksw_b200_batch_free", "ksw_b200_count_cells", "sd_stats_derive_fp",
-           "ksw_b200_batch_io_bytes", "ksw_b200_batch_set_stats", "ksw_b200_free_cigars", "ksw_b200_batch_host_ms", "ksw_b200_last_call_io"]
+           "ksw_b200_batch_io_bytes", "ksw_b200_batch_set_stats", "ksw_b200_free_cigars", "ksw_b200_batch_host_ms", "ksw_b200_last_call_io", "ksw_b200_set_host_threads"]
 
 
 def load():
@@ -104,6 +104,7 @@ def load():
     lib.ksw_b200_batch_set_stats.argtypes = [vp, i32]
     lib.ksw_b200_free_cigars.argtypes = [vp, i32]
     lib.ksw_b200_batch_host_ms.argtypes = [vp, C.POINTER(C.c_double)]
+    lib.ksw_b200_set_host_threads.argtypes = [i32]
     lib.ksw_b200_last_call_io.argtypes = [C.POINTER(i64), C.POINTER(i64), C.POINTER(i32)]
     lib.sd_stats_derive_fp.argtypes = [C.POINTER(SdStats), C.POINTER(SdStatsFp)]
     lib.free = C.CDLL(None).free
@@ -123,6 +124,10 @@ def init(first_dev: int = 0, ndev: int = 0) -> int:
     if n <= 0:
         _check(n if n < 0 else -1)
     return n
+
+
+def set_host_threads(n: int) -> None:
+    load().ksw_b200_set_host_threads(int(n))
 
 
 def count_cells(qlen: int, tlen: int, w: int) -> int:

@@ -9,13 +9,17 @@ length = int(sys.argv[3]) if len(sys.argv) > 3 else 1000
 flag = int(sys.argv[4], 0) if len(sys.argv) > 4 else 0
 mat = synth.sedef_matrix()
 engine.init(0, 1)
-t0 = time.time(); ps = synth.make_pairs_small(n, length=length, div=0.05); print("gen %.2fs" % (time.time() - t0))
-t0 = time.time(); rb = engine.ResidentBatch(ps, mat, 40, 1, w, -1, flag); print("upload %.3fs cells %.3e" % (time.time() - t0, rb.cells()))
+zd = int(os.environ.get("PERF_ZDROP", "-1"))
+t0 = time.time()
+ps = synth.make_pairs_large(n, min_len=length, max_len=5 * length) if os.environ.get("PERF_LARGE") else synth.make_pairs_small(n, length=length, div=0.05)
+print("gen %.2fs" % (time.time() - t0))
+t0 = time.time(); rb = engine.ResidentBatch(ps, mat, 40, 1, w, zd, flag); print("upload %.3fs cells %.3e" % (time.time() - t0, rb.cells()))
 for it in range(4):
     ms = rb.run(); k = rb.kernel_ms()
     print("run %d: %.2f ms  -> %.1f GCUPS, %.0f pairs/s  (dp %.2f tb %.2f aux %.2f ms, launches %d)" % (
         it, ms, rb.cells() / ms / 1e6, n / ms * 1e3, k["dp_ms"], k["tb_ms"], k["aux_ms"], rb.launches()))
 t0 = time.time(); res = rb.fetch(); print("fetch %.3fs" % (time.time() - t0))
+if os.environ.get("PERF_LARGE"): sys.exit(0)
 for it in range(3):
     t0 = time.time(); b = engine.ResidentBatch(ps, mat, 40, 1, w, -1, flag); t1 = time.time(); b.run(); t2 = time.time()
     r2 = b.fetch(keep_cigars=False); t3 = time.time(); hm = b.host_ms(); b.free(); t4 = time.time()

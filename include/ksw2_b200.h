@@ -150,6 +150,16 @@ int ksw_extz2_batch_flat(int n, const int *qlen, const int64_t *qoff, const uint
                          ksw_extz_t *ez, sd_stats_t *stats,
                          const uint8_t *q_raw_buf, const uint8_t *t_raw_buf);
 
+/* ---- Alignment(fa, fb, cigar): statistics from existing CIGARs ------------------------------ */
+/* Replaces src/align.cc:90-105 + populate_nice_alignment + the stat loop for `sedef stats generate`
+ * (src/stats_main.cc:224,244-271): n alignments, raw ksw ops ((len<<4)|op, 0=M, 1=I query only, 2=D target only)
+ * in one flat buffer, a/b = original-case bytes.  status[i] = -1 when the CIGAR overruns a sequence on an
+ * M column (the reference asserts, src/align.cc:281-282), else 0. */
+int sd_stats_from_cigar_batch_flat(int n, const int64_t *cig_off, const int64_t *n_cigar, const uint32_t *cig_buf,
+                                   const int *alen, const int64_t *aoff, const uint8_t *abuf,
+                                   const int *blen, const int64_t *boff, const uint8_t *bbuf,
+                                   sd_stats_t *out, int *status);
+
 /* ---- resident batches (measurement + pipelined callers) -------------------------------- */
 /*
  * A resident batch keeps the encoded inputs in HBM so that repeated runs time the device

@@ -1,0 +1,61 @@
+// sedef_align.hpp -- C++ host-side mirror of SEDEF's Alignment front end for the batched ksw_extz2 engine.
+//
+// Mirrors (argument meaning, results and error behaviour; not code) of the reference:
+//   Alignment::Alignment(fa, fb)            src/align.cc:76-88   (align_dna + align_helper + populate_nice_alignment)
+//   Alignment::Alignment(fa, fb, cigar)     src/align.cc:90-105  ("from_cigar")
+//   align_helper                             src/align.cc:39-68   (60 kbp chunking, ksw op -> "MDI" remap)
+//   getters span/matches/.../total_error     src/align.h:79-92
+//   BEDPE stat loop + fp fields of process() src/stats_main.cc:231-283,297-299
+// The difference is batching: requests are queued (AlignQueue) and flushed through ONE ksw_extz2_batch call, which is
+// what src/chain.cc, src/refine.cc and src/align.cc call sites do once they collect pairs per wave.
+#pragma once
+#include <deque>
+#include <string>
+#include <utility>
+#include <vector>
+#include "ksw2_b200.h"
+
+namespace sedef_b200 {
+
+struct AlignParams {                       // reference defaults: src/globals.cc:25-28
+	int match = 5, mismatch = -4, gap_open = 40, gap_extend = 1, bandwidth = -1;
+};
+
+class Alignment {
+public:
+	std::string a, b;                                  // original-case strings (fa = query, fb = target)
+	std::deque<std::pair<char, int>> cigar;            // SEDEF alphabet: M, D (a only), I (b only)
+	sd_stats_t stats{};                                // every integer SEDEF derives from the alignment
+
+	int span() const { return stats.span; }
+	int matches() const { return stats.matches; }
+	int mismatches() const { return stats.mismatches; }
+	int gap_bases() const { return stats.gap_bases; }
+	int gaps() const { return stats.gaps; }
+	double gap_error() const;                          // src/align.h:84-87
+	double mismatch_error() const;                     // src/align.h:88-91
+	double total_error() const { return mismatch_error() + gap_error(); }
+	std::string cigar_string() const;                  // src/align.cc:614-621
+	sd_stats_fp_t bedpe_fp() const;                    // src/stats_main.cc:273-283,297-299
+};
+
+// Batched Alignment(fa, fb) for every pair.  Throws std::runtime_error with the engine's message on failure.
+std::vector<Alignment> align_batch(const std::vector<std::pair<std::string, std::string>> &pairs, const AlignParams &p = AlignParams());
+// Batched Alignment(fa, fb, cigar_string): statistics from an existing CIGAR (no DP), computed on the GPU.
+std::vector<Alignment> from_cigar_batch(const std::vector<std::pair<std::string, std::string>> &pairs,
+                                        const std::vector<std::string> &cigars);
+
+// Deferred-alignment queue: call sites push requests, the driver flushes a whole wave at once.
+class AlignQueue {
+public:
+	explicit AlignQueue(const AlignParams &p = AlignParams()) : params_(p) {}
+	// returns the ticket (index into the vector flush() returns)
+	size_t push(std::string fa, std::string fb) { reqs_.emplace_back(std::move(fa), std::move(fb)); return reqs_.size() - 1; }
+	size_t size() const { return reqs_.size(); }
+	std::vector<Alignment> flush() { auto r = align_batch(reqs_, params_); reqs_.clear(); return r; }
+private:
+	AlignParams params_;
+	std::vector<std::pair<std::string, std::string>> reqs_;
+};
+
+} // namespace sedef_b200

@@ -102,3 +102,22 @@ def align_pairs(pairs: Sequence[Tuple[str, str]], match: int = synth.SEDEF_MATCH
 def align(fa: str, fb: str) -> Alignment:
     """Single `Alignment(fa, fb)` (a batch of one)."""
     return align_pairs([(fa, fb)])[0]
+
+
+def from_cigars(pairs: Sequence[Tuple[str, str]], cigar_strings: Sequence[str]) -> List[Alignment]:
+    """Batched `Alignment(fa, fb, cigar_string)` (src/align.cc:90-105): parse "\\d+[MID]" (';' skipped), statistics on the GPU."""
+    import re
+    parsed, raw = [], []
+    for cs in cigar_strings:
+        ops = [(m.group(2), int(m.group(1))) for m in re.finditer(r"(\d+)([A-Za-z])", cs.replace(";", ""))]
+        parsed.append(ops)
+        raw.append(np.array([(n << 4) | {"M": 0, "D": 1, "I": 2}.get(op, 3) for op, n in ops], np.uint32))   # SEDEF 'D' = a only = ksw I
+    a_list = [np.frombuffer(fa.encode(), np.uint8) for fa, _ in pairs]
+    b_list = [np.frombuffer(fb.encode(), np.uint8) for _, fb in pairs]
+    st, status = engine.stats_from_cigars(raw, a_list, b_list)
+    out = []
+    for i, (fa, fb) in enumerate(pairs):
+        if status[i]:
+            raise ValueError(f"CIGAR {i} overruns a sequence (the reference asserts, src/align.cc:281-282)")
+        out.append(Alignment(fa, fb, parsed[i], {n: int(st[i][n]) for n in engine.STAT_FIELDS}))
+    return out

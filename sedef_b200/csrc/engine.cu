@@ -929,6 +929,63 @@ extern "C" void ksw_extz2_b200(void *km, int qlen, const uint8_t *query, int tle
 }
 
 // ------------------------------------------------------------------------------------------------
+// Alignment(fa, fb, cigar): statistics from existing CIGARs
+// ------------------------------------------------------------------------------------------------
+extern "C" int sd_stats_from_cigar_batch_flat(int n, const int64_t *cig_off, const int64_t *n_cigar, const uint32_t *cig_buf,
+                                              const int *alen, const int64_t *aoff, const uint8_t *abuf,
+                                              const int *blen, const int64_t *boff, const uint8_t *bbuf,
+                                              sd_stats_t *out, int *status)
+{
+	if (n < 0 || (n > 0 && (!cig_off || !n_cigar || !cig_buf || !alen || !aoff || !abuf || !blen || !boff || !bbuf || !out || !status)))
+		return fail(KSW_B200_ERR_ARG, "null pointer or negative count");
+	if (n == 0) return 0;
+	int nd = ensure_init();
+	if (nd <= 0) return nd;
+	DevCtx &dc = g_devs[0];
+	CUDA_TRY(cudaSetDevice(dc.dev));
+	size_t cig_total = 0, a_total = 0, b_total = 0;
+	for (int i = 0; i < n; ++i) {
+		cig_total = std::max<size_t>(cig_total, (size_t)(cig_off[i] + n_cigar[i]));
+		a_total = std::max<size_t>(a_total, (size_t)(aoff[i] + std::max(0, alen[i])));
+		b_total = std::max<size_t>(b_total, (size_t)(boff[i] + std::max(0, blen[i])));
+	}
+	DevBuf d_cig, d_a, d_b, d_meta, d_out;
+	const size_t meta = (size_t)n * (4 * sizeof(int64_t) + 2 * sizeof(int));
+	if (d_cig.ensure(cig_total * 4 + 16) || d_a.ensure(a_total + 16) || d_b.ensure(b_total + 16) || d_meta.ensure(meta + 64) ||
+	    d_out.ensure((size_t)n * (sizeof(sd_stats_t) + sizeof(int)) + 64)) {
+		d_cig.release(); d_a.release(); d_b.release(); d_meta.release(); d_out.release();
+		return fail(KSW_B200_ERR_NOMEM, "device allocation failed");
+	}
+	cudaStream_t st = dc.stream;
+	char *mp = (char *)d_meta.p;
+	int64_t *m_coff = (int64_t *)mp, *m_cn = m_coff + n, *m_ao = m_cn + n, *m_bo = m_ao + n;
+	int *m_al = (int *)(m_bo + n), *m_bl = m_al + n;
+	bool ok = cudaMemcpyAsync(d_cig.p, cig_buf, cig_total * 4, cudaMemcpyHostToDevice, st) == cudaSuccess &&
+	          cudaMemcpyAsync(d_a.p, abuf, a_total, cudaMemcpyHostToDevice, st) == cudaSuccess &&
+	          cudaMemcpyAsync(d_b.p, bbuf, b_total, cudaMemcpyHostToDevice, st) == cudaSuccess &&
+	          cudaMemcpyAsync(m_coff, cig_off, n * sizeof(int64_t), cudaMemcpyHostToDevice, st) == cudaSuccess &&
+	          cudaMemcpyAsync(m_cn, n_cigar, n * sizeof(int64_t), cudaMemcpyHostToDevice, st) == cudaSuccess &&
+	          cudaMemcpyAsync(m_ao, aoff, n * sizeof(int64_t), cudaMemcpyHostToDevice, st) == cudaSuccess &&
+	          cudaMemcpyAsync(m_bo, boff, n * sizeof(int64_t), cudaMemcpyHostToDevice, st) == cudaSuccess &&
+	          cudaMemcpyAsync(m_al, alen, n * sizeof(int), cudaMemcpyHostToDevice, st) == cudaSuccess &&
+	          cudaMemcpyAsync(m_bl, blen, n * sizeof(int), cudaMemcpyHostToDevice, st) == cudaSuccess;
+	sd_stats_t *d_stats = (sd_stats_t *)d_out.p;
+	int *d_status = (int *)(d_stats + n);
+	if (ok) {
+		CigarStatsLaunch L{(const uint32_t *)d_cig.p, m_coff, m_cn, (const uint8_t *)d_a.p, m_ao, m_al, (const uint8_t *)d_b.p, m_bo, m_bl,
+		                   d_stats, d_status, n};
+		sd_stats_from_cigar_kernel<<<(n + 127) / 128, 128, 0, st>>>(L);
+		ok = cudaGetLastError() == cudaSuccess &&
+		     cudaMemcpyAsync(out, d_stats, (size_t)n * sizeof(sd_stats_t), cudaMemcpyDeviceToHost, st) == cudaSuccess &&
+		     cudaMemcpyAsync(status, d_status, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, st) == cudaSuccess &&
+		     cudaStreamSynchronize(st) == cudaSuccess;
+	}
+	std::string msg = ok ? "" : cudaGetErrorString(cudaGetLastError());
+	d_cig.release(); d_a.release(); d_b.release(); d_meta.release(); d_out.release();
+	return ok ? 0 : fail(KSW_B200_ERR_CUDA, "sd_stats_from_cigar: " + msg);
+}
+
+// ------------------------------------------------------------------------------------------------
 // host-side floating point fields (src/stats_main.cc:273-283,297-299; src/align.h:84-92)
 // ------------------------------------------------------------------------------------------------
 extern "C" void sd_stats_derive_fp(const sd_stats_t *s, sd_stats_fp_t *o)

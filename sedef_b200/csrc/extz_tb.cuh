@@ -142,4 +142,45 @@ extz_traceback_kernel(TbLaunch L)
 	}
 }
 
+// ---- Alignment(fa, fb, cigar): SD statistics from an EXISTING CIGAR (src/align.cc:90-105,274-315; the consumer is
+// `sedef stats generate`, src/stats_main.cc:224).  One thread per alignment, forward walk over the raw ksw ops. ----
+struct CigarStatsLaunch {
+	const uint32_t *cig; const int64_t *cig_off; const int64_t *n_cig;
+	const uint8_t *a; const int64_t *a_off; const int *alen;
+	const uint8_t *b; const int64_t *b_off; const int *blen;
+	sd_stats_t *out; int *status; int n;
+};
+__global__ void __launch_bounds__(128)
+sd_stats_from_cigar_kernel(CigarStatsLaunch L)
+{
+	int k = blockIdx.x * blockDim.x + threadIdx.x;
+	if (k >= L.n) return;
+	StatAcc sa;
+	sa.span = sa.gap_bases = sa.matches = sa.mismatches = sa.indel_a = sa.indel_b = sa.alnB = sa.matchB = 0;
+	sa.mismatchB = sa.transitionsB = sa.transversionsB = sa.uppercaseA = sa.uppercaseB = sa.uppercaseMatches = 0;
+	const uint32_t *c = L.cig + L.cig_off[k];
+	const uint8_t *a = L.a + L.a_off[k], *b = L.b + L.b_off[k];
+	const int alen = L.alen[k], blen = L.blen[k];
+	int ia = 0, ib = 0, gaps = 0, bad = 0;
+	for (int64_t x = 0; x < L.n_cig[k] && !bad; ++x) {
+		const uint32_t op = c[x] & 0xfu; const int len = (int)(c[x] >> 4);
+		if (op >= 3) continue;                                        // align_helper drops them (src/align.cc:61)
+		if (op != 0) ++gaps;                                          // every non-M run counts, zero-length ones too (src/align.cc:300-305)
+		for (int y = 0; y < len; ++y) {
+			if (op == 0) {
+				if (ia >= alen || ib >= blen) { bad = 1; break; }     // the reference asserts (src/align.cc:281-282)
+				stat_match_col(sa, a[ia++], b[ib++]);
+			} else if (op == 1) { stat_qonly_col(sa, ia < alen ? a[ia] : 0); ++ia; }
+			else { stat_tonly_col(sa, ib < blen ? b[ib] : 0); ++ib; }
+		}
+	}
+	sd_stats_t s;
+	s.span = sa.span; s.gaps = gaps; s.gap_bases = sa.gap_bases; s.matches = sa.matches; s.mismatches = sa.mismatches;
+	s.indel_a = sa.indel_a; s.indel_b = sa.indel_b; s.alnB = sa.alnB; s.matchB = sa.matchB; s.mismatchB = sa.mismatchB;
+	s.transitionsB = sa.transitionsB; s.transversionsB = sa.transversionsB;
+	s.uppercaseA = sa.uppercaseA; s.uppercaseB = sa.uppercaseB; s.uppercaseMatches = sa.uppercaseMatches; s.reserved = 0;
+	L.out[k] = s;
+	L.status[k] = bad ? -1 : 0;
+}
+
 } // namespace extz

@@ -61,7 +61,7 @@ EXPORTS = ["ksw_b200_strerror", "ksw_b200_last_error", "ksw_b200_init", "ksw_b20
            "ksw_extz2_batch_flat", "ksw_b200_batch_upload", "ksw_b200_batch_run", "ksw_b200_batch_fetch",
            "ksw_b200_batch_launches", "ksw_b200_batch_kernel_ms", "ksw_b200_batch_cells",
            "ksw_b200_batch_free", "ksw_b200_count_cells", "sd_stats_derive_fp",
-           "ksw_b200_batch_io_bytes", "ksw_b200_batch_set_stats", "ksw_b200_free_cigars", "ksw_b200_batch_host_ms", "ksw_b200_last_call_io", "ksw_b200_set_host_threads"]
+           "ksw_b200_batch_io_bytes", "ksw_b200_batch_set_stats", "ksw_b200_free_cigars", "ksw_b200_batch_host_ms", "ksw_b200_last_call_io", "ksw_b200_set_host_threads", "sd_stats_from_cigar_batch_flat"]
 
 
 def load():
@@ -105,6 +105,8 @@ def load():
     lib.ksw_b200_free_cigars.argtypes = [vp, i32]
     lib.ksw_b200_batch_host_ms.argtypes = [vp, C.POINTER(C.c_double)]
     lib.ksw_b200_set_host_threads.argtypes = [i32]
+    lib.sd_stats_from_cigar_batch_flat.argtypes = [i32] + [vp] * 11
+    lib.sd_stats_from_cigar_batch_flat.restype = i32
     lib.ksw_b200_last_call_io.argtypes = [C.POINTER(i64), C.POINTER(i64), C.POINTER(i32)]
     lib.sd_stats_derive_fp.argtypes = [C.POINTER(SdStats), C.POINTER(SdStatsFp)]
     lib.free = C.CDLL(None).free
@@ -263,6 +265,23 @@ class ResidentBatch:
             self.free()
         except Exception:
             pass
+
+
+def stats_from_cigars(cigars, a_list, b_list):
+    """Batched `Alignment(fa, fb, cigar)` statistics (sd_stats_from_cigar_batch_flat): cigars = raw ksw ops per alignment,
+    a_list/b_list = original-case byte arrays.  Returns (stats structured array, status int32 array)."""
+    lib = load()
+    n = len(cigars)
+    cn = np.array([len(c) for c in cigars], np.int64); coff = np.zeros(n, np.int64); coff[1:] = np.cumsum(cn[:-1])
+    cbuf = np.concatenate([np.asarray(c, np.uint32) for c in cigars] + [np.zeros(1, np.uint32)])
+    al = np.array([len(x) for x in a_list], np.int32); ao = np.zeros(n, np.int64); ao[1:] = np.cumsum(al[:-1])
+    bl = np.array([len(x) for x in b_list], np.int32); bo = np.zeros(n, np.int64); bo[1:] = np.cumsum(bl[:-1])
+    ab = np.concatenate([np.asarray(x, np.uint8) for x in a_list] + [np.zeros(1, np.uint8)])
+    bb = np.concatenate([np.asarray(x, np.uint8) for x in b_list] + [np.zeros(1, np.uint8)])
+    out = np.zeros(n, STATS_DTYPE); status = np.zeros(n, np.int32)
+    _check(lib.sd_stats_from_cigar_batch_flat(n, _ptr(coff), _ptr(cn), _ptr(cbuf), _ptr(al), _ptr(ao), _ptr(ab),
+                                              _ptr(bl), _ptr(bo), _ptr(bb), _ptr(out), _ptr(status)))
+    return out, status
 
 
 def derive_fp(stats_row) -> dict:

@@ -260,3 +260,52 @@ def test_reference_call_sites_with_cuda_kernel(checker, golden_dir):
         assert lib2.ksw_redirect_calls() > 0            # the CUDA kernel really was underneath
         assert (n1, out1) == (reg["n_hits"], reg["hits"])
         assert (n2, out2) == (n1, out1)
+
+
+def test_from_cigar_statistics(checker, mat, golden_dir):
+    """Alignment(fa, fb, cigar) ("from_cigar", src/align.cc:90-105): statistics from EXISTING CIGARs on the GPU, against the
+    oracle port, the reference's own class (when oracle/_ref is present) and the golden records."""
+    import ctypes as C, os
+    g = load_json(golden_dir, "sd_stats_golden.json")
+    pairs = [(r["a"], r["b"]) for r in g["records"]]
+    res = align.from_cigars(pairs, [r["cigar"] for r in g["records"]])
+    path = os.path.join(os.path.dirname(oracle.__file__), "_ref", "libsedef_ref.so")
+    lib = C.CDLL(path) if os.path.exists(path) else None
+    for r, a in zip(g["records"], res):
+        assert a.cigar_string() == r["cigar"]
+        assert (a.span(), a.matches(), a.mismatches(), a.gaps(), a.gap_bases()) == (r["span"], r["matches"], r["mismatches"], r["gaps"], r["gap_bases"])
+        raw = [(n << 4) | "MDI".index(op) for op, n in a.cigar]
+        assert a.stats == oracle.sd_stats(raw, np.frombuffer(r["a"].encode(), np.uint8), np.frombuffer(r["b"].encode(), np.uint8))
+        if lib is not None:
+            v = [C.c_int(0) for _ in range(5)]
+            lib.ref_alignment_from_cigar(r["a"].encode(), r["b"].encode(), r["cigar"].encode(), *[C.byref(x) for x in v])
+            assert [x.value for x in v] == [a.span(), a.matches(), a.mismatches(), a.gaps(), a.gap_bases()]
+    # a CIGAR that overruns its sequences is reported, not silently accepted
+    with pytest.raises(ValueError):
+        align.from_cigars([("ACGT", "ACGT")], ["9M"])
+
+
+def test_cpp_host_layer(checker, golden_dir):
+    """The C++ host layer (include/sedef_align.hpp: AlignQueue / from_cigar_batch) driven from C++ (tests/cpp), against the
+    golden records produced by the reference's own Alignment class and the oracle's statistics."""
+    import os, subprocess
+    drv = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "cpp", "align_queue_driver")
+    assert os.path.exists(drv), "build() did not produce tests/cpp/align_queue_driver"
+    g = load_json(golden_dir, "sd_stats_golden.json")
+    text = "".join(f"{r['a']} {r['b']} {r['cigar']}\n" for r in g["records"])
+    for mode in ("queue", "from_cigar"):
+        out = subprocess.run([drv, mode], input=text, capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stderr
+        lines = out.stdout.strip().split("\n")
+        assert len(lines) == len(g["records"])
+        for r, ln in zip(g["records"], lines):
+            f = ln.split()
+            assert f[0] == r["cigar"], mode
+            assert [int(x) for x in f[1:6]] == [r["span"], r["matches"], r["mismatches"], r["gaps"], r["gap_bases"]]
+            raw = [(int(n) << 4) | "MDI".index(op) for n, op in __import__("re").findall(r"(\d+)([MDI])", r["cigar"])]
+            st = oracle.sd_stats(raw, np.frombuffer(r["a"].encode(), np.uint8), np.frombuffer(r["b"].encode(), np.uint8))
+            keys = ["span", "matches", "mismatches", "gaps", "gap_bases", "indel_a", "indel_b", "alnB", "matchB", "mismatchB",
+                    "transitionsB", "transversionsB", "uppercaseA", "uppercaseB", "uppercaseMatches"]
+            assert [int(x) for x in f[1:16]] == [st[k] for k in keys]
+            tot = st["matches"] + st["gap_bases"] + st["mismatches"]
+            assert f[16] == "%.1f" % (100.0 * st["mismatches"] / tot + 100.0 * st["gap_bases"] / tot)

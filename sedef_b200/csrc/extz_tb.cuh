@@ -78,7 +78,7 @@ extz_traceback_kernel(TbLaunch L)
 			int r = i + j;
 			// the walk is a dependent chain of nibble reads; pull the rows it will need next into L2/L1 early
 			// (the column moves by at most one slot per row, so row r-16 is read within 8 bytes of the current column)
-			if (r >= kPrefetchRows) {
+			if (NS >= 512 && r >= kPrefetchRows) {                    // narrow rows (<= 128 B) are adjacent in memory already
 				const uint8_t *pf = tbp + (int64_t)(r - kPrefetchRows) * rowB + (((i - kPrefetchRows / 2) & (NS - 1)) >> 1);
 				asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
 			}

@@ -62,16 +62,18 @@ extern "C" const char *ksw_b200_last_error(void) { return g_last_error.c_str(); 
 // ------------------------------------------------------------------------------------------------
 // kernel classes
 // ------------------------------------------------------------------------------------------------
-struct KClass { int G, S; bool wide; };
-// narrow classes: G <= 32 lanes per pair, 128-thread CTAs; wide classes: one CTA of G lanes per pair
-static const KClass kClasses[] = { {2, 16, false}, {4, 16, false}, {8, 16, false}, {16, 16, false}, {32, 16, false},
-                                   {32, 32, false}, {64, 16, true}, {128, 16, true}, {256, 16, true} };
+struct KClass { int G, S; bool wide; int cluster; };
+// narrow classes: G <= 32 lanes per pair, 128-thread CTAs, 32/G pairs per warp in lock-step;
+// wide classes: one CTA of G lanes per pair; cluster classes: one thread-block cluster of `cluster` CTAs x 256 lanes per pair
+static const KClass kClasses[] = { {2, 16, false, 0}, {4, 16, false, 0}, {8, 16, false, 0}, {16, 16, false, 0}, {32, 16, false, 0},
+                                   {32, 32, false, 0}, {64, 16, true, 0}, {128, 16, true, 0}, {256, 16, true, 0},
+                                   {512, 16, true, 2}, {1024, 16, true, 4} };
 static const int kNumClasses = sizeof(kClasses) / sizeof(kClasses[0]);
 static const int kNumSizedClasses = kNumClasses;                        // all classes are ordered by capacity
 static inline int class_ns(int c) { return kClasses[c].G * kClasses[c].S; }
 // S == 32 lanes switch whole-lane (two 16-blocks), which costs 16 slots of window (extz_dp.cuh)
 static inline int class_capacity(int c) { return kClasses[c].S > 16 ? class_ns(c) - 16 : class_ns(c); }
-static inline int class_threads(int c) { return kClasses[c].wide ? kClasses[c].G : 128; }
+static inline int class_threads(int c) { return kClasses[c].cluster ? 256 : (kClasses[c].wide ? kClasses[c].G : 128); }
 static inline int class_pairs_per_block(int c) { return kClasses[c].wide ? 1 : 128 / kClasses[c].G; }
 
 // kernel selection: every (class, cigar, right) combination is a distinct instantiation
@@ -90,7 +92,7 @@ static cudaError_t launch_dp_gs(const DpLaunch &L, bool cigar, bool right, int g
 	return cudaGetLastError();
 }
 template <int G, int S, bool W>
-static int dp_occupancy_gs(bool cigar, bool right)
+static int dp_occupancy_gs(bool cigar, bool right, int)
 {
 	constexpr int threads = W ? G : 128;
 	int nb = 0;
@@ -100,21 +102,55 @@ static int dp_occupancy_gs(bool cigar, bool right)
 	} else       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, KSel<G, S, W, false, false>::fn, threads, 0);
 	return nb;
 }
+// cluster kernels: launched with a cluster dimension attribute; "occupancy" = co-resident clusters on the device
+template <int C, bool CG, bool R>
+static cudaError_t cluster_launch_one(const DpLaunch &L, int nclusters, cudaStream_t st, int *max_clusters)
+{
+	cudaLaunchConfig_t cfg = {};
+	cfg.gridDim = dim3((unsigned)(nclusters * C)); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+	cudaLaunchAttribute attr[1];
+	attr[0].id = cudaLaunchAttributeClusterDimension;
+	attr[0].val.clusterDim.x = C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+	cfg.attrs = attr; cfg.numAttrs = 1;
+	if (max_clusters) {
+		cfg.gridDim = dim3((unsigned)C);
+		return cudaOccupancyMaxActiveClusters(max_clusters, extz_dp_cluster_kernel<C, 16, CG, R>, &cfg);
+	}
+	return cudaLaunchKernelEx(&cfg, extz_dp_cluster_kernel<C, 16, CG, R>, L);
+}
+template <int C>
+static cudaError_t cluster_dispatch(const DpLaunch &L, bool cigar, bool right, int nclusters, cudaStream_t st, int *max_clusters)
+{
+	if (cigar) return right ? cluster_launch_one<C, true, true>(L, nclusters, st, max_clusters)
+	                        : cluster_launch_one<C, true, false>(L, nclusters, st, max_clusters);
+	return cluster_launch_one<C, false, false>(L, nclusters, st, max_clusters);
+}
 #define EXTZ_FOR_CLASS(c, CALL) \
 	switch (c) { \
 	case 0: return CALL(2, 16, false); case 1: return CALL(4, 16, false); case 2: return CALL(8, 16, false); \
 	case 3: return CALL(16, 16, false); case 4: return CALL(32, 16, false); case 5: return CALL(32, 32, false); \
 	case 6: return CALL(64, 16, true); case 7: return CALL(128, 16, true); case 8: return CALL(256, 16, true); }
+// grid: CTAs for narrow / wide classes, clusters for cluster classes
 static cudaError_t launch_dp(int c, const DpLaunch &L, bool cigar, bool right, int grid, cudaStream_t st)
 {
+	if (kClasses[c].cluster == 2) return cluster_dispatch<2>(L, cigar, right, grid, st, nullptr);
+	if (kClasses[c].cluster == 4) return cluster_dispatch<4>(L, cigar, right, grid, st, nullptr);
 #define EXTZ_CALL(G, S, W) launch_dp_gs<G, S, W>(L, cigar, right, grid, st)
 	EXTZ_FOR_CLASS(c, EXTZ_CALL)
 #undef EXTZ_CALL
 	return cudaErrorInvalidValue;
 }
+// resident CTAs per SM (narrow / wide) or co-resident clusters on the whole device (cluster classes)
 static int dp_occupancy(int c, bool cigar, bool right)
 {
-#define EXTZ_CALL(G, S, W) dp_occupancy_gs<G, S, W>(cigar, right)
+	if (kClasses[c].cluster) {
+		int n = 0; DpLaunch dummy = {};
+		cudaError_t e = kClasses[c].cluster == 2 ? cluster_dispatch<2>(dummy, cigar, right, 1, nullptr, &n)
+		                                         : cluster_dispatch<4>(dummy, cigar, right, 1, nullptr, &n);
+		if (e != cudaSuccess) { cudaGetLastError(); return 0; }
+		return n;
+	}
+#define EXTZ_CALL(G, S, W) dp_occupancy_gs<G, S, W>(cigar, right, 0)
 	EXTZ_FOR_CLASS(c, EXTZ_CALL)
 #undef EXTZ_CALL
 	return 0;
@@ -601,7 +637,8 @@ static int launch_sub(ksw_b200_batch &B, SubBatch &sb)
 		int occ = dp_occupancy(c, cigar, right);
 		if (occ <= 0) return fail(KSW_B200_ERR_CUDA, "DP kernel cannot be resident (occupancy 0)");
 		const int groups_per_block = class_pairs_per_block(c);
-		int grid = std::min((wv.count + groups_per_block - 1) / groups_per_block, sb.dc->sms * occ);
+		int grid = kClasses[c].cluster ? std::min(wv.count, occ)                              // clusters, one pair each
+		                               : std::min((wv.count + groups_per_block - 1) / groups_per_block, sb.dc->sms * occ);
 		cudaEvent_t a, b2, c2;
 		CUDA_TRY(cudaEventCreate(&a)); CUDA_TRY(cudaEventCreate(&b2)); CUDA_TRY(cudaEventCreate(&c2));
 		CUDA_TRY(cudaEventRecord(a, st));

@@ -121,11 +121,14 @@ __device__ __forceinline__ void lane_prepare(LaneState<S> &ls, const Band &b, in
 
 // the cells of one anti-diagonal for this lane (:149-220), traceback codes, u' dump and lazy-H update (:233-255).
 // Returns the maximum of the lane's updated lazy-H entries (slot en0 was knocked out by the leader beforehand).
-template <int G, int S, bool kCigar, bool kRight>
+// G / lane: lanes that share the H rows (one CTA) and this lane's index among them; GT / lane_tb: lanes of the whole pair
+// (a cluster spans several CTAs) and this lane's index among those -- they differ only in the cluster kernel.
+template <int G, int S, bool kCigar, bool kRight, int GT = G>
 __device__ __forceinline__ int32_t lane_cells(LaneState<S> &ls, const Band &b, int r, int last_st, int lane, uint32_t xin, uint32_t vin,
-                                              uint8_t *tbp, int32_t *H, uint32_t *Us, const Scoring &sc)
+                                              uint8_t *tbp, int32_t *H, uint32_t *Us, const Scoring &sc, int lane_tb = -1)
 {
-	constexpr int NS = G * S;
+	constexpr int NS = GT * S;
+	if (lane_tb < 0) lane_tb = lane;
 	constexpr int NSUB = (S + 15) / 16;                 // 16-slot sub-blocks per lane (1 unless S == 32)
 	constexpr int SUBW = S < 16 ? S : 16;
 	int32_t lane_max = kNegInf;
@@ -152,7 +155,7 @@ __device__ __forceinline__ int32_t lane_cells(LaneState<S> &ls, const Band &b, i
 				if (kCigar) codes |= c << ((ii & 7) * 4);
 				if (kCigar && (ii & 7) == 0) {
 					// 8 codes = one 32-bit word; S == 4 packs 4 codes into 16 bits
-					const int c0 = lane * S + i;                                   // == (t0 + i) mod NS
+					const int c0 = lane_tb * S + i;                                // == (t0 + i) mod NS
 					uint8_t *dst = tbp + (int64_t)r * (NS >> 1) + (c0 >> 1);
 					if (S >= 8) *(uint32_t *)dst = codes; else *(uint16_t *)dst = (uint16_t)codes;
 					codes = 0;
@@ -210,6 +213,15 @@ __device__ __forceinline__ uint32_t lane_argmax_key(const LaneState<S> &ls, cons
 	return key;
 }
 
+// H / u' rows in the CTA's own shared memory (narrow and wide kernels)
+template <int G, int S>
+struct LocalRows {
+	static constexpr int kMask = G * S - 1;
+	int32_t *H; uint32_t *Us;
+	__device__ __forceinline__ int32_t &h(int c) const { return H[hidx<G, S>(c)]; }
+	__device__ __forceinline__ uint32_t u(int c) const { return Us[hidx<G, S>(c)]; }
+};
+
 // ---- the scalar per-pair bookkeeping done by the group leader (:222-267) -----------------------------------
 struct Leader {
 	EzState ez;
@@ -220,62 +232,55 @@ struct Leader {
 
 	__device__ __forceinline__ void reset() { ez_reset(ez); st0_prev = 0; exit_slot = -2; exit_H = kNegInf; Hprev_true = kNegInf; Hen0_lazy = gmax = kNegInf; }
 
+	// `A` gives access to the H / u' rows by circular slot index: a.h(c) (int32_t&), a.u(c) (uint32_t), A::kMask.
 	// before the cells: remember/knock out slots that must not take part in the regular H update
-	template <int G, int S>
-	__device__ __forceinline__ void pre(int32_t *H, const Band &b, int r, int qe)
+	template <class A>
+	__device__ __forceinline__ void pre(const A &acc, const Band &b, int r, int qe)
 	{
 		Hprev_true = kNegInf;
 		if (r == 0) return;
 		if (b.st0 > st0_prev) {                              // slot st0-1 left the band: keep its TRUE H, drop it from the max
 			int xs = b.st0 - 1;
-			const int hx = hidx<G, S>(xs & (G * S - 1));
-			exit_slot = xs; exit_H = H[hx] - qe * (r - 1);
-			H[hx] = kNegInf;
+			int32_t &hx = acc.h(xs & A::kMask);
+			exit_slot = xs; exit_H = hx - qe * (r - 1);
+			hx = kNegInf;
 		}
 		if (b.en0 > 0) {
 			int ps = b.en0 - 1;
-			Hprev_true = (ps == exit_slot) ? exit_H : H[hidx<G, S>(ps & (G * S - 1))] - qe * (r - 1);
-			H[hidx<G, S>(b.en0 & (G * S - 1))] = kNegInf;    // the regular update must not count for slot en0
+			Hprev_true = (ps == exit_slot) ? exit_H : acc.h(ps & A::kMask) - qe * (r - 1);
+			acc.h(b.en0 & A::kMask) = kNegInf;               // the regular update must not count for slot en0
 		}
 	}
 	// after the cells: H[en0] (:228 / :259), diagonal max in the lazy domain; returns need_arg
-	template <int G, int S>
-	__device__ __forceinline__ int mid(int32_t *H, const uint32_t *Us, const Band &b, int r, int qe, int32_t reduced_max,
-	                                   uint32_t v0_r0, int zdrop)
+	template <class A>
+	__device__ __forceinline__ int mid(const A &acc, const Band &b, int r, int qe, int32_t reduced_max, uint32_t v0_r0, int zdrop)
 	{
 		gmax = reduced_max;
-		if (r == 0) { Hen0_lazy = (int32_t)(v0_r0 >> 24) - 2 * qe; H[0] = Hen0_lazy; gmax = Hen0_lazy; }   // :259
+		if (r == 0) { Hen0_lazy = (int32_t)(v0_r0 >> 24) - 2 * qe; acc.h(0) = Hen0_lazy; gmax = Hen0_lazy; }   // :259
 		else if (b.en0 > 0) {
-			const int he = hidx<G, S>(b.en0 & (G * S - 1));
-			Hen0_lazy = Hprev_true + (int32_t)(Us[he] >> 24) - qe + qe * r;                                  // :228, true -> lazy
-			H[he] = Hen0_lazy;
+			Hen0_lazy = Hprev_true + (int32_t)(acc.u(b.en0 & A::kMask) >> 24) - qe + qe * r;                  // :228, true -> lazy
+			acc.h(b.en0 & A::kMask) = Hen0_lazy;
 			gmax = gmax > Hen0_lazy ? gmax : Hen0_lazy;
-		} else Hen0_lazy = H[0];                              // en0 == 0: regular update (:228 else-arm)
+		} else Hen0_lazy = acc.h(0);                          // en0 == 0: regular update (:228 else-arm)
 		int32_t maxH_true = gmax - qe * r;
 		// ksw_apply_zdrop (extern/ksw2.h:161-177) only looks at the arg-max slot when the maximum improves, or when
 		// max - H > zdrop (+ l*e >= 0) can fire; in every other case it has no effect, so the arg-max is not needed
 		return (maxH_true > ez.max) || (zdrop >= 0 && ez.max - maxH_true > zdrop);
-	}
-	// contribution of slot en0 to the fast arg-max pass
-	__device__ __forceinline__ uint32_t en0_count(const Band &b, int r) const
-	{
-		return 0u;   // unused: the count pass reads the final H[en0] from shared memory
 	}
 	__device__ __forceinline__ uint32_t en0_key(const Band &b, int r) const
 	{
 		return (Hen0_lazy == gmax && (r == 0 || b.en0 > 0)) ? 0u : 0xffffffffu;   // slot en0 wins every tie (:229-231)
 	}
 	// end scores, z-drop (:261-267); returns stop
-	template <int G, int S>
-	__device__ __forceinline__ int fin(const int32_t *H, const Band &b, int r, int qe, int max_t, int qlen, int tlen,
-	                                   int zdrop, int e)
+	template <class A>
+	__device__ __forceinline__ int fin(const A &acc, const Band &b, int r, int qe, int max_t, int qlen, int tlen, int zdrop, int e)
 	{
 		const int R = qlen + tlen - 1;
 		int32_t Hen0_true = Hen0_lazy - qe * r;
 		int32_t maxH_true = gmax - qe * r;
 		if (b.en0 == tlen - 1 && Hen0_true > ez.mte) { ez.mte = Hen0_true; ez.mte_q = r - b.en; }          // :261-262
 		if (r - b.st0 == qlen - 1) {                                                                      // :263-264
-			int32_t Hst0 = (b.st0 == b.en0) ? Hen0_true : H[hidx<G, S>(b.st0 & (G * S - 1))] - qe * r;
+			int32_t Hst0 = (b.st0 == b.en0) ? Hen0_true : acc.h(b.st0 & A::kMask) - qe * r;
 			if (Hst0 > ez.mqe) { ez.mqe = Hst0; ez.mqe_t = b.st0; }
 		}
 		int stop = 0;
@@ -353,6 +358,7 @@ extz_dp_kernel(DpLaunch L)
 	const int pred_lane = (gl + G - 1) & (G - 1);                    // circular predecessor (relative to group)
 	int32_t *H = sH[gidx];
 	uint32_t *Us = sU[gidx];
+	const LocalRows<G, S> rows{H, Us};
 	const Scoring sc = L.sc;
 	const int qe = sc.qe;
 	const bool generic = (sc.flag & kFlagGenericSc) != 0;
@@ -396,7 +402,7 @@ extz_dp_kernel(DpLaunch L)
 			const uint32_t vin = __shfl_sync(FULL, ls.V[S - 1], pred_lane, G);
 			if (act) {
 				lane_prepare<S, NS>(ls, b, r, qseq, tseq, tlen, table_saddr, sc);
-				if (gl == 0) ld.pre<G, S>(H, b, r, qe);
+				if (gl == 0) ld.pre(rows, b, r, qe);
 			}
 			__syncwarp();
 			int32_t lane_max = kNegInf;
@@ -404,7 +410,7 @@ extz_dp_kernel(DpLaunch L)
 			__syncwarp();
 			const int32_t red = group_max<G>(lane_max);
 			int need = 0;
-			if (act && gl == 0) need = ld.mid<G, S>(H, Us, b, r, qe, red, ls.V[0], sc.zdrop);
+			if (act && gl == 0) need = ld.mid(rows, b, r, qe, red, ls.V[0], sc.zdrop);
 			__syncwarp();
 			need = __shfl_sync(FULL, need, 0, G);
 			int max_t = b.en0;
@@ -426,7 +432,7 @@ extz_dp_kernel(DpLaunch L)
 				}
 			}
 			int stop = 0;
-			if (act && gl == 0) stop = ld.fin<G, S>(H, b, r, qe, max_t, qlen, tlen, sc.zdrop, sc.e);
+			if (act && gl == 0) stop = ld.fin(rows, b, r, qe, max_t, qlen, tlen, sc.zdrop, sc.e);
 			stop = __shfl_sync(FULL, stop, 0, G);
 			if (act) { n_diag = r + 1; last_st = b.st; if (stop) alive = false; }
 		}
@@ -460,6 +466,7 @@ extz_dp_wide_kernel(DpLaunch L)
 	__syncthreads();
 
 	const uint32_t table_saddr = (uint32_t)__cvta_generic_to_shared(sTable);
+	const LocalRows<G, S> rows{H, Us};
 	const int gl = threadIdx.x;
 	const int lane = gl & 31, wid = gl >> 5;
 	const Scoring sc = L.sc;
@@ -496,7 +503,7 @@ extz_dp_wide_kernel(DpLaunch L)
 			uint32_t xin = __shfl_up_sync(0xffffffffu, ls.X[S - 1], 1);
 			uint32_t vin = __shfl_up_sync(0xffffffffu, ls.V[S - 1], 1);
 			if (lane == 31) { sCarryX[wid] = ls.X[S - 1]; sCarryV[wid] = ls.V[S - 1]; }
-			if (gl == 0) ld.pre<G, S>(H, b, r, qe);
+			if (gl == 0) ld.pre(rows, b, r, qe);
 			__syncthreads();                                                                   // A
 			// phase 2: cells
 			if (lane == 0) { int pw = (wid + NW - 1) % NW; xin = sCarryX[pw]; vin = sCarryV[pw]; }
@@ -510,9 +517,9 @@ extz_dp_wide_kernel(DpLaunch L)
 				int32_t red = sWarpMax[0];
 #pragma unroll
 				for (int k = 1; k < NW; ++k) red = red > sWarpMax[k] ? red : sWarpMax[k];
-				int need = ld.mid<G, S>(H, Us, b, r, qe, red, ls.V[0], sc.zdrop);
+				int need = ld.mid(rows, b, r, qe, red, ls.V[0], sc.zdrop);
 				sNeedArg = need; sGmax = ld.gmax;
-				if (!need) sStop = ld.fin<G, S>(H, b, r, qe, b.en0, qlen, tlen, sc.zdrop, sc.e);
+				if (!need) sStop = ld.fin(rows, b, r, qe, b.en0, qlen, tlen, sc.zdrop, sc.e);
 			}
 			__syncthreads();                                                                   // C
 			if (sNeedArg) {
@@ -524,7 +531,7 @@ extz_dp_wide_kernel(DpLaunch L)
 					uint32_t k = ld.en0_key(b, r);
 #pragma unroll
 					for (int j = 0; j < NW; ++j) k = sWarpKey[j] < k ? sWarpKey[j] : k;
-					sStop = ld.fin<G, S>(H, b, r, qe, tie_key_slot(k, b.en0), qlen, tlen, sc.zdrop, sc.e);
+					sStop = ld.fin(rows, b, r, qe, tie_key_slot(k, b.en0), qlen, tlen, sc.zdrop, sc.e);
 				}
 				__syncthreads();                                                               // E
 			}
@@ -535,6 +542,152 @@ extz_dp_wide_kernel(DpLaunch L)
 		}
 		if (gl == 0) { if (zdropped_band) ld.ez.zdropped = 1; ld.store(&L.results[pi], n_diag); }
 		__syncthreads();
+	}
+}
+
+// =====================================================================================================
+// cluster kernel: one thread-block CLUSTER of C CTAs (256 lanes each) per pair -- 8192 / 16384 live slots, for the
+// unbanded multi-kbp gap fills SEDEF issues (src/align.cc:130-139 with MAX_GAP = 10 kbp, src/refine.cc:77).
+// Every CTA keeps the H / u' rows of its own lanes in its shared memory; the carries between CTAs, the leader's
+// accesses to arbitrary slots and the per-diagonal reductions go through DISTRIBUTED SHARED MEMORY
+// (cluster.map_shared_rank), ordering by cluster.sync().
+// =====================================================================================================
+} // namespace extz
+#include <cooperative_groups.h>
+namespace extz {
+namespace cg = cooperative_groups;
+
+template <int C, int S>
+struct ClusterRows {                                    // H / u' rows spread over the CTAs of the cluster
+	static constexpr int GC = 256, NSC = GC * S, kMask = C * NSC - 1;
+	int32_t *H; uint32_t *Us;                           // this CTA's arrays (same offset in every CTA)
+	__device__ __forceinline__ int32_t &h(int c) const
+	{
+		cg::cluster_group cl = cg::this_cluster();
+		return cl.map_shared_rank(H, c / NSC)[hidx<GC, S>(c % NSC)];
+	}
+	__device__ __forceinline__ uint32_t u(int c) const
+	{
+		cg::cluster_group cl = cg::this_cluster();
+		return cl.map_shared_rank(Us, c / NSC)[hidx<GC, S>(c % NSC)];
+	}
+};
+
+template <int C, int S, bool kCigar, bool kRight>
+__global__ void __launch_bounds__(256, 1)
+extz_dp_cluster_kernel(DpLaunch L)
+{
+	constexpr int GC = 256, G = GC * C, NS = G * S, NW = GC / 32;
+	static_assert(S == 16 && (C == 2 || C == 4 || C == 8), "cluster kernel: 16 slots per lane, 2/4/8 CTAs");
+	cg::cluster_group cluster = cg::this_cluster();
+	const int rank = (int)cluster.block_rank();
+
+	__shared__ __align__(16) int32_t H[GC * S];
+	__shared__ __align__(16) uint32_t Us[GC * S];
+	__shared__ uint32_t sTable[kTableStride * kTableStride];
+	__shared__ uint32_t sCarryX[NW], sCarryV[NW];       // OLD x,v of every warp's top slot (read by the next warp / next CTA)
+	__shared__ int32_t sAllMax[8 * NW];                 // [rank][warp], only CTA 0's copy is used
+	__shared__ uint32_t sAllKey[8 * NW];
+	__shared__ int sPair, sNeedArg, sStop;              // written into EVERY CTA's copy by the leader
+	__shared__ int32_t sGmax;
+
+	for (int i = threadIdx.x; i < kTableStride * kTableStride; i += blockDim.x) sTable[i] = L.table[i];
+	__syncthreads();
+
+	const uint32_t table_saddr = (uint32_t)__cvta_generic_to_shared(sTable);
+	const ClusterRows<C, S> rows{H, Us};
+	const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+	const int gl = rank * GC + tid;                      // lane within the pair
+	const bool leader = gl == 0;
+	const Scoring sc = L.sc;
+	const int qe = sc.qe;
+	const bool generic = (sc.flag & kFlagGenericSc) != 0;
+	int32_t *max0 = cluster.map_shared_rank(sAllMax, 0);
+	uint32_t *key0 = cluster.map_shared_rank(sAllKey, 0);
+
+	for (;;) {
+		if (leader) {
+			const int p = atomicAdd(L.work_counter, 1);
+			for (int k = 0; k < C; ++k) *cluster.map_shared_rank(&sPair, k) = p;
+		}
+		cluster.sync();
+		const int pi = sPair;
+		if (pi >= L.n) break;
+		const PairDesc pd = L.pairs[pi];
+		const int qlen = pd.qlen, tlen = pd.tlen, w = pd.w;
+		const int T = (tlen + 15) & ~15;
+		const uint8_t *qseq = L.seq + pd.q_off;
+		const uint8_t *tseq = L.seq + pd.t_off;
+		uint8_t *tbp = kCigar ? L.tb + pd.tb_off : nullptr;
+
+		LaneState<S> ls;
+		ls.t0 = gl * S;
+		lane_load_slots<S>(ls, tseq, tlen, qseq, 0, sc);
+#pragma unroll
+		for (int j = 0; j < S / 4; ++j) *(int4 *)&H[(j * GC + tid) << 2] = make_int4(kNegInf, kNegInf, kNegInf, kNegInf);
+		Leader ld; ld.reset();
+		int last_st = -1, n_diag = 0, zdropped_band = 0;
+		const int R = qlen + tlen - 1;
+		cluster.sync();
+
+		for (int r = 0; r < R; ++r) {
+			Band b;
+			if (!band_of(r, qlen, tlen, w, T, generic, b)) { zdropped_band = 1; break; }
+
+			// phase 1: publish the OLD top slot of every warp; the leader prepares H (nobody else touches H now)
+			uint32_t xin = __shfl_up_sync(0xffffffffu, ls.X[S - 1], 1);
+			uint32_t vin = __shfl_up_sync(0xffffffffu, ls.V[S - 1], 1);
+			if (lane == 31) { sCarryX[wid] = ls.X[S - 1]; sCarryV[wid] = ls.V[S - 1]; }
+			if (leader) ld.pre(rows, b, r, qe);
+			cluster.sync();                                                                    // A
+			// phase 2: cells; warp 0 of a CTA takes its carry from the last warp of the previous CTA (DSMEM)
+			if (lane == 0) {
+				if (wid > 0) { xin = sCarryX[wid - 1]; vin = sCarryV[wid - 1]; }
+				else {
+					const int pr = (rank + C - 1) % C;
+					xin = cluster.map_shared_rank(sCarryX, pr)[NW - 1];
+					vin = cluster.map_shared_rank(sCarryV, pr)[NW - 1];
+				}
+			}
+			lane_prepare<S, NS>(ls, b, r, qseq, tseq, tlen, table_saddr, sc);
+			int32_t lane_max = lane_cells<GC, S, kCigar, kRight, G>(ls, b, r, last_st, tid, xin, vin, tbp, H, Us, sc, gl);
+			int32_t wmax = __reduce_max_sync(0xffffffffu, lane_max);
+			if (lane == 0) max0[rank * NW + wid] = wmax;
+			cluster.sync();                                                                    // B
+			// phase 3: leader
+			if (leader) {
+				int32_t red = sAllMax[0];
+				for (int k = 1; k < C * NW; ++k) red = red > sAllMax[k] ? red : sAllMax[k];
+				const int need = ld.mid(rows, b, r, qe, red, ls.V[0], sc.zdrop);
+				int stop = 0;
+				if (!need) stop = ld.fin(rows, b, r, qe, b.en0, qlen, tlen, sc.zdrop, sc.e);
+				for (int k = 0; k < C; ++k) {
+					*cluster.map_shared_rank(&sNeedArg, k) = need;
+					*cluster.map_shared_rank(&sGmax, k) = ld.gmax;
+					*cluster.map_shared_rank(&sStop, k) = stop;
+				}
+			}
+			cluster.sync();                                                                    // C
+			if (sNeedArg) {
+				uint32_t key = lane_argmax_key<GC, S>(ls, b, tid, H, sGmax);
+				key = __reduce_min_sync(0xffffffffu, key);
+				if (lane == 0) key0[rank * NW + wid] = key;
+				cluster.sync();                                                                // D
+				if (leader) {
+					uint32_t k = ld.en0_key(b, r);
+					for (int j = 0; j < C * NW; ++j) k = sAllKey[j] < k ? sAllKey[j] : k;
+					const int stop = ld.fin(rows, b, r, qe, tie_key_slot(k, b.en0), qlen, tlen, sc.zdrop, sc.e);
+					for (int kk = 0; kk < C; ++kk) *cluster.map_shared_rank(&sStop, kk) = stop;
+				}
+				cluster.sync();                                                                // E
+			}
+			const int stop = sStop;
+			n_diag = r + 1;
+			last_st = b.st;
+			if (stop) break;
+		}
+		if (leader) { if (zdropped_band) ld.ez.zdropped = 1; ld.store(&L.results[pi], n_diag); }
+		cluster.sync();
 	}
 }
 

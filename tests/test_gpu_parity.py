@@ -149,14 +149,19 @@ def test_empty_and_degenerate_inputs(checker, mat):
 
 
 def test_widest_pair_and_too_wide(checker, mat):
-    """1000x1000 unbanded (SEDEF's largest direct gap fill, src/align.cc:233-236) and 4 kbp unbanded pairs run on the
-    CTA-wide kernels; beyond 4096 live slots the engine refuses (no silent fallback)."""
+    """Unbanded pairs of growing size walk through every kernel family: 1000x1000 (SEDEF's largest direct gap fill,
+    src/align.cc:233-236) and 4 kbp on the CTA-wide kernels, 6 kbp / 10 kbp (SEDEF's MAX_GAP fills, src/refine.cc:77) on the
+    thread-block-cluster kernels (DSMEM); beyond 16384 live slots the engine refuses (no silent fallback)."""
     ps = synth.make_pairs_small(6, length=1000, div=0.1, seed=3)
     compare(ps, mat, checker, -1, -1, 0)
     ps4k = synth.make_pairs_small(3, length=4000, div=0.1, seed=8)
     ps4k.tlen[:] = np.minimum(ps4k.tlen, 4090)
     compare(ps4k, mat, checker, -1, -1, 0)
-    big = synth.make_pairs_small(2, length=6000, div=0.05, seed=4)
+    compare(synth.make_pairs_small(3, length=6000, div=0.08, seed=9), mat, checker, -1, -1, 0)        # cluster of 2 CTAs
+    compare(synth.make_pairs_small(2, length=10000, div=0.08, seed=10), mat, checker, -1, -1, 0)      # cluster of 4 CTAs
+    compare(synth.make_pairs_small(2, length=9000, div=0.3, seed=11), mat, checker, -1, 500, 0x42)    # z-drop, right, extz-only
+    compare(synth.make_pairs_large(3, min_len=12000, max_len=20000, seed=12), mat, checker, 5000, 600, 0)   # banded, 5 k wide
+    big = synth.make_pairs_small(2, length=17000, div=0.05, seed=4)
     with pytest.raises(engine.EngineError) as ei:
         engine.extz2_batch(big, mat, 40, 1, -1, -1, 0)
     assert ei.value.code == -5

@@ -32,6 +32,9 @@ configs = [
     ("large", 12, dict(min_len=4000, max_len=9000), 500, 400, 0),                # w=500: 528 slots
     ("large", 8, dict(min_len=4000, max_len=9000), 1500, -1, 0),                 # w=1500: wide banded
     ("mixed", 12, dict(min_len=1500, max_len=3500, div=0.3), -1, 300, 2),        # wide, z-drop, right-align
+    ("small", 6, dict(length=6000, div=0.08), -1, -1, 0),                        # cluster of 2 CTAs (8192 slots)
+    ("small", 4, dict(length=10000, div=0.08), -1, -1, 0),                       # cluster of 4 CTAs (16384 slots), SEDEF's MAX_GAP fills
+    ("small", 4, dict(length=9000, div=0.3), -1, 500, 0x42),                     # cluster, z-drop, right-align, EXTZ_ONLY
 ]
 only = [int(x) for x in sys.argv[1:]] if len(sys.argv) > 1 else None
 for ci, (gen, n, kw, w, zdrop, flag) in enumerate(configs):

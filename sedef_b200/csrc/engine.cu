@@ -839,11 +839,12 @@ extern "C" int ksw_extz2_batch_flat(int n, const int *qlen, const int64_t *qoff,
 	const char *env = getenv("KSW_B200_CHUNK_PAIRS");
 	const int chunk_pairs = env ? std::max(1, atoi(env)) : 25000;
 	// chunk sizes ramp up (1 : 2 : 4 : 4 ...) so that the first H2D copy -- the only one nothing can hide -- is short
-	int nchunks = std::max(1, std::min(16, n / chunk_pairs + (n >= 2 * chunk_pairs ? 1 : 0)));
+	int nchunks = std::max(1, std::min(16, n / chunk_pairs + (n >= 2 * chunk_pairs ? 2 : 0)));
 	std::vector<int> start(nchunks + 1, 0);
 	{
 		std::vector<double> wgt(nchunks, 4.0);
 		if (nchunks >= 3) { wgt[0] = 1.0; wgt[1] = 2.0; }
+		if (nchunks >= 5) wgt[nchunks - 1] = 2.0;                      // a short last chunk keeps the un-overlapped D2H + gather small
 		double tot = 0; for (double x : wgt) tot += x;
 		double acc = 0;
 		for (int c = 0; c < nchunks; ++c) { acc += wgt[c]; start[c + 1] = (int)((double)n * acc / tot + 0.5); }

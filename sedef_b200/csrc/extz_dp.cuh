@@ -435,6 +435,7 @@ extz_dp_kernel(DpLaunch L)
 			if (act && gl == 0) stop = ld.fin(rows, b, r, qe, max_t, qlen, tlen, sc.zdrop, sc.e);
 			stop = __shfl_sync(FULL, stop, 0, G);
 			if (act) { n_diag = r + 1; last_st = b.st; if (stop) alive = false; }
+			__syncwarp();            // the arg-max passes read H; the next diagonal's leader writes it (racecheck-clean ordering)
 		}
 		if (pi < L.n && gl == 0) { if (zdropped_band) ld.ez.zdropped = 1; ld.store(&L.results[pi], n_diag); }
 		__syncwarp();

@@ -188,6 +188,10 @@ __device__ __forceinline__ uint32_t lane_argmax_count(const LaneState<S> &ls, in
 #pragma unroll
 	for (int j = 0; j < S / 4; ++j) {
 		const int4 h = *(const int4 *)&H[((j * G + lane) << 2)];
+#ifdef EXTZ_OPT_QUAD
+		const int32_t m01 = h.x > h.y ? h.x : h.y, m23 = h.z > h.w ? h.z : h.w;
+		if ((m01 > m23 ? m01 : m23) != gm) continue;             // only the quad holding the diagonal maximum is examined
+#endif
 		const uint32_t base = (1u << 24) + (uint32_t)(ls.t0 + 4 * j);
 		if (h.x == gm) acc += base;
 		if (h.y == gm) acc += base + 1;

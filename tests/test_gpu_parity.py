@@ -314,3 +314,39 @@ def test_cpp_host_layer(checker, golden_dir):
             assert [int(x) for x in f[1:16]] == [st[k] for k in keys]
             tot = st["matches"] + st["gap_bases"] + st["mismatches"]
             assert f[16] == "%.1f" % (100.0 * st["mismatches"] / tot + 100.0 * st["gap_bases"] / tot)
+
+
+def test_traceback_waves_and_multi_device(checker, mat, tmp_path):
+    """(1) A tiny traceback budget forces every class into many waves (KSW_B200_TB_BUDGET_MB is read at init, hence the
+    subprocess); (2) when more than one GPU is visible, the in-process LPT sharding over all devices gives the same results."""
+    import os, subprocess, sys, textwrap
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "waves.py"
+    script.write_text(textwrap.dedent(f"""
+        import sys, numpy as np
+        sys.path.insert(0, {root!r})
+        import oracle
+        from sedef_b200 import engine, synth
+        import torch
+        mat = synth.sedef_matrix()
+        ndev = engine.init(0, int(sys.argv[1]))
+        ps = synth.make_pairs_mixed(600, seed=99, min_len=1, max_len=700, div=0.12)
+        chk = oracle.ref() if oracle.have_ref() else oracle.port()
+        for (w, zd, flag) in [(-1, -1, 0), (30, 60, 0)]:
+            got = engine.extz2_batch(ps, mat, 40, 1, w, zd, flag)
+            _, fr, cr = chk.batch(ps, mat, 40, 1, w, zd, flag, nthreads=8)
+            for i in range(ps.n):
+                assert got.fields(i) == fr[i], i
+                assert got.cigars[i].tolist() == cr[i], i
+                assert got.stats_dict(i) == oracle.sd_stats(cr[i], *ps.raw_pair(i)), i
+        print("ok devices", ndev, "launches", engine.last_call_io()[2])
+    """))
+    env = dict(os.environ, KSW_B200_TB_BUDGET_MB="4")
+    out = subprocess.run([sys.executable, str(script), "1"], capture_output=True, text=True, env=env, timeout=600)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert int(out.stdout.split("launches")[1]) > 4, out.stdout           # w=30 needs 2 classes = 4 launches without waves
+    import torch
+    if torch.cuda.device_count() > 1:
+        out = subprocess.run([sys.executable, str(script), "0"], capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0 and "ok devices" in out.stdout, out.stdout + out.stderr
+        assert int(out.stdout.split("devices")[1].split()[0]) == torch.cuda.device_count()

@@ -45,6 +45,24 @@ std::vector<Alignment> align_batch(const std::vector<std::pair<std::string, std:
 std::vector<Alignment> from_cigar_batch(const std::vector<std::pair<std::string, std::string>> &pairs,
                                         const std::vector<std::string> &cigars);
 
+// ---- the chain wave -----------------------------------------------------------------
+// Mirror of Alignment::Alignment(qstr, rstr, vector<Anchor> guide, vector<int> guide_idx) (src/align.cc:199-270) for MANY
+// chains at once: every gap between consecutive anchors of every chain becomes one request of a single batched
+// ksw_extz2 call ("close" gaps <= 1000 x 1000 as they are, larger ones as the mi x mi prefix fill -- the reference's
+// second mi x mi alignment is dead work, its result is never selected, src/align.cc:244), the CIGARs are stitched with
+// append_cigar's run merging (src/align.cc:468-477) and the statistics of the stitched alignments come from one
+// sd_stats_from_cigar call.
+struct Anchor { int q, r, l, has_u; };                  // src/align.h:25-28
+struct ChainGuide {
+	const std::string *qstr, *rstr;                     // the region pair the chain lives in
+	const std::vector<Anchor> *anchors;
+	std::vector<int> guide_idx;                         // anchors of the chain, in query order
+};
+struct GuidedAlignment : Alignment {
+	int start_a = 0, end_a = 0, start_b = 0, end_b = 0; // src/align.h: start_a/end_a/start_b/end_b
+};
+std::vector<GuidedAlignment> align_chains_batch(const std::vector<ChainGuide> &chains, const AlignParams &p = AlignParams());
+
 // Deferred-alignment queue: call sites push requests, the driver flushes a whole wave at once.
 class AlignQueue {
 public:

@@ -11,6 +11,11 @@
 #include "hash.h"
 #include <memory>
 #include <sstream>
+#include "globals.h"
+
+// non-static functions of /root/reference/src/chain.cc that chain.h does not declare (chain.cc:24,103)
+std::vector<Anchor> generate_anchors(const std::string &query, const std::string &ref, const Hit &orig, const int kmer_size);
+std::pair<std::vector<int>, std::vector<std::pair<int, bool>>> chain_anchors(std::vector<Anchor> &anchors);
 
 extern "C" {
 // Alignment(fa, fb): reference src/align.cc:76-88 (align_dna + align_helper + populate_nice_alignment)
@@ -50,5 +55,45 @@ int ref_fast_align(const char *query, const char *ref, int kmer_size, char *out,
 	if ((int)sres.size() + 1 > cap) return -1;
 	memcpy(out, sres.c_str(), sres.size() + 1);
 	return (int)hits.size();
+}
+// The chain wave of fast_align (src/chain.cc:211-258): anchors, chaining, the chain filter, and for every kept chain
+// the reference's Alignment(query, ref, anchors, guide_idx) constructor (src/align.cc:199-270).  One line per chain:
+//   start_a end_a start_b end_b cigar span matches mismatches gaps gap_bases n  q r l  q r l ...   (anchors in guide order)
+int ref_chain_guides(const char *query, const char *ref, int kmer_size, char *out, int cap)
+{
+	std::string q(query), r(ref);
+	auto qp = std::make_shared<Sequence>("QRY", q);
+	auto rp = std::make_shared<Sequence>("REF", r);
+	Hit orig{qp, 0, (int)q.size(), rp, 0, (int)r.size()};
+	auto anchors = generate_anchors(q, r, orig, kmer_size);
+	auto chains_init = chain_anchors(anchors);
+	auto &bounds = chains_init.second;
+	auto &chain = chains_init.first;
+	std::ostringstream os;
+	int n = 0;
+	for (int bi = 1; bi < (int)bounds.size(); bi++) {                   // the loop of src/chain.cc:222-247, called, not changed
+		bool has_u = bounds[bi].second;
+		int be = bounds[bi].first, bs = bounds[bi - 1].first;
+		int qlo = anchors[chain[be - 1]].q, qhi = anchors[chain[bs]].q + anchors[chain[bs]].l;
+		int rlo = anchors[chain[be - 1]].r, rhi = anchors[chain[bs]].r + anchors[chain[bs]].l;
+		int span = std::max(rhi - rlo, qhi - qlo);
+		if ((!has_u || span < Globals::Chain::MIN_UPPERCASE_MATCH) &&
+		    span < Globals::Search::MIN_READ_SIZE * (1 - Globals::Search::MAX_ERROR)) continue;
+		std::vector<int> guide;
+		for (int k = be - 1; k >= bs; k--) guide.emplace_back(chain[k]);
+		Alignment a(q, r, anchors, guide);
+		Hit h{qp, qlo, qhi, rp, rlo, rhi};
+		h.aln = a;
+		update_from_alignment(h);
+		os << h.query_start << ' ' << h.query_end << ' ' << h.ref_start << ' ' << h.ref_end << ' ' << a.cigar_string() << ' ' << a.span() << ' '
+		   << a.matches() << ' ' << a.mismatches() << ' ' << a.gaps() << ' ' << a.gap_bases() << ' ' << guide.size();
+		for (int g : guide) os << ' ' << anchors[g].q << ' ' << anchors[g].r << ' ' << anchors[g].l;
+		os << '\n';
+		++n;
+	}
+	std::string sres = os.str();
+	if ((int)sres.size() + 1 > cap) return -1;
+	memcpy(out, sres.c_str(), sres.size() + 1);
+	return n;
 }
 }

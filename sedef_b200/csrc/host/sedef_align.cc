@@ -133,4 +133,79 @@ std::vector<Alignment> from_cigar_batch(const std::vector<std::pair<std::string,
 	return out;
 }
 
+// append_cigar (src/align.cc:468-477): merge the first appended run into the last one when the ops are equal
+static void append_cigar(std::deque<std::pair<char, int>> &cigar, const std::deque<std::pair<char, int>> &app)
+{
+	if (app.empty()) return;
+	if (!cigar.empty() && cigar.back().first == app.front().first) {
+		cigar.back().second += app.front().second;
+		cigar.insert(cigar.end(), std::next(app.begin()), app.end());
+	} else cigar.insert(cigar.end(), app.begin(), app.end());
+}
+
+std::vector<GuidedAlignment> align_chains_batch(const std::vector<ChainGuide> &chains, const AlignParams &p)
+{
+	// pass 1: walk every chain, queue its gap fills
+	struct Fill { size_t chain; size_t step; char tail_op; int tail_len; };   // fill result is spliced in at `step`
+	std::vector<std::pair<std::string, std::string>> reqs;
+	std::vector<Fill> fills;
+	for (size_t ci = 0; ci < chains.size(); ++ci) {
+		const ChainGuide &cg = chains[ci];
+		const std::vector<Anchor> &g = *cg.anchors;
+		for (size_t k = 1; k < cg.guide_idx.size(); ++k) {
+			const Anchor &pv = g[cg.guide_idx[k - 1]], &cu = g[cg.guide_idx[k]];
+			const int qpe = pv.q + pv.l, rpe = pv.r + pv.l, qs = cu.q, rs = cu.r;
+			const int qgap = qs - qpe, rgap = rs - rpe;
+			if (qgap && rgap) {
+				if (qgap <= 1000 && rgap <= 1000) {                                     // "close" hits, src/align.cc:233-236
+					reqs.emplace_back(cg.qstr->substr(qpe, qgap), cg.rstr->substr(rpe, rgap));
+					fills.push_back({ci, k, 0, 0});
+				} else {                                                                // src/align.cc:237-246: ma1 is always taken
+					const int ma = std::max(qgap, rgap), mi = std::min(qgap, rgap);
+					reqs.emplace_back(cg.qstr->substr(qpe, mi), cg.rstr->substr(rpe, mi));
+					fills.push_back({ci, k, qgap == mi ? 'I' : 'D', ma - mi});
+				}
+			}
+		}
+	}
+	std::vector<Alignment> filled = align_batch(reqs, p);                              // ONE batched ksw_extz2 call
+	// pass 2: stitch
+	std::vector<GuidedAlignment> out(chains.size());
+	std::vector<std::pair<std::string, std::string>> finals(chains.size());
+	std::vector<std::string> final_cigars(chains.size());
+	size_t fpos = 0;
+	for (size_t ci = 0; ci < chains.size(); ++ci) {
+		const ChainGuide &cg = chains[ci];
+		GuidedAlignment &al = out[ci];
+		if (cg.guide_idx.empty()) continue;                                             // src/align.cc:202-205
+		const std::vector<Anchor> &g = *cg.anchors;
+		const Anchor &a0 = g[cg.guide_idx[0]];
+		al.start_a = a0.q; al.end_a = a0.q + a0.l; al.start_b = a0.r; al.end_b = a0.r + a0.l;
+		al.cigar = {{'M', a0.l}};
+		for (size_t k = 1; k < cg.guide_idx.size(); ++k) {
+			const Anchor &pv = g[cg.guide_idx[k - 1]], &cu = g[cg.guide_idx[k]];
+			const int qpe = pv.q + pv.l, rpe = pv.r + pv.l, qs = cu.q, rs = cu.r;
+			const int qgap = qs - qpe, rgap = rs - rpe;
+			al.end_a = cu.q + cu.l; al.end_b = cu.r + cu.l;
+			if (qgap && rgap) {
+				const Fill &f = fills[fpos];
+				std::deque<std::pair<char, int>> gc = filled[fpos].cigar;
+				if (f.tail_op) gc.push_back({f.tail_op, f.tail_len});
+				append_cigar(al.cigar, gc);
+				++fpos;
+			} else if (qgap) append_cigar(al.cigar, {{'D', qgap}});
+			else if (rgap) append_cigar(al.cigar, {{'I', rgap}});
+			append_cigar(al.cigar, {{'M', cu.l}});
+		}
+		al.a = cg.qstr->substr(al.start_a, al.end_a - al.start_a);
+		al.b = cg.rstr->substr(al.start_b, al.end_b - al.start_b);
+		finals[ci] = {al.a, al.b};
+		final_cigars[ci] = al.cigar_string();
+	}
+	// populate_nice_alignment for every stitched alignment: one statistics-from-CIGAR call
+	std::vector<Alignment> st = from_cigar_batch(finals, final_cigars);
+	for (size_t ci = 0; ci < chains.size(); ++ci) out[ci].stats = st[ci].stats;
+	return out;
+}
+
 } // namespace sedef_b200

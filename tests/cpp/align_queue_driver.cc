@@ -8,8 +8,34 @@
 #include <vector>
 #include "sedef_align.hpp"
 
+// mode "chains": line 1 = query region, line 2 = reference region, then one line per chain: n  q r l  q r l ...
+static int run_chains()
+{
+	std::string q, r, line;
+	std::getline(std::cin, q); std::getline(std::cin, r);
+	std::vector<sedef_b200::Anchor> anchors;
+	std::vector<sedef_b200::ChainGuide> chains;
+	std::vector<std::vector<int>> idx;
+	while (std::getline(std::cin, line)) {
+		std::istringstream is(line);
+		int n; if (!(is >> n)) continue;
+		std::vector<int> g;
+		for (int k = 0; k < n; ++k) { sedef_b200::Anchor a{}; is >> a.q >> a.r >> a.l; g.push_back((int)anchors.size()); anchors.push_back(a); }
+		idx.push_back(g);
+	}
+	for (auto &g : idx) chains.push_back({&q, &r, &anchors, g});
+	std::vector<sedef_b200::GuidedAlignment> res;
+	try { res = sedef_b200::align_chains_batch(chains); }
+	catch (const std::exception &e) { fprintf(stderr, "error: %s\n", e.what()); return 2; }
+	for (auto &a : res)
+		printf("%d %d %d %d %s %d %d %d %d %d\n", a.start_a, a.end_a, a.start_b, a.end_b, a.cigar_string().c_str(), a.span(), a.matches(),
+		       a.mismatches(), a.gaps(), a.gap_bases());
+	return 0;
+}
+
 int main(int argc, char **argv)
 {
+	if (argc > 1 && std::string(argv[1]) == "chains") return run_chains();
 	const bool from_cigar = argc > 1 && std::string(argv[1]) == "from_cigar";
 	std::vector<std::pair<std::string, std::string>> pairs;
 	std::vector<std::string> cigars;

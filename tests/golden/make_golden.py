@@ -113,7 +113,19 @@ def main():
     json.dump(dict(source="oracle/_ref/libsedef_ref.so: reference fast_align(query, ref, orig, 11) (src/chain.cc:203-268) on "
                           "synth.make_region_pair(length, div, seed=seed); one line per hit: qs qe rs re cigar span matches mismatches gaps gap_bases",
                    regions=regs), open(os.path.join(HERE, "fast_align_golden.json"), "w"))
-    for f in ("ksw2_kat.json", "ksw2_golden.json", "sd_stats_golden.json", "fast_align_golden.json"):
+    # ---- chain-wave golden: anchors -> chains -> Alignment(query, ref, anchors, guide_idx) of the reference ----
+    slib.ref_chain_guides.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_char_p, C.c_int]
+    cregs = []
+    for (L, div, seed) in [(2500, 0.03, 11), (6000, 0.06, 12), (9000, 0.10, 13), (5000, 0.2, 14)]:
+        qs, ts = synth.make_region_pair(L, div, seed=seed)
+        buf = C.create_string_buffer(1 << 22)
+        n = slib.ref_chain_guides(qs.encode(), ts.encode(), 11, buf, len(buf))
+        cregs.append(dict(length=L, div=div, seed=seed, n_chains=n, chains=buf.value.decode()))
+    json.dump(dict(source="oracle/_ref/libsedef_ref.so: reference generate_anchors + chain_anchors + Alignment(query, ref, anchors, guide_idx) "
+                          "(src/chain.cc:211-258, src/align.cc:199-270); one line per chain: start_a end_a start_b end_b cigar span matches "
+                          "mismatches gaps gap_bases n  q r l ...",
+                   regions=cregs), open(os.path.join(HERE, "chain_wave_golden.json"), "w"))
+    for f in ("ksw2_kat.json", "ksw2_golden.json", "sd_stats_golden.json", "fast_align_golden.json", "chain_wave_golden.json"):
         print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")
 
 

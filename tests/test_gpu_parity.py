@@ -350,3 +350,24 @@ def test_traceback_waves_and_multi_device(checker, mat, tmp_path):
         out = subprocess.run([sys.executable, str(script), "0"], capture_output=True, text=True, timeout=600)
         assert out.returncode == 0 and "ok devices" in out.stdout, out.stdout + out.stderr
         assert int(out.stdout.split("devices")[1].split()[0]) == torch.cuda.device_count()
+
+
+def test_chain_wave_batched(checker, golden_dir):
+    """SURVEY section 8 f1, first wave: the C++ `align_chains_batch` (every anchor-gap fill of every chain in ONE batched
+    ksw_extz2 call + one statistics-from-CIGAR call) against the reference's own Alignment(query, ref, anchors, guide_idx)
+    constructor run on the reference's own anchors and chains (tests/golden/chain_wave_golden.json)."""
+    import os, subprocess
+    drv = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "cpp", "align_queue_driver")
+    g = load_json(golden_dir, "chain_wave_golden.json")
+    total = 0
+    for reg in g["regions"]:
+        q, t = synth.make_region_pair(reg["length"], reg["div"], seed=reg["seed"])
+        lines = [ln for ln in reg["chains"].split("\n") if ln.strip()]
+        assert len(lines) == reg["n_chains"]
+        text = q + "\n" + t + "\n" + "".join(" ".join(ln.split()[10:]) + "\n" for ln in lines)
+        out = subprocess.run([drv, "chains"], input=text, capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stderr
+        got = [ln for ln in out.stdout.split("\n") if ln.strip()]
+        assert got == [" ".join(ln.split()[:10]) for ln in lines]
+        total += len(lines)
+    assert total >= 10

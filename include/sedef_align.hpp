@@ -63,6 +63,22 @@ struct GuidedAlignment : Alignment {
 };
 std::vector<GuidedAlignment> align_chains_batch(const std::vector<ChainGuide> &chains, const AlignParams &p = AlignParams());
 
+// ---- the refine wave's final constructor -----------------------------------------------
+// Mirror of Alignment::Alignment(qstr, rstr, vector<Hit> guide, side) (src/align.cc:107-197) for MANY guides at once: the
+// gap fills between consecutive (co-linear, non-overlapping) hits and the two +-side extensions of every guide -- the
+// 500 x 500 unbanded alignments that hold 80-95 % of SEDEF's ksw cells -- go through ONE batched
+// ksw_extz2 call; trim_front / trim_back (src/align.cc:343-456) run on the host over the <= 1000 columns of each side
+// extension; the statistics of the finished alignments come from one sd_stats_from_cigar call.
+struct HitGuide {
+	const std::string *qstr, *rstr;
+	std::vector<GuidedAlignment> guide;                 // hits in order; only start/end coordinates and cigar are used
+	int side = 500;                                     // Globals::Chain::Refine::SIDE_ALIGN
+};
+std::vector<GuidedAlignment> align_hit_guides_batch(const std::vector<HitGuide> &guides, const AlignParams &p = AlignParams());
+// trim_front / trim_back of one alignment whose start/end are relative to its own a/b (as after Alignment(fa, fb))
+void trim_front(GuidedAlignment &g, const AlignParams &p = AlignParams());
+void trim_back(GuidedAlignment &g, const AlignParams &p = AlignParams());
+
 // Deferred-alignment queue: call sites push requests, the driver flushes a whole wave at once.
 class AlignQueue {
 public:

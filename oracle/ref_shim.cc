@@ -9,6 +9,7 @@
 #include "chain.h"   // /root/reference/src/chain.h
 #include "hit.h"
 #include "hash.h"
+#include <algorithm>
 #include <memory>
 #include <sstream>
 #include "globals.h"
@@ -95,5 +96,51 @@ int ref_chain_guides(const char *query, const char *ref, int kmer_size, char *ou
 	if ((int)sres.size() + 1 > cap) return -1;
 	memcpy(out, sres.c_str(), sres.size() + 1);
 	return n;
+}
+// The final constructor of the refine wave: Alignment(qstr, rstr, vector<Hit> guide, side) (src/align.cc:107-197:
+// gap fills between consecutive hits, +-side extensions with trim_front / trim_back, src/align.cc:343-456), run on a
+// guide made of the reference's own chain alignments: the chains of the chain wave, sorted, greedily thinned to a
+// strictly co-linear, non-overlapping sequence (what refine_chains' merges guarantee, src/refine.cc:164-183).
+// Line 1: the result (start_a end_a start_b end_b cigar span matches mismatches gaps gap_bases);
+// following lines: the guide hits (query_start query_end ref_start ref_end cigar).
+int ref_hit_guide(const char *query, const char *ref, int kmer_size, int side, char *out, int cap)
+{
+	std::string q(query), r(ref);
+	auto qp = std::make_shared<Sequence>("QRY", q);
+	auto rp = std::make_shared<Sequence>("REF", r);
+	Hit orig{qp, 0, (int)q.size(), rp, 0, (int)r.size()};
+	auto anchors = generate_anchors(q, r, orig, kmer_size);
+	auto chains_init = chain_anchors(anchors);
+	auto &bounds = chains_init.second;
+	auto &chain = chains_init.first;
+	std::vector<Hit> hits;
+	for (int bi = 1; bi < (int)bounds.size(); bi++) {
+		int be = bounds[bi].first, bs = bounds[bi - 1].first;
+		std::vector<int> guide;
+		for (int k = be - 1; k >= bs; k--) guide.emplace_back(chain[k]);
+		if (guide.empty()) continue;
+		Hit h{qp, 0, 0, rp, 0, 0};
+		h.aln = Alignment(q, r, anchors, guide);
+		update_from_alignment(h);
+		hits.push_back(h);
+	}
+	std::sort(hits.begin(), hits.end());
+	std::vector<Hit> guide;
+	for (auto &h : hits)
+		if (guide.empty() || (h.query_start >= guide.back().query_end && h.ref_start >= guide.back().ref_end)) guide.push_back(h);
+	if (guide.empty()) return 0;
+	Alignment res(q, r, guide, side);
+	Hit hr{qp, 0, 0, rp, 0, 0};
+	hr.aln = res;
+	update_from_alignment(hr);
+	std::ostringstream os;
+	os << hr.query_start << ' ' << hr.query_end << ' ' << hr.ref_start << ' ' << hr.ref_end << ' ' << res.cigar_string() << ' ' << res.span() << ' '
+	   << res.matches() << ' ' << res.mismatches() << ' ' << res.gaps() << ' ' << res.gap_bases() << '\n';
+	for (auto &h : guide)
+		os << h.query_start << ' ' << h.query_end << ' ' << h.ref_start << ' ' << h.ref_end << ' ' << h.aln.cigar_string() << '\n';
+	std::string sres = os.str();
+	if ((int)sres.size() + 1 > cap) return -1;
+	memcpy(out, sres.c_str(), sres.size() + 1);
+	return (int)guide.size();
 }
 }

@@ -208,4 +208,188 @@ std::vector<GuidedAlignment> align_chains_batch(const std::vector<ChainGuide> &c
 	return out;
 }
 
+// prepend_cigar (src/align.cc:458-466)
+static void prepend_cigar(std::deque<std::pair<char, int>> &cigar, const std::deque<std::pair<char, int>> &app)
+{
+	if (app.empty()) return;
+	if (!cigar.empty() && cigar.front().first == app.back().first) {
+		cigar.front().second += app.back().second;
+		cigar.insert(cigar.begin(), app.begin(), app.begin() + (app.size() - 1));
+	} else cigar.insert(cigar.begin(), app.begin(), app.end());
+}
+
+static inline bool ceq(char x, char y)                                  // src/align.cc:29-35
+{
+	auto up = [](char c) { return (c >= 'a' && c <= 'z') ? char(c - 32) : c; };
+	if (x == '-' || y == '-') return false;
+	if (up(x) == 'N' || up(y) == 'N') return false;
+	return up(x) == up(y);
+}
+
+// column classes of an alignment: 0 = '|' (M and ceq), 1 = mismatch (both bases), 2 = a is '-' (SEDEF 'I'), 3 = b is '-' ('D')
+static std::vector<uint8_t> columns_of(const GuidedAlignment &g)
+{
+	std::vector<uint8_t> col;
+	size_t ia = 0, ib = 0;
+	for (auto &c : g.cigar)
+		for (int k = 0; k < c.second; ++k) {
+			if (c.first == 'M') { col.push_back(ceq(g.a[ia], g.b[ib]) ? 0 : 1); ++ia; ++ib; }
+			else if (c.first == 'I') { col.push_back(2); ++ib; }
+			else { col.push_back(3); ++ia; }
+		}
+	return col;
+}
+static void clear_alignment(GuidedAlignment &g) { g.a.clear(); g.b.clear(); g.cigar.clear(); }
+
+void trim_front(GuidedAlignment &g, const AlignParams &p)              // src/align.cc:343-398   ABCD -> --CD
+{
+	const std::vector<uint8_t> col = columns_of(g);
+	const int n = (int)col.size();
+	int max_score = 0, max_i = (int)g.a.size(), score = 0;            // (sic) initialised with the SEQUENCE length
+	for (int i = n - 1; i >= 0; --i) {
+		if (col[i] == 0) score += p.match;
+		else if (col[i] == 1) score += p.mismatch;
+		else {
+			if (i == n - 1 || (col[i] == 2 && col[i + 1] != 2) || (col[i] == 3 && col[i + 1] != 3)) score += -p.gap_open;
+			score += -p.gap_extend;
+		}
+		if (score >= max_score) { max_score = score; max_i = i; }
+	}
+	if (max_i == (int)g.a.size()) { clear_alignment(g); g.start_a = g.end_a; g.start_b = g.end_b; return; }
+	for (int ci = 0, cur_len = 0; ci < (int)g.cigar.size(); ++ci) {
+		if (g.cigar[ci].second + cur_len > max_i) {
+			const int need = max_i - cur_len;
+			g.cigar[ci].second -= need;
+			for (int cj = 0; cj < ci; ++cj) g.cigar.pop_front();
+			g.start_a += need; g.start_b += need;
+			break;
+		}
+		cur_len += g.cigar[ci].second;
+		if (g.cigar[ci].first == 'M') { g.start_a += g.cigar[ci].second; g.start_b += g.cigar[ci].second; }
+		else if (g.cigar[ci].first == 'I') g.start_b += g.cigar[ci].second;
+		else g.start_a += g.cigar[ci].second;
+	}
+	g.a = g.a.substr(g.start_a, g.end_a - g.start_a);
+	g.b = g.b.substr(g.start_b, g.end_b - g.start_b);
+}
+
+void trim_back(GuidedAlignment &g, const AlignParams &p)               // src/align.cc:400-456   ABCD -> AB--
+{
+	const std::vector<uint8_t> col = columns_of(g);
+	const int n = (int)col.size();
+	int max_score = 0, max_i = -1, score = 0;
+	for (int i = 0; i < n; ++i) {
+		if (col[i] == 0) score += p.match;
+		else if (col[i] == 1) score += p.mismatch;
+		else {
+			if (i == 0 || (col[i] == 2 && col[i - 1] != 2) || (col[i] == 3 && col[i - 1] != 3)) score += -p.gap_open;
+			score += -p.gap_extend;
+		}
+		if (score >= max_score) { max_score = score; max_i = i; }
+	}
+	if (max_i == -1) { clear_alignment(g); g.end_a = g.start_a; g.end_b = g.start_b; return; }
+	++max_i;
+	g.end_a = g.start_a; g.end_b = g.start_b;
+	for (int ci = 0, cur_len = 0; ci < (int)g.cigar.size(); ++ci) {
+		if (g.cigar[ci].second + cur_len >= max_i) {
+			const int need = max_i - cur_len;
+			g.cigar[ci].second = need;
+			while ((int)g.cigar.size() - 1 > ci) g.cigar.pop_back();
+			g.end_a += need; g.end_b += need;
+			break;
+		}
+		cur_len += g.cigar[ci].second;
+		if (g.cigar[ci].first == 'M') { g.end_a += g.cigar[ci].second; g.end_b += g.cigar[ci].second; }
+		else if (g.cigar[ci].first == 'I') g.end_b += g.cigar[ci].second;
+		else g.end_a += g.cigar[ci].second;
+	}
+	g.a = g.a.substr(g.start_a, g.end_a - g.start_a);
+	g.b = g.b.substr(g.start_b, g.end_b - g.start_b);
+}
+
+std::vector<GuidedAlignment> align_hit_guides_batch(const std::vector<HitGuide> &guides, const AlignParams &p)
+{
+	enum { FILL = 0, LEFT = 1, RIGHT = 2 };
+	struct Req { size_t guide; int kind; char tail_op; int tail_len; };
+	std::vector<std::pair<std::string, std::string>> reqs;
+	std::vector<Req> meta;
+	for (size_t gi = 0; gi < guides.size(); ++gi) {
+		const HitGuide &hg = guides[gi];
+		if (hg.guide.empty()) continue;
+		const std::string &qstr = *hg.qstr, &rstr = *hg.rstr;
+		for (size_t k = 1; k < hg.guide.size(); ++k) {
+			const GuidedAlignment &pv = hg.guide[k - 1], &cu = hg.guide[k];
+			const int qpe = pv.end_a, rpe = pv.end_b, qs = cu.start_a, rs = cu.start_b;
+			const int qgap = qs - qpe, rgap = rs - rpe;
+			if (qgap && rgap) {
+				if (qgap <= 1000 && rgap <= 1000) { reqs.emplace_back(qstr.substr(qpe, qgap), rstr.substr(rpe, rgap)); meta.push_back({gi, FILL, 0, 0}); }
+				else {
+					const int ma = std::max(qgap, rgap), mi = std::min(qgap, rgap);
+					reqs.emplace_back(qstr.substr(qpe, mi), rstr.substr(rpe, mi));
+					meta.push_back({gi, FILL, qgap == mi ? 'I' : 'D', ma - mi});
+				}
+			}
+		}
+		if (hg.side) {                                                                   // src/align.cc:153-186
+			const int qlo = hg.guide.front().start_a, rlo = hg.guide.front().start_b;
+			const int qhi = hg.guide.back().end_a, rhi = hg.guide.back().end_b;
+			const int qlo_n = std::max(0, qlo - hg.side), rlo_n = std::max(0, rlo - hg.side);
+			if (qlo - qlo_n && rlo - rlo_n) { reqs.emplace_back(qstr.substr(qlo_n, qlo - qlo_n), rstr.substr(rlo_n, rlo - rlo_n)); meta.push_back({gi, LEFT, 0, 0}); }
+			const int qhi_n = std::min(qhi + hg.side, (int)qstr.size()), rhi_n = std::min(rhi + hg.side, (int)rstr.size());
+			if (qhi_n - qhi && rhi_n - rhi) { reqs.emplace_back(qstr.substr(qhi, qhi_n - qhi), rstr.substr(rhi, rhi_n - rhi)); meta.push_back({gi, RIGHT, 0, 0}); }
+		}
+	}
+	std::vector<Alignment> done = align_batch(reqs, p);                                 // ONE batched ksw_extz2 call
+	std::vector<GuidedAlignment> out(guides.size());
+	std::vector<std::pair<std::string, std::string>> finals(guides.size());
+	std::vector<std::string> final_cigars(guides.size());
+	size_t pos = 0;
+	for (size_t gi = 0; gi < guides.size(); ++gi) {
+		const HitGuide &hg = guides[gi];
+		GuidedAlignment &al = out[gi];
+		if (hg.guide.empty()) continue;
+		const std::string &qstr = *hg.qstr, &rstr = *hg.rstr;
+		al.cigar = hg.guide.front().cigar;
+		for (size_t k = 1; k < hg.guide.size(); ++k) {
+			const GuidedAlignment &pv = hg.guide[k - 1], &cu = hg.guide[k];
+			const int qgap = cu.start_a - pv.end_a, rgap = cu.start_b - pv.end_b;
+			if (qgap && rgap) {
+				std::deque<std::pair<char, int>> gc = done[pos].cigar;
+				if (meta[pos].tail_op) gc.push_back({meta[pos].tail_op, meta[pos].tail_len});
+				append_cigar(al.cigar, gc);
+				++pos;
+			} else if (qgap) append_cigar(al.cigar, {{'D', qgap}});
+			else if (rgap) append_cigar(al.cigar, {{'I', rgap}});
+			append_cigar(al.cigar, cu.cigar);
+		}
+		int qlo = hg.guide.front().start_a, rlo = hg.guide.front().start_b;
+		int qhi = hg.guide.back().end_a, rhi = hg.guide.back().end_b;
+		if (hg.side) {
+			if (pos < meta.size() && meta[pos].guide == gi && meta[pos].kind == LEFT) {
+				GuidedAlignment gap; gap.a = done[pos].a; gap.b = done[pos].b; gap.cigar = done[pos].cigar;
+				gap.start_a = gap.start_b = 0; gap.end_a = (int)gap.a.size(); gap.end_b = (int)gap.b.size();
+				trim_front(gap, p);
+				qlo -= gap.end_a - gap.start_a; rlo -= gap.end_b - gap.start_b;
+				prepend_cigar(al.cigar, gap.cigar);
+				++pos;
+			}
+			if (pos < meta.size() && meta[pos].guide == gi && meta[pos].kind == RIGHT) {
+				GuidedAlignment gap; gap.a = done[pos].a; gap.b = done[pos].b; gap.cigar = done[pos].cigar;
+				gap.start_a = gap.start_b = 0; gap.end_a = (int)gap.a.size(); gap.end_b = (int)gap.b.size();
+				trim_back(gap, p);
+				qhi += gap.end_a; rhi += gap.end_b;
+				append_cigar(al.cigar, gap.cigar);
+				++pos;
+			}
+		}
+		al.start_a = qlo; al.end_a = qhi; al.start_b = rlo; al.end_b = rhi;
+		al.a = qstr.substr(qlo, qhi - qlo); al.b = rstr.substr(rlo, rhi - rlo);
+		finals[gi] = {al.a, al.b};
+		final_cigars[gi] = al.cigar_string();
+	}
+	std::vector<Alignment> st = from_cigar_batch(finals, final_cigars);
+	for (size_t gi = 0; gi < guides.size(); ++gi) out[gi].stats = st[gi].stats;
+	return out;
+}
+
 } // namespace sedef_b200

@@ -33,9 +33,34 @@ static int run_chains()
 	return 0;
 }
 
+// mode "hitguide": line 1 = query region, line 2 = reference region, line 3 = side, then one guide hit per line:
+// query_start query_end ref_start ref_end cigar
+static int run_hitguide()
+{
+	std::string q, r, line;
+	std::getline(std::cin, q); std::getline(std::cin, r); std::getline(std::cin, line);
+	sedef_b200::HitGuide hg; hg.qstr = &q; hg.rstr = &r; hg.side = atoi(line.c_str());
+	while (std::getline(std::cin, line)) {
+		std::istringstream is(line);
+		sedef_b200::GuidedAlignment g; std::string cig;
+		if (!(is >> g.start_a >> g.end_a >> g.start_b >> g.end_b >> cig)) continue;
+		int num = 0;
+		for (char ch : cig) { if (ch >= '0' && ch <= '9') num = 10 * num + (ch - '0'); else { g.cigar.push_back({ch, num}); num = 0; } }
+		hg.guide.push_back(g);
+	}
+	std::vector<sedef_b200::GuidedAlignment> res;
+	try { res = sedef_b200::align_hit_guides_batch({hg}); }
+	catch (const std::exception &e) { fprintf(stderr, "error: %s\n", e.what()); return 2; }
+	for (auto &a : res)
+		printf("%d %d %d %d %s %d %d %d %d %d\n", a.start_a, a.end_a, a.start_b, a.end_b, a.cigar_string().c_str(), a.span(), a.matches(),
+		       a.mismatches(), a.gaps(), a.gap_bases());
+	return 0;
+}
+
 int main(int argc, char **argv)
 {
 	if (argc > 1 && std::string(argv[1]) == "chains") return run_chains();
+	if (argc > 1 && std::string(argv[1]) == "hitguide") return run_hitguide();
 	const bool from_cigar = argc > 1 && std::string(argv[1]) == "from_cigar";
 	std::vector<std::pair<std::string, std::string>> pairs;
 	std::vector<std::string> cigars;

@@ -125,7 +125,20 @@ def main():
                           "(src/chain.cc:211-258, src/align.cc:199-270); one line per chain: start_a end_a start_b end_b cigar span matches "
                           "mismatches gaps gap_bases n  q r l ...",
                    regions=cregs), open(os.path.join(HERE, "chain_wave_golden.json"), "w"))
-    for f in ("ksw2_kat.json", "ksw2_golden.json", "sd_stats_golden.json", "fast_align_golden.json", "chain_wave_golden.json"):
+    # ---- refine-wave golden: Alignment(qstr, rstr, vector<Hit> guide, side) of the reference (gap fills + side extensions + trims) ----
+    slib.ref_hit_guide.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_char_p, C.c_int]
+    hregs = []
+    for (L, div, seed, side) in [(2500, 0.03, 11, 500), (6000, 0.06, 12, 500), (9000, 0.10, 13, 500), (5000, 0.2, 14, 500),
+                                 (4000, 0.05, 15, 0), (7000, 0.3, 16, 500), (3000, 0.02, 17, 200)]:
+        qs, ts = synth.make_region_pair(L, div, seed=seed)
+        buf = C.create_string_buffer(1 << 22)
+        n = slib.ref_hit_guide(qs.encode(), ts.encode(), 11, side, buf, len(buf))
+        hregs.append(dict(length=L, div=div, seed=seed, side=side, n_guide=n, text=buf.value.decode()))
+    json.dump(dict(source="oracle/_ref/libsedef_ref.so: reference Alignment(qstr, rstr, vector<Hit> guide, side) (src/align.cc:107-197) on a "
+                          "co-linear guide of the reference's own chain alignments; line 1 = result, then the guide hits",
+                   regions=hregs), open(os.path.join(HERE, "hit_guide_golden.json"), "w"))
+    for f in ("ksw2_kat.json", "ksw2_golden.json", "sd_stats_golden.json", "fast_align_golden.json", "chain_wave_golden.json",
+              "hit_guide_golden.json"):
         print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")
 
 

@@ -371,3 +371,20 @@ def test_chain_wave_batched(checker, golden_dir):
         assert got == [" ".join(ln.split()[:10]) for ln in lines]
         total += len(lines)
     assert total >= 10
+
+
+def test_refine_wave_hit_guides_batched(checker, golden_dir):
+    """SURVEY section 8 f1, second wave: the C++ `align_hit_guides_batch` (gap fills between guide hits + the two +-side
+    extensions in ONE batched ksw_extz2 call, trim_front / trim_back on the host) against the reference's own
+    Alignment(qstr, rstr, vector<Hit> guide, side) constructor (tests/golden/hit_guide_golden.json)."""
+    import os, subprocess
+    drv = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "cpp", "align_queue_driver")
+    g = load_json(golden_dir, "hit_guide_golden.json")
+    for reg in g["regions"]:
+        q, t = synth.make_region_pair(reg["length"], reg["div"], seed=reg["seed"])
+        lines = [ln for ln in reg["text"].split("\n") if ln.strip()]
+        assert len(lines) == reg["n_guide"] + 1
+        text = q + "\n" + t + "\n" + str(reg["side"]) + "\n" + "\n".join(lines[1:]) + "\n"
+        out = subprocess.run([drv, "hitguide"], input=text, capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stderr
+        assert out.stdout.strip() == lines[0], (reg["seed"], reg["side"])

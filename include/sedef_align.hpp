@@ -79,6 +79,12 @@ std::vector<GuidedAlignment> align_hit_guides_batch(const std::vector<HitGuide> 
 void trim_front(GuidedAlignment &g, const AlignParams &p = AlignParams());
 void trim_back(GuidedAlignment &g, const AlignParams &p = AlignParams());
 
+// Alignment::merge (src/align.cc:505-610) for MANY (prev, cur) pairs: the overlap is trimmed from prev's tail and cur's
+// head on the host (column walks on the CIGARs), the gap fills of all pairs go through ONE batched ksw_extz2 call.
+// A refine path with several merges is processed level by level (k-th merge of every path per call).
+struct MergeRequest { GuidedAlignment prev, cur; const std::string *qstr, *rstr; };
+std::vector<GuidedAlignment> merge_batch(const std::vector<MergeRequest> &reqs, const AlignParams &p = AlignParams());
+
 // Deferred-alignment queue: call sites push requests, the driver flushes a whole wave at once.
 class AlignQueue {
 public:

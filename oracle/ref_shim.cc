@@ -143,4 +143,57 @@ int ref_hit_guide(const char *query, const char *ref, int kmer_size, int side, c
 	memcpy(out, sres.c_str(), sres.size() + 1);
 	return (int)guide.size();
 }
+// Alignment::merge (src/align.cc:505-610) on overlapping pairs of the reference's own chain alignments (what
+// refine_chains does at src/refine.cc:171-173).  Per merged pair three lines: "P ..." prev before, "C ..." cur before,
+// "M ..." result; each: start_a end_a start_b end_b cigar (+ span matches mismatches gaps gap_bases for M).
+int ref_merge_pairs(const char *query, const char *ref, int kmer_size, char *out, int cap)
+{
+	std::string q(query), r(ref);
+	auto qp = std::make_shared<Sequence>("QRY", q);
+	auto rp = std::make_shared<Sequence>("REF", r);
+	Hit orig{qp, 0, (int)q.size(), rp, 0, (int)r.size()};
+	auto anchors = generate_anchors(q, r, orig, kmer_size);
+	auto chains_init = chain_anchors(anchors);
+	auto &bounds = chains_init.second;
+	auto &chain = chains_init.first;
+	std::vector<Hit> hits;
+	for (int bi = 1; bi < (int)bounds.size(); bi++) {
+		int be = bounds[bi].first, bs = bounds[bi - 1].first;
+		std::vector<int> guide;
+		for (int k = be - 1; k >= bs; k--) guide.emplace_back(chain[k]);
+		if (guide.empty()) continue;
+		Hit h{qp, 0, 0, rp, 0, 0};
+		h.aln = Alignment(q, r, anchors, guide);
+		update_from_alignment(h);
+		hits.push_back(h);
+	}
+	std::sort(hits.begin(), hits.end());
+	std::ostringstream os;
+	int n = 0;
+	auto line = [&](char tag, const Hit &h, bool full) {
+		os << tag << ' ' << h.query_start << ' ' << h.query_end << ' ' << h.ref_start << ' ' << h.ref_end << ' ' << h.aln.cigar_string();
+		if (full) os << ' ' << h.aln.span() << ' ' << h.aln.matches() << ' ' << h.aln.mismatches() << ' ' << h.aln.gaps() << ' ' << h.aln.gap_bases();
+		os << '\n';
+	};
+	for (size_t i = 0; i < hits.size(); ++i)
+		for (size_t j = 0; j < hits.size(); ++j) {
+			if (i == j) continue;
+			Hit p = hits[i], c = hits[j];
+			// the preconditions merge() asserts (src/align.cc:506-508) plus strict progress, as on a refine path
+			if (!(c.query_start < p.query_end || c.ref_start < p.ref_end)) continue;
+			if (!(p.query_end <= c.query_end && p.ref_end <= c.ref_end)) continue;
+			if (!(p.query_start < c.query_start && p.ref_start < c.ref_start)) continue;
+			if (p.query_end - c.query_start > 2000 || p.ref_end - c.ref_start > 2000) continue;
+			line('P', p, false); line('C', c, false);
+			p.aln.merge(c.aln, q, r);
+			update_from_alignment(p);
+			line('M', p, true);
+			if (++n >= 40) goto done;
+		}
+done:
+	std::string sres = os.str();
+	if ((int)sres.size() + 1 > cap) return -1;
+	memcpy(out, sres.c_str(), sres.size() + 1);
+	return n;
+}
 }

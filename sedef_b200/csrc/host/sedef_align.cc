@@ -30,7 +30,8 @@ double Alignment::mismatch_error() const
 std::string Alignment::cigar_string() const
 {
 	std::string s;
-	for (auto &c : cigar) { s += std::to_string(c.second); s += c.first; }
+	for (auto &c : cigar)
+		if (c.second) { s += std::to_string(c.second); s += c.first; }               // zero-length runs are not printed
 	return s;
 }
 sd_stats_fp_t Alignment::bedpe_fp() const
@@ -90,29 +91,23 @@ std::vector<Alignment> align_batch(const std::vector<std::pair<std::string, std:
 	return out;
 }
 
-std::vector<Alignment> from_cigar_batch(const std::vector<std::pair<std::string, std::string>> &pairs,
-                                        const std::vector<std::string> &cigars)
+// statistics of alignments given as SEDEF-alphabet run lists (populate_nice_alignment, src/align.cc:274-315).
+// Zero-length runs are kept: the reference counts every non-M run in `gaps`, also the ('\0', 0) run that
+// cigar_from_alignment leaves for an alignment trimmed to nothing (src/align.cc:300-305,479-501).
+static std::vector<sd_stats_t> stats_of(const std::vector<std::pair<std::string, std::string>> &pairs,
+                                        const std::vector<std::deque<std::pair<char, int>>> &cigars)
 {
-	if (pairs.size() != cigars.size()) throw std::runtime_error("from_cigar_batch: size mismatch");
 	const int n = (int)pairs.size();
-	std::vector<Alignment> out(n);
 	std::vector<int64_t> coff(n), cn(n), ao(n), bo(n);
 	std::vector<int> al(n), bl(n);
 	std::vector<uint32_t> cbuf;
 	std::vector<uint8_t> abuf, bbuf;
 	for (int i = 0; i < n; ++i) {
-		out[i].a = pairs[i].first; out[i].b = pairs[i].second;
 		coff[i] = (int64_t)cbuf.size();
-		int num = 0;
-		for (char ch : cigars[i]) {                                                          // src/align.cc:94-103
-			if (ch >= '0' && ch <= '9') num = 10 * num + (ch - '0');
-			else if (ch == ';') continue;
-			else {
-				out[i].cigar.push_back({ch, num});
-				const uint32_t op = ch == 'M' ? 0u : (ch == 'D' ? 1u : (ch == 'I' ? 2u : 3u));   // SEDEF 'D' = a only = ksw I
-				cbuf.push_back((uint32_t)num << 4 | op);
-				num = 0;
-			}
+		for (auto &run : cigars[i]) {
+			const char ch = run.first;
+			uint32_t op = ch == 'M' ? 0u : (ch == 'D' ? 1u : (ch == 'I' ? 2u : (run.second == 0 ? 1u : 3u)));   // SEDEF 'D' = a only = ksw I
+			cbuf.push_back((uint32_t)run.second << 4 | op);
 		}
 		cn[i] = (int64_t)cbuf.size() - coff[i];
 		ao[i] = (int64_t)abuf.size(); bo[i] = (int64_t)bbuf.size();
@@ -126,10 +121,30 @@ std::vector<Alignment> from_cigar_batch(const std::vector<std::pair<std::string,
 	int rc = sd_stats_from_cigar_batch_flat(n, coff.data(), cn.data(), cbuf.data(), al.data(), ao.data(), abuf.data(),
 	                                       bl.data(), bo.data(), bbuf.data(), st.data(), status.data());
 	if (rc) throw std::runtime_error(std::string("sd_stats_from_cigar_batch_flat: ") + ksw_b200_strerror(rc) + " -- " + ksw_b200_last_error());
+	for (int i = 0; i < n; ++i)
+		if (status[i]) throw std::runtime_error("CIGAR " + std::to_string(i) + " overruns a sequence (the reference asserts, src/align.cc:281-282)");
+	return st;
+}
+
+std::vector<Alignment> from_cigar_batch(const std::vector<std::pair<std::string, std::string>> &pairs,
+                                        const std::vector<std::string> &cigars)
+{
+	if (pairs.size() != cigars.size()) throw std::runtime_error("from_cigar_batch: size mismatch");
+	const int n = (int)pairs.size();
+	std::vector<Alignment> out(n);
+	std::vector<std::deque<std::pair<char, int>>> runs(n);
 	for (int i = 0; i < n; ++i) {
-		if (status[i]) throw std::runtime_error("from_cigar_batch: CIGAR " + std::to_string(i) + " overruns a sequence (the reference asserts, src/align.cc:281-282)");
-		out[i].stats = st[i];
+		out[i].a = pairs[i].first; out[i].b = pairs[i].second;
+		int num = 0;
+		for (char ch : cigars[i]) {                                                          // src/align.cc:94-103
+			if (ch >= '0' && ch <= '9') num = 10 * num + (ch - '0');
+			else if (ch == ';') continue;
+			else { runs[i].push_back({ch, num}); num = 0; }
+		}
+		out[i].cigar = runs[i];
 	}
+	std::vector<sd_stats_t> st = stats_of(pairs, runs);
+	for (int i = 0; i < n; ++i) out[i].stats = st[i];
 	return out;
 }
 
@@ -172,7 +187,7 @@ std::vector<GuidedAlignment> align_chains_batch(const std::vector<ChainGuide> &c
 	// pass 2: stitch
 	std::vector<GuidedAlignment> out(chains.size());
 	std::vector<std::pair<std::string, std::string>> finals(chains.size());
-	std::vector<std::string> final_cigars(chains.size());
+	std::vector<std::deque<std::pair<char, int>>> final_cigars(chains.size());
 	size_t fpos = 0;
 	for (size_t ci = 0; ci < chains.size(); ++ci) {
 		const ChainGuide &cg = chains[ci];
@@ -200,11 +215,11 @@ std::vector<GuidedAlignment> align_chains_batch(const std::vector<ChainGuide> &c
 		al.a = cg.qstr->substr(al.start_a, al.end_a - al.start_a);
 		al.b = cg.rstr->substr(al.start_b, al.end_b - al.start_b);
 		finals[ci] = {al.a, al.b};
-		final_cigars[ci] = al.cigar_string();
+		final_cigars[ci] = al.cigar;
 	}
 	// populate_nice_alignment for every stitched alignment: one statistics-from-CIGAR call
-	std::vector<Alignment> st = from_cigar_batch(finals, final_cigars);
-	for (size_t ci = 0; ci < chains.size(); ++ci) out[ci].stats = st[ci].stats;
+	std::vector<sd_stats_t> st = stats_of(finals, final_cigars);
+	for (size_t ci = 0; ci < chains.size(); ++ci) out[ci].stats = st[ci];
 	return out;
 }
 
@@ -342,7 +357,7 @@ std::vector<GuidedAlignment> align_hit_guides_batch(const std::vector<HitGuide> 
 	std::vector<Alignment> done = align_batch(reqs, p);                                 // ONE batched ksw_extz2 call
 	std::vector<GuidedAlignment> out(guides.size());
 	std::vector<std::pair<std::string, std::string>> finals(guides.size());
-	std::vector<std::string> final_cigars(guides.size());
+	std::vector<std::deque<std::pair<char, int>>> final_cigars(guides.size());
 	size_t pos = 0;
 	for (size_t gi = 0; gi < guides.size(); ++gi) {
 		const HitGuide &hg = guides[gi];
@@ -385,10 +400,105 @@ std::vector<GuidedAlignment> align_hit_guides_batch(const std::vector<HitGuide> 
 		al.start_a = qlo; al.end_a = qhi; al.start_b = rlo; al.end_b = rhi;
 		al.a = qstr.substr(qlo, qhi - qlo); al.b = rstr.substr(rlo, rhi - rlo);
 		finals[gi] = {al.a, al.b};
-		final_cigars[gi] = al.cigar_string();
+		final_cigars[gi] = al.cigar;
 	}
-	std::vector<Alignment> st = from_cigar_batch(finals, final_cigars);
-	for (size_t gi = 0; gi < guides.size(); ++gi) out[gi].stats = st[gi].stats;
+	std::vector<sd_stats_t> st = stats_of(finals, final_cigars);
+	for (size_t gi = 0; gi < guides.size(); ++gi) out[gi].stats = st[gi];
+	return out;
+}
+
+// ---- merge ---------------------------------------------------------------------------------------------------------
+static std::vector<char> expand_ops(const std::deque<std::pair<char, int>> &cigar)
+{
+	std::vector<char> ops;
+	for (auto &c : cigar) ops.insert(ops.end(), c.second, c.first);
+	return ops;
+}
+// cigar_from_alignment (src/align.cc:479-501): an empty alignment yields the single run ('\0', 0)
+static std::deque<std::pair<char, int>> cigar_from_ops(const std::vector<char> &ops)
+{
+	std::deque<std::pair<char, int>> cigar;
+	int sz = 0; char op = 0;
+	for (char top : ops) {
+		if (op != top) { if (op) cigar.push_back({op, sz}); op = top; sz = 0; }
+		sz++;
+	}
+	cigar.push_back({op, sz});
+	return cigar;
+}
+// cut columns from the tail of `ops` until `lim` bases of a (by_a) / b have been removed; returns removed (q, r)
+static void cut_tail(std::vector<char> &ops, int lim, bool by_a, int &q, int &r)
+{
+	q = 0; r = 0;
+	while (!ops.empty() && (by_a ? q : r) < lim) {
+		const char op = ops.back(); ops.pop_back();
+		if (op != 'I') q++;                                              // align_a[i] != '-'
+		if (op != 'D') r++;                                              // align_b[i] != '-'
+	}
+}
+static void cut_head(std::vector<char> &ops, int lim, bool by_a, int &q, int &r)
+{
+	q = 0; r = 0;
+	size_t i = 0;
+	for (; i < ops.size() && (by_a ? q : r) < lim; ++i) {
+		if (ops[i] != 'I') q++;
+		if (ops[i] != 'D') r++;
+	}
+	ops.erase(ops.begin(), ops.begin() + i);
+}
+
+std::vector<GuidedAlignment> merge_batch(const std::vector<MergeRequest> &reqs, const AlignParams &p)
+{
+	struct Work { GuidedAlignment prev, cur; int fill = -1; char tail_op = 0; int tail_len = 0; int qgap = 0, rgap = 0; };
+	std::vector<Work> work(reqs.size());
+	std::vector<std::pair<std::string, std::string>> fills;
+	for (size_t k = 0; k < reqs.size(); ++k) {
+		Work &w = work[k];
+		w.prev = reqs[k].prev; w.cur = reqs[k].cur;
+		const std::string &qstr = *reqs[k].qstr, &rstr = *reqs[k].rstr;
+		std::vector<char> po = expand_ops(w.prev.cigar), co = expand_ops(w.cur.cigar);
+		int q, r;
+		int trim = w.prev.end_a - w.cur.start_a;                                           // src/align.cc:510-538
+		cut_tail(po, trim, true, q, r); w.prev.end_a -= q; w.prev.end_b -= r;
+		cut_head(co, trim, true, q, r); w.cur.start_a += q; w.cur.start_b += r;
+		trim = w.prev.end_b - w.cur.start_b;                                               // src/align.cc:540-568
+		cut_tail(po, trim, false, q, r); w.prev.end_a -= q; w.prev.end_b -= r;
+		cut_head(co, trim, false, q, r); w.cur.start_a += q; w.cur.start_b += r;
+		w.prev.cigar = cigar_from_ops(po); w.cur.cigar = cigar_from_ops(co);               // src/align.cc:570-571
+		w.qgap = w.cur.start_a - w.prev.end_a; w.rgap = w.cur.start_b - w.prev.end_b;
+		if (w.qgap && w.rgap) {                                                            // src/align.cc:579-594
+			w.fill = (int)fills.size();
+			if (w.qgap <= 1000 && w.rgap <= 1000) fills.emplace_back(qstr.substr(w.prev.end_a, w.qgap), rstr.substr(w.prev.end_b, w.rgap));
+			else {
+				const int ma = std::max(w.qgap, w.rgap), mi = std::min(w.qgap, w.rgap);
+				fills.emplace_back(qstr.substr(w.prev.end_a, mi), rstr.substr(w.prev.end_b, mi));
+				w.tail_op = w.qgap == mi ? 'I' : 'D'; w.tail_len = ma - mi;
+			}
+		}
+	}
+	std::vector<Alignment> done = align_batch(fills, p);                                  // ONE batched ksw_extz2 call
+	std::vector<GuidedAlignment> out(reqs.size());
+	std::vector<std::pair<std::string, std::string>> finals(reqs.size());
+	std::vector<std::deque<std::pair<char, int>>> final_cigars(reqs.size());
+	for (size_t k = 0; k < reqs.size(); ++k) {
+		Work &w = work[k];
+		GuidedAlignment &al = out[k];
+		al = w.prev;
+		if (w.fill >= 0) {
+			std::deque<std::pair<char, int>> gc = done[w.fill].cigar;
+			if (w.tail_op) gc.push_back({w.tail_op, w.tail_len});
+			append_cigar(al.cigar, gc);
+		} else if (w.qgap) append_cigar(al.cigar, {{'D', w.qgap}});
+		else if (w.rgap) append_cigar(al.cigar, {{'I', w.rgap}});
+		al.end_a = w.cur.end_a; al.end_b = w.cur.end_b;
+		append_cigar(al.cigar, w.cur.cigar);
+		al.a = reqs[k].qstr->substr(al.start_a, al.end_a - al.start_a);
+		al.b = reqs[k].rstr->substr(al.start_b, al.end_b - al.start_b);
+		finals[k] = {al.a, al.b};
+		final_cigars[k] = al.cigar;
+	}
+	std::vector<sd_stats_t> st = stats_of(finals, final_cigars);
+	for (size_t k = 0; k < reqs.size(); ++k) out[k].stats = st[k];
 	return out;
 }
 

@@ -57,8 +57,39 @@ static int run_hitguide()
 	return 0;
 }
 
+static sedef_b200::GuidedAlignment parse_hit(std::istringstream &is)
+{
+	sedef_b200::GuidedAlignment g; std::string cig;
+	is >> g.start_a >> g.end_a >> g.start_b >> g.end_b >> cig;
+	int num = 0;
+	for (char ch : cig) { if (ch >= '0' && ch <= '9') num = 10 * num + (ch - '0'); else { g.cigar.push_back({ch, num}); num = 0; } }
+	return g;
+}
+// mode "merge": line 1 = query region, line 2 = reference region, then pairs of lines "P ..." / "C ..." (hit format)
+static int run_merge()
+{
+	std::string q, r, line;
+	std::getline(std::cin, q); std::getline(std::cin, r);
+	std::vector<sedef_b200::MergeRequest> reqs;
+	sedef_b200::GuidedAlignment prev;
+	while (std::getline(std::cin, line)) {
+		std::istringstream is(line);
+		char tag; if (!(is >> tag)) continue;
+		if (tag == 'P') prev = parse_hit(is);
+		else if (tag == 'C') reqs.push_back({prev, parse_hit(is), &q, &r});
+	}
+	std::vector<sedef_b200::GuidedAlignment> res;
+	try { res = sedef_b200::merge_batch(reqs); }
+	catch (const std::exception &e) { fprintf(stderr, "error: %s\n", e.what()); return 2; }
+	for (auto &a : res)
+		printf("M %d %d %d %d %s %d %d %d %d %d\n", a.start_a, a.end_a, a.start_b, a.end_b, a.cigar_string().c_str(), a.span(), a.matches(),
+		       a.mismatches(), a.gaps(), a.gap_bases());
+	return 0;
+}
+
 int main(int argc, char **argv)
 {
+	if (argc > 1 && std::string(argv[1]) == "merge") return run_merge();
 	if (argc > 1 && std::string(argv[1]) == "chains") return run_chains();
 	if (argc > 1 && std::string(argv[1]) == "hitguide") return run_hitguide();
 	const bool from_cigar = argc > 1 && std::string(argv[1]) == "from_cigar";

@@ -137,8 +137,18 @@ def main():
     json.dump(dict(source="oracle/_ref/libsedef_ref.so: reference Alignment(qstr, rstr, vector<Hit> guide, side) (src/align.cc:107-197) on a "
                           "co-linear guide of the reference's own chain alignments; line 1 = result, then the guide hits",
                    regions=hregs), open(os.path.join(HERE, "hit_guide_golden.json"), "w"))
+    # ---- merge golden: Alignment::merge of the reference on overlapping pairs of its own chain alignments ----
+    slib.ref_merge_pairs.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_char_p, C.c_int]
+    mregs = []
+    for (L, div, seed) in [(2500, 0.03, 11), (6000, 0.06, 12), (9000, 0.10, 13), (5000, 0.2, 14), (7000, 0.3, 16), (12000, 0.15, 18)]:
+        qs, ts = synth.make_region_pair(L, div, seed=seed)
+        buf = C.create_string_buffer(1 << 22)
+        n = slib.ref_merge_pairs(qs.encode(), ts.encode(), 11, buf, len(buf))
+        mregs.append(dict(length=L, div=div, seed=seed, n_merges=n, text=buf.value.decode()))
+    json.dump(dict(source="oracle/_ref/libsedef_ref.so: reference Alignment::merge (src/align.cc:505-610); per pair: P prev, C cur, M merged",
+                   regions=mregs), open(os.path.join(HERE, "merge_golden.json"), "w"))
     for f in ("ksw2_kat.json", "ksw2_golden.json", "sd_stats_golden.json", "fast_align_golden.json", "chain_wave_golden.json",
-              "hit_guide_golden.json"):
+              "hit_guide_golden.json", "merge_golden.json"):
         print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")
 
 

@@ -388,3 +388,25 @@ def test_refine_wave_hit_guides_batched(checker, golden_dir):
         out = subprocess.run([drv, "hitguide"], input=text, capture_output=True, text=True, timeout=300)
         assert out.returncode == 0, out.stderr
         assert out.stdout.strip() == lines[0], (reg["seed"], reg["side"])
+
+
+def test_merge_batched(checker, golden_dir):
+    """the C++ `merge_batch` (overlap trimming on the host, every gap fill in ONE batched call) against the
+    reference's own Alignment::merge on overlapping pairs of its own chain alignments (tests/golden/merge_golden.json)."""
+    import os, subprocess
+    drv = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "cpp", "align_queue_driver")
+    g = load_json(golden_dir, "merge_golden.json")
+    total = 0
+    for reg in g["regions"]:
+        q, t = synth.make_region_pair(reg["length"], reg["div"], seed=reg["seed"])
+        lines = [ln for ln in reg["text"].split("\n") if ln.strip()]
+        want = [ln for ln in lines if ln.startswith("M ")]
+        assert len(want) == reg["n_merges"]
+        if not want:
+            continue
+        text = q + "\n" + t + "\n" + "\n".join(ln for ln in lines if ln[0] in "PC") + "\n"
+        out = subprocess.run([drv, "merge"], input=text, capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stderr
+        assert [ln for ln in out.stdout.split("\n") if ln.strip()] == want, reg["seed"]
+        total += len(want)
+    assert total >= 10

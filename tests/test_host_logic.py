@@ -59,10 +59,19 @@ def test_two_rank_gloo_sharding(tmp_path):
         "tot = work.clone(); dist.all_reduce(tot)\n"
         "assert int(mask.min()) == 1 and int(mask.max()) == 1, 'shards must partition the pairs'\n"
         "assert float(mx) / (float(tot) / w) < 1.02, 'LPT shards must be balanced'\n"
-        "dist.barrier(); print('rank', r, 'ok')\n")
+        # one marker file per rank: stdout is shared between the ranks and their writes interleave
+        f"open(os.path.join({str(tmp_path)!r}, 'rank%d.ok' % r), 'w').write('%d %d' % (r, len(idx)))\n"
+        "dist.barrier()\n")
     env = dict(os.environ, MASTER_ADDR="127.0.0.1")
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
                           "--master-addr", "127.0.0.1", "--master-port", "29577", str(script)],
                          capture_output=True, text=True, env=env, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
-    assert "rank 0 ok" in out.stdout and "rank 1 ok" in out.stdout
+    sizes = []
+    for r in range(2):
+        marker = tmp_path / f"rank{r}.ok"
+        assert marker.exists(), f"rank {r} did not finish: " + out.stdout + out.stderr
+        rr, n = map(int, marker.read_text().split())
+        assert rr == r and n > 0
+        sizes.append(n)
+    assert sum(sizes) == 301

@@ -30,6 +30,7 @@
 #include "../../include/ksw2_b200.h"
 #include "extz_core.cuh"
 #include "extz_dp.cuh"
+#include "extz_dp16.cuh"
 #include "extz_tb.cuh"
 
 using namespace extz;
@@ -72,9 +73,20 @@ static const int kNumClasses = sizeof(kClasses) / sizeof(kClasses[0]);
 static const int kNumSizedClasses = kNumClasses;                        // all classes are ordered by capacity
 static inline int class_ns(int c) { return kClasses[c].G * kClasses[c].S; }
 // S == 32 lanes switch whole-lane (two 16-blocks), which costs 16 slots of window (extz_dp.cuh)
-static inline int class_capacity(int c) { return kClasses[c].S > 16 ? class_ns(c) - 16 : class_ns(c); }
+// The narrow classes (up to 1024 live slots) run the PACKED kernel (extz_dp16.cuh: two slots per register, NS / 32 lanes
+// per pair) unless KSW_B200_PACKED=0 selects the one-slot-per-register kernels of extz_dp.cuh for A/B runs.
+static inline bool packed_enabled()
+{
+	static const bool on = [] { const char *e = getenv("KSW_B200_PACKED"); return !(e && e[0] == '0'); }();
+	return on;
+}
+static inline bool class_packed(int c) { return packed_enabled() && !kClasses[c].wide && !kClasses[c].cluster; }
+static inline int class_capacity(int c) { return (kClasses[c].S > 16 && !class_packed(c)) ? class_ns(c) - 16 : class_ns(c); }
 static inline int class_threads(int c) { return kClasses[c].cluster ? 256 : (kClasses[c].wide ? kClasses[c].G : 128); }
-static inline int class_pairs_per_block(int c) { return kClasses[c].wide ? 1 : 128 / kClasses[c].G; }
+static inline int class_pairs_per_block(int c)
+{
+	return kClasses[c].wide ? 1 : (class_packed(c) ? 128 * 32 / class_ns(c) : 128 / kClasses[c].G);
+}
 
 // kernel selection: every (class, cigar, right) combination is a distinct instantiation
 template <int G, int S, bool W, bool C, bool R> struct KSel;
@@ -125,6 +137,30 @@ static cudaError_t cluster_dispatch(const DpLaunch &L, bool cigar, bool right, i
 	                        : cluster_launch_one<C, true, false>(L, nclusters, st, max_clusters);
 	return cluster_launch_one<C, false, false>(L, nclusters, st, max_clusters);
 }
+// packed narrow kernels: G lanes x 32 slots
+template <int G>
+static cudaError_t launch_dp16(const DpLaunch &L, bool cigar, bool right, int grid, cudaStream_t st)
+{
+	if (cigar) {
+		if (right) extz_dp16_kernel<G, true, true><<<grid, 128, 0, st>>>(L);
+		else       extz_dp16_kernel<G, true, false><<<grid, 128, 0, st>>>(L);
+	} else       extz_dp16_kernel<G, false, false><<<grid, 128, 0, st>>>(L);
+	return cudaGetLastError();
+}
+template <int G>
+static int dp16_occupancy(bool cigar, bool right)
+{
+	int nb = 0;
+	if (cigar) {
+		if (right) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, extz_dp16_kernel<G, true, true>, 128, 0);
+		else       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, extz_dp16_kernel<G, true, false>, 128, 0);
+	} else       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, extz_dp16_kernel<G, false, false>, 128, 0);
+	return nb;
+}
+#define EXTZ_FOR_PACKED(ns, CALL) \
+	switch (ns) { \
+	case 32: return CALL(1); case 64: return CALL(2); case 128: return CALL(4); \
+	case 256: return CALL(8); case 512: return CALL(16); case 1024: return CALL(32); }
 #define EXTZ_FOR_CLASS(c, CALL) \
 	switch (c) { \
 	case 0: return CALL(2, 16, false); case 1: return CALL(4, 16, false); case 2: return CALL(8, 16, false); \
@@ -135,6 +171,12 @@ static cudaError_t launch_dp(int c, const DpLaunch &L, bool cigar, bool right, i
 {
 	if (kClasses[c].cluster == 2) return cluster_dispatch<2>(L, cigar, right, grid, st, nullptr);
 	if (kClasses[c].cluster == 4) return cluster_dispatch<4>(L, cigar, right, grid, st, nullptr);
+	if (class_packed(c)) {
+#define EXTZ_CALL16(G) launch_dp16<G>(L, cigar, right, grid, st)
+		EXTZ_FOR_PACKED(class_ns(c), EXTZ_CALL16)
+#undef EXTZ_CALL16
+		return cudaErrorInvalidValue;
+	}
 #define EXTZ_CALL(G, S, W) launch_dp_gs<G, S, W>(L, cigar, right, grid, st)
 	EXTZ_FOR_CLASS(c, EXTZ_CALL)
 #undef EXTZ_CALL
@@ -149,6 +191,12 @@ static int dp_occupancy(int c, bool cigar, bool right)
 		                                         : cluster_dispatch<4>(dummy, cigar, right, 1, nullptr, &n);
 		if (e != cudaSuccess) { cudaGetLastError(); return 0; }
 		return n;
+	}
+	if (class_packed(c)) {
+#define EXTZ_CALL16(G) dp16_occupancy<G>(cigar, right)
+		EXTZ_FOR_PACKED(class_ns(c), EXTZ_CALL16)
+#undef EXTZ_CALL16
+		return 0;
 	}
 #define EXTZ_CALL(G, S, W) dp_occupancy_gs<G, S, W>(cigar, right, 0)
 	EXTZ_FOR_CLASS(c, EXTZ_CALL)
@@ -654,7 +702,7 @@ static int launch_sub(ksw_b200_batch &B, SubBatch &sb)
 			TL.cigar_arena = (uint32_t *)sb.d_cigar.p; TL.cigar_cursor = d_cursor; TL.cigar_capacity = sb.cigar_cap;
 			TL.stats = B.want_stats ? (sd_stats_t *)sb.d_stats.p + wv.first : nullptr;
 			TL.overflow = d_overflow;
-			TL.n = wv.count; TL.NS = class_ns(c); TL.flag = B.flag;
+			TL.n = wv.count; TL.NS = class_ns(c); TL.flag = B.flag; TL.packed = class_packed(c) ? 1 : 0;
 			int tgrid = (wv.count + 127) / 128;
 			if (B.want_stats) extz_traceback_kernel<true><<<tgrid, 128, 0, st>>>(TL);
 			else extz_traceback_kernel<false><<<tgrid, 128, 0, st>>>(TL);

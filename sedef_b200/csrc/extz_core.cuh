@@ -178,11 +178,16 @@ EXTZ_HD bool ez_apply_zdrop(EzState &z, int32_t H, int r, int t, int zdrop, int 
 // Lane L of the group owns nibbles [L*S, L*S+S) = S/2 contiguous bytes, so a group writes one
 // contiguous NS/2-byte segment per diagonal (S=8: one 32-bit word per lane, 128 B per warp).
 EXTZ_HD int64_t tb_row_bytes(int NS) { return NS >> 1; }
-EXTZ_HD uint32_t tb_fetch(const uint8_t *tb_pair, int NS, int64_t r, int t)
+//
+// Packed kernel (extz_dp16.cuh): same row size; a lane owns 16 bytes, byte i of lane L holds slot 32L + i in its
+// low nibble (block A) and slot 32L + 16 + i in its high nibble (block B).
+EXTZ_HD uint32_t tb_fetch(const uint8_t *tb_pair, int NS, int64_t r, int t, bool packed = false)
 {
 	int c = t & (NS - 1);
-	uint8_t byte = tb_pair[r * (int64_t)(NS >> 1) + (c >> 1)];
-	return (byte >> ((c & 1) * 4)) & 0xfu;
+	int byte_idx = packed ? (((c >> 5) << 4) | (c & 15)) : (c >> 1);
+	int nib = packed ? ((c >> 4) & 1) : (c & 1);
+	uint8_t byte = tb_pair[r * (int64_t)(NS >> 1) + byte_idx];
+	return (byte >> (nib * 4)) & 0xfu;
 }
 
 // ---- ksw_backtrack (extern/ksw2.h:117-151, is_rot = 1) + fused SD statistics -------------------------

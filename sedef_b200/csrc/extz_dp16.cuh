@@ -1,0 +1,425 @@
+// extz_dp16.cuh -- the PACKED anti-diagonal DP kernel: two cells per 32-bit register lane-op.
+//
+// Same recurrence, band geometry, bookkeeping and bit-exactness contract as extz_dp.cuh (which see); what changes is
+// the representation.  Every u/v/x/y/z value is the reference's int8 kept in the TOP BYTE OF A 16-BIT HALF (value << 8,
+// low byte 0), two slots per register.  16-bit wrap-around of a multiple of 256 is exactly the reference's int8
+// wrap-around, signed / unsigned 16-bit compares are exactly _mm_cmpgt_epi8 / _mm_max_epu8 / _mm_min_epu8, and the
+// sm_100a packed integer instructions (VIADD.16x2, VIMNMX.{S,U}16x2 with per-half predicate outputs) process both
+// slots in ONE ALU-pipe issue slot -- the pipe that bounds this kernel (profiles/r01_int_peak.json: VIADD.16x2 and
+// VIMNMX.16x2 issue at the same 64 lanes/clk/SM as their 32-bit forms).
+//
+// sm_100a has no packed subtract.  z - v is computed as ~(~z + v): per half ~X = -X - 1, so ~z + v = -(z - v) - 1 and
+// the outer complement gives z - v with a clean (zero) low byte; z - q is folded into one add of ~z + (q + 1).
+//
+// Lane layout: a lane owns TWO 16-slot blocks, block A in the low halves and block B in the high halves of its 16
+// state registers, i.e. register i holds slots (tA + i, tB + i).  The blocks are the 2G "virtual lanes" of the pair:
+// virtual lane 2l is block A of lane l, 2l+1 its block B; virtual lane v owns the slots congruent to [16v, 16v+16)
+// modulo NS = 32 G and slides by NS when the band has left it -- each block independently, so the window holds NS
+// live slots like the S = 16 classes of extz_dp.cuh.  Neighbour slot i-1 is register i-1 for both halves at once; the
+// carries into register 0 are the predecessor lane's block-B top (one shuffle, into the low half) and the lane's own
+// block-A top (into the high half).
+//
+// There is no per-block "active" branch on the cell path: all 32 slots of a lane are computed on every anti-diagonal.
+// Blocks outside the rounded band [st, en] compute garbage, which is harmless because
+//   * a block below st is never read again (its storage is re-initialised when it slides),
+//   * a block above en is zeroed (u, v, x, y) on the anti-diagonal it enters the band -- the state calloc() gave it
+//     in the reference (extern/ksw2_extz2_sse.cc:83) -- while its z (the persistent s[] of :124-141, which the
+//     reference's score fill does write up to 15 slots beyond en) is never touched by the cell code,
+//   * their lazy-H entries sit at ~KSW_NEG_INF and their traceback nibbles are never visited.
+#pragma once
+#include <cuda_runtime.h>
+#include "extz_dp.cuh"
+
+namespace extz {
+
+struct Sc16 {
+	uint32_t q16;        // q << 8
+	uint32_t qeps2;      // (q << 8) + 1 in both halves: ~z + qeps2 == q - z
+	uint32_t maxsc2;     // max_sc_ (:69) in both halves
+	uint32_t s0_2;       // z of a never-filled slot in both halves
+	uint32_t zr;         // 0, but not a compile-time constant (see cell2)
+};
+__device__ __forceinline__ Sc16 make_sc16(const Scoring &sc)
+{
+	Sc16 s;
+	s.q16 = sc.q_s >> 16;
+	s.qeps2 = s.q16 * 0x00010001u + 0x00010001u;
+	s.maxsc2 = (sc.maxsc_s >> 16) * 0x00010001u;
+	s.s0_2 = (sc.s0_s >> 16) * 0x00010001u;
+	s.zr = sc.q_s & 0x00ffffffu;
+	return s;
+}
+
+// ---- the recurrence for the two slots of one register (:36-47 and the traceback arms :175-218) ----
+// SH: bit position of this register's code byte in the code word `cw` (low nibble: block A slot, high nibble: block B).
+// __vibmax_s16x2(a, b, &hi, &lo) returns max(a, b) per half and the predicates (a >= b).
+// CAUTION (ptxas 12.9, tools/probes/vibmax_probe.cu): when the FIRST operand is a compile-time constant ptxas commutes
+// the operands of the fused VIMNMX and the predicates come out wrong.  The zero operand of the strict "> 0" tests is
+// therefore sc.zr, a run-time zero.
+template <bool kRight, bool kCigar, int SH>
+__device__ __forceinline__ void cell2(uint32_t z, uint32_t xt1, uint32_t vt1, uint32_t &U, uint32_t &V, uint32_t &X, uint32_t &Y,
+                                      const Sc16 &sc, uint32_t &cw)
+{
+	const uint32_t ut = U;
+	const uint32_t a = __vadd2(xt1, vt1);                                  // :36
+	const uint32_t b = __vadd2(Y, ut);                                     // :38
+	bool h0 = false, l0 = false, h1 = false, l1 = false, h2 = false, l2 = false, h3 = false, l3 = false;
+	uint32_t z1;
+	if (!kCigar) z1 = __vmaxs2(z, a);                                      // :153
+	else if (!kRight) {
+		z1 = __vibmax_s16x2(z, a, &h0, &l0);                               // :175-177  d = a > z ? 1 : 0   (bit = !(z >= a))
+		(void)__vibmax_s16x2(z1, b, &h1, &l1);                             // :178-179  d = b > z ? 2 : d   (bit = !(z >= b))
+	} else {
+		z1 = __vibmax_s16x2(a, z, &h0, &l0);                               // :201-203  d = z > a ? 0 : 1   (bit = (a >= z))
+		(void)__vibmax_s16x2(b, z1, &h1, &l1);                             // :204-205  d = z > b ? d : 2   (bit = (b >= z))
+	}
+	const uint32_t zz = __vminu2(__vmaxu2(z1, b), sc.maxsc2);              // :41-42
+	const uint32_t cz = ~zz;
+	U = ~__vadd2(cz, vt1);                                                 // :43  z - v(t-1)
+	V = ~__vadd2(cz, ut);                                                  // :44  z - u(t)
+	const uint32_t t = __vadd2(cz, sc.qeps2);                              // :45  -(z - q)
+	if (!kCigar) {
+		X = __viaddmax_s16x2(a, t, 0u);                                    // :46,160
+		Y = __viaddmax_s16x2(b, t, 0u);                                    // :47,161
+		return;
+	}
+	const uint32_t a2 = __vadd2(a, t), b2 = __vadd2(b, t);                 // :46-47
+	if (!kRight) {
+		X = __vibmax_s16x2(sc.zr, a2, &h2, &l2);                              // :187-189  bit = a > 0 = !(0 >= a)
+		Y = __vibmax_s16x2(sc.zr, b2, &h3, &l3);                              // :190-192
+		if (!l0) cw |= 0x01u << SH;
+		if (!l1) cw |= 0x02u << SH;
+		if (!l2) cw |= 0x04u << SH;
+		if (!l3) cw |= 0x08u << SH;
+		if (!h0) cw |= 0x10u << SH;
+		if (!h1) cw |= 0x20u << SH;
+		if (!h2) cw |= 0x40u << SH;
+		if (!h3) cw |= 0x80u << SH;
+	} else {
+		X = __vibmax_s16x2(a2, 0u, &h2, &l2);                              // :213-215  bit = !(0 > a) = (a >= 0)
+		Y = __vibmax_s16x2(b2, 0u, &h3, &l3);                              // :216-218
+		if (l0) cw |= 0x01u << SH;
+		if (l1) cw |= 0x02u << SH;
+		if (l2) cw |= 0x04u << SH;
+		if (l3) cw |= 0x08u << SH;
+		if (h0) cw |= 0x10u << SH;
+		if (h1) cw |= 0x20u << SH;
+		if (h2) cw |= 0x40u << SH;
+		if (h3) cw |= 0x80u << SH;
+	}
+}
+
+// sign-extended top byte of the low / high half.  prmt's selector nibble 8+k replicates the sign bit of byte k;
+// __byte_perm() masks the selector to 3 bits per nibble, hence the inline PTX.
+__device__ __forceinline__ int32_t sext_lo(uint32_t v) { int32_t r; asm("prmt.b32 %0, %1, %1, 0x9991;" : "=r"(r) : "r"(v)); return r; }
+__device__ __forceinline__ int32_t sext_hi(uint32_t v) { int32_t r; asm("prmt.b32 %0, %1, %1, 0xbbb3;" : "=r"(r) : "r"(v)); return r; }
+
+// ---- per-lane state ----
+struct Lane16 {
+	uint32_t U[16], V[16], X[16], Y[16];   // register i: low half = slot t0[0] + i (block A), high half = slot t0[1] + i (block B)
+	uint32_t Z[16];                         // s + 2(q+e), persistent / stale-aware like LaneState::Z
+	uint32_t TW[8], QW[8];                  // [0..3] block A, [4..7] block B: byte i = 32 * target[t0 + i] / 4 * query[r - (t0 + i)]
+	int t0[2];
+};
+
+template <int HALF>
+__device__ __forceinline__ void lane16_load_seq(Lane16 &ls, const uint8_t *tseq, int tlen, const uint8_t *qseq, int r)
+{
+#pragma unroll
+	for (int k = 0; k < 4; ++k) {
+		uint32_t tw = 0, qw = 0;
+#pragma unroll
+		for (int b = 0; b < 4; ++b) {
+			const int t = ls.t0[HALF] + 4 * k + b;
+			tw |= (t < tlen ? ld_u8(tseq + t) << 5 : 0u) << (8 * b);
+			qw |= qbyte4(qseq, r - 1 - t) << (8 * b);
+		}
+		ls.TW[HALF * 4 + k] = tw; ls.QW[HALF * 4 + k] = qw;
+	}
+}
+template <int HALF>
+__device__ __forceinline__ void lane16_zero_state(Lane16 &ls)
+{
+	constexpr uint32_t keep = HALF ? 0x0000ffffu : 0xffff0000u;
+#pragma unroll
+	for (int i = 0; i < 16; ++i) { ls.U[i] &= keep; ls.V[i] &= keep; ls.X[i] &= keep; ls.Y[i] &= keep; }
+}
+template <int HALF>
+__device__ __forceinline__ void lane16_reset_z(Lane16 &ls, uint32_t s0_2)
+{
+	constexpr uint32_t keep = HALF ? 0x0000ffffu : 0xffff0000u;
+#pragma unroll
+	for (int i = 0; i < 16; ++i) ls.Z[i] = (ls.Z[i] & keep) | (s0_2 & ~keep);
+}
+
+// window slide / band entry, query shift, top-row boundary and score fill for one anti-diagonal
+template <int NS>
+__device__ __forceinline__ void lane16_prepare(Lane16 &ls, const Band &b, int r, int last_en, const uint8_t *qseq, const uint8_t *tseq,
+                                               int tlen, uint32_t table_saddr, const Sc16 &sc)
+{
+	// block left the rounded band: take the slots NS further up (z back to its calloc'ed value, fresh sequence bytes)
+	if (ls.t0[0] + 15 < b.st) { ls.t0[0] += NS; lane16_load_seq<0>(ls, tseq, tlen, qseq, r); lane16_reset_z<0>(ls, sc.s0_2); }
+	if (ls.t0[1] + 15 < b.st) { ls.t0[1] += NS; lane16_load_seq<1>(ls, tseq, tlen, qseq, r); lane16_reset_z<1>(ls, sc.s0_2); }
+	// block enters the rounded band: u, v, x, y are the reference's calloc'ed zeros (whatever was computed above en is dropped)
+	if (ls.t0[0] <= b.en && ls.t0[0] > last_en) lane16_zero_state<0>(ls);
+	if (ls.t0[1] <= b.en && ls.t0[1] > last_en) lane16_zero_state<1>(ls);
+	// the query slides past the slots by one per anti-diagonal
+#pragma unroll
+	for (int h = 0; h < 2; ++h) {
+		const uint32_t nb = qbyte4(qseq, r - ls.t0[h]);
+#pragma unroll
+		for (int k = 3; k > 0; --k) ls.QW[h * 4 + k] = __funnelshift_l(ls.QW[h * 4 + k - 1], ls.QW[h * 4 + k], 8);
+		ls.QW[h * 4] = (ls.QW[h * 4] << 8) | nb;
+	}
+	// top-row boundary (:122): y[r] = 0, u[r] = r ? q : 0 when the rounded range reaches slot r
+	if (b.en >= r) {
+		const uint32_t uq = r ? sc.q16 : 0u;
+		const int kA = r - ls.t0[0], kB = r - ls.t0[1];
+		if ((unsigned)kA < 16u) {
+#pragma unroll
+			for (int i = 0; i < 16; ++i) if (kA == i) { ls.Y[i] &= 0xffff0000u; ls.U[i] = (ls.U[i] & 0xffff0000u) | uq; }
+		}
+		if ((unsigned)kB < 16u) {
+#pragma unroll
+			for (int i = 0; i < 16; ++i) if (kB == i) { ls.Y[i] &= 0x0000ffffu; ls.U[i] = (ls.U[i] & 0x0000ffffu) | (uq << 16); }
+		}
+	}
+	// score fill (:124-141): slots st0..fe get a fresh s, all others keep the stale one
+	uint32_t fillmask = 0;
+#pragma unroll
+	for (int h = 0; h < 2; ++h) {
+		int lo = b.st0 - ls.t0[h], hi = b.fe - ls.t0[h] + 1;
+		lo = lo < 0 ? 0 : (lo > 16 ? 16 : lo);
+		hi = hi < 0 ? 0 : (hi > 16 ? 16 : hi);
+		const uint32_t m = hi > lo ? (((1u << hi) - 1u) & ~((1u << lo) - 1u)) : 0u;
+		fillmask |= m << (16 * h);
+	}
+#pragma unroll
+	for (int k = 0; k < 4; ++k) {
+		const uint32_t offA = ls.TW[k] + ls.QW[k], offB = ls.TW[4 + k] + ls.QW[4 + k];   // byte b: 32*target + 4*query <= 252
+#pragma unroll
+		for (int bb = 0; bb < 4; ++bb) {
+			const int i = 4 * k + bb;
+			const uint32_t zA = lds_u32(table_saddr + __byte_perm(offA, 0u, 0x4440 | bb));
+			const uint32_t zB = lds_u32(table_saddr + __byte_perm(offB, 0u, 0x4440 | bb));
+			if (fillmask & (1u << i)) ls.Z[i] = __byte_perm(ls.Z[i], zA, 0x3254);          // low half <- table entry
+			if (fillmask & (1u << (16 + i))) ls.Z[i] = __byte_perm(ls.Z[i], zB, 0x5410);   // high half <- table entry
+		}
+	}
+}
+
+// the cells of one anti-diagonal for this lane, traceback codes, u' dump and lazy-H update (:233-255).
+// Hrow / Urow point at this thread's column of the CTA-wide row arrays: row k of the thread is Hrow[k * 128].
+// H rows 2j / 2j+1 hold slots 4j..4j+3 of block A / block B; U row j holds registers 4j..4j+3.
+template <bool kCigar, bool kRight>
+__device__ __forceinline__ int32_t lane16_cells(Lane16 &ls, const Band &b, int r, int last_st, uint32_t xin, uint32_t vin,
+                                                uint4 *tb_dst, int4 *Hrow, uint4 *Urow, const Sc16 &sc)
+{
+	// carry into the first slot of a block that starts the rounded range (:117-121)
+	if (ls.t0[0] == b.st || ls.t0[1] == b.st) {
+		const uint32_t keep = ls.t0[0] == b.st ? 0xffff0000u : 0x0000ffffu;
+		if (b.st > 0) { if (!(b.st > last_st)) { xin &= keep; vin &= keep; } }       // slot st-1 was not computed on the last diagonal
+		else { xin &= keep; vin = (vin & keep) | ((r ? sc.q16 : 0u) << (ls.t0[0] == b.st ? 0 : 16)); }
+	}
+	uint32_t cw[4] = {0u, 0u, 0u, 0u};
+#define EXTZ_CELL2(ii) \
+	cell2<kRight, kCigar, 8 * ((ii) & 3)>(ls.Z[ii], (ii) ? ls.X[(ii) ? (ii) - 1 : 0] : xin, (ii) ? ls.V[(ii) ? (ii) - 1 : 0] : vin, \
+	                                       ls.U[ii], ls.V[ii], ls.X[ii], ls.Y[ii], sc, cw[(ii) >> 2]);
+	// descending: register i reads the OLD x, v of register i-1
+	EXTZ_CELL2(15) EXTZ_CELL2(14) EXTZ_CELL2(13) EXTZ_CELL2(12) EXTZ_CELL2(11) EXTZ_CELL2(10) EXTZ_CELL2(9) EXTZ_CELL2(8)
+	EXTZ_CELL2(7) EXTZ_CELL2(6) EXTZ_CELL2(5) EXTZ_CELL2(4) EXTZ_CELL2(3) EXTZ_CELL2(2) EXTZ_CELL2(1) EXTZ_CELL2(0)
+#undef EXTZ_CELL2
+	if (kCigar) *tb_dst = make_uint4(cw[0], cw[1], cw[2], cw[3]);
+	int32_t lane_max = kNegInf;
+#pragma unroll
+	for (int j = 0; j < 4; ++j) {
+		Urow[j * 128] = make_uint4(ls.U[4 * j], ls.U[4 * j + 1], ls.U[4 * j + 2], ls.U[4 * j + 3]);
+		int4 ha = Hrow[(2 * j) * 128], hb = Hrow[(2 * j + 1) * 128];
+		ha.x += sext_lo(ls.V[4 * j]);     hb.x += sext_hi(ls.V[4 * j]);
+		ha.y += sext_lo(ls.V[4 * j + 1]); hb.y += sext_hi(ls.V[4 * j + 1]);
+		ha.z += sext_lo(ls.V[4 * j + 2]); hb.z += sext_hi(ls.V[4 * j + 2]);
+		ha.w += sext_lo(ls.V[4 * j + 3]); hb.w += sext_hi(ls.V[4 * j + 3]);
+		Hrow[(2 * j) * 128] = ha; Hrow[(2 * j + 1) * 128] = hb;
+		int32_t m0 = ha.x > ha.y ? ha.x : ha.y, m1 = ha.z > ha.w ? ha.z : ha.w;
+		int32_t m2 = hb.x > hb.y ? hb.x : hb.y, m3 = hb.z > hb.w ? hb.z : hb.w;
+		m0 = m0 > m1 ? m0 : m1; m2 = m2 > m3 ? m2 : m3; m0 = m0 > m2 ? m0 : m2;
+		lane_max = lane_max > m0 ? lane_max : m0;
+	}
+	return lane_max;
+}
+
+// arg-max, fast pass: (count << 24) + sum of t over this lane's slots whose lazy H equals gm
+__device__ __forceinline__ uint32_t lane16_argmax_count(const Lane16 &ls, const int4 *Hrow, int32_t gm)
+{
+	uint32_t acc = 0;
+#pragma unroll
+	for (int k = 0; k < 8; ++k) {
+		const int4 h = Hrow[k * 128];
+		const uint32_t base = (1u << 24) + (uint32_t)(ls.t0[k & 1] + 4 * (k >> 1));
+		if (h.x == gm) acc += base;
+		if (h.y == gm) acc += base + 1;
+		if (h.z == gm) acc += base + 2;
+		if (h.w == gm) acc += base + 3;
+	}
+	return acc;
+}
+// arg-max, exact pass (only on real ties): smallest tie-break key among this lane's slots whose lazy H equals gm
+__device__ __forceinline__ uint32_t lane16_argmax_key(const Lane16 &ls, const Band &b, const int4 *Hrow, int32_t gm)
+{
+	uint32_t key = 0xffffffffu;
+#pragma unroll
+	for (int k = 0; k < 8; ++k) {
+		const int4 h = Hrow[k * 128];
+		const int32_t hv[4] = {h.x, h.y, h.z, h.w};
+#pragma unroll
+		for (int e = 0; e < 4; ++e) {
+			const int t = ls.t0[k & 1] + 4 * (k >> 1) + e;
+			if (t >= b.st0 && t <= b.en0 && !(t == b.en0 && b.en0 > 0) && hv[e] == gm) {
+				const uint32_t kk = tie_key(t, b.st0, b.en0);
+				key = kk < key ? kk : key;
+			}
+		}
+	}
+	return key;
+}
+
+// H / u' rows of one pair inside the CTA-wide row arrays, addressed by circular slot index (for the Leader)
+template <int G>
+struct PackedRows {
+	static constexpr int kMask = G * 32 - 1;
+	int32_t *H;         // (int32_t *)&sH[0][first thread of the group]
+	uint32_t *Us;       // (uint32_t *)&sU[0][first thread of the group]
+	__device__ __forceinline__ int32_t &h(int c) const
+	{
+		const int vl = c >> 4, i = c & 15;
+		return H[(((((i >> 2) << 1) | (vl & 1)) * 128 + (vl >> 1)) << 2) | (i & 3)];
+	}
+	__device__ __forceinline__ uint32_t u(int c) const          // top-byte form (value << 24), like LocalRows::u
+	{
+		const int vl = c >> 4, i = c & 15;
+		const uint32_t w = Us[((((i >> 2) * 128) + (vl >> 1)) << 2) | (i & 3)];
+		return (vl & 1) ? (w & 0xffff0000u) : (w << 16);
+	}
+};
+
+// =====================================================================================================
+// packed narrow kernel: G <= 32 lanes x 32 slots per pair, the 32/G pairs of a warp advance in lock-step
+// =====================================================================================================
+#ifndef EXTZ_MIN_BLOCKS_P
+#define EXTZ_MIN_BLOCKS_P 3
+#endif
+template <int G, bool kCigar, bool kRight>
+__global__ void __launch_bounds__(128, EXTZ_MIN_BLOCKS_P)
+extz_dp16_kernel(DpLaunch L)
+{
+	constexpr int NS = G * 32;
+	constexpr int PPW = 32 / G;                          // pairs per warp
+	constexpr unsigned FULL = 0xffffffffu;
+	static_assert(G >= 1 && G <= 32 && (G & (G - 1)) == 0, "G must be a power of two");
+
+	__shared__ int4 sH[8][128];                          // lazy H: H + (q+e)*r, row k of thread x at sH[k][x]
+	__shared__ uint4 sU[4][128];                         // u' of the current diagonal (for H[en0], :228), packed
+	__shared__ uint32_t sTable[kTableStride * kTableStride];
+
+	for (int i = threadIdx.x; i < kTableStride * kTableStride; i += blockDim.x) sTable[i] = (L.table[i] >> 16) * 0x00010001u;
+	__syncthreads();
+
+	const uint32_t table_saddr = (uint32_t)__cvta_generic_to_shared(sTable);
+	const int lane_w = threadIdx.x & 31;
+	const int gl = threadIdx.x % G;                                  // lane within group
+	const int pred_lane = (gl + G - 1) & (G - 1);                    // circular predecessor (relative to group)
+	int4 *Hrow = &sH[0][threadIdx.x];
+	uint4 *Urow = &sU[0][threadIdx.x];
+	const PackedRows<G> rows{(int32_t *)&sH[0][threadIdx.x - gl], (uint32_t *)&sU[0][threadIdx.x - gl]};
+	const Scoring sc = L.sc;
+	const Sc16 sc16 = make_sc16(sc);
+	const int qe = sc.qe;
+	const bool generic = (sc.flag & kFlagGenericSc) != 0;
+
+	for (;;) {
+		int base = 0;
+		if (lane_w == 0) base = atomicAdd(L.work_counter, PPW);      // dynamic work queue, pairs sorted by descending work
+		base = __shfl_sync(FULL, base, 0);
+		if (base >= L.n) break;
+		const int pi = base + lane_w / G;
+		bool alive = pi < L.n;
+		const PairDesc pd = L.pairs[alive ? pi : base];
+		const int qlen = pd.qlen, tlen = pd.tlen, w = pd.w;
+		const int T = (tlen + 15) & ~15;
+		const uint8_t *qseq = L.seq + pd.q_off;                      // qseq[j], j in [-kQPadL, qlen) readable
+		const uint8_t *tseq = L.seq + pd.t_off;
+		uint8_t *tbp = kCigar ? L.tb + pd.tb_off + gl * 16 : nullptr;
+		const int R = alive ? qlen + tlen - 1 : 0;
+		int maxR = R;
+#pragma unroll
+		for (int d = G; d < 32; d <<= 1) { int o = __shfl_xor_sync(FULL, maxR, d); maxR = maxR > o ? maxR : o; }
+
+		Lane16 ls;
+		ls.t0[0] = gl * 32; ls.t0[1] = gl * 32 + 16;
+#pragma unroll
+		for (int i = 0; i < 16; ++i) { ls.U[i] = ls.V[i] = ls.X[i] = ls.Y[i] = 0u; ls.Z[i] = sc16.s0_2; }   // calloc'ed arrays (:83)
+		lane16_load_seq<0>(ls, tseq, tlen, qseq, 0);
+		lane16_load_seq<1>(ls, tseq, tlen, qseq, 0);
+#pragma unroll
+		for (int k = 0; k < 8; ++k) Hrow[k * 128] = make_int4(kNegInf, kNegInf, kNegInf, kNegInf);           // :86-89
+		__syncwarp();
+
+		Leader ld; ld.reset();                                       // meaningful in the leader lane only
+		int last_st = -1, last_en = -1, n_diag = 0, zdropped_band = 0;
+
+		for (int r = 0; r < maxR; ++r) {
+			bool act = alive && r < R;
+			Band b;
+			const bool okb = band_of(r, qlen, tlen, w, T, generic, b);
+			if (act && !okb) { zdropped_band = 1; alive = false; act = false; }                // :110-113
+
+			// carries: OLD x,v of the slot below each block (:28-35)
+			uint32_t xin, vin;
+			if (G == 1) { xin = __byte_perm(ls.X[15], ls.X[15], 0x5432); vin = __byte_perm(ls.V[15], ls.V[15], 0x5432); }
+			else {
+				xin = __byte_perm(__shfl_sync(FULL, ls.X[15], pred_lane, G), ls.X[15], 0x5432);
+				vin = __byte_perm(__shfl_sync(FULL, ls.V[15], pred_lane, G), ls.V[15], 0x5432);
+			}
+			if (act) {
+				lane16_prepare<NS>(ls, b, r, last_en, qseq, tseq, tlen, table_saddr, sc16);
+				if (gl == 0) ld.pre(rows, b, r, qe);
+			}
+			__syncwarp();
+			int32_t lane_max = kNegInf;
+			if (act) lane_max = lane16_cells<kCigar, kRight>(ls, b, r, last_st, xin, vin, (uint4 *)(tbp + (int64_t)r * (NS >> 1)), Hrow, Urow, sc16);
+			__syncwarp();
+			const int32_t red = group_max<G>(lane_max);
+			int need = 0;
+			if (act && gl == 0) need = ld.mid(rows, b, r, qe, red, ls.V[0] << 16, sc.zdrop);
+			__syncwarp();
+			need = __shfl_sync(FULL, need, 0, G);
+			int max_t = b.en0;
+			if (__any_sync(FULL, need)) {
+				const int32_t gm = __shfl_sync(FULL, ld.gmax, 0, G);
+				uint32_t cnt = 0;
+				if (need) cnt = lane16_argmax_count(ls, Hrow, gm);
+				cnt = group_sum_u<G>(cnt);
+				max_t = (int)(cnt & 0x00ffffffu);
+				const int tie = need && (cnt >> 24) != 1u;
+				if (__any_sync(FULL, tie)) {                                                      // real ties: exact 4-lane rule
+					uint32_t key = 0xffffffffu;
+					if (tie) {
+						key = lane16_argmax_key(ls, b, Hrow, gm);
+						if (gl == 0) { uint32_t k0 = ld.en0_key(b, r); key = k0 < key ? k0 : key; }
+					}
+					key = group_min_u<G>(key);
+					if (tie) max_t = tie_key_slot(key, b.en0);
+				}
+			}
+			int stop = 0;
+			if (act && gl == 0) stop = ld.fin(rows, b, r, qe, max_t, qlen, tlen, sc.zdrop, sc.e);
+			stop = __shfl_sync(FULL, stop, 0, G);
+			if (act) { n_diag = r + 1; last_st = b.st; last_en = b.en; if (stop) alive = false; }
+			__syncwarp();            // the arg-max passes read H; the next diagonal's leader writes it
+		}
+		if (pi < L.n && gl == 0) { if (zdropped_band) ld.ez.zdropped = 1; ld.store(&L.results[pi], n_diag); }
+		__syncwarp();
+	}
+}
+
+} // namespace extz

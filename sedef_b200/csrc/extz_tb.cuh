@@ -28,6 +28,7 @@ struct TbLaunch {
 	sd_stats_t *stats;           // [n] indexed like pairs, or nullptr
 	int *overflow;               // set to 1 when the compact arena is too small
 	int n, NS, flag;
+	int packed;                  // traceback rows written by the packed kernel (extz_dp16.cuh layout)
 };
 
 __device__ __forceinline__ int raw_byte(const TbLaunch &L, int64_t off, int idx)
@@ -79,7 +80,8 @@ extz_traceback_kernel(TbLaunch L)
 			// the walk is a dependent chain of nibble reads; pull the rows it will need next into L2/L1 early
 			// (the column moves by at most one slot per row, so row r-16 is read within 8 bytes of the current column)
 			if (NS >= 512 && r >= kPrefetchRows) {                    // narrow rows (<= 128 B) are adjacent in memory already
-				const uint8_t *pf = tbp + (int64_t)(r - kPrefetchRows) * rowB + (((i - kPrefetchRows / 2) & (NS - 1)) >> 1);
+				const int pc = (i - kPrefetchRows / 2) & (NS - 1);
+				const uint8_t *pf = tbp + (int64_t)(r - kPrefetchRows) * rowB + (L.packed ? (((pc >> 5) << 4) | (pc & 15)) : (pc >> 1));
 				asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
 			}
 			Band b; band_of(r, qlen, tlen, w, T, false, b);
@@ -87,7 +89,7 @@ extz_traceback_kernel(TbLaunch L)
 			if (i < b.st) force = 2;
 			if (i > b.en) force = 1;
 			uint32_t tmp = 0;
-			if (force < 0) tmp = tb_fetch(tbp, NS, r, i);
+			if (force < 0) tmp = tb_fetch(tbp, NS, r, i, L.packed != 0);
 			int hstate = (tmp & 2u) ? 2 : (int)(tmp & 1u);          // which of H/E/F gave the max
 			if (state == 0) state = hstate;
 			else if (!((tmp >> (state + 1)) & 1u)) state = 0;       // continuation bits: E -> bit2, F -> bit3

@@ -37,7 +37,6 @@ struct Sc16 {
 	uint32_t qeps2;      // (q << 8) + 1 in both halves: ~z + qeps2 == q - z
 	uint32_t maxsc2;     // max_sc_ (:69) in both halves
 	uint32_t s0_2;       // z of a never-filled slot in both halves
-	uint32_t zr;         // 0, but not a compile-time constant (see cell2)
 };
 __device__ __forceinline__ Sc16 make_sc16(const Scoring &sc)
 {
@@ -46,7 +45,6 @@ __device__ __forceinline__ Sc16 make_sc16(const Scoring &sc)
 	s.qeps2 = s.q16 * 0x00010001u + 0x00010001u;
 	s.maxsc2 = (sc.maxsc_s >> 16) * 0x00010001u;
 	s.s0_2 = (sc.s0_s >> 16) * 0x00010001u;
-	s.zr = sc.q_s & 0x00ffffffu;
 	return s;
 }
 
@@ -54,8 +52,8 @@ __device__ __forceinline__ Sc16 make_sc16(const Scoring &sc)
 // SH: bit position of this register's code byte in the code word `cw` (low nibble: block A slot, high nibble: block B).
 // __vibmax_s16x2(a, b, &hi, &lo) returns max(a, b) per half and the predicates (a >= b).
 // CAUTION (ptxas 12.9, tools/probes/vibmax_probe.cu): when the FIRST operand is a compile-time constant ptxas commutes
-// the operands of the fused VIMNMX and the predicates come out wrong.  The zero operand of the strict "> 0" tests is
-// therefore sc.zr, a run-time zero.
+// the operands of the fused VIMNMX and the predicates come out wrong; a constant SECOND operand is fine.  Only the
+// right-aligned arm uses the predicate form (all its tests are ">=" with the variable first).
 template <bool kRight, bool kCigar, int SH>
 __device__ __forceinline__ void cell2(uint32_t z, uint32_t xt1, uint32_t vt1, uint32_t &U, uint32_t &V, uint32_t &X, uint32_t &Y,
                                       const Sc16 &sc, uint32_t &cw)
@@ -64,11 +62,11 @@ __device__ __forceinline__ void cell2(uint32_t z, uint32_t xt1, uint32_t vt1, ui
 	const uint32_t a = __vadd2(xt1, vt1);                                  // :36
 	const uint32_t b = __vadd2(Y, ut);                                     // :38
 	bool h0 = false, l0 = false, h1 = false, l1 = false, h2 = false, l2 = false, h3 = false, l3 = false;
-	uint32_t z1;
+	uint32_t z1, m1 = 0u;
 	if (!kCigar) z1 = __vmaxs2(z, a);                                      // :153
 	else if (!kRight) {
-		z1 = __vibmax_s16x2(z, a, &h0, &l0);                               // :175-177  d = a > z ? 1 : 0   (bit = !(z >= a))
-		(void)__vibmax_s16x2(z1, b, &h1, &l1);                             // :178-179  d = b > z ? 2 : d   (bit = !(z >= b))
+		z1 = __vmaxs2(z, a);                                               // :177
+		m1 = __vmaxs2(z1, b);                                              // only for the d = 2 flag below
 	} else {
 		z1 = __vibmax_s16x2(a, z, &h0, &l0);                               // :201-203  d = z > a ? 0 : 1   (bit = (a >= z))
 		(void)__vibmax_s16x2(b, z1, &h1, &l1);                             // :204-205  d = z > b ? d : 2   (bit = (b >= z))
@@ -83,19 +81,24 @@ __device__ __forceinline__ void cell2(uint32_t z, uint32_t xt1, uint32_t vt1, ui
 		Y = __viaddmax_s16x2(b, t, 0u);                                    // :47,161
 		return;
 	}
-	const uint32_t a2 = __vadd2(a, t), b2 = __vadd2(b, t);                 // :46-47
 	if (!kRight) {
-		X = __vibmax_s16x2(sc.zr, a2, &h2, &l2);                              // :187-189  bit = a > 0 = !(0 >= a)
-		Y = __vibmax_s16x2(sc.zr, b2, &h3, &l3);                              // :190-192
-		if (!l0) cw |= 0x01u << SH;
-		if (!l1) cw |= 0x02u << SH;
-		if (!l2) cw |= 0x04u << SH;
-		if (!l3) cw |= 0x08u << SH;
-		if (!h0) cw |= 0x10u << SH;
-		if (!h1) cw |= 0x20u << SH;
-		if (!h2) cw |= 0x40u << SH;
-		if (!h3) cw |= 0x80u << SH;
-	} else {
+		// Left-aligned arm.  The four code bits come out as packed FLAGS (0x0100 per half when set) of values that are
+		// already there -- no predicates (8 live predicates per register pair spill; r01 line profile):
+		//   d = a > z            <=> max(z, a) != z                  (:175-177)
+		//   d = b > z' ? 2 : d   <=> max_s(z', b) != z'              (:178-179)
+		//   x' > 0, y' > 0       <=> relu(..) != 0                   (:187-192)
+		// Every operand is a multiple of 0x100 per half, so umin(v, 0x0100) is the "non-zero" flag.
+		constexpr uint32_t K = 0x01000100u;
+		X = __viaddmax_s16x2(a, t, 0u);                                    // :46,187
+		Y = __viaddmax_s16x2(b, t, 0u);                                    // :47,190
+		const uint32_t f0 = __vminu2(z1 ^ z, K), f1 = __vminu2(m1 ^ z1, K), f2 = __vminu2(X, K), f3 = __vminu2(Y, K);
+		const uint32_t c = (f3 * 2u + f2) * 4u + (f1 * 2u + f0);           // per half: code nibble at bits 8..11 (FMA pipe)
+		const uint32_t byte = (uint32_t)__dp4a((int)c, 0x10000100, 0);     // low-half nibble + 16 * high-half nibble
+		cw = byte * (1u << SH) + cw;
+		return;
+	}
+	const uint32_t a2 = __vadd2(a, t), b2 = __vadd2(b, t);                 // :46-47
+	{
 		X = __vibmax_s16x2(a2, 0u, &h2, &l2);                              // :213-215  bit = !(0 > a) = (a >= 0)
 		Y = __vibmax_s16x2(b2, 0u, &h3, &l3);                              // :216-218
 		if (l0) cw |= 0x01u << SH;
@@ -108,11 +111,6 @@ __device__ __forceinline__ void cell2(uint32_t z, uint32_t xt1, uint32_t vt1, ui
 		if (h3) cw |= 0x80u << SH;
 	}
 }
-
-// sign-extended top byte of the low / high half.  prmt's selector nibble 8+k replicates the sign bit of byte k;
-// __byte_perm() masks the selector to 3 bits per nibble, hence the inline PTX.
-__device__ __forceinline__ int32_t sext_lo(uint32_t v) { int32_t r; asm("prmt.b32 %0, %1, %1, 0x9991;" : "=r"(r) : "r"(v)); return r; }
-__device__ __forceinline__ int32_t sext_hi(uint32_t v) { int32_t r; asm("prmt.b32 %0, %1, %1, 0xbbb3;" : "=r"(r) : "r"(v)); return r; }
 
 // ---- per-lane state ----
 struct Lane16 {
@@ -233,12 +231,13 @@ __device__ __forceinline__ int32_t lane16_cells(Lane16 &ls, const Band &b, int r
 	int32_t lane_max = kNegInf;
 #pragma unroll
 	for (int j = 0; j < 4; ++j) {
+		// H += sign-extended v: IDP.4A against a one-hot byte vector picks and sign-extends the top byte of a half
 		Urow[j * 128] = make_uint4(ls.U[4 * j], ls.U[4 * j + 1], ls.U[4 * j + 2], ls.U[4 * j + 3]);
 		int4 ha = Hrow[(2 * j) * 128], hb = Hrow[(2 * j + 1) * 128];
-		ha.x += sext_lo(ls.V[4 * j]);     hb.x += sext_hi(ls.V[4 * j]);
-		ha.y += sext_lo(ls.V[4 * j + 1]); hb.y += sext_hi(ls.V[4 * j + 1]);
-		ha.z += sext_lo(ls.V[4 * j + 2]); hb.z += sext_hi(ls.V[4 * j + 2]);
-		ha.w += sext_lo(ls.V[4 * j + 3]); hb.w += sext_hi(ls.V[4 * j + 3]);
+		ha.x = __dp4a((int)ls.V[4 * j], 0x00000100, ha.x);     hb.x = __dp4a((int)ls.V[4 * j], 0x01000000, hb.x);
+		ha.y = __dp4a((int)ls.V[4 * j + 1], 0x00000100, ha.y); hb.y = __dp4a((int)ls.V[4 * j + 1], 0x01000000, hb.y);
+		ha.z = __dp4a((int)ls.V[4 * j + 2], 0x00000100, ha.z); hb.z = __dp4a((int)ls.V[4 * j + 2], 0x01000000, hb.z);
+		ha.w = __dp4a((int)ls.V[4 * j + 3], 0x00000100, ha.w); hb.w = __dp4a((int)ls.V[4 * j + 3], 0x01000000, hb.w);
 		Hrow[(2 * j) * 128] = ha; Hrow[(2 * j + 1) * 128] = hb;
 		int32_t m0 = ha.x > ha.y ? ha.x : ha.y, m1 = ha.z > ha.w ? ha.z : ha.w;
 		int32_t m2 = hb.x > hb.y ? hb.x : hb.y, m3 = hb.z > hb.w ? hb.z : hb.w;
@@ -256,6 +255,25 @@ __device__ __forceinline__ uint32_t lane16_argmax_count(const Lane16 &ls, const 
 	for (int k = 0; k < 8; ++k) {
 		const int4 h = Hrow[k * 128];
 		const uint32_t base = (1u << 24) + (uint32_t)(ls.t0[k & 1] + 4 * (k >> 1));
+		if (h.x == gm) acc += base;
+		if (h.y == gm) acc += base + 1;
+		if (h.z == gm) acc += base + 2;
+		if (h.w == gm) acc += base + 3;
+	}
+	return acc;
+}
+// the same count over the 8 rows of ONE lane (`wl`, group-relative), split between the G lanes of the group
+template <int G>
+__device__ __forceinline__ uint32_t group_argmax_count(const int4 *Hgroup, int wl, int wt0a, int wt0b, int gl, int32_t gm)
+{
+	constexpr int RPL = G >= 8 ? 1 : 8 / G;              // rows per lane
+	uint32_t acc = 0;
+	if (G > 8 && gl >= 8) return 0u;
+#pragma unroll
+	for (int j = 0; j < RPL; ++j) {
+		const int k = gl * RPL + j;
+		const int4 h = Hgroup[k * 128 + wl];
+		const uint32_t base = (1u << 24) + (uint32_t)(((k & 1) ? wt0b : wt0a) + 4 * (k >> 1));
 		if (h.x == gm) acc += base;
 		if (h.y == gm) acc += base + 1;
 		if (h.z == gm) acc += base + 2;
@@ -397,7 +415,22 @@ extz_dp16_kernel(DpLaunch L)
 			if (__any_sync(FULL, need)) {
 				const int32_t gm = __shfl_sync(FULL, ld.gmax, 0, G);
 				uint32_t cnt = 0;
-				if (need) cnt = lane16_argmax_count(ls, Hrow, gm);
+				if (G == 1) { if (need) cnt = lane16_argmax_count(ls, Hrow, gm); }
+				else {
+					// Only a lane whose own maximum reaches gm, or the owner of slot en0 when the leader's H[en0] does, can
+					// hold the arg-max.  With ONE such lane (the rule) the G lanes of the group split ITS 8 rows between
+					// them instead of every lane scanning its own 32 entries.
+					const int en0_max = __shfl_sync(FULL, (int)(ld.Hen0_lazy == ld.gmax), 0, G);
+					const bool cand = need && (lane_max == gm || (en0_max && ((b.en0 & (NS - 1)) >> 5) == gl));
+					const unsigned bal = __ballot_sync(FULL, cand);
+					const unsigned gmask = G == 32 ? bal : ((bal >> (lane_w & ~(G - 1))) & ((1u << (G & 31)) - 1u));
+					const int wl = gmask ? __ffs(gmask) - 1 : 0;
+					const int wt0a = __shfl_sync(FULL, ls.t0[0], wl, G), wt0b = __shfl_sync(FULL, ls.t0[1], wl, G);
+					if (need) {
+						if (__popc(gmask) == 1) cnt = group_argmax_count<G>(Hrow - gl, wl, wt0a, wt0b, gl, gm);
+						else cnt = lane16_argmax_count(ls, Hrow, gm);
+					}
+				}
 				cnt = group_sum_u<G>(cnt);
 				max_t = (int)(cnt & 0x00ffffffu);
 				const int tie = need && (cnt >> 24) != 1u;

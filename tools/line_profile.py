@@ -29,7 +29,7 @@ for k, (txt, f) in enumerate(insts):
     agg[key] += v; sagg[key] += float(data[k][isamp])
     op = re.match(r"(@!?U?P\d+\s+)?([A-Z0-9_.]+)", txt.strip()).group(2)
     ops[key][op] += v
-text = {fn: open(os.path.join(root, "sedef_b200", "csrc", fn)).read().split("\n") for fn in ("extz_dp.cuh", "extz_core.cuh")}
+text = {fn: open(os.path.join(root, "sedef_b200", "csrc", fn)).read().split("\n") for fn in ("extz_dp.cuh", "extz_core.cuh", "extz_dp16.cuh")}
 tot, ts = sum(agg.values()), sum(sagg.values()) or 1
 print("total warp-instructions per warp-diagonal: %.1f" % tot)
 for key, v in agg.most_common(int(sys.argv[4]) if len(sys.argv) > 4 else 70):

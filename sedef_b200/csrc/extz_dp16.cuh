@@ -37,6 +37,7 @@ struct Sc16 {
 	uint32_t qeps2;      // (q << 8) + 1 in both halves: ~z + qeps2 == q - z
 	uint32_t maxsc2;     // max_sc_ (:69) in both halves
 	uint32_t s0_2;       // z of a never-filled slot in both halves
+	uint32_t zr;         // 0 held in a register: as an immediate ptxas re-materialises it (PRMT RZ) for every VIADDMNMX
 };
 __device__ __forceinline__ Sc16 make_sc16(const Scoring &sc)
 {
@@ -45,6 +46,7 @@ __device__ __forceinline__ Sc16 make_sc16(const Scoring &sc)
 	s.qeps2 = s.q16 * 0x00010001u + 0x00010001u;
 	s.maxsc2 = (sc.maxsc_s >> 16) * 0x00010001u;
 	s.s0_2 = (sc.s0_s >> 16) * 0x00010001u;
+	s.zr = sc.q_s & 0x00ffffffu;
 	return s;
 }
 
@@ -77,8 +79,8 @@ __device__ __forceinline__ void cell2(uint32_t z, uint32_t xt1, uint32_t vt1, ui
 	V = ~__vadd2(cz, ut);                                                  // :44  z - u(t)
 	const uint32_t t = __vadd2(cz, sc.qeps2);                              // :45  -(z - q)
 	if (!kCigar) {
-		X = __viaddmax_s16x2(a, t, 0u);                                    // :46,160
-		Y = __viaddmax_s16x2(b, t, 0u);                                    // :47,161
+		X = __viaddmax_s16x2(a, t, sc.zr);                                    // :46,160
+		Y = __viaddmax_s16x2(b, t, sc.zr);                                    // :47,161
 		return;
 	}
 	if (!kRight) {
@@ -89,8 +91,8 @@ __device__ __forceinline__ void cell2(uint32_t z, uint32_t xt1, uint32_t vt1, ui
 		//   x' > 0, y' > 0       <=> relu(..) != 0                   (:187-192)
 		// Every operand is a multiple of 0x100 per half, so umin(v, 0x0100) is the "non-zero" flag.
 		constexpr uint32_t K = 0x01000100u;
-		X = __viaddmax_s16x2(a, t, 0u);                                    // :46,187
-		Y = __viaddmax_s16x2(b, t, 0u);                                    // :47,190
+		X = __viaddmax_s16x2(a, t, sc.zr);                                    // :46,187
+		Y = __viaddmax_s16x2(b, t, sc.zr);                                    // :47,190
 		const uint32_t f0 = __vminu2(z1 ^ z, K), f1 = __vminu2(m1 ^ z1, K), f2 = __vminu2(X, K), f3 = __vminu2(Y, K);
 		const uint32_t c = (f3 * 2u + f2) * 4u + (f1 * 2u + f0);           // per half: code nibble at bits 8..11 (FMA pipe)
 		const uint32_t byte = (uint32_t)__dp4a((int)c, 0x10000100, 0);     // low-half nibble + 16 * high-half nibble

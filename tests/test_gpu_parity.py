@@ -170,6 +170,49 @@ def test_widest_pair_and_too_wide(checker, mat):
     assert ei.value.code == -4
 
 
+def test_packed_class_boundaries(checker, mat):
+    """Pairs that fill the live-slot window of every packed class exactly (32 .. 1024 slots: the window wraps with no
+    slack), one slot less, and one block more (next class), unbanded and banded, both traceback arms."""
+    for L in (32, 64, 128, 256, 512, 1024):
+        ps = synth.make_pairs_small(8, length=L + 60, div=0.08, seed=700 + L)
+        ps.tlen[:] = np.minimum(ps.tlen, np.array([L, L, L - 1, L - 15, L - 16, L + 1, L + 16, L], np.int32))
+        ps.qlen[:] = np.minimum(ps.qlen, np.array([L + 60, L, L + 7, L + 60, L, L + 60, L + 3, L - 9], np.int32))
+        for flag in (0, 0x02):
+            compare(ps, mat, checker, -1, -1, flag)
+        compare(ps, mat, checker, L // 2, 60, 0)
+
+
+def test_one_slot_per_register_kernels(checker, mat, tmp_path):
+    """KSW_B200_PACKED=0 routes the narrow classes to the one-slot-per-register kernels of extz_dp.cuh (the A/B switch is
+    read once per process, hence the subprocess): they must stay bit-exact too."""
+    import os, subprocess, sys, textwrap
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "unpacked.py"
+    script.write_text(textwrap.dedent(f"""
+        import sys
+        sys.path.insert(0, {root!r})
+        import oracle
+        from sedef_b200 import engine, synth
+        mat = synth.sedef_matrix()
+        engine.init(0, 1)
+        chk = oracle.ref() if oracle.have_ref() else oracle.port()
+        n = 0
+        for (kw, w, zd, flag) in [(dict(min_len=1, max_len=700, div=0.12), -1, -1, 0), (dict(min_len=1, max_len=600, div=0.2), 30, 80, 2),
+                                  (dict(min_len=300, max_len=1000, div=0.1), 100, -1, 0), (dict(min_len=1, max_len=600, div=0.2), 30, 80, 1)]:
+            ps = synth.make_pairs_mixed(300, seed=4242 + w, **kw)
+            got = engine.extz2_batch(ps, mat, 40, 1, w, zd, flag)
+            _, fr, cr = chk.batch(ps, mat, 40, 1, w, zd, flag, nthreads=8)
+            for i in range(ps.n):
+                assert got.fields(i) == fr[i], i
+                if not flag & 1:
+                    assert got.cigars[i].tolist() == cr[i], i
+                n += 1
+        print("ok", n)
+    """))
+    out = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, env=dict(os.environ, KSW_B200_PACKED="0"), timeout=600)
+    assert out.returncode == 0 and "ok 1200" in out.stdout, out.stdout + out.stderr
+
+
 def test_other_scoring_parameters(checker):
     """Scoring is not hard-wired: user-supplied --match/--mismatch/--gap-open/--gap-extend (src/align_main.cc:343-373)."""
     ps = synth.make_pairs_mixed(150, seed=77, min_len=1, max_len=400, div=0.15)

@@ -237,10 +237,14 @@ def run_ours(args):
                     "checksum_score_sum": score_sum, "host_threads_per_rank": host_threads},
             "roofline": {"bound": "int_alu", "achieved": round(achieved_tops, 3), "peak": round(p_int, 3), "unit": "Tlane-op/s",
                          "frac": round(achieved_tops / p_int, 4), "traffic": traffic,
-                         "kernel": "extz_dp_kernel<8,16,cigar,left> (8 lanes x 16 slots per pair, 4 pairs per warp)", "ops_per_cell": OPS_PER_CELL,
-                         "peak_source": p_int_src,
-                         "note": "integer min/max DP: the binding unit is the INT ALU pipe, not HBM or tensor cores; "
-                                 "achieved = in-band cells/s x 34 reference lane-ops per cell / DP-kernel device time"},
+                         "kernel": "extz_dp16_kernel<4,cigar,left> (packed: 4 lanes x 32 slots per pair, 2 slots per register, 8 pairs per warp)",
+                         "ops_per_cell": OPS_PER_CELL, "peak_source": p_int_src,
+                         "frac_vs_packed_peak": round(achieved_tops / (2.0 * p_int), 4),
+                         "note": "integer min/max DP: the binding unit is the INT ALU pipe, not HBM or tensor cores; achieved = in-band "
+                                 "cells/s x 34 reference lane-ops per cell (SURVEY 8d) / DP-kernel device time; peak = measured 32-bit "
+                                 "lane-op issue rate of the ALU pipe (64 lanes/clk/SM).  The kernel issues VIADD.16x2 / VIMNMX.16x2, "
+                                 "which retire two of those reference ops per lane slot at the same issue rate, so the stricter ceiling "
+                                 "for the 28 packable ops is 2 x peak: frac_vs_packed_peak states the fraction of that"},
             "roofline_hbm": {"bound": "hbm", "achieved": round(tb_gbs, 2), "peak": p_hbm, "unit": "GB/s",
                              "frac": round(tb_gbs / p_hbm, 5), "traffic": traffic,
                              "peak_source": p_hbm_src, "note": "traceback write stream, 0.5 B per in-band cell (algorithmic)"},

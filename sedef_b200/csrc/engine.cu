@@ -20,6 +20,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <mutex>
 #include <numeric>
 #include <string>
@@ -211,6 +212,8 @@ struct DevCtx {
 	int dev = -1;
 	int sms = 0;
 	cudaStream_t stream = nullptr;
+	cudaStream_t tb_stream = nullptr;   // highest priority: a finished chunk's traceback must not queue behind the persistent
+	                                    // DP CTAs of the chunks launched after it (one-shot pipeline)
 	size_t tb_budget = 0;          // bytes of traceback memory one wave may use
 };
 static std::mutex g_mu;
@@ -232,7 +235,7 @@ extern "C" int ksw_b200_init(int first_dev, int ndev)
 	if (ndev <= 0 || first_dev + ndev > count) ndev = count - first_dev;
 	if (ndev <= 0) return fail(KSW_B200_ERR_NO_DEVICE, "no device in the requested range");
 	if ((int)g_devs.size() == ndev && g_devs[0].dev == first_dev) return ndev;
-	for (auto &d : g_devs) { cudaSetDevice(d.dev); if (d.stream) cudaStreamDestroy(d.stream); }
+	for (auto &d : g_devs) { cudaSetDevice(d.dev); if (d.stream) cudaStreamDestroy(d.stream); if (d.tb_stream) cudaStreamDestroy(d.tb_stream); }
 	g_devs.clear();
 	for (int i = 0; i < ndev; ++i) {
 		DevCtx d; d.dev = first_dev + i;
@@ -240,6 +243,9 @@ extern "C" int ksw_b200_init(int first_dev, int ndev)
 		cudaDeviceProp p; CUDA_TRY(cudaGetDeviceProperties(&p, d.dev));
 		d.sms = p.multiProcessorCount;
 		CUDA_TRY(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
+		int prio_least = 0, prio_greatest = 0;
+		CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+		CUDA_TRY(cudaStreamCreateWithPriority(&d.tb_stream, cudaStreamNonBlocking, prio_greatest));
 		size_t fr = 0, tot = 0; CUDA_TRY(cudaMemGetInfo(&fr, &tot));
 		const char *env = getenv("KSW_B200_TB_BUDGET_MB");
 		d.tb_budget = env ? (size_t)atoll(env) << 20 : std::min<size_t>(fr / 2, (size_t)48 << 30);
@@ -252,7 +258,7 @@ extern "C" void ksw_b200_destroy(void)
 {
 	pool_clear();
 	std::lock_guard<std::mutex> lk(g_mu);
-	for (auto &d : g_devs) { cudaSetDevice(d.dev); if (d.stream) cudaStreamDestroy(d.stream); }
+	for (auto &d : g_devs) { cudaSetDevice(d.dev); if (d.stream) cudaStreamDestroy(d.stream); if (d.tb_stream) cudaStreamDestroy(d.tb_stream); }
 	g_devs.clear();
 }
 extern "C" int ksw_b200_num_devices(void) { return (int)g_devs.size(); }
@@ -360,7 +366,7 @@ struct SubBatch {
 	std::vector<Wave> waves;
 	int class_first[kNumClasses + 1] = {0};
 	size_t arena_bytes = 0;
-	PinBuf h_arena, h_raw, h_results, h_cigar, h_stats;
+	PinBuf h_arena, h_raw, h_results, h_cigar, h_stats, h_pairs;
 	DevBuf d_arena, d_raw, d_pairs, d_results, d_tb, d_cigar, d_stats, d_misc, d_table;
 	size_t cigar_cap = 0;               // entries
 	unsigned long long cigar_used = 0;
@@ -372,7 +378,7 @@ struct SubBatch {
 	std::vector<std::pair<cudaEvent_t, cudaEvent_t>> dp_ev, tb_ev;   // per-wave kernel timing events of the last launch
 	bool launched = false;
 	void release() {
-		h_arena.release(); h_raw.release(); h_results.release(); h_cigar.release(); h_stats.release();
+		h_arena.release(); h_raw.release(); h_results.release(); h_cigar.release(); h_stats.release(); h_pairs.release();
 		d_arena.release(); d_raw.release(); d_pairs.release(); d_results.release(); d_tb.release();
 		d_cigar.release(); d_stats.release(); d_misc.release(); d_table.release();
 		for (auto &e : ev) if (e) { cudaEventDestroy(e); e = nullptr; }
@@ -433,6 +439,44 @@ static inline int slots_needed(int qlen, int tlen, int w)
 // ------------------------------------------------------------------------------------------------
 // upload
 // ------------------------------------------------------------------------------------------------
+// A persistent helper thread for the one-shot pipeline's producer stage: a fresh std::thread per call would also build
+// (and tear down) a fresh OpenMP team for the packing loops, ~3 ms on a 32-thread host.
+class PipelineWorker {
+	std::thread th_;
+	std::mutex mu_;
+	std::condition_variable cv_;
+	std::function<void()> job_;
+	bool has_job_ = false, running_ = false, stop_ = false;
+	void loop()
+	{
+		for (;;) {
+			std::function<void()> job;
+			{
+				std::unique_lock<std::mutex> lk(mu_);
+				cv_.wait(lk, [&] { return has_job_ || stop_; });
+				if (stop_ && !has_job_) return;
+				job.swap(job_); has_job_ = false; running_ = true;
+			}
+			job();
+			{ std::lock_guard<std::mutex> lk(mu_); running_ = false; }
+			cv_.notify_all();
+		}
+	}
+public:
+	std::mutex claim;                                   // one call at a time owns the worker (others spawn their own thread)
+	~PipelineWorker() { { std::lock_guard<std::mutex> lk(mu_); stop_ = true; } cv_.notify_all(); if (th_.joinable()) th_.join(); }
+	void start(std::function<void()> f)
+	{
+		std::lock_guard<std::mutex> lk(mu_);
+		if (!th_.joinable()) th_ = std::thread([this] { loop(); });
+		job_ = std::move(f); has_job_ = true;
+		cv_.notify_all();
+	}
+	void join() { std::unique_lock<std::mutex> lk(mu_); cv_.wait(lk, [&] { return !has_job_ && !running_; }); }
+};
+static PipelineWorker g_worker;
+
+static thread_local bool tl_async_upload = false;      // set by the one-shot pipeline around its chunk uploads
 extern "C" ksw_b200_batch_t *ksw_b200_batch_upload(int n, const int *qlen, const int64_t *qoff, const uint8_t *qbuf,
                                                    const int *tlen, const int64_t *toff, const uint8_t *tbuf,
                                                    int8_t m, const int8_t *mat, int8_t q, int8_t e,
@@ -569,7 +613,7 @@ extern "C" ksw_b200_batch_t *ksw_b200_batch_upload(int n, const int *qlen, const
 		}
 	}
 	B->cq.assign(qlen, qlen + n); B->ct.assign(tlen, tlen + n);
-	{
+	if (!tl_async_upload) {           // resident API: the inputs are in HBM when this returns (the one-shot pipeline does not wait)
 		const double t0 = now_ms();
 		for (auto &sb : B->subs) if (!sb.pairs.empty()) { cudaSetDevice(sb.dc->dev); cudaStreamSynchronize(sb.stream ? sb.stream : sb.dc->stream); }
 		B->t_h2d = now_ms() - t0;
@@ -659,7 +703,10 @@ static int launch_sub(ksw_b200_batch &B, SubBatch &sb)
 	int rc = plan_waves(B, sb, cigar);
 	if (rc) return rc;
 	// descriptors carry tb offsets -> (re)upload
-	CUDA_TRY(cudaMemcpyAsync(sb.d_pairs.p, sb.pairs.data(), sb.pairs.size() * sizeof(PairDesc), cudaMemcpyHostToDevice, st));
+	// (staged through pinned memory: a pageable source would make this call wait for the sequence copies queued before it)
+	if (sb.h_pairs.ensure(sb.pairs.size() * sizeof(PairDesc))) return fail(KSW_B200_ERR_NOMEM, "pinned descriptor allocation failed");
+	memcpy(sb.h_pairs.p, sb.pairs.data(), sb.pairs.size() * sizeof(PairDesc));
+	CUDA_TRY(cudaMemcpyAsync(sb.d_pairs.p, sb.h_pairs.p, sb.pairs.size() * sizeof(PairDesc), cudaMemcpyHostToDevice, st));
 	sb.h2d_bytes += sb.pairs.size() * sizeof(PairDesc);
 	// misc: [0..63] work counters (one per wave, reused round-robin), [64] cigar cursor (u64 at byte 512), [66] overflow
 	CUDA_TRY(cudaMemsetAsync(sb.d_misc.p, 0, 4096, st));
@@ -704,11 +751,15 @@ static int launch_sub(ksw_b200_batch &B, SubBatch &sb)
 			TL.overflow = d_overflow;
 			TL.n = wv.count; TL.NS = class_ns(c); TL.flag = B.flag; TL.packed = class_packed(c) ? 1 : 0;
 			int tgrid = (wv.count + 127) / 128;
-			if (B.want_stats) extz_traceback_kernel<true><<<tgrid, 128, 0, st>>>(TL);
-			else extz_traceback_kernel<false><<<tgrid, 128, 0, st>>>(TL);
+			cudaStream_t tbs = sb.dc->tb_stream;
+			CUDA_TRY(cudaStreamWaitEvent(tbs, b2, 0));
+			if (B.want_stats) extz_traceback_kernel<true><<<tgrid, 128, 0, tbs>>>(TL);
+			else extz_traceback_kernel<false><<<tgrid, 128, 0, tbs>>>(TL);
 			CUDA_TRY(cudaGetLastError());
 			++sb.launches;
-		}
+			CUDA_TRY(cudaEventRecord(c2, tbs));
+			CUDA_TRY(cudaStreamWaitEvent(st, c2, 0));             // the next wave reuses the traceback arena
+		} else
 		CUDA_TRY(cudaEventRecord(c2, st));
 		tb_ev.push_back({b2, c2});
 		++wave_no;
@@ -899,17 +950,25 @@ extern "C" int ksw_extz2_batch_flat(int n, const int *qlen, const int64_t *qoff,
 		start[nchunks] = n;
 	}
 
+	const bool trace = getenv("KSW_B200_TRACE") != nullptr;                // developer aid: per-chunk timeline on stderr
+	const double t_call = now_ms();
+	auto mark = [&](const char *what, int c) { if (trace) fprintf(stderr, "[ksw_b200] %8.2f ms  chunk %d  %s\n", now_ms() - t_call, c, what); };
 	auto upload_chunk = [&](int c, int *err) -> ksw_b200_batch_t * {
 		const int s0 = start[c], cnt = start[c + 1] - s0;
+		tl_async_upload = nchunks > 1;
+		struct Reset { ~Reset() { tl_async_upload = false; } } reset;
 		return ksw_b200_batch_upload(cnt, qlen + s0, qoff + s0, qbuf, tlen + s0, toff + s0, tbuf, m, mat, q, e, w, zdrop, flag,
 		                             q_raw_buf, t_raw_buf, err);
 	};
 	auto consume = [&](ksw_b200_batch_t *B, int c, bool launched) -> int {
 		const int s0 = start[c];
 		int rc = 0;
+		mark("wait", c);
 		if (!launched) { if (!stats) B->want_stats = false; rc = ksw_b200_batch_run(B, nullptr); }
 		else for (auto &sb : B->subs) { rc = finish_sub(*B, sb); if (rc) break; }
+		mark("kernels done", c);
 		if (rc == 0) rc = ksw_b200_batch_fetch(B, ez + s0, stats ? stats + s0 : nullptr);
+		mark("fetched", c);
 		int64_t a = 0, d = 0; ksw_b200_batch_io_bytes(B, &a, &d);
 		g_last_h2d += a; g_last_d2h += d; g_last_launches += ksw_b200_batch_launches(B);
 		ksw_b200_batch_free(B);
@@ -927,7 +986,7 @@ extern "C" int ksw_extz2_batch_flat(int n, const int *qlen, const int64_t *qoff,
 	std::vector<int> errs(nchunks, 0), done(nchunks, 0);
 	int consumed = 0; bool abort_all = false;
 	std::string producer_error;
-	std::thread producer([&] {
+	auto producer_fn = [&] {
 		for (int c = 0; c < nchunks; ++c) {
 			{
 				std::unique_lock<std::mutex> lk(mu);
@@ -935,12 +994,16 @@ extern "C" int ksw_extz2_batch_flat(int n, const int *qlen, const int64_t *qoff,
 				if (abort_all) return;
 			}
 			int err = 0;
+			mark("upload begin", c);
 			ksw_b200_batch_t *B = upload_chunk(c, &err);
+			mark("upload end", c);
+			if (trace && B) fprintf(stderr, "[ksw_b200]             chunk %d  plan %.2f ms, pack %.2f ms, %d pairs\n", c, B->t_plan, B->t_pack, B->n);
 			if (B) {                                                        // enqueue the kernels right behind the H2D copy
 				if (!stats) B->want_stats = false;
 				for (auto &sb : B->subs) { err = launch_sub(*B, sb); if (err) break; }
 				if (err) { ksw_b200_batch_free(B); B = nullptr; }
 			}
+			mark("launched", c);
 			{
 				std::lock_guard<std::mutex> lk(mu);
 				ready[c] = B; errs[c] = err; done[c] = 1;
@@ -949,7 +1012,10 @@ extern "C" int ksw_extz2_batch_flat(int n, const int *qlen, const int64_t *qoff,
 			cv.notify_all();
 			if (!B) return;
 		}
-	});
+	};
+	const bool own_worker = g_worker.claim.try_lock();
+	std::thread producer;
+	if (own_worker) g_worker.start(producer_fn); else producer = std::thread(producer_fn);
 	int rc = 0;
 	for (int c = 0; c < nchunks && rc == 0; ++c) {
 		ksw_b200_batch_t *B = nullptr;
@@ -969,7 +1035,7 @@ extern "C" int ksw_extz2_batch_flat(int n, const int *qlen, const int64_t *qoff,
 	}
 	{ std::lock_guard<std::mutex> lk(mu); abort_all = abort_all || rc != 0; }
 	cv.notify_all();
-	producer.join();
+	if (own_worker) { g_worker.join(); g_worker.claim.unlock(); } else producer.join();
 	if (rc) {                                                           // leave nothing allocated on error
 		for (int c = 0; c < nchunks; ++c) if (ready[c] && c >= consumed) ksw_b200_batch_free(ready[c]);
 		ksw_b200_free_cigars(ez, n);

@@ -81,12 +81,19 @@ static inline bool packed_enabled()
 	static const bool on = [] { const char *e = getenv("KSW_B200_PACKED"); return !(e && e[0] == '0'); }();
 	return on;
 }
-static inline bool class_packed(int c) { return packed_enabled() && !kClasses[c].wide && !kClasses[c].cluster; }
+static inline bool class_packed(int c) { return packed_enabled() && !kClasses[c].cluster; }      // narrow (<= 1024 slots) and CTA-wide
+static inline bool class_packed_wide(int c) { return class_packed(c) && class_ns(c) > 1024; }    // one CTA of NS/32 lanes per pair
 static inline int class_capacity(int c) { return (kClasses[c].S > 16 && !class_packed(c)) ? class_ns(c) - 16 : class_ns(c); }
-static inline int class_threads(int c) { return kClasses[c].cluster ? 256 : (kClasses[c].wide ? kClasses[c].G : 128); }
+static inline int class_threads(int c)
+{
+	if (kClasses[c].cluster) return 256;
+	if (class_packed(c)) return class_packed_wide(c) ? class_ns(c) / 32 : 128;
+	return kClasses[c].wide ? kClasses[c].G : 128;
+}
 static inline int class_pairs_per_block(int c)
 {
-	return kClasses[c].wide ? 1 : (class_packed(c) ? 128 * 32 / class_ns(c) : 128 / kClasses[c].G);
+	if (class_packed(c)) return class_packed_wide(c) ? 1 : 128 * 32 / class_ns(c);
+	return kClasses[c].wide ? 1 : 128 / kClasses[c].G;
 }
 
 // kernel selection: every (class, cigar, right) combination is a distinct instantiation
@@ -158,6 +165,25 @@ static int dp16_occupancy(bool cigar, bool right)
 	} else       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, extz_dp16_kernel<G, false, false>, 128, 0);
 	return nb;
 }
+template <int G>
+static cudaError_t launch_dp16_wide(const DpLaunch &L, bool cigar, bool right, int grid, cudaStream_t st)
+{
+	if (cigar) {
+		if (right) extz_dp16_wide_kernel<G, true, true><<<grid, G, 0, st>>>(L);
+		else       extz_dp16_wide_kernel<G, true, false><<<grid, G, 0, st>>>(L);
+	} else       extz_dp16_wide_kernel<G, false, false><<<grid, G, 0, st>>>(L);
+	return cudaGetLastError();
+}
+template <int G>
+static int dp16_wide_occupancy(bool cigar, bool right)
+{
+	int nb = 0;
+	if (cigar) {
+		if (right) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, extz_dp16_wide_kernel<G, true, true>, G, 0);
+		else       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, extz_dp16_wide_kernel<G, true, false>, G, 0);
+	} else       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, extz_dp16_wide_kernel<G, false, false>, G, 0);
+	return nb;
+}
 #define EXTZ_FOR_PACKED(ns, CALL) \
 	switch (ns) { \
 	case 32: return CALL(1); case 64: return CALL(2); case 128: return CALL(4); \
@@ -172,6 +198,11 @@ static cudaError_t launch_dp(int c, const DpLaunch &L, bool cigar, bool right, i
 {
 	if (kClasses[c].cluster == 2) return cluster_dispatch<2>(L, cigar, right, grid, st, nullptr);
 	if (kClasses[c].cluster == 4) return cluster_dispatch<4>(L, cigar, right, grid, st, nullptr);
+	if (class_packed_wide(c)) {
+		if (class_ns(c) == 2048) return launch_dp16_wide<64>(L, cigar, right, grid, st);
+		if (class_ns(c) == 4096) return launch_dp16_wide<128>(L, cigar, right, grid, st);
+		return cudaErrorInvalidValue;
+	}
 	if (class_packed(c)) {
 #define EXTZ_CALL16(G) launch_dp16<G>(L, cigar, right, grid, st)
 		EXTZ_FOR_PACKED(class_ns(c), EXTZ_CALL16)
@@ -193,6 +224,7 @@ static int dp_occupancy(int c, bool cigar, bool right)
 		if (e != cudaSuccess) { cudaGetLastError(); return 0; }
 		return n;
 	}
+	if (class_packed_wide(c)) return class_ns(c) == 2048 ? dp16_wide_occupancy<64>(cigar, right) : dp16_wide_occupancy<128>(cigar, right);
 	if (class_packed(c)) {
 #define EXTZ_CALL16(G) dp16_occupancy<G>(cigar, right)
 		EXTZ_FOR_PACKED(class_ns(c), EXTZ_CALL16)

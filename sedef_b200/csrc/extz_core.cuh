@@ -13,7 +13,8 @@
 //     are exactly _mm_{max,min}_ep{i,u}8 / _mm_cmpgt_epi8, and every reference vector op is ONE
 //     sm_100a integer instruction (IADD3 / VIMNMX / ISETP) per cell.  This matters: fringe cells
 //     of the rounded band DO wrap in the reference and (rarely) feed in-band cells, so a wider
-//     non-wrapping representation is not bit-exact ("why not 16x2 DPX").
+//     non-wrapping representation is not bit-exact.  extz_dp16.cuh applies the same idea to
+//     16-bit halves (value << 8, two slots per register) for the packed sm_100a instructions.
 //   * neighbours: slot t needs the OLD x,v of slot t-1 -> in-lane register of slot i-1, or one
 //     __shfl from the circular predecessor lane for slot 0.
 //   * the 32-bit H[] row lives in SHARED memory (the only state that needs dynamic slot
@@ -22,9 +23,8 @@
 //   * traceback codes are 4 bits per cell (bit0: E beats H, bit1: F beats both, bit2: E
 //     continues, bit3: F continues), one coalesced store per lane per diagonal.
 //
-// The same header compiles for the host (no __CUDACC__): tests/sim runs the identical per-lane
-// code with the lanes of a group executed in lock-step phases, so that the kernel logic can be
-// fuzzed against the oracle without a GPU.  The simulator is test infrastructure only.
+// EXTZ_HD functions (band geometry, z-drop, tie keys, statistics columns) also compile for the host: engine.cu uses
+// them for planning and cell counting.
 #pragma once
 #include <stdint.h>
 

@@ -209,9 +209,10 @@ __device__ __forceinline__ void lane16_prepare(Lane16 &ls, const Band &b, int r,
 }
 
 // the cells of one anti-diagonal for this lane, traceback codes, u' dump and lazy-H update (:233-255).
-// Hrow / Urow point at this thread's column of the CTA-wide row arrays: row k of the thread is Hrow[k * 128].
+// Hrow / Urow point at this thread's column of the CTA-wide row arrays: row k of the thread is Hrow[k * RS]
+// (RS = threads per CTA).
 // H rows 2j / 2j+1 hold slots 4j..4j+3 of block A / block B; U row j holds registers 4j..4j+3.
-template <bool kCigar, bool kRight>
+template <bool kCigar, bool kRight, int RS = 128>
 __device__ __forceinline__ int32_t lane16_cells(Lane16 &ls, const Band &b, int r, int last_st, uint32_t xin, uint32_t vin,
                                                 uint4 *tb_dst, int4 *Hrow, uint4 *Urow, const Sc16 &sc)
 {
@@ -234,13 +235,13 @@ __device__ __forceinline__ int32_t lane16_cells(Lane16 &ls, const Band &b, int r
 #pragma unroll
 	for (int j = 0; j < 4; ++j) {
 		// H += sign-extended v: IDP.4A against a one-hot byte vector picks and sign-extends the top byte of a half
-		Urow[j * 128] = make_uint4(ls.U[4 * j], ls.U[4 * j + 1], ls.U[4 * j + 2], ls.U[4 * j + 3]);
-		int4 ha = Hrow[(2 * j) * 128], hb = Hrow[(2 * j + 1) * 128];
+		Urow[j * RS] = make_uint4(ls.U[4 * j], ls.U[4 * j + 1], ls.U[4 * j + 2], ls.U[4 * j + 3]);
+		int4 ha = Hrow[(2 * j) * RS], hb = Hrow[(2 * j + 1) * RS];
 		ha.x = __dp4a((int)ls.V[4 * j], 0x00000100, ha.x);     hb.x = __dp4a((int)ls.V[4 * j], 0x01000000, hb.x);
 		ha.y = __dp4a((int)ls.V[4 * j + 1], 0x00000100, ha.y); hb.y = __dp4a((int)ls.V[4 * j + 1], 0x01000000, hb.y);
 		ha.z = __dp4a((int)ls.V[4 * j + 2], 0x00000100, ha.z); hb.z = __dp4a((int)ls.V[4 * j + 2], 0x01000000, hb.z);
 		ha.w = __dp4a((int)ls.V[4 * j + 3], 0x00000100, ha.w); hb.w = __dp4a((int)ls.V[4 * j + 3], 0x01000000, hb.w);
-		Hrow[(2 * j) * 128] = ha; Hrow[(2 * j + 1) * 128] = hb;
+		Hrow[(2 * j) * RS] = ha; Hrow[(2 * j + 1) * RS] = hb;
 		int32_t m0 = ha.x > ha.y ? ha.x : ha.y, m1 = ha.z > ha.w ? ha.z : ha.w;
 		int32_t m2 = hb.x > hb.y ? hb.x : hb.y, m3 = hb.z > hb.w ? hb.z : hb.w;
 		m0 = m0 > m1 ? m0 : m1; m2 = m2 > m3 ? m2 : m3; m0 = m0 > m2 ? m0 : m2;
@@ -250,12 +251,13 @@ __device__ __forceinline__ int32_t lane16_cells(Lane16 &ls, const Band &b, int r
 }
 
 // arg-max, fast pass: (count << 24) + sum of t over this lane's slots whose lazy H equals gm
+template <int RS = 128>
 __device__ __forceinline__ uint32_t lane16_argmax_count(const Lane16 &ls, const int4 *Hrow, int32_t gm)
 {
 	uint32_t acc = 0;
 #pragma unroll
 	for (int k = 0; k < 8; ++k) {
-		const int4 h = Hrow[k * 128];
+		const int4 h = Hrow[k * RS];
 		const uint32_t base = (1u << 24) + (uint32_t)(ls.t0[k & 1] + 4 * (k >> 1));
 		if (h.x == gm) acc += base;
 		if (h.y == gm) acc += base + 1;
@@ -284,12 +286,13 @@ __device__ __forceinline__ uint32_t group_argmax_count(const int4 *Hgroup, int w
 	return acc;
 }
 // arg-max, exact pass (only on real ties): smallest tie-break key among this lane's slots whose lazy H equals gm
+template <int RS = 128>
 __device__ __forceinline__ uint32_t lane16_argmax_key(const Lane16 &ls, const Band &b, const int4 *Hrow, int32_t gm)
 {
 	uint32_t key = 0xffffffffu;
 #pragma unroll
 	for (int k = 0; k < 8; ++k) {
-		const int4 h = Hrow[k * 128];
+		const int4 h = Hrow[k * RS];
 		const int32_t hv[4] = {h.x, h.y, h.z, h.w};
 #pragma unroll
 		for (int e = 0; e < 4; ++e) {
@@ -304,7 +307,7 @@ __device__ __forceinline__ uint32_t lane16_argmax_key(const Lane16 &ls, const Ba
 }
 
 // H / u' rows of one pair inside the CTA-wide row arrays, addressed by circular slot index (for the Leader)
-template <int G>
+template <int G, int RS = 128>
 struct PackedRows {
 	static constexpr int kMask = G * 32 - 1;
 	int32_t *H;         // (int32_t *)&sH[0][first thread of the group]
@@ -312,12 +315,12 @@ struct PackedRows {
 	__device__ __forceinline__ int32_t &h(int c) const
 	{
 		const int vl = c >> 4, i = c & 15;
-		return H[(((((i >> 2) << 1) | (vl & 1)) * 128 + (vl >> 1)) << 2) | (i & 3)];
+		return H[(((((i >> 2) << 1) | (vl & 1)) * RS + (vl >> 1)) << 2) | (i & 3)];
 	}
 	__device__ __forceinline__ uint32_t u(int c) const          // top-byte form (value << 24), like LocalRows::u
 	{
 		const int vl = c >> 4, i = c & 15;
-		const uint32_t w = Us[((((i >> 2) * 128) + (vl >> 1)) << 2) | (i & 3)];
+		const uint32_t w = Us[((((i >> 2) * RS) + (vl >> 1)) << 2) | (i & 3)];
 		return (vl & 1) ? (w & 0xffff0000u) : (w << 16);
 	}
 };
@@ -454,6 +457,119 @@ extz_dp16_kernel(DpLaunch L)
 		}
 		if (pi < L.n && gl == 0) { if (zdropped_band) ld.ez.zdropped = 1; ld.store(&L.results[pi], n_diag); }
 		__syncwarp();
+	}
+}
+
+// =====================================================================================================
+// packed wide kernel: one CTA of G = 64 / 128 lanes x 32 slots per pair (2048 / 4096 live slots: unbanded gap fills of a
+// few kbp).  Carries between warps and the per-diagonal reductions go through shared memory, ordering by __syncthreads;
+// otherwise the per-lane code of the narrow kernel.
+// =====================================================================================================
+template <int G, bool kCigar, bool kRight>
+__global__ void __launch_bounds__(G)
+extz_dp16_wide_kernel(DpLaunch L)
+{
+	constexpr int NS = G * 32;
+	constexpr int NW = G / 32;
+	static_assert(G > 32 && G % 32 == 0 && (G & (G - 1)) == 0, "wide kernel: whole warps, power of two");
+
+	__shared__ int4 sH[8][G];
+	__shared__ uint4 sU[4][G];
+	__shared__ uint32_t sTable[kTableStride * kTableStride];
+	__shared__ uint32_t sCarryX[NW], sCarryV[NW];       // OLD x,v (packed) of every warp's top register
+	__shared__ int32_t sWarpMax[NW];
+	__shared__ uint32_t sWarpKey[NW];
+	__shared__ int sPair, sNeedArg, sStop;
+	__shared__ int32_t sGmax;
+
+	for (int i = threadIdx.x; i < kTableStride * kTableStride; i += blockDim.x) sTable[i] = (L.table[i] >> 16) * 0x00010001u;
+	__syncthreads();
+
+	const uint32_t table_saddr = (uint32_t)__cvta_generic_to_shared(sTable);
+	const int gl = threadIdx.x;
+	const int lane = gl & 31, wid = gl >> 5;
+	int4 *Hrow = &sH[0][gl];
+	uint4 *Urow = &sU[0][gl];
+	const PackedRows<G, G> rows{(int32_t *)&sH[0][0], (uint32_t *)&sU[0][0]};
+	const Scoring sc = L.sc;
+	const Sc16 sc16 = make_sc16(sc);
+	const int qe = sc.qe;
+	const bool generic = (sc.flag & kFlagGenericSc) != 0;
+
+	for (;;) {
+		if (gl == 0) sPair = atomicAdd(L.work_counter, 1);
+		__syncthreads();
+		const int pi = sPair;
+		if (pi >= L.n) break;
+		const PairDesc pd = L.pairs[pi];
+		const int qlen = pd.qlen, tlen = pd.tlen, w = pd.w;
+		const int T = (tlen + 15) & ~15;
+		const uint8_t *qseq = L.seq + pd.q_off;
+		const uint8_t *tseq = L.seq + pd.t_off;
+		uint8_t *tbp = kCigar ? L.tb + pd.tb_off + gl * 16 : nullptr;
+
+		Lane16 ls;
+		ls.t0[0] = gl * 32; ls.t0[1] = gl * 32 + 16;
+#pragma unroll
+		for (int i = 0; i < 16; ++i) { ls.U[i] = ls.V[i] = ls.X[i] = ls.Y[i] = 0u; ls.Z[i] = sc16.s0_2; }
+		lane16_load_seq<0>(ls, tseq, tlen, qseq, 0);
+		lane16_load_seq<1>(ls, tseq, tlen, qseq, 0);
+#pragma unroll
+		for (int k = 0; k < 8; ++k) Hrow[k * G] = make_int4(kNegInf, kNegInf, kNegInf, kNegInf);
+		Leader ld; ld.reset();
+		int last_st = -1, last_en = -1, n_diag = 0, zdropped_band = 0;
+		const int R = qlen + tlen - 1;
+		__syncthreads();
+
+		for (int r = 0; r < R; ++r) {
+			Band b;
+			if (!band_of(r, qlen, tlen, w, T, generic, b)) { zdropped_band = 1; break; }
+
+			// phase 1: publish the OLD top register of every warp; the leader prepares H (nobody else touches H now)
+			uint32_t xp = __shfl_up_sync(0xffffffffu, ls.X[15], 1);
+			uint32_t vp = __shfl_up_sync(0xffffffffu, ls.V[15], 1);
+			if (lane == 31) { sCarryX[wid] = ls.X[15]; sCarryV[wid] = ls.V[15]; }
+			if (gl == 0) ld.pre(rows, b, r, qe);
+			__syncthreads();                                                                   // A
+			// phase 2: cells
+			if (lane == 0) { const int pw = (wid + NW - 1) % NW; xp = sCarryX[pw]; vp = sCarryV[pw]; }
+			const uint32_t xin = __byte_perm(xp, ls.X[15], 0x5432), vin = __byte_perm(vp, ls.V[15], 0x5432);
+			lane16_prepare<NS>(ls, b, r, last_en, qseq, tseq, tlen, table_saddr, sc16);
+			const int32_t lane_max = lane16_cells<kCigar, kRight, G>(ls, b, r, last_st, xin, vin, (uint4 *)(tbp + (int64_t)r * (NS >> 1)),
+			                                                         Hrow, Urow, sc16);
+			const int32_t wmax = __reduce_max_sync(0xffffffffu, lane_max);
+			if (lane == 0) sWarpMax[wid] = wmax;
+			__syncthreads();                                                                   // B
+			// phase 3: leader
+			if (gl == 0) {
+				int32_t red = sWarpMax[0];
+#pragma unroll
+				for (int k = 1; k < NW; ++k) red = red > sWarpMax[k] ? red : sWarpMax[k];
+				const int need = ld.mid(rows, b, r, qe, red, ls.V[0] << 16, sc.zdrop);
+				sNeedArg = need; sGmax = ld.gmax;
+				if (!need) sStop = ld.fin(rows, b, r, qe, b.en0, qlen, tlen, sc.zdrop, sc.e);
+			}
+			__syncthreads();                                                                   // C
+			if (sNeedArg) {
+				uint32_t key = lane16_argmax_key<G>(ls, b, Hrow, sGmax);
+				key = __reduce_min_sync(0xffffffffu, key);
+				if (lane == 0) sWarpKey[wid] = key;
+				__syncthreads();                                                               // D
+				if (gl == 0) {
+					uint32_t k = ld.en0_key(b, r);
+#pragma unroll
+					for (int j = 0; j < NW; ++j) k = sWarpKey[j] < k ? sWarpKey[j] : k;
+					sStop = ld.fin(rows, b, r, qe, tie_key_slot(k, b.en0), qlen, tlen, sc.zdrop, sc.e);
+				}
+				__syncthreads();                                                               // E
+			}
+			const int stop = sStop;
+			n_diag = r + 1;
+			last_st = b.st; last_en = b.en;
+			if (stop) break;
+		}
+		if (gl == 0) { if (zdropped_band) ld.ez.zdropped = 1; ld.store(&L.results[pi], n_diag); }
+		__syncthreads();
 	}
 }
 

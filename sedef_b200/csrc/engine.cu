@@ -782,11 +782,21 @@ static int launch_sub(ksw_b200_batch &B, SubBatch &sb)
 			TL.stats = B.want_stats ? (sd_stats_t *)sb.d_stats.p + wv.first : nullptr;
 			TL.overflow = d_overflow;
 			TL.n = wv.count; TL.NS = class_ns(c); TL.flag = B.flag; TL.packed = class_packed(c) ? 1 : 0;
-			int tgrid = (wv.count + 127) / 128;
 			cudaStream_t tbs = sb.dc->tb_stream;
 			CUDA_TRY(cudaStreamWaitEvent(tbs, b2, 0));
-			if (B.want_stats) extz_traceback_kernel<true><<<tgrid, 128, 0, tbs>>>(TL);
-			else extz_traceback_kernel<false><<<tgrid, 128, 0, tbs>>>(TL);
+			// long walks are latency chains: one warp per pair with staged row tiles; short ones: one thread per pair
+			int64_t steps = 0;
+			for (int k = wv.first; k < wv.first + wv.count; ++k) steps += (int64_t)sb.pairs[k].qlen + sb.pairs[k].tlen;
+			static const int warp_min_steps = [] { const char *e = getenv("KSW_B200_TB_WARP_MIN"); return e ? atoi(e) : 6000; }();
+			if (steps / std::max(1, wv.count) >= warp_min_steps) {
+				const int tgrid = (wv.count + 3) / 4;
+				if (B.want_stats) extz_traceback_warp_kernel<true><<<tgrid, 128, 0, tbs>>>(TL);
+				else extz_traceback_warp_kernel<false><<<tgrid, 128, 0, tbs>>>(TL);
+			} else {
+				const int tgrid = (wv.count + 127) / 128;
+				if (B.want_stats) extz_traceback_kernel<true><<<tgrid, 128, 0, tbs>>>(TL);
+				else extz_traceback_kernel<false><<<tgrid, 128, 0, tbs>>>(TL);
+			}
 			CUDA_TRY(cudaGetLastError());
 			++sb.launches;
 			CUDA_TRY(cudaEventRecord(c2, tbs));

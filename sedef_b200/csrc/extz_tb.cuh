@@ -144,6 +144,135 @@ extz_traceback_kernel(TbLaunch L)
 	}
 }
 
+// ---- long pairs: one WARP per pair ---------------------------------------------------------------------------------
+// The walk of a long pair is a chain of dependent reads, each of them a DRAM access (consecutive rows are NS/2 bytes
+// apart and the arena does not fit L2): ~0.8 us per step, 80 ms for a 100k-step pair.  Here the warp stages a TILE of 32
+// rows first -- lane k loads, from row r-k, the two 16-byte chunks that hold slots [i-31, i] (the column moves by at most
+// one slot per row, so every nibble the next 32 rows can ask for is in there) -- and lane 0 then walks the tile out of
+// shared memory.  One DRAM latency per 32 rows instead of one per step.  Same state machine, same in-place reversed
+// CIGAR (writes stay in rows >= the current one; the tile's rows are already staged), same statistics.
+template <bool kStats>
+__global__ void __launch_bounds__(128)
+extz_traceback_warp_kernel(TbLaunch L)
+{
+	__shared__ __align__(16) uint8_t sTile[4][32][32];
+	const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int pi = blockIdx.x * 4 + wid;
+	if (pi >= L.n) return;                                         // whole warps leave together
+	const PairDesc pd = L.pairs[pi];
+	const PairResult pr = L.results[pi];
+	const int qlen = pd.qlen, tlen = pd.tlen, w = pd.w, NS = L.NS;
+	const int T = (tlen + 15) & ~15;
+	const int rowB = NS >> 1;
+	const bool packed = L.packed != 0;
+
+	StatAcc sa;
+	sa.span = sa.gap_bases = sa.matches = sa.mismatches = sa.indel_a = sa.indel_b = sa.alnB = sa.matchB = 0;
+	sa.mismatchB = sa.transitionsB = sa.transversionsB = sa.uppercaseA = sa.uppercaseB = sa.uppercaseMatches = 0;
+
+	int i0, j0; bool run = true;                                   // extern/ksw2_extz2_sse.cc:290-295
+	if (!pr.zdropped && !(L.flag & kFlagExtzOnly)) { i0 = tlen - 1; j0 = qlen - 1; }
+	else if (pr.max_t >= 0 && pr.max_q >= 0) { i0 = pr.max_t; j0 = pr.max_q; }
+	else { i0 = j0 = -1; run = false; }
+
+	uint8_t *tbp = L.tb + pd.tb_off;
+	uint32_t *cend = (uint32_t *)(tbp + ((int64_t)(run ? i0 + j0 : 0) + 1) * rowB);
+	int64_t n = 0; int32_t gaps = 0; uint32_t last = 0;             // lane 0 only
+	auto push = [&](uint32_t op, int len) {                         // ksw_push_cigar (extern/ksw2.h:98-111)
+		if (n == 0 || op != (last & 0xfu)) {
+			if (n) cend[-n] = last;
+			++n; last = (uint32_t)len << 4 | op;
+			if (op != 0) ++gaps;
+		} else last += (uint32_t)len << 4;
+	};
+
+	int i = i0, j = j0, state = 0;                                  // i, j are warp-uniform at tile boundaries
+	while (run && i >= 0 && j >= 0) {
+		const int r_top = i + j;
+		const int c_lo = (i - 31) & (NS - 1), c_hi = i & (NS - 1);
+		const int g_lo = c_lo >> 5, g_hi = c_hi >> 5;               // 32 slots per 16-byte chunk in both row layouts
+		if (r_top - lane >= 0) {
+			const uint4 *row = (const uint4 *)(tbp + (int64_t)(r_top - lane) * rowB);
+			*(uint4 *)&sTile[wid][lane][0] = row[g_lo];
+			*(uint4 *)&sTile[wid][lane][16] = row[g_hi];
+		}
+		__syncwarp();
+		if (lane == 0) {
+			while (i >= 0 && j >= 0 && i + j > r_top - 32) {          // extern/ksw2.h:124-144
+				const int r = i + j;
+				Band b; band_of(r, qlen, tlen, w, T, false, b);
+				int force = -1;
+				if (i < b.st) force = 2;
+				if (i > b.en) force = 1;
+				uint32_t tmp = 0;
+				if (force < 0) {
+					const int c = i & (NS - 1);
+					const int off = ((c >> 5) == g_hi ? 16 : 0) + (packed ? (c & 15) : ((c >> 1) & 15));
+					const int nib = packed ? ((c >> 4) & 1) : (c & 1);
+					tmp = (sTile[wid][r_top - r][off] >> (nib * 4)) & 0xfu;
+				}
+				int hstate = (tmp & 2u) ? 2 : (int)(tmp & 1u);
+				if (state == 0) state = hstate;
+				else if (!((tmp >> (state + 1)) & 1u)) state = 0;
+				if (state == 0) state = hstate;
+				if (force >= 0) state = force;
+				if (state == 0) {
+					push(0, 1);
+					if (kStats) stat_match_col(sa, raw_byte(L, pd.q_off, j), raw_byte(L, pd.t_off, i));
+					--i; --j;
+				} else if (state == 1) {
+					push(2, 1);
+					if (kStats) stat_tonly_col(sa, raw_byte(L, pd.t_off, i));
+					--i;
+				} else {
+					push(1, 1);
+					if (kStats) stat_qonly_col(sa, raw_byte(L, pd.q_off, j));
+					--j;
+				}
+			}
+		}
+		i = __shfl_sync(0xffffffffu, i, 0);
+		j = __shfl_sync(0xffffffffu, j, 0);
+		__syncwarp();                                                // the tile is rewritten next
+	}
+	if (lane == 0 && run) {
+		if (i >= 0) {                                               // extern/ksw2.h:145
+			push(2, i + 1);
+			if (kStats) for (int k = i; k >= 0; --k) stat_tonly_col(sa, raw_byte(L, pd.t_off, k));
+		}
+		if (j >= 0) {                                               // extern/ksw2.h:146
+			push(1, j + 1);
+			if (kStats) for (int k = j; k >= 0; --k) stat_qonly_col(sa, raw_byte(L, pd.q_off, k));
+		}
+		if (n) cend[-n] = last;
+	}
+	__syncwarp();                                                   // lane 0's CIGAR stores are visible to the copy below
+
+	// ---- copy to the compact arena (all lanes): memory order [cend-n, cend) is the FORWARD cigar ----
+	unsigned long long off = 0;
+	if (lane == 0 && n) {
+		off = atomicAdd(L.cigar_cursor, (unsigned long long)n);
+		if (off + (unsigned long long)n > L.cigar_capacity) { *L.overflow = 1; n = 0; }
+	}
+	n = __shfl_sync(0xffffffffu, n, 0);
+	off = __shfl_sync(0xffffffffu, off, 0);
+	const bool rev = (L.flag & kFlagRevCigar) != 0;
+	for (int64_t k = lane; k < n; k += 32)
+		L.cigar_arena[off + k] = rev ? cend[-1 - k] : cend[-n + k];
+	if (lane == 0) {
+		L.results[pi].n_cigar = (int32_t)n;
+		L.results[pi].cigar_off = (int32_t)off;
+		if (kStats && L.stats) {
+			sd_stats_t s;
+			s.span = sa.span; s.gaps = gaps; s.gap_bases = sa.gap_bases; s.matches = sa.matches; s.mismatches = sa.mismatches;
+			s.indel_a = sa.indel_a; s.indel_b = sa.indel_b; s.alnB = sa.alnB; s.matchB = sa.matchB; s.mismatchB = sa.mismatchB;
+			s.transitionsB = sa.transitionsB; s.transversionsB = sa.transversionsB;
+			s.uppercaseA = sa.uppercaseA; s.uppercaseB = sa.uppercaseB; s.uppercaseMatches = sa.uppercaseMatches; s.reserved = 0;
+			L.stats[pi] = s;
+		}
+	}
+}
+
 // ---- Alignment(fa, fb, cigar): SD statistics from an EXISTING CIGAR (src/align.cc:90-105,274-315; the consumer is
 // `sedef stats generate`, src/stats_main.cc:224).  One thread per alignment, forward walk over the raw ksw ops. ----
 struct CigarStatsLaunch {

@@ -213,6 +213,40 @@ def test_one_slot_per_register_kernels(checker, mat, tmp_path):
     assert out.returncode == 0 and "ok 1200" in out.stdout, out.stdout + out.stderr
 
 
+def test_warp_traceback_kernel_forced(checker, mat, tmp_path):
+    """The one-warp-per-pair traceback (staged 32-row tiles) normally serves long pairs only; KSW_B200_TB_WARP_MIN=0 sends
+    every pair through it (read once per process, hence the subprocess), in both traceback-row layouts."""
+    import os, subprocess, sys, textwrap
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "warp_tb.py"
+    script.write_text(textwrap.dedent(f"""
+        import sys
+        sys.path.insert(0, {root!r})
+        import oracle
+        from sedef_b200 import engine, synth
+        mat = synth.sedef_matrix()
+        engine.init(0, 1)
+        chk = oracle.ref() if oracle.have_ref() else oracle.port()
+        n = 0
+        for (kw, w, zd, flag) in [(dict(min_len=1, max_len=700, div=0.12), -1, -1, 0), (dict(min_len=1, max_len=600, div=0.2), 30, 80, 0x42),
+                                  (dict(min_len=300, max_len=1000, div=0.1), 100, -1, 0x80), (dict(min_len=900, max_len=2500, div=0.1), -1, 200, 0)]:
+            ps = synth.make_pairs_mixed(120, seed=777 + w, **kw)
+            got = engine.extz2_batch(ps, mat, 40, 1, w, zd, flag)
+            _, fr, cr = chk.batch(ps, mat, 40, 1, w, zd, flag, nthreads=8)
+            for i in range(ps.n):
+                assert got.fields(i) == fr[i], i
+                assert got.cigars[i].tolist() == cr[i], i
+                if not flag & 0x80:
+                    assert got.stats_dict(i) == oracle.sd_stats(cr[i], *ps.raw_pair(i)), i
+                n += 1
+        print("ok", n)
+    """))
+    for packed in ("1", "0"):
+        env = dict(os.environ, KSW_B200_TB_WARP_MIN="0", KSW_B200_PACKED=packed)
+        out = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, env=env, timeout=600)
+        assert out.returncode == 0 and "ok 480" in out.stdout, out.stdout + out.stderr
+
+
 def test_other_scoring_parameters(checker):
     """Scoring is not hard-wired: user-supplied --match/--mismatch/--gap-open/--gap-extend (src/align_main.cc:343-373)."""
     ps = synth.make_pairs_mixed(150, seed=77, min_len=1, max_len=400, div=0.15)

@@ -413,19 +413,24 @@ extz_dp16_kernel(DpLaunch L)
 			__syncwarp();
 			const int32_t red = group_max<G>(lane_max);
 			int need = 0;
-			if (act && gl == 0) need = ld.mid(rows, b, r, qe, red, ls.V[0] << 16, sc.zdrop);
+			if (act && gl == 0) {
+				need = ld.mid(rows, b, r, qe, red, ls.V[0] << 16, sc.zdrop);
+				need |= (int)(ld.Hen0_lazy == ld.gmax) << 1;             // bit 1: the leader's H[en0] reaches the maximum
+			}
 			__syncwarp();
+			// the leader's answers travel together (independent shuffles overlap their latency)
 			need = __shfl_sync(FULL, need, 0, G);
+			const int32_t gm = __shfl_sync(FULL, ld.gmax, 0, G);
+			const int en0_max = need >> 1;
+			need &= 1;
 			int max_t = b.en0;
 			if (__any_sync(FULL, need)) {
-				const int32_t gm = __shfl_sync(FULL, ld.gmax, 0, G);
 				uint32_t cnt = 0;
 				if (G == 1) { if (need) cnt = lane16_argmax_count(ls, Hrow, gm); }
 				else {
 					// Only a lane whose own maximum reaches gm, or the owner of slot en0 when the leader's H[en0] does, can
 					// hold the arg-max.  With ONE such lane (the rule) the G lanes of the group split ITS 8 rows between
 					// them instead of every lane scanning its own 32 entries.
-					const int en0_max = __shfl_sync(FULL, (int)(ld.Hen0_lazy == ld.gmax), 0, G);
 					const bool cand = need && (lane_max == gm || (en0_max && ((b.en0 & (NS - 1)) >> 5) == gl));
 					const unsigned bal = __ballot_sync(FULL, cand);
 					const unsigned gmask = G == 32 ? bal : ((bal >> (lane_w & ~(G - 1))) & ((1u << (G & 31)) - 1u));

@@ -116,6 +116,13 @@ def test_config3_shape_vs_oracle(checker, mat):
     compare(ps, mat, checker, 1200, 400, 0)             # CTA-wide banded
 
 
+def test_config3_full_length_pairs_vs_oracle(checker, mat):
+    """BASELINE.json configs[2] at its real pair sizes (10-50 kbp, w=500, z-drop 400, 15 % divergence with indels): 160 pairs,
+    9 GB of traceback rows, the warp-per-pair traceback -- every field, CIGAR and statistic against the oracle."""
+    ps = synth.make_pairs_large(160, min_len=10000, max_len=50000, seed=0x5EDEF003)
+    compare(ps, mat, checker, 500, 400, 0)
+
+
 def test_no_raw_bytes_decodes_codes(checker, mat):
     ps = synth.make_pairs_mixed(100, seed=5, min_len=1, max_len=300, div=0.1)
     compare(ps, mat, checker, -1, -1, 0, use_raw=False)

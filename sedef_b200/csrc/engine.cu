@@ -449,6 +449,11 @@ static int build_scoring(ksw_b200_batch &B)
 	auto top = [](int v) { return (uint32_t)(uint8_t)(int8_t)v << 24; };            // int8 truncation like _mm_set1_epi8
 	B.sc.q_s = top(q); B.sc.maxsc_s = top(B.mat[0] + qe2); B.sc.s0_s = top(0 + qe2);
 	B.sc.q = q; B.sc.e = e; B.sc.qe = q + e; B.sc.zdrop = B.zdrop; B.sc.flag = B.flag; B.sc.w_in = B.w;
+	B.sc.q16 = B.sc.q_s >> 16;
+	B.sc.qeps2 = B.sc.q16 * 0x00010001u + 0x00010001u;          // ~z + qeps2 == q - z per half
+	B.sc.maxsc2 = (B.sc.maxsc_s >> 16) * 0x00010001u;
+	B.sc.s0_2 = (B.sc.s0_s >> 16) * 0x00010001u;
+	B.sc.zr2 = 0u;                                               // a zero the compiler cannot fold (see extz_dp16.cuh)
 	for (int a = 0; a < kTableStride; ++a)
 		for (int b = 0; b < kTableStride; ++b) {
 			int s;

@@ -52,6 +52,9 @@ struct Scoring {
 	uint32_t s0_s;         // (0 + 2(q+e)) << 24: z of a never-filled slot (s[] starts zeroed, :83)
 	int q, e, qe;
 	int zdrop, flag, w_in; // w as passed by the caller (<0: unbanded)
+	// the same constants for the packed kernel (extz_dp16.cuh): int8 << 8 in BOTH 16-bit halves.  Precomputed on the host so
+	// that the kernel can take them straight from the constant bank instead of holding them in registers.
+	uint32_t q16, qeps2, maxsc2, s0_2, zr2;
 };
 
 // One pair, as the DP kernel sees it.

@@ -39,14 +39,10 @@ struct Sc16 {
 	uint32_t s0_2;       // z of a never-filled slot in both halves
 	uint32_t zr;         // 0 held in a register: as an immediate ptxas re-materialises it (PRMT RZ) for every VIADDMNMX
 };
-__device__ __forceinline__ Sc16 make_sc16(const Scoring &sc)
+__device__ __forceinline__ Sc16 make_sc16(const Scoring &sc)      // host-computed (engine.cu build_scoring)
 {
 	Sc16 s;
-	s.q16 = sc.q_s >> 16;
-	s.qeps2 = s.q16 * 0x00010001u + 0x00010001u;
-	s.maxsc2 = (sc.maxsc_s >> 16) * 0x00010001u;
-	s.s0_2 = (sc.s0_s >> 16) * 0x00010001u;
-	s.zr = sc.q_s & 0x00ffffffu;
+	s.q16 = sc.q16; s.qeps2 = sc.qeps2; s.maxsc2 = sc.maxsc2; s.s0_2 = sc.s0_2; s.zr = sc.zr2;
 	return s;
 }
 
@@ -354,8 +350,8 @@ extz_dp16_kernel(DpLaunch L)
 	int4 *Hrow = &sH[0][threadIdx.x];
 	uint4 *Urow = &sU[0][threadIdx.x];
 	const PackedRows<G> rows{(int32_t *)&sH[0][threadIdx.x - gl], (uint32_t *)&sU[0][threadIdx.x - gl]};
-	const Scoring sc = L.sc;
-	const Sc16 sc16 = make_sc16(sc);
+	const Scoring &sc = L.sc;
+	const Sc16 sc16 = make_sc16(L.sc);
 	const int qe = sc.qe;
 	const bool generic = (sc.flag & kFlagGenericSc) != 0;
 
@@ -496,8 +492,8 @@ extz_dp16_wide_kernel(DpLaunch L)
 	int4 *Hrow = &sH[0][gl];
 	uint4 *Urow = &sU[0][gl];
 	const PackedRows<G, G> rows{(int32_t *)&sH[0][0], (uint32_t *)&sU[0][0]};
-	const Scoring sc = L.sc;
-	const Sc16 sc16 = make_sc16(sc);
+	const Scoring &sc = L.sc;
+	const Sc16 sc16 = make_sc16(L.sc);
 	const int qe = sc.qe;
 	const bool generic = (sc.flag & kFlagGenericSc) != 0;
 

@@ -946,7 +946,8 @@ extern "C" int ksw_b200_batch_fetch(ksw_b200_batch_t *B, ksw_extz_t *ez, sd_stat
 extern "C" void ksw_b200_free_cigars(ksw_extz_t *ez, int n)
 {
 	if (!ez) return;
-#pragma omp parallel for num_threads(host_threads()) schedule(static)
+	// serial on purpose: the blocks were malloc'ed by the gather threads, so a parallel loop frees into foreign glibc arenas
+	// and contends on their locks (measured on the 32-thread host: 3.2 ms serial vs 4.7 ms parallel for 100k CIGARs)
 	for (int i = 0; i < n; ++i) { free(ez[i].cigar); ez[i].cigar = nullptr; ez[i].n_cigar = ez[i].m_cigar = 0; }
 }
 

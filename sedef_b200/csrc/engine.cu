@@ -542,31 +542,69 @@ extern "C" ksw_b200_batch_t *ksw_b200_batch_upload(int n, const int *qlen, const
 	const double t_start = now_ms();
 	// ---- classify + LPT partition ----
 	struct Item { int idx; int cls; int64_t work; };
-	std::vector<Item> items; items.reserve(n);
+	std::vector<Item> items(n);
+	const bool skip_s32 = getenv("KSW_B200_SKIP_S32") != nullptr;                       // A/B: 32 lanes x 32 slots vs 64-lane CTA
+	int too_wide = -1;
+#pragma omp parallel for num_threads(host_threads()) schedule(static) if (n >= 4096)
 	for (int i = 0; i < n; ++i) {
-		if (m <= 0 || qlen[i] <= 0 || tlen[i] <= 0 || B->early_out) { B->is_empty[i] = 1; continue; }
+		items[i].idx = i; items[i].cls = -1; items[i].work = 0;
+		if (m <= 0 || qlen[i] <= 0 || tlen[i] <= 0 || B->early_out) continue;           // empty record (:57,81)
 		int wi = w < 0 ? std::max(qlen[i], tlen[i]) : std::min(w, std::max(qlen[i], tlen[i]));
 		int need = slots_needed(qlen[i], tlen[i], wi);
 		int c = 0;
 		while (c < kNumSizedClasses && class_capacity(c) < need) ++c;
-		if (c == 5 && getenv("KSW_B200_SKIP_S32")) c = 6;                              // A/B: 32 lanes x 32 slots vs 64-lane CTA
+		if (c == 5 && skip_s32) c = 6;
 		if (c == kNumSizedClasses) {
-			delete B;
-			return bail(fail(KSW_B200_ERR_TOO_WIDE, "pair " + std::to_string(i) + " needs " + std::to_string(need) +
-			                 " live slots; widest kernel holds " + std::to_string(class_capacity(kNumSizedClasses - 1))));
+#pragma omp critical
+			{ if (too_wide < 0 || i < too_wide) too_wide = i; }
+			continue;
 		}
-		items.push_back({i, c, est_cells(qlen[i], tlen[i], wi)});
+		items[i].cls = c; items[i].work = est_cells(qlen[i], tlen[i], wi);
 	}
-	std::vector<int> order(items.size());
-	std::iota(order.begin(), order.end(), 0);
-	std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return items[a].work > items[b].work; });
-	std::vector<int64_t> load(nd, 0);
+	if (too_wide >= 0) {
+		const int i = too_wide;
+		int wi = w < 0 ? std::max(qlen[i], tlen[i]) : std::min(w, std::max(qlen[i], tlen[i]));
+		delete B;
+		return bail(fail(KSW_B200_ERR_TOO_WIDE, "pair " + std::to_string(i) + " needs " + std::to_string(slots_needed(qlen[i], tlen[i], wi)) +
+		                 " live slots; widest kernel holds " + std::to_string(class_capacity(kNumSizedClasses - 1))));
+	}
+	std::vector<int> order; order.reserve(n);
+	for (int i = 0; i < n; ++i) { if (items[i].cls < 0) B->is_empty[i] = 1; else order.push_back(i); }
 	std::vector<std::vector<int>> per_dev(nd);
-	for (int oi : order) {                                                          // greedy LPT
-		int best = 0;
-		for (int d = 1; d < nd; ++d) if (load[d] < load[best]) best = d;
-		load[best] += items[oi].work + 1;
-		per_dev[best].push_back(oi);
+	if (nd == 1) {
+		// one device: the order the kernels want directly -- by class, descending work inside a class (the device-side
+		// dynamic queue then hands out the long pairs first).  The order only steers load balance (results are gathered by
+		// original index), so the work is quantised to 20 bits and the keys go through a stable LSD radix sort: O(n), no
+		// comparison sort on the producer thread's critical path.
+		int64_t max_work = 1;
+		for (int i : order) max_work = std::max(max_work, items[i].work);
+		int shift = 0;
+		while ((max_work >> shift) >= (1 << 20)) ++shift;
+		const size_t no = order.size();
+		std::vector<uint32_t> key(no), key2(no);
+		std::vector<int> order2(no);
+		for (size_t k = 0; k < no; ++k) {
+			const Item &it = items[order[k]];
+			key[k] = ((uint32_t)it.cls << 20) | (uint32_t)((1 << 20) - 1 - (it.work >> shift));
+		}
+		for (int pass = 0; pass < 2; ++pass) {                                         // 2 x 12 bits
+			const int sh = 12 * pass;
+			uint32_t cnt[4097] = {0};
+			for (size_t k = 0; k < no; ++k) ++cnt[((key[k] >> sh) & 4095u) + 1];
+			for (int b = 0; b < 4096; ++b) cnt[b + 1] += cnt[b];
+			for (size_t k = 0; k < no; ++k) { const uint32_t d = cnt[(key[k] >> sh) & 4095u]++; key2[d] = key[k]; order2[d] = order[k]; }
+			key.swap(key2); order.swap(order2);
+		}
+		per_dev[0].swap(order);
+	} else {
+		std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return items[a].work > items[b].work; });
+		std::vector<int64_t> load(nd, 0);
+		for (int oi : order) {                                                          // greedy LPT
+			int best = 0;
+			for (int d = 1; d < nd; ++d) if (load[d] < load[best]) best = d;
+			load[best] += items[oi].work + 1;
+			per_dev[best].push_back(oi);
+		}
 	}
 
 	B->t_plan = now_ms() - t_start;
@@ -574,7 +612,7 @@ extern "C" ksw_b200_batch_t *ksw_b200_batch_upload(int n, const int *qlen, const
 	for (int d = 0; d < nd; ++d) {
 		SubBatch &sb = B->subs[d];
 		auto &lst = per_dev[d];
-		std::stable_sort(lst.begin(), lst.end(), [&](int a, int b) { return items[a].cls < items[b].cls; });
+		if (nd > 1) std::stable_sort(lst.begin(), lst.end(), [&](int a, int b) { return items[a].cls < items[b].cls; });
 		size_t pos = 0;
 		sb.pairs.resize(lst.size());
 		for (int c = 0; c <= kNumClasses; ++c) {

@@ -81,12 +81,14 @@ static inline bool packed_enabled()
 	static const bool on = [] { const char *e = getenv("KSW_B200_PACKED"); return !(e && e[0] == '0'); }();
 	return on;
 }
-static inline bool class_packed(int c) { return packed_enabled() && !kClasses[c].cluster; }      // narrow (<= 1024 slots) and CTA-wide
+// narrow (<= 1024 slots) and CTA-wide (<= 8192 slots: the packed CTA of 256 lanes replaces the cluster of 2 CTAs x 256 lanes x 16 slots)
+static inline bool class_packed(int c) { return packed_enabled() && class_ns(c) <= 8192; }
+static inline int class_cluster(int c) { return class_packed(c) ? 0 : kClasses[c].cluster; }
 static inline bool class_packed_wide(int c) { return class_packed(c) && class_ns(c) > 1024; }    // one CTA of NS/32 lanes per pair
 static inline int class_capacity(int c) { return (kClasses[c].S > 16 && !class_packed(c)) ? class_ns(c) - 16 : class_ns(c); }
 static inline int class_threads(int c)
 {
-	if (kClasses[c].cluster) return 256;
+	if (class_cluster(c)) return 256;
 	if (class_packed(c)) return class_packed_wide(c) ? class_ns(c) / 32 : 128;
 	return kClasses[c].wide ? kClasses[c].G : 128;
 }
@@ -165,23 +167,33 @@ static int dp16_occupancy(bool cigar, bool right)
 	} else       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, extz_dp16_kernel<G, false, false>, 128, 0);
 	return nb;
 }
+// packed CTA-wide kernels: 192 B of dynamic shared memory per lane (H and u' rows)
+template <int G, bool C, bool R>
+static cudaError_t dp16_wide_prepare()
+{
+	static cudaError_t once = cudaFuncSetAttribute(extz_dp16_wide_kernel<G, C, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, G * 192);
+	return once;
+}
 template <int G>
 static cudaError_t launch_dp16_wide(const DpLaunch &L, bool cigar, bool right, int grid, cudaStream_t st)
 {
+	const size_t dyn = (size_t)G * 192;
+	cudaError_t e;
 	if (cigar) {
-		if (right) extz_dp16_wide_kernel<G, true, true><<<grid, G, 0, st>>>(L);
-		else       extz_dp16_wide_kernel<G, true, false><<<grid, G, 0, st>>>(L);
-	} else       extz_dp16_wide_kernel<G, false, false><<<grid, G, 0, st>>>(L);
+		if (right) { if ((e = dp16_wide_prepare<G, true, true>()) != cudaSuccess) return e; extz_dp16_wide_kernel<G, true, true><<<grid, G, dyn, st>>>(L); }
+		else       { if ((e = dp16_wide_prepare<G, true, false>()) != cudaSuccess) return e; extz_dp16_wide_kernel<G, true, false><<<grid, G, dyn, st>>>(L); }
+	} else         { if ((e = dp16_wide_prepare<G, false, false>()) != cudaSuccess) return e; extz_dp16_wide_kernel<G, false, false><<<grid, G, dyn, st>>>(L); }
 	return cudaGetLastError();
 }
 template <int G>
 static int dp16_wide_occupancy(bool cigar, bool right)
 {
 	int nb = 0;
+	const size_t dyn = (size_t)G * 192;
 	if (cigar) {
-		if (right) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, extz_dp16_wide_kernel<G, true, true>, G, 0);
-		else       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, extz_dp16_wide_kernel<G, true, false>, G, 0);
-	} else       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, extz_dp16_wide_kernel<G, false, false>, G, 0);
+		if (right) { dp16_wide_prepare<G, true, true>(); cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, extz_dp16_wide_kernel<G, true, true>, G, dyn); }
+		else       { dp16_wide_prepare<G, true, false>(); cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, extz_dp16_wide_kernel<G, true, false>, G, dyn); }
+	} else         { dp16_wide_prepare<G, false, false>(); cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, extz_dp16_wide_kernel<G, false, false>, G, dyn); }
 	return nb;
 }
 #define EXTZ_FOR_PACKED(ns, CALL) \
@@ -196,11 +208,12 @@ static int dp16_wide_occupancy(bool cigar, bool right)
 // grid: CTAs for narrow / wide classes, clusters for cluster classes
 static cudaError_t launch_dp(int c, const DpLaunch &L, bool cigar, bool right, int grid, cudaStream_t st)
 {
-	if (kClasses[c].cluster == 2) return cluster_dispatch<2>(L, cigar, right, grid, st, nullptr);
-	if (kClasses[c].cluster == 4) return cluster_dispatch<4>(L, cigar, right, grid, st, nullptr);
+	if (class_cluster(c) == 2) return cluster_dispatch<2>(L, cigar, right, grid, st, nullptr);
+	if (class_cluster(c) == 4) return cluster_dispatch<4>(L, cigar, right, grid, st, nullptr);
 	if (class_packed_wide(c)) {
 		if (class_ns(c) == 2048) return launch_dp16_wide<64>(L, cigar, right, grid, st);
 		if (class_ns(c) == 4096) return launch_dp16_wide<128>(L, cigar, right, grid, st);
+		if (class_ns(c) == 8192) return launch_dp16_wide<256>(L, cigar, right, grid, st);
 		return cudaErrorInvalidValue;
 	}
 	if (class_packed(c)) {
@@ -217,14 +230,16 @@ static cudaError_t launch_dp(int c, const DpLaunch &L, bool cigar, bool right, i
 // resident CTAs per SM (narrow / wide) or co-resident clusters on the whole device (cluster classes)
 static int dp_occupancy(int c, bool cigar, bool right)
 {
-	if (kClasses[c].cluster) {
+	if (class_cluster(c)) {
 		int n = 0; DpLaunch dummy = {};
-		cudaError_t e = kClasses[c].cluster == 2 ? cluster_dispatch<2>(dummy, cigar, right, 1, nullptr, &n)
+		cudaError_t e = class_cluster(c) == 2 ? cluster_dispatch<2>(dummy, cigar, right, 1, nullptr, &n)
 		                                         : cluster_dispatch<4>(dummy, cigar, right, 1, nullptr, &n);
 		if (e != cudaSuccess) { cudaGetLastError(); return 0; }
 		return n;
 	}
-	if (class_packed_wide(c)) return class_ns(c) == 2048 ? dp16_wide_occupancy<64>(cigar, right) : dp16_wide_occupancy<128>(cigar, right);
+	if (class_packed_wide(c))
+		return class_ns(c) == 2048 ? dp16_wide_occupancy<64>(cigar, right)
+		     : class_ns(c) == 4096 ? dp16_wide_occupancy<128>(cigar, right) : dp16_wide_occupancy<256>(cigar, right);
 	if (class_packed(c)) {
 #define EXTZ_CALL16(G) dp16_occupancy<G>(cigar, right)
 		EXTZ_FOR_PACKED(class_ns(c), EXTZ_CALL16)
@@ -807,7 +822,7 @@ static int launch_sub(ksw_b200_batch &B, SubBatch &sb)
 		int occ = dp_occupancy(c, cigar, right);
 		if (occ <= 0) return fail(KSW_B200_ERR_CUDA, "DP kernel cannot be resident (occupancy 0)");
 		const int groups_per_block = class_pairs_per_block(c);
-		int grid = kClasses[c].cluster ? std::min(wv.count, occ)                              // clusters, one pair each
+		int grid = class_cluster(c) ? std::min(wv.count, occ)                                 // clusters, one pair each
 		                               : std::min((wv.count + groups_per_block - 1) / groups_per_block, sb.dc->sms * occ);
 		cudaEvent_t a, b2, c2;
 		CUDA_TRY(cudaEventCreate(&a)); CUDA_TRY(cudaEventCreate(&b2)); CUDA_TRY(cudaEventCreate(&c2));

@@ -462,8 +462,8 @@ extz_dp16_kernel(DpLaunch L)
 }
 
 // =====================================================================================================
-// packed wide kernel: one CTA of G = 64 / 128 lanes x 32 slots per pair (2048 / 4096 live slots: unbanded gap fills of a
-// few kbp).  Carries between warps and the per-diagonal reductions go through shared memory, ordering by __syncthreads;
+// packed wide kernel: one CTA of G = 64 / 128 / 256 lanes x 32 slots per pair (2048 / 4096 / 8192 live slots: unbanded gap
+// fills of a few kbp).  Carries between warps and the per-diagonal reductions go through shared memory, ordering by __syncthreads;
 // otherwise the per-lane code of the narrow kernel.
 // =====================================================================================================
 template <int G, bool kCigar, bool kRight>
@@ -474,8 +474,10 @@ extz_dp16_wide_kernel(DpLaunch L)
 	constexpr int NW = G / 32;
 	static_assert(G > 32 && G % 32 == 0 && (G & (G - 1)) == 0, "wide kernel: whole warps, power of two");
 
-	__shared__ int4 sH[8][G];
-	__shared__ uint4 sU[4][G];
+	// the H / u' rows are dynamic shared memory: 192 B per lane, 48 KB for G = 256 (beyond the static limit with the rest)
+	extern __shared__ __align__(16) unsigned char extz_dyn_smem[];
+	int4 (*sH)[G] = reinterpret_cast<int4 (*)[G]>(extz_dyn_smem);
+	uint4 (*sU)[G] = reinterpret_cast<uint4 (*)[G]>(extz_dyn_smem + sizeof(int4) * 8 * G);
 	__shared__ uint32_t sTable[kTableStride * kTableStride];
 	__shared__ uint32_t sCarryX[NW], sCarryV[NW];       // OLD x,v (packed) of every warp's top register
 	__shared__ int32_t sWarpMax[NW];

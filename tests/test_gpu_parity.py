@@ -178,9 +178,9 @@ def test_widest_pair_and_too_wide(checker, mat):
 
 
 def test_packed_class_boundaries(checker, mat):
-    """Pairs that fill the live-slot window of every packed class exactly (32 .. 4096 slots: the window wraps with no
+    """Pairs that fill the live-slot window of every packed class exactly (32 .. 8192 slots: the window wraps with no
     slack), one slot less, and one block more (next class), unbanded and banded, both traceback arms."""
-    for L in (32, 64, 128, 256, 512, 1024, 2048, 4096):              # 2048 / 4096: the packed CTA-wide kernel
+    for L in (32, 64, 128, 256, 512, 1024, 2048, 4096, 8192):        # 2048 .. 8192: the packed CTA-wide kernel
         ps = synth.make_pairs_small(8, length=L + 60, div=0.08, seed=700 + L)
         ps.tlen[:] = np.minimum(ps.tlen, np.array([L, L, L - 1, L - 15, L - 16, L + 1, L + 16, L], np.int32))
         ps.qlen[:] = np.minimum(ps.qlen, np.array([L + 60, L, L + 7, L + 60, L, L + 60, L + 3, L - 9], np.int32))

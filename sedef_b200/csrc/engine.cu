@@ -82,9 +82,10 @@ static inline bool packed_enabled()
 	return on;
 }
 // narrow (<= 1024 slots) and CTA-wide (<= 8192 slots: the packed CTA of 256 lanes replaces the cluster of 2 CTAs x 256 lanes x 16 slots)
-static inline bool class_packed(int c) { return packed_enabled() && class_ns(c) <= 8192; }
-static inline int class_cluster(int c) { return class_packed(c) ? 0 : kClasses[c].cluster; }
-static inline bool class_packed_wide(int c) { return class_packed(c) && class_ns(c) > 1024; }    // one CTA of NS/32 lanes per pair
+static inline bool class_packed(int c) { return packed_enabled(); }                              // every class has a packed kernel
+static inline bool class_packed_cluster(int c) { return class_packed(c) && class_ns(c) > 8192; } // 2 CTAs x 256 lanes x 32 slots
+static inline int class_cluster(int c) { return class_packed(c) ? (class_ns(c) > 8192 ? 2 : 0) : kClasses[c].cluster; }
+static inline bool class_packed_wide(int c) { return class_packed(c) && class_ns(c) > 1024 && class_ns(c) <= 8192; }    // one CTA of NS/32 lanes per pair
 static inline int class_capacity(int c) { return (kClasses[c].S > 16 && !class_packed(c)) ? class_ns(c) - 16 : class_ns(c); }
 static inline int class_threads(int c)
 {
@@ -94,7 +95,7 @@ static inline int class_threads(int c)
 }
 static inline int class_pairs_per_block(int c)
 {
-	if (class_packed(c)) return class_packed_wide(c) ? 1 : 128 * 32 / class_ns(c);
+	if (class_packed(c)) return class_ns(c) > 1024 ? 1 : 128 * 32 / class_ns(c);
 	return kClasses[c].wide ? 1 : 128 / kClasses[c].G;
 }
 
@@ -139,6 +140,32 @@ static cudaError_t cluster_launch_one(const DpLaunch &L, int nclusters, cudaStre
 		return cudaOccupancyMaxActiveClusters(max_clusters, extz_dp_cluster_kernel<C, 16, CG, R>, &cfg);
 	}
 	return cudaLaunchKernelEx(&cfg, extz_dp_cluster_kernel<C, 16, CG, R>, L);
+}
+// packed cluster kernel (2 CTAs x 256 lanes x 32 slots = 16384 live slots): 48 KB of dynamic shared memory per CTA
+template <bool CG, bool R>
+static cudaError_t cluster16_launch_one(const DpLaunch &L, int nclusters, cudaStream_t st, int *max_clusters)
+{
+	constexpr int C = 2;
+	const size_t dyn = 256 * 192;
+	static cudaError_t once = cudaFuncSetAttribute(extz_dp16_cluster_kernel<C, CG, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+	if (once != cudaSuccess) return once;
+	cudaLaunchConfig_t cfg = {};
+	cfg.gridDim = dim3((unsigned)(nclusters * C)); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = dyn; cfg.stream = st;
+	cudaLaunchAttribute attr[1];
+	attr[0].id = cudaLaunchAttributeClusterDimension;
+	attr[0].val.clusterDim.x = C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+	cfg.attrs = attr; cfg.numAttrs = 1;
+	if (max_clusters) {
+		cfg.gridDim = dim3((unsigned)C);
+		return cudaOccupancyMaxActiveClusters(max_clusters, extz_dp16_cluster_kernel<C, CG, R>, &cfg);
+	}
+	return cudaLaunchKernelEx(&cfg, extz_dp16_cluster_kernel<C, CG, R>, L);
+}
+static cudaError_t cluster16_dispatch(const DpLaunch &L, bool cigar, bool right, int nclusters, cudaStream_t st, int *max_clusters)
+{
+	if (cigar) return right ? cluster16_launch_one<true, true>(L, nclusters, st, max_clusters)
+	                        : cluster16_launch_one<true, false>(L, nclusters, st, max_clusters);
+	return cluster16_launch_one<false, false>(L, nclusters, st, max_clusters);
 }
 template <int C>
 static cudaError_t cluster_dispatch(const DpLaunch &L, bool cigar, bool right, int nclusters, cudaStream_t st, int *max_clusters)
@@ -208,6 +235,7 @@ static int dp16_wide_occupancy(bool cigar, bool right)
 // grid: CTAs for narrow / wide classes, clusters for cluster classes
 static cudaError_t launch_dp(int c, const DpLaunch &L, bool cigar, bool right, int grid, cudaStream_t st)
 {
+	if (class_packed_cluster(c)) return cluster16_dispatch(L, cigar, right, grid, st, nullptr);
 	if (class_cluster(c) == 2) return cluster_dispatch<2>(L, cigar, right, grid, st, nullptr);
 	if (class_cluster(c) == 4) return cluster_dispatch<4>(L, cigar, right, grid, st, nullptr);
 	if (class_packed_wide(c)) {
@@ -230,6 +258,11 @@ static cudaError_t launch_dp(int c, const DpLaunch &L, bool cigar, bool right, i
 // resident CTAs per SM (narrow / wide) or co-resident clusters on the whole device (cluster classes)
 static int dp_occupancy(int c, bool cigar, bool right)
 {
+	if (class_packed_cluster(c)) {
+		int n = 0; DpLaunch dummy = {};
+		if (cluster16_dispatch(dummy, cigar, right, 1, nullptr, &n) != cudaSuccess) { cudaGetLastError(); return 0; }
+		return n;
+	}
 	if (class_cluster(c)) {
 		int n = 0; DpLaunch dummy = {};
 		cudaError_t e = class_cluster(c) == 2 ? cluster_dispatch<2>(dummy, cigar, right, 1, nullptr, &n)

@@ -576,4 +576,157 @@ extz_dp16_wide_kernel(DpLaunch L)
 	}
 }
 
+// =====================================================================================================
+// packed cluster kernel: one thread-block CLUSTER of C CTAs x 256 lanes x 32 slots per pair (C = 2: 16384 live slots, the
+// unbanded <= 10 kbp gap fills of src/align.cc:130-139).  Every CTA keeps the H / u' rows of its own lanes; the carry
+// between CTAs, the leader's accesses to arbitrary slots and the per-diagonal reductions go through DISTRIBUTED SHARED
+// MEMORY (cluster.map_shared_rank), ordering by cluster.sync() -- the choreography of extz_dp_cluster_kernel with the
+// packed lane code.
+// =====================================================================================================
+template <int C>
+struct ClusterRows16 {
+	static constexpr int GC = 256, kMask = C * GC * 32 - 1;
+	int32_t *H; uint32_t *Us;                           // this CTA's arrays (same offset in every CTA)
+	__device__ __forceinline__ int32_t &h(int c) const
+	{
+		cg::cluster_group cl = cg::this_cluster();
+		const int gl = c >> 5, half = (c >> 4) & 1, i = c & 15;
+		return cl.map_shared_rank(H, gl / GC)[(((((i >> 2) << 1) | half) * GC + (gl % GC)) << 2) | (i & 3)];
+	}
+	__device__ __forceinline__ uint32_t u(int c) const
+	{
+		cg::cluster_group cl = cg::this_cluster();
+		const int gl = c >> 5, half = (c >> 4) & 1, i = c & 15;
+		const uint32_t w = cl.map_shared_rank(Us, gl / GC)[((((i >> 2) * GC) + (gl % GC)) << 2) | (i & 3)];
+		return half ? (w & 0xffff0000u) : (w << 16);
+	}
+};
+
+template <int C, bool kCigar, bool kRight>
+__global__ void __launch_bounds__(256, 1)
+extz_dp16_cluster_kernel(DpLaunch L)
+{
+	constexpr int GC = 256, G = GC * C, NS = G * 32, NW = GC / 32;
+	static_assert(C == 2 || C == 4, "packed cluster kernel: 2 or 4 CTAs");
+	cg::cluster_group cluster = cg::this_cluster();
+	const int rank = (int)cluster.block_rank();
+
+	extern __shared__ __align__(16) unsigned char extz_dyn_smem[];
+	int4 (*sH)[GC] = reinterpret_cast<int4 (*)[GC]>(extz_dyn_smem);
+	uint4 (*sU)[GC] = reinterpret_cast<uint4 (*)[GC]>(extz_dyn_smem + sizeof(int4) * 8 * GC);
+	__shared__ uint32_t sTable[kTableStride * kTableStride];
+	__shared__ uint32_t sCarryX[NW], sCarryV[NW];       // OLD x,v (packed) of every warp's top register
+	__shared__ int32_t sAllMax[4 * NW];                 // [rank][warp], only CTA 0's copy is used
+	__shared__ uint32_t sAllKey[4 * NW];
+	__shared__ int sPair, sNeedArg, sStop;              // written into EVERY CTA's copy by the leader
+	__shared__ int32_t sGmax;
+
+	for (int i = threadIdx.x; i < kTableStride * kTableStride; i += blockDim.x) sTable[i] = (L.table[i] >> 16) * 0x00010001u;
+	__syncthreads();
+
+	const uint32_t table_saddr = (uint32_t)__cvta_generic_to_shared(sTable);
+	const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+	const int gl = rank * GC + tid;                      // lane within the pair
+	const bool leader = gl == 0;
+	int4 *Hrow = &sH[0][tid];
+	uint4 *Urow = &sU[0][tid];
+	const ClusterRows16<C> rows{(int32_t *)&sH[0][0], (uint32_t *)&sU[0][0]};
+	const Scoring &sc = L.sc;
+	const Sc16 sc16 = make_sc16(L.sc);
+	const int qe = sc.qe;
+	const bool generic = (sc.flag & kFlagGenericSc) != 0;
+	int32_t *max0 = cluster.map_shared_rank(sAllMax, 0);
+	uint32_t *key0 = cluster.map_shared_rank(sAllKey, 0);
+
+	for (;;) {
+		if (leader) {
+			const int p = atomicAdd(L.work_counter, 1);
+			for (int k = 0; k < C; ++k) *cluster.map_shared_rank(&sPair, k) = p;
+		}
+		cluster.sync();
+		const int pi = sPair;
+		if (pi >= L.n) break;
+		const PairDesc pd = L.pairs[pi];
+		const int qlen = pd.qlen, tlen = pd.tlen, w = pd.w;
+		const int T = (tlen + 15) & ~15;
+		const uint8_t *qseq = L.seq + pd.q_off;
+		const uint8_t *tseq = L.seq + pd.t_off;
+		uint8_t *tbp = kCigar ? L.tb + pd.tb_off + gl * 16 : nullptr;
+
+		Lane16 ls;
+		ls.t0[0] = gl * 32; ls.t0[1] = gl * 32 + 16;
+#pragma unroll
+		for (int i = 0; i < 16; ++i) { ls.U[i] = ls.V[i] = ls.X[i] = ls.Y[i] = 0u; ls.Z[i] = sc16.s0_2; }
+		lane16_load_seq<0>(ls, tseq, tlen, qseq, 0);
+		lane16_load_seq<1>(ls, tseq, tlen, qseq, 0);
+#pragma unroll
+		for (int k = 0; k < 8; ++k) Hrow[k * GC] = make_int4(kNegInf, kNegInf, kNegInf, kNegInf);
+		Leader ld; ld.reset();
+		int last_st = -1, last_en = -1, n_diag = 0, zdropped_band = 0;
+		const int R = qlen + tlen - 1;
+		cluster.sync();
+
+		for (int r = 0; r < R; ++r) {
+			Band b;
+			if (!band_of(r, qlen, tlen, w, T, generic, b)) { zdropped_band = 1; break; }
+
+			// phase 1: publish the OLD top register of every warp; the leader prepares H (nobody else touches H now)
+			uint32_t xp = __shfl_up_sync(0xffffffffu, ls.X[15], 1);
+			uint32_t vp = __shfl_up_sync(0xffffffffu, ls.V[15], 1);
+			if (lane == 31) { sCarryX[wid] = ls.X[15]; sCarryV[wid] = ls.V[15]; }
+			if (leader) ld.pre(rows, b, r, qe);
+			cluster.sync();                                                                    // A
+			// phase 2: cells; warp 0 of a CTA takes its carry from the last warp of the previous CTA (DSMEM)
+			if (lane == 0) {
+				if (wid > 0) { xp = sCarryX[wid - 1]; vp = sCarryV[wid - 1]; }
+				else {
+					const int pr = (rank + C - 1) % C;
+					xp = cluster.map_shared_rank(sCarryX, pr)[NW - 1];
+					vp = cluster.map_shared_rank(sCarryV, pr)[NW - 1];
+				}
+			}
+			const uint32_t xin = __byte_perm(xp, ls.X[15], 0x5432), vin = __byte_perm(vp, ls.V[15], 0x5432);
+			lane16_prepare<NS>(ls, b, r, last_en, qseq, tseq, tlen, table_saddr, sc16);
+			const int32_t lane_max = lane16_cells<kCigar, kRight, GC>(ls, b, r, last_st, xin, vin, (uint4 *)(tbp + (int64_t)r * (NS >> 1)),
+			                                                          Hrow, Urow, sc16);
+			const int32_t wmax = __reduce_max_sync(0xffffffffu, lane_max);
+			if (lane == 0) max0[rank * NW + wid] = wmax;
+			cluster.sync();                                                                    // B
+			// phase 3: leader
+			if (leader) {
+				int32_t red = sAllMax[0];
+				for (int k = 1; k < C * NW; ++k) red = red > sAllMax[k] ? red : sAllMax[k];
+				const int need = ld.mid(rows, b, r, qe, red, ls.V[0] << 16, sc.zdrop);
+				int stop = 0;
+				if (!need) stop = ld.fin(rows, b, r, qe, b.en0, qlen, tlen, sc.zdrop, sc.e);
+				for (int k = 0; k < C; ++k) {
+					*cluster.map_shared_rank(&sNeedArg, k) = need;
+					*cluster.map_shared_rank(&sGmax, k) = ld.gmax;
+					*cluster.map_shared_rank(&sStop, k) = stop;
+				}
+			}
+			cluster.sync();                                                                    // C
+			if (sNeedArg) {
+				uint32_t key = lane16_argmax_key<GC>(ls, b, Hrow, sGmax);
+				key = __reduce_min_sync(0xffffffffu, key);
+				if (lane == 0) key0[rank * NW + wid] = key;
+				cluster.sync();                                                                // D
+				if (leader) {
+					uint32_t k = ld.en0_key(b, r);
+					for (int j = 0; j < C * NW; ++j) k = sAllKey[j] < k ? sAllKey[j] : k;
+					const int stop = ld.fin(rows, b, r, qe, tie_key_slot(k, b.en0), qlen, tlen, sc.zdrop, sc.e);
+					for (int kk = 0; kk < C; ++kk) *cluster.map_shared_rank(&sStop, kk) = stop;
+				}
+				cluster.sync();                                                                // E
+			}
+			const int stop = sStop;
+			n_diag = r + 1;
+			last_st = b.st; last_en = b.en;
+			if (stop) break;
+		}
+		if (leader) { if (zdropped_band) ld.ez.zdropped = 1; ld.store(&L.results[pi], n_diag); }
+		cluster.sync();
+	}
+}
+
 } // namespace extz

@@ -214,10 +214,17 @@ def test_one_slot_per_register_kernels(checker, mat, tmp_path):
                 if not flag & 1:
                     assert got.cigars[i].tolist() == cr[i], i
                 n += 1
+        for (length, cnt) in [(1500, 3), (4500, 2), (9000, 1)]:        # one-slot CTA-wide, cluster x2 and cluster x4 kernels
+            ps = synth.make_pairs_small(cnt, length=length, div=0.08, seed=length)
+            got = engine.extz2_batch(ps, mat, 40, 1, -1, -1, 0)
+            _, fr, cr = chk.batch(ps, mat, 40, 1, -1, -1, 0, nthreads=8)
+            for i in range(ps.n):
+                assert got.fields(i) == fr[i] and got.cigars[i].tolist() == cr[i], (length, i)
+                n += 1
         print("ok", n)
     """))
     out = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, env=dict(os.environ, KSW_B200_PACKED="0"), timeout=600)
-    assert out.returncode == 0 and "ok 1200" in out.stdout, out.stdout + out.stderr
+    assert out.returncode == 0 and "ok 1206" in out.stdout, out.stdout + out.stderr
 
 
 def test_warp_traceback_kernel_forced(checker, mat, tmp_path):

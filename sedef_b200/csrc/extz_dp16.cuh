@@ -282,8 +282,11 @@ __device__ __forceinline__ uint32_t group_argmax_count(const int4 *Hgroup, int w
 	return acc;
 }
 // arg-max, exact pass (only on real ties): smallest tie-break key among this lane's slots whose lazy H equals gm
+// t0a / t0b: slot bases of the lane's two blocks ON THE DIAGONAL BEING SCANNED.  The pipelined kernels call this after
+// prepare(r+1) has run, which may already have moved a block NS further up -- and the block that leaves the band at r+1
+// can hold the maximum of diagonal r (a maximum on the last query row sits at slot st0), so ls.t0 must not be used there.
 template <int RS = 128>
-__device__ __forceinline__ uint32_t lane16_argmax_key(const Lane16 &ls, const Band &b, const int4 *Hrow, int32_t gm)
+__device__ __forceinline__ uint32_t lane16_argmax_key(const Band &b, const int4 *Hrow, int32_t gm, int t0a, int t0b)
 {
 	uint32_t key = 0xffffffffu;
 #pragma unroll
@@ -292,7 +295,7 @@ __device__ __forceinline__ uint32_t lane16_argmax_key(const Lane16 &ls, const Ba
 		const int32_t hv[4] = {h.x, h.y, h.z, h.w};
 #pragma unroll
 		for (int e = 0; e < 4; ++e) {
-			const int t = ls.t0[k & 1] + 4 * (k >> 1) + e;
+			const int t = ((k & 1) ? t0b : t0a) + 4 * (k >> 1) + e;
 			if (t >= b.st0 && t <= b.en0 && !(t == b.en0 && b.en0 > 0) && hv[e] == gm) {
 				const uint32_t kk = tie_key(t, b.st0, b.en0);
 				key = kk < key ? kk : key;
@@ -443,7 +446,7 @@ extz_dp16_kernel(DpLaunch L)
 				if (__any_sync(FULL, tie)) {                                                      // real ties: exact 4-lane rule
 					uint32_t key = 0xffffffffu;
 					if (tie) {
-						key = lane16_argmax_key(ls, b, Hrow, gm);
+						key = lane16_argmax_key(b, Hrow, gm, ls.t0[0], ls.t0[1]);
 						if (gl == 0) { uint32_t k0 = ld.en0_key(b, r); key = k0 < key ? k0 : key; }
 					}
 					key = group_min_u<G>(key);
@@ -467,7 +470,7 @@ extz_dp16_kernel(DpLaunch L)
 // otherwise the per-lane code of the narrow kernel.
 // =====================================================================================================
 template <int G, bool kCigar, bool kRight>
-__global__ void __launch_bounds__(G)
+__global__ void __launch_bounds__(G, G == 128 ? 3 : 1)       // 128 lanes: 3 CTAs/SM at <= 170 registers; 64: 5 fit anyway; 256: 1
 extz_dp16_wide_kernel(DpLaunch L)
 {
 	constexpr int NS = G * 32;
@@ -524,52 +527,67 @@ extz_dp16_wide_kernel(DpLaunch L)
 		const int R = qlen + tlen - 1;
 		__syncthreads();
 
-		for (int r = 0; r < R; ++r) {
-			Band b;
-			if (!band_of(r, qlen, tlen, w, T, generic, b)) { zdropped_band = 1; break; }
-
-			// phase 1: publish the OLD top register of every warp; the leader prepares H (nobody else touches H now)
-			uint32_t xp = __shfl_up_sync(0xffffffffu, ls.X[15], 1);
-			uint32_t vp = __shfl_up_sync(0xffffffffu, ls.V[15], 1);
-			if (lane == 31) { sCarryX[wid] = ls.X[15]; sCarryV[wid] = ls.V[15]; }
-			if (gl == 0) ld.pre(rows, b, r, qe);
-			__syncthreads();                                                                   // A
-			// phase 2: cells
-			if (lane == 0) { const int pw = (wid + NW - 1) % NW; xp = sCarryX[pw]; vp = sCarryV[pw]; }
+		// Software pipeline over anti-diagonals: while the leader does the bookkeeping of diagonal r (and knocks out the H
+		// entries of r+1), every other lane already runs prepare(r+1) -- window slide, query shift, score fill -- which
+		// touches neither H nor the leader's state.  Two barriers per diagonal (plus two when the arg-max is needed).
+		Band b;
+		bool okb = band_of(0, qlen, tlen, w, T, generic, b);
+		if (okb) {
+			lane16_prepare<NS>(ls, b, 0, -1, qseq, tseq, tlen, table_saddr, sc16);
+			if (gl == 0) ld.pre(rows, b, 0, qe);
+		} else zdropped_band = 1;
+		uint32_t xp = 0u, vp = 0u;                                    // OLD x,v of the register below (zero state at r = 0)
+		__syncthreads();
+		for (int r = 0; okb && r < R; ++r) {
+			// cells of diagonal r
 			const uint32_t xin = __byte_perm(xp, ls.X[15], 0x5432), vin = __byte_perm(vp, ls.V[15], 0x5432);
-			lane16_prepare<NS>(ls, b, r, last_en, qseq, tseq, tlen, table_saddr, sc16);
 			const int32_t lane_max = lane16_cells<kCigar, kRight, G>(ls, b, r, last_st, xin, vin, (uint4 *)(tbp + (int64_t)r * (NS >> 1)),
 			                                                         Hrow, Urow, sc16);
 			const int32_t wmax = __reduce_max_sync(0xffffffffu, lane_max);
 			if (lane == 0) sWarpMax[wid] = wmax;
-			__syncthreads();                                                                   // B
-			// phase 3: leader
+			if (lane == 31) { sCarryX[wid] = ls.X[15]; sCarryV[wid] = ls.V[15]; }      // OLD values for diagonal r+1
+			xp = __shfl_up_sync(0xffffffffu, ls.X[15], 1);
+			vp = __shfl_up_sync(0xffffffffu, ls.V[15], 1);
+			Band bn;
+			const bool okn = (r + 1 < R) && band_of(r + 1, qlen, tlen, w, T, generic, bn);
+			__syncthreads();                                                                   // 1
+			if (lane == 0) { const int pw = (wid + NW - 1) % NW; xp = sCarryX[pw]; vp = sCarryV[pw]; }
 			if (gl == 0) {
 				int32_t red = sWarpMax[0];
 #pragma unroll
 				for (int k = 1; k < NW; ++k) red = red > sWarpMax[k] ? red : sWarpMax[k];
 				const int need = ld.mid(rows, b, r, qe, red, ls.V[0] << 16, sc.zdrop);
 				sNeedArg = need; sGmax = ld.gmax;
-				if (!need) sStop = ld.fin(rows, b, r, qe, b.en0, qlen, tlen, sc.zdrop, sc.e);
+				if (!need) {
+					const int stop = ld.fin(rows, b, r, qe, b.en0, qlen, tlen, sc.zdrop, sc.e);
+					sStop = stop;
+					if (!stop && okn) ld.pre(rows, bn, r + 1, qe);
+				}
 			}
-			__syncthreads();                                                                   // C
+			const int t0a = ls.t0[0], t0b = ls.t0[1];                     // slot bases of diagonal r, for its arg-max pass
+			if (okn) lane16_prepare<NS>(ls, bn, r + 1, b.en, qseq, tseq, tlen, table_saddr, sc16);
+			__syncthreads();                                                                   // 2
 			if (sNeedArg) {
-				uint32_t key = lane16_argmax_key<G>(ls, b, Hrow, sGmax);
+				uint32_t key = lane16_argmax_key<G>(b, Hrow, sGmax, t0a, t0b);
 				key = __reduce_min_sync(0xffffffffu, key);
 				if (lane == 0) sWarpKey[wid] = key;
-				__syncthreads();                                                               // D
+				__syncthreads();                                                               // 3
 				if (gl == 0) {
 					uint32_t k = ld.en0_key(b, r);
 #pragma unroll
 					for (int j = 0; j < NW; ++j) k = sWarpKey[j] < k ? sWarpKey[j] : k;
-					sStop = ld.fin(rows, b, r, qe, tie_key_slot(k, b.en0), qlen, tlen, sc.zdrop, sc.e);
+					const int stop = ld.fin(rows, b, r, qe, tie_key_slot(k, b.en0), qlen, tlen, sc.zdrop, sc.e);
+					sStop = stop;
+					if (!stop && okn) ld.pre(rows, bn, r + 1, qe);
 				}
-				__syncthreads();                                                               // E
+				__syncthreads();                                                               // 4
 			}
 			const int stop = sStop;
 			n_diag = r + 1;
 			last_st = b.st; last_en = b.en;
 			if (stop) break;
+			if (r + 1 < R && !okn) { zdropped_band = 1; break; }                               // band exhausted (:110-113)
+			b = bn;
 		}
 		if (gl == 0) { if (zdropped_band) ld.ez.zdropped = 1; ld.store(&L.results[pi], n_diag); }
 		__syncthreads();
@@ -666,17 +684,29 @@ extz_dp16_cluster_kernel(DpLaunch L)
 		const int R = qlen + tlen - 1;
 		cluster.sync();
 
-		for (int r = 0; r < R; ++r) {
-			Band b;
-			if (!band_of(r, qlen, tlen, w, T, generic, b)) { zdropped_band = 1; break; }
-
-			// phase 1: publish the OLD top register of every warp; the leader prepares H (nobody else touches H now)
-			uint32_t xp = __shfl_up_sync(0xffffffffu, ls.X[15], 1);
-			uint32_t vp = __shfl_up_sync(0xffffffffu, ls.V[15], 1);
-			if (lane == 31) { sCarryX[wid] = ls.X[15]; sCarryV[wid] = ls.V[15]; }
-			if (leader) ld.pre(rows, b, r, qe);
-			cluster.sync();                                                                    // A
-			// phase 2: cells; warp 0 of a CTA takes its carry from the last warp of the previous CTA (DSMEM)
+		// software pipeline over anti-diagonals, as in extz_dp16_wide_kernel: prepare(r+1) of every lane overlaps the leader's
+		// bookkeeping of diagonal r; two cluster barriers per diagonal (plus two when the arg-max is needed)
+		Band b;
+		bool okb = band_of(0, qlen, tlen, w, T, generic, b);
+		if (okb) {
+			lane16_prepare<NS>(ls, b, 0, -1, qseq, tseq, tlen, table_saddr, sc16);
+			if (leader) ld.pre(rows, b, 0, qe);
+		} else zdropped_band = 1;
+		uint32_t xp = 0u, vp = 0u;
+		cluster.sync();
+		for (int r = 0; okb && r < R; ++r) {
+			const uint32_t xin = __byte_perm(xp, ls.X[15], 0x5432), vin = __byte_perm(vp, ls.V[15], 0x5432);
+			const int32_t lane_max = lane16_cells<kCigar, kRight, GC>(ls, b, r, last_st, xin, vin, (uint4 *)(tbp + (int64_t)r * (NS >> 1)),
+			                                                          Hrow, Urow, sc16);
+			const int32_t wmax = __reduce_max_sync(0xffffffffu, lane_max);
+			if (lane == 0) max0[rank * NW + wid] = wmax;
+			if (lane == 31) { sCarryX[wid] = ls.X[15]; sCarryV[wid] = ls.V[15]; }      // OLD values for diagonal r+1
+			xp = __shfl_up_sync(0xffffffffu, ls.X[15], 1);
+			vp = __shfl_up_sync(0xffffffffu, ls.V[15], 1);
+			Band bn;
+			const bool okn = (r + 1 < R) && band_of(r + 1, qlen, tlen, w, T, generic, bn);
+			cluster.sync();                                                                    // 1
+			// warp 0 of a CTA takes its carry from the last warp of the previous CTA (DSMEM)
 			if (lane == 0) {
 				if (wid > 0) { xp = sCarryX[wid - 1]; vp = sCarryV[wid - 1]; }
 				else {
@@ -685,44 +715,44 @@ extz_dp16_cluster_kernel(DpLaunch L)
 					vp = cluster.map_shared_rank(sCarryV, pr)[NW - 1];
 				}
 			}
-			const uint32_t xin = __byte_perm(xp, ls.X[15], 0x5432), vin = __byte_perm(vp, ls.V[15], 0x5432);
-			lane16_prepare<NS>(ls, b, r, last_en, qseq, tseq, tlen, table_saddr, sc16);
-			const int32_t lane_max = lane16_cells<kCigar, kRight, GC>(ls, b, r, last_st, xin, vin, (uint4 *)(tbp + (int64_t)r * (NS >> 1)),
-			                                                          Hrow, Urow, sc16);
-			const int32_t wmax = __reduce_max_sync(0xffffffffu, lane_max);
-			if (lane == 0) max0[rank * NW + wid] = wmax;
-			cluster.sync();                                                                    // B
-			// phase 3: leader
 			if (leader) {
 				int32_t red = sAllMax[0];
 				for (int k = 1; k < C * NW; ++k) red = red > sAllMax[k] ? red : sAllMax[k];
 				const int need = ld.mid(rows, b, r, qe, red, ls.V[0] << 16, sc.zdrop);
 				int stop = 0;
-				if (!need) stop = ld.fin(rows, b, r, qe, b.en0, qlen, tlen, sc.zdrop, sc.e);
+				if (!need) {
+					stop = ld.fin(rows, b, r, qe, b.en0, qlen, tlen, sc.zdrop, sc.e);
+					if (!stop && okn) ld.pre(rows, bn, r + 1, qe);
+				}
 				for (int k = 0; k < C; ++k) {
 					*cluster.map_shared_rank(&sNeedArg, k) = need;
 					*cluster.map_shared_rank(&sGmax, k) = ld.gmax;
 					*cluster.map_shared_rank(&sStop, k) = stop;
 				}
 			}
-			cluster.sync();                                                                    // C
+			const int t0a = ls.t0[0], t0b = ls.t0[1];                     // slot bases of diagonal r, for its arg-max pass
+			if (okn) lane16_prepare<NS>(ls, bn, r + 1, b.en, qseq, tseq, tlen, table_saddr, sc16);
+			cluster.sync();                                                                    // 2
 			if (sNeedArg) {
-				uint32_t key = lane16_argmax_key<GC>(ls, b, Hrow, sGmax);
+				uint32_t key = lane16_argmax_key<GC>(b, Hrow, sGmax, t0a, t0b);
 				key = __reduce_min_sync(0xffffffffu, key);
 				if (lane == 0) key0[rank * NW + wid] = key;
-				cluster.sync();                                                                // D
+				cluster.sync();                                                                // 3
 				if (leader) {
 					uint32_t k = ld.en0_key(b, r);
 					for (int j = 0; j < C * NW; ++j) k = sAllKey[j] < k ? sAllKey[j] : k;
 					const int stop = ld.fin(rows, b, r, qe, tie_key_slot(k, b.en0), qlen, tlen, sc.zdrop, sc.e);
+					if (!stop && okn) ld.pre(rows, bn, r + 1, qe);
 					for (int kk = 0; kk < C; ++kk) *cluster.map_shared_rank(&sStop, kk) = stop;
 				}
-				cluster.sync();                                                                // E
+				cluster.sync();                                                                // 4
 			}
 			const int stop = sStop;
 			n_diag = r + 1;
 			last_st = b.st; last_en = b.en;
 			if (stop) break;
+			if (r + 1 < R && !okn) { zdropped_band = 1; break; }                               // band exhausted (:110-113)
+			b = bn;
 		}
 		if (leader) { if (zdropped_band) ld.ez.zdropped = 1; ld.store(&L.results[pi], n_diag); }
 		cluster.sync();

@@ -253,6 +253,25 @@ def pairs_from_strings(pairs) -> PairSet:
     return PairSet(qlen, _offsets(qlen), encode(qraw), tlen, _offsets(tlen), encode(traw), qraw.copy(), traw.copy())
 
 
+def make_pairs_max_on_last_row(lengths, tail: int = 200, sub: float = 0.04, seed: int = 1) -> PairSet:
+    """Pairs whose best score ends on the LAST QUERY ROW at a slot t with (t + 1) % 16 == 0 while the target goes on:
+    target = substitution-only copy of the query (no indels, so the copy ends at t = qlen - 1) + `tail` unrelated bases,
+    qlen a multiple of 16.  On the anti-diagonal after the maximum the band's lowest 16-slot block leaves the band; a
+    kernel that slides that block before it has looked for the arg-max of the previous diagonal loses max_t / max_q."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    pairs = []
+    for L in lengths:
+        L = (int(L) // 16) * 16
+        q = rng.integers(0, 4, L)
+        t = q.copy()
+        hit = rng.random(L) < sub
+        t[hit] = (t[hit] + rng.integers(1, 4, int(hit.sum()))) % 4
+        t[-24:] = q[-24:]                                      # a clean end: the copy scores best exactly at its last base
+        t = np.concatenate([t, rng.integers(0, 4, tail)])
+        pairs.append(("".join("ACGT"[x] for x in q), "".join("ACGT"[x] for x in t)))
+    return pairs_from_strings(pairs)
+
+
 def count_cells(qlen: int, tlen: int, w: int) -> int:
     """In-band cells over all anti-diagonals: sum_r (en0 - st0 + 1)
     (reference extern/ksw2_extz2_sse.cc:105-109)."""

@@ -189,6 +189,21 @@ def test_packed_class_boundaries(checker, mat):
         compare(ps, mat, checker, L // 2, 60, 0)
 
 
+def test_maximum_in_the_block_that_leaves_the_band(checker, mat):
+    """The arg-max of a diagonal can sit in the lowest 16-slot block, which leaves the band on the next diagonal (a
+    maximum on the last query row is at slot st0).  The pipelined CTA-wide / cluster kernels run prepare(r+1) -- which
+    slides that block -- before the arg-max pass of diagonal r; they must scan with the slot bases of diagonal r.
+    One pair per kernel family: 32-lane narrow, CTA-wide with 64 / 128 / 256 lanes, cluster of 2 CTAs; with and
+    without z-drop, both traceback arms."""
+    ps = synth.make_pairs_max_on_last_row([480, 992, 1504, 3008, 6000, 9008], tail=200, seed=5)
+    for (zd, flag) in [(-1, 0), (200, 0), (-1, 0x02)]:
+        got = compare(ps, mat, checker, -1, zd, flag)
+    ps = synth.make_pairs_max_on_last_row([1200 + 16 * k for k in range(12)] + [2800 + 16 * k for k in range(6)], tail=120, seed=6)
+    compare(ps, mat, checker, -1, -1, 0)
+    chk = checker.batch(ps, mat, 40, 1, -1, -1, 0, nthreads=8)[1]
+    assert sum((f["max_t"] + 1) % 16 == 0 and f["max_q"] == int(ps.qlen[i]) - 1 for i, f in enumerate(chk)) >= 12   # the case is hit
+
+
 def test_one_slot_per_register_kernels(checker, mat, tmp_path):
     """KSW_B200_PACKED=0 routes the narrow classes to the one-slot-per-register kernels of extz_dp.cuh (the A/B switch is
     read once per process, hence the subprocess): they must stay bit-exact too."""

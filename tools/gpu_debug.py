@@ -35,12 +35,16 @@ configs = [
     ("small", 6, dict(length=6000, div=0.08), -1, -1, 0),                        # cluster of 2 CTAs (8192 slots)
     ("small", 4, dict(length=10000, div=0.08), -1, -1, 0),                       # cluster of 4 CTAs (16384 slots), SEDEF's MAX_GAP fills
     ("small", 4, dict(length=9000, div=0.3), -1, 500, 0x42),                     # cluster, z-drop, right-align, EXTZ_ONLY
+    ("lastrow", 0, dict(lengths=[480, 992, 1504, 3008, 6000, 9008] + [1200 + 16 * k for k in range(12)], tail=200, seed=5), -1, -1, 0),
+    ("lastrow", 0, dict(lengths=[992, 1504, 3008, 6000, 9008], tail=150, seed=7), -1, 200, 0),   # maximum in the block that leaves the band
 ]
 only = [int(x) for x in sys.argv[1:]] if len(sys.argv) > 1 else None
 for ci, (gen, n, kw, w, zdrop, flag) in enumerate(configs):
     if only and ci not in only:
         continue
-    if gen == "mixed":
+    if gen == "lastrow":
+        ps = synth.make_pairs_max_on_last_row(**kw); n = ps.n
+    elif gen == "mixed":
         ps = synth.make_pairs_mixed(n, seed=1000 + ci, **kw)
     elif gen == "small":
         ps = synth.make_pairs_small(n, seed=1000 + ci, **kw)

@@ -640,7 +640,10 @@ extz_dp16_cluster_kernel(DpLaunch L)
 	__shared__ int32_t sGmax;
 
 	for (int i = threadIdx.x; i < kTableStride * kTableStride; i += blockDim.x) sTable[i] = (L.table[i] >> 16) * 0x00010001u;
-	__syncthreads();
+	// cluster.sync(), not __syncthreads(): the first thing the leader does is write sPair into the OTHER CTAs' shared memory,
+	// and a peer's distributed shared memory may only be touched once that CTA is known to be running (racecheck:
+	// "write to a block that might not have entered yet").  It also orders the table fill inside each CTA.
+	cluster.sync();
 
 	const uint32_t table_saddr = (uint32_t)__cvta_generic_to_shared(sTable);
 	const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;

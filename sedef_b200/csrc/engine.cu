@@ -1073,6 +1073,21 @@ extern "C" int ksw_extz2_batch_flat(int n, const int *qlen, const int64_t *qoff,
 	const int chunk_pairs = env ? std::max(1, atoi(env)) : 25000;
 	// chunk sizes ramp up (1 : 2 : 4 : 4 ...) so that the first H2D copy -- the only one nothing can hide -- is short
 	int nchunks = std::max(1, std::min(16, n / chunk_pairs + (n >= 2 * chunk_pairs ? 2 : 0)));
+	if (!env && nchunks > 1) {
+		// A chunk also has to be worth a set of kernel launches.  Every chunk runs one DP + one traceback kernel PER CLASS,
+		// each with a latency floor of one pair (1-2 ms) and a tail, so chunks of mid-size pairs that carry little work
+		// under-fill the GPU (100k pairs of <= 250 bp: 18 ms resident, 45 ms in six chunks; profiles/r01_tuning.md).  Keep
+		// at least ~2.5 G cells per chunk.  Batches of TINY pairs (< 2000 cells per pair) are host-bound instead -- there the
+		// pipeline exists to overlap packing with gathering, and many chunks stay the better choice.
+		const int step = std::max(1, n / 512);
+		int64_t cells = 0; int cnt = 0;
+		for (int i = 0; i < n; i += step, ++cnt) {
+			const int ql = std::max(0, qlen[i]), tl = std::max(0, tlen[i]);
+			cells += est_cells(ql, tl, w < 0 ? std::max(ql, tl) : std::min(w, std::max(ql, tl)));
+		}
+		const double avg = cnt ? (double)cells / cnt : 0.0;
+		if (avg >= 2000.0) nchunks = std::max(1, std::min(nchunks, (int)(avg * n / 2.5e9 + 0.5)));
+	}
 	std::vector<int> start(nchunks + 1, 0);
 	{
 		std::vector<double> wgt(nchunks, 4.0);

@@ -64,28 +64,31 @@ extern "C" const char *ksw_b200_last_error(void) { return g_last_error.c_str(); 
 // ------------------------------------------------------------------------------------------------
 // kernel classes
 // ------------------------------------------------------------------------------------------------
+// A class is a live-slot capacity: 32, 64, ..., 16384 (a pair needs min(16*ceil(tlen/16), 16*n_col_) slots).  Every class has
+// two implementations:
+//   * packed (default, extz_dp16.cuh; two slots per register, NS / 32 lanes per pair):
+//       NS <= 1024           extz_dp16_kernel<NS/32>          128-thread CTAs, 32 / (NS/32) pairs per warp in lock-step
+//       NS = 2048/4096/8192  extz_dp16_wide_kernel<NS/32>     one CTA of 64 / 128 / 256 lanes per pair
+//       NS = 16384           extz_dp16_cluster_kernel<2>      one cluster of 2 CTAs x 256 lanes per pair (DSMEM)
+//   * one slot per register (KSW_B200_PACKED=0, extz_dp.cuh; the table below: G lanes x S slots), kept for A/B runs and
+//     under test: narrow (G <= 32), CTA-wide (one CTA of G lanes), cluster (`cluster` CTAs x 256 lanes).
 struct KClass { int G, S; bool wide; int cluster; };
-// narrow classes: G <= 32 lanes per pair, 128-thread CTAs, 32/G pairs per warp in lock-step;
-// wide classes: one CTA of G lanes per pair; cluster classes: one thread-block cluster of `cluster` CTAs x 256 lanes per pair
 static const KClass kClasses[] = { {2, 16, false, 0}, {4, 16, false, 0}, {8, 16, false, 0}, {16, 16, false, 0}, {32, 16, false, 0},
                                    {32, 32, false, 0}, {64, 16, true, 0}, {128, 16, true, 0}, {256, 16, true, 0},
                                    {512, 16, true, 2}, {1024, 16, true, 4} };
 static const int kNumClasses = sizeof(kClasses) / sizeof(kClasses[0]);
 static const int kNumSizedClasses = kNumClasses;                        // all classes are ordered by capacity
 static inline int class_ns(int c) { return kClasses[c].G * kClasses[c].S; }
-// S == 32 lanes switch whole-lane (two 16-blocks), which costs 16 slots of window (extz_dp.cuh)
-// The narrow classes (up to 1024 live slots) run the PACKED kernel (extz_dp16.cuh: two slots per register, NS / 32 lanes
-// per pair) unless KSW_B200_PACKED=0 selects the one-slot-per-register kernels of extz_dp.cuh for A/B runs.
 static inline bool packed_enabled()
 {
 	static const bool on = [] { const char *e = getenv("KSW_B200_PACKED"); return !(e && e[0] == '0'); }();
 	return on;
 }
-// narrow (<= 1024 slots) and CTA-wide (<= 8192 slots: the packed CTA of 256 lanes replaces the cluster of 2 CTAs x 256 lanes x 16 slots)
 static inline bool class_packed(int c) { return packed_enabled(); }                              // every class has a packed kernel
 static inline bool class_packed_cluster(int c) { return class_packed(c) && class_ns(c) > 8192; } // 2 CTAs x 256 lanes x 32 slots
 static inline int class_cluster(int c) { return class_packed(c) ? (class_ns(c) > 8192 ? 2 : 0) : kClasses[c].cluster; }
 static inline bool class_packed_wide(int c) { return class_packed(c) && class_ns(c) > 1024 && class_ns(c) <= 8192; }    // one CTA of NS/32 lanes per pair
+// one-slot lanes with S == 32 switch whole-lane (two 16-blocks at once), which costs 16 slots of window (extz_dp.cuh)
 static inline int class_capacity(int c) { return (kClasses[c].S > 16 && !class_packed(c)) ? class_ns(c) - 16 : class_ns(c); }
 static inline int class_threads(int c)
 {

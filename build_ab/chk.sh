@@ -1,7 +1,7 @@
-echo "=== BUGGY build (stale slot bases in the key pass): the new cases must FAIL here"
-SEDEF_B200_LIB=build_ab/lib_bug.so timeout 600 python tools/gpu_debug.py 23 24 2>&1 | grep -E "^config|TOTAL"
-SEDEF_B200_LIB=build_ab/lib_bug.so timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "leaves_the_band" 2>&1 | tail -2
-echo "=== FIXED build"
-timeout 800 python tools/gpu_debug.py 2>&1 | grep -E "TOTAL|mismatches [1-9]"
-timeout 300 python tools/repro_fields.py 2>&1 | grep "^cfg"
-python -m pytest tests -x -q -m gpu 2>&1 | tail -2
+echo "== packed, rand scoring, seed 31337 (was 118, then 6)"; timeout 1500 python tools/gpu_soak.py 1200 31337 rand 2>&1 | grep -E "SOAK|^cfg" | tail -4
+echo "== one-slot, rand scoring, seed 31337 (was 6)"; KSW_B200_PACKED=0 timeout 1500 python tools/gpu_soak.py 1200 31337 rand 2>&1 | grep -E "SOAK|^cfg" | tail -4
+echo "== packed, rand scoring, fresh seeds"; timeout 1500 python tools/gpu_soak.py 1500 424242 rand 2>&1 | grep -E "SOAK|^cfg" | tail -4
+echo "== packed, SEDEF scoring"; timeout 900 python tools/gpu_soak.py 600 5150 2>&1 | grep -E "SOAK|^cfg" | tail -3
+echo "== differential suite"; timeout 800 python tools/gpu_debug.py 2>&1 | grep -E "TOTAL|mismatches [1-9]"
+echo "== test suite"; python -m pytest tests -x -q -m gpu 2>&1 | tail -2
+echo "== throughput"; timeout 300 python tools/gpu_perf.py 100000 100 1000 2>&1 | grep -E "run 3"

@@ -203,6 +203,13 @@ void oracle_ksw_extz2(void *km, int qlen, const uint8_t *query, int tlen, const 
 			for (t = st; t <= en; ++t) {
 				int8_t z, a, b, xt1, vt1, ut, d, zc;
 				xt1 = px; vt1 = pv; px = (int8_t)x8[t]; pv = (int8_t)v8[t];
+				/* :102,144-145: x1 / v1 are int8_t and go through _mm_cvtsi32_si128(), so a carry byte >= 0x80 is sign-extended
+				 * into lanes 1..3 of x1_ / v1_, and the _mm_or_si128 of the FIRST block (:30,34) turns x[t-1] / v[t-1] of slots
+				 * st+1..st+3 into 0xff.  x is always in [0,127]; v reaches 128+ once 2(q+e) + match exceeds 127. */
+				if (t > st && t <= st + 3) {
+					if (x1 < 0) xt1 = (int8_t)0xff;
+					if (v1 < 0) vt1 = (int8_t)0xff;
+				}
 				WRAPCHK((int8_t)s8a[t] + qe2);  z = s8((int8_t)s8a[t] + qe2);
 				WRAPCHK(xt1 + vt1);             a = s8(xt1 + vt1);
 				ut = (int8_t)u8[t];

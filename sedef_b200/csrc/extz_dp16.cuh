@@ -213,14 +213,22 @@ __device__ __forceinline__ int32_t lane16_cells(Lane16 &ls, const Band &b, int r
                                                 uint4 *tb_dst, int4 *Hrow, uint4 *Urow, const Sc16 &sc)
 {
 	// carry into the first slot of a block that starts the rounded range (:117-121)
+	uint32_t orx = 0u, orv = 0u;
 	if (ls.t0[0] == b.st || ls.t0[1] == b.st) {
 		const uint32_t keep = ls.t0[0] == b.st ? 0xffff0000u : 0x0000ffffu;
 		if (b.st > 0) { if (!(b.st > last_st)) { xin &= keep; vin &= keep; } }       // slot st-1 was not computed on the last diagonal
 		else { xin &= keep; vin = (vin & keep) | ((r ? sc.q16 : 0u) << (ls.t0[0] == b.st ? 0 : 16)); }
+		// x1 / v1 are int8_t and go through _mm_cvtsi32_si128() (:102,144-145): a carry byte >= 0x80 is sign-extended into lanes
+		// 1..3, and the _mm_or_si128 of the first block (:30,34) turns x[t-1] / v[t-1] of slots st+1..st+3 into 0xff.  (x is
+		// always in [0,127]; v reaches 128+ once 2(q+e) + match exceeds 127 -- never with SEDEF's scoring.)
+		const uint32_t sign = ~keep & 0x80008000u, ff = ~keep & 0xff00ff00u;
+		if (xin & sign) orx = ff;
+		if (vin & sign) orv = ff;
 	}
 	uint32_t cw[4] = {0u, 0u, 0u, 0u};
 #define EXTZ_CELL2(ii) \
-	cell2<kRight, kCigar, 8 * ((ii) & 3)>(ls.Z[ii], (ii) ? ls.X[(ii) ? (ii) - 1 : 0] : xin, (ii) ? ls.V[(ii) ? (ii) - 1 : 0] : vin, \
+	cell2<kRight, kCigar, 8 * ((ii) & 3)>(ls.Z[ii], (ii) ? (ls.X[(ii) ? (ii) - 1 : 0] | (((ii) >= 1 && (ii) <= 3) ? orx : 0u)) : xin, \
+	                                       (ii) ? (ls.V[(ii) ? (ii) - 1 : 0] | (((ii) >= 1 && (ii) <= 3) ? orv : 0u)) : vin, \
 	                                       ls.U[ii], ls.V[ii], ls.X[ii], ls.Y[ii], sc, cw[(ii) >> 2]);
 	// descending: register i reads the OLD x, v of register i-1
 	EXTZ_CELL2(15) EXTZ_CELL2(14) EXTZ_CELL2(13) EXTZ_CELL2(12) EXTZ_CELL2(11) EXTZ_CELL2(10) EXTZ_CELL2(9) EXTZ_CELL2(8)
@@ -230,13 +238,15 @@ __device__ __forceinline__ int32_t lane16_cells(Lane16 &ls, const Band &b, int r
 	int32_t lane_max = kNegInf;
 #pragma unroll
 	for (int j = 0; j < 4; ++j) {
-		// H += sign-extended v: IDP.4A against a one-hot byte vector picks and sign-extends the top byte of a half
+		// H += v8[t] (extern/ksw2_extz2_sse.cc:103,255: v8 is uint8_t*, the byte is ZERO-extended): the UNSIGNED IDP.4A against a
+		// one-hot byte vector picks the top byte of a half.  (A signed pick is the same for SEDEF's 5/-4/40/1, where every v byte is
+		// below 128, and wrong as soon as 2(q+e) + max score exceeds 127 -- found by the random-scoring soak, profiles/r01_soak.md.)
 		Urow[j * RS] = make_uint4(ls.U[4 * j], ls.U[4 * j + 1], ls.U[4 * j + 2], ls.U[4 * j + 3]);
 		int4 ha = Hrow[(2 * j) * RS], hb = Hrow[(2 * j + 1) * RS];
-		ha.x = __dp4a((int)ls.V[4 * j], 0x00000100, ha.x);     hb.x = __dp4a((int)ls.V[4 * j], 0x01000000, hb.x);
-		ha.y = __dp4a((int)ls.V[4 * j + 1], 0x00000100, ha.y); hb.y = __dp4a((int)ls.V[4 * j + 1], 0x01000000, hb.y);
-		ha.z = __dp4a((int)ls.V[4 * j + 2], 0x00000100, ha.z); hb.z = __dp4a((int)ls.V[4 * j + 2], 0x01000000, hb.z);
-		ha.w = __dp4a((int)ls.V[4 * j + 3], 0x00000100, ha.w); hb.w = __dp4a((int)ls.V[4 * j + 3], 0x01000000, hb.w);
+		ha.x = (int32_t)__dp4a(ls.V[4 * j], 0x00000100u, (uint32_t)ha.x);     hb.x = (int32_t)__dp4a(ls.V[4 * j], 0x01000000u, (uint32_t)hb.x);
+		ha.y = (int32_t)__dp4a(ls.V[4 * j + 1], 0x00000100u, (uint32_t)ha.y); hb.y = (int32_t)__dp4a(ls.V[4 * j + 1], 0x01000000u, (uint32_t)hb.y);
+		ha.z = (int32_t)__dp4a(ls.V[4 * j + 2], 0x00000100u, (uint32_t)ha.z); hb.z = (int32_t)__dp4a(ls.V[4 * j + 2], 0x01000000u, (uint32_t)hb.z);
+		ha.w = (int32_t)__dp4a(ls.V[4 * j + 3], 0x00000100u, (uint32_t)ha.w); hb.w = (int32_t)__dp4a(ls.V[4 * j + 3], 0x01000000u, (uint32_t)hb.w);
 		Hrow[(2 * j) * RS] = ha; Hrow[(2 * j + 1) * RS] = hb;
 		int32_t m0 = ha.x > ha.y ? ha.x : ha.y, m1 = ha.z > ha.w ? ha.z : ha.w;
 		int32_t m2 = hb.x > hb.y ? hb.x : hb.y, m3 = hb.z > hb.w ? hb.z : hb.w;

@@ -278,15 +278,23 @@ def test_warp_traceback_kernel_forced(checker, mat, tmp_path):
 
 def test_other_scoring_parameters(checker):
     """Scoring is not hard-wired: user-supplied --match/--mismatch/--gap-open/--gap-extend (src/align_main.cc:343-373)."""
-    ps = synth.make_pairs_mixed(150, seed=77, min_len=1, max_len=400, div=0.15)
-    for (ma, mi, go, ge) in [(1, -1, 2, 1), (2, -4, 4, 2), (5, -4, 40, 1), (10, -9, 30, 3), (5, -4, 50, 1)]:
+    ps = synth.make_pairs_small(300, length=200, div=0.05, seed=871792603, len_jitter=40)
+    # the last six have 2(q+e) + match > 127: u / v bytes above 127, which the reference reads as uint8_t (:103,228,255)
+    for (ma, mi, go, ge) in [(1, -1, 2, 1), (2, -4, 4, 2), (5, -4, 40, 1), (10, -9, 30, 3), (5, -4, 50, 1),
+                             (2, -6, 60, 5), (12, -8, 59, 1), (6, -3, 58, 4), (12, -4, 59, 4), (20, -4, 55, 4), (11, -4, 59, 5)]:
         m = synth.sedef_matrix(ma, mi)
-        for w in (-1, 25):
-            got = engine.extz2_batch(ps, m, go, ge, w, -1, 0)
-            _, fr, cr = checker.batch(ps, m, go, ge, w, -1, 0, nthreads=8)
+        for (w, flag) in ((-1, 0), (25, 0), (16, 0x02)):
+            got = engine.extz2_batch(ps, m, go, ge, w, -1, flag)
+            _, fr, cr = checker.batch(ps, m, go, ge, w, -1, flag, nthreads=8)
             for i in range(ps.n):
-                assert got.fields(i) == fr[i], (ma, mi, go, ge, w, i)
+                assert got.fields(i) == fr[i], (ma, mi, go, ge, w, flag, i)
                 assert got.cigars[i].tolist() == cr[i]
+    wide = synth.make_pairs_small(3, length=1500, div=0.1, seed=78)           # the CTA-wide kernel shares the lane code
+    m = synth.sedef_matrix(12, -8)
+    got = engine.extz2_batch(wide, m, 59, 1, -1, -1, 0)
+    _, fr, cr = checker.batch(wide, m, 59, 1, -1, -1, 0, nthreads=8)
+    for i in range(wide.n):
+        assert got.fields(i) == fr[i] and got.cigars[i].tolist() == cr[i], i
 
 
 def test_full_size_config2_properties(checker, mat):

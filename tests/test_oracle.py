@@ -93,6 +93,22 @@ def test_port_vs_compiled_reference_fuzz(built, mat, w, zdrop, flag, maxlen, div
     assert cr == cp
 
 
+@pytest.mark.skipif(not oracle.have_ref(), reason="oracle/_ref not built (no /root/reference here)")
+@pytest.mark.parametrize("ma,mi,go,ge", [(1, -1, 2, 1), (2, -6, 60, 5), (12, -8, 59, 1), (12, -4, 59, 4), (12, -4, 59, 5),
+                                         (11, -4, 59, 5), (8, -4, 59, 5), (20, -4, 55, 4), (30, -4, 50, 2), (6, -3, 58, 4)])
+def test_port_vs_compiled_reference_scoring_regimes(built, ma, mi, go, ge):
+    """Scoring with 2(q+e) + match above 127 puts u / v bytes above 127: the reference reads them as uint8_t in the H update
+    (:103,228,255) but carries them through an int8_t + _mm_cvtsi32_si128 at the start of every diagonal (:102,144-145), which
+    sign-extends into the next three lanes.  The port must restate both."""
+    m = synth.sedef_matrix(ma, mi)
+    ps = synth.make_pairs_small(300, length=200, div=0.05, seed=871792603, len_jitter=40)
+    for (w, flag) in ((100, 0), (-1, 0x02), (16, 0x80)):
+        _, fr, cr = oracle.ref().batch(ps, m, go, ge, w, -1, flag, nthreads=4)
+        _, fp, cp = oracle.port().batch(ps, m, go, ge, w, -1, flag, nthreads=4)
+        assert fr == fp, (w, flag)
+        assert cr == cp, (w, flag)
+
+
 @pytest.mark.skipif(not oracle.have_ref(), reason="oracle/_ref not built")
 def test_region_golden_reproducible(built, golden_dir):
     """tests/golden/fast_align_golden.json is what the compiled reference align stage produces here (CPU, SSE kernel)."""

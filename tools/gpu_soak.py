@@ -1,6 +1,8 @@
 """Randomised soak: many seeded random configurations (band, z-drop, flags, length ranges, divergence, bursts, last-row
 maxima, class-boundary lengths) through the engine and the reference; every field and CIGAR must agree.
-usage: gpu_soak.py [n_configs] [seed]        (developer tool; the fixed suites live in tests/)"""
+usage: gpu_soak.py [n_configs] [seed] [scoring]   (developer tool; the fixed suites live in tests/)
+scoring = "rand": every configuration also draws match 1..12, mismatch -1..-12, gap open 1..60, gap extend 1..5 and sometimes
+a non-zero N row (fringe-cell wrap-around depends on the scoring; default is SEDEF's 5/-4/40/1)."""
 import sys, os, time
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -10,7 +12,8 @@ from sedef_b200 import engine, synth
 ncfg = int(sys.argv[1]) if len(sys.argv) > 1 else 200
 seed = int(sys.argv[2]) if len(sys.argv) > 2 else 12345
 rng = np.random.Generator(np.random.PCG64(seed))
-mat = synth.sedef_matrix()
+rand_scoring = len(sys.argv) > 3 and sys.argv[3] == "rand"
+mat0 = synth.sedef_matrix()
 engine.init(0, 1)
 chk = oracle.ref() if oracle.have_ref() else oracle.port()
 FLAGS = [0, 0, 0, 0, 0x02, 0x01, 0x40, 0x80, 0x42, 0xc2, 0x04]
@@ -22,6 +25,13 @@ for ci in range(ncfg):
     zd = int(rng.choice([-1, -1, 10, 40, 100, 300, 1000]))
     flag = int(rng.choice(FLAGS))
     s = int(rng.integers(1, 1 << 30))
+    mat, go, ge = mat0, 40, 1
+    if rand_scoring:
+        ma, mi = int(rng.integers(1, 13)), -int(rng.integers(1, 13))
+        go, ge = int(rng.integers(1, 61)), int(rng.integers(1, 6))
+        mat = synth.sedef_matrix(ma, mi)
+        if rng.random() < 0.3:                          # N scores something (ksw2's sc_ambi style) instead of 0
+            m5 = mat.reshape(5, 5).copy(); m5[4, :] = m5[:, 4] = -int(rng.integers(0, 4)); mat = m5.reshape(-1).copy()
     if kind == "mixed":
         hi = int(rng.choice([40, 150, 400, 700, 1100, 2200]))
         n = max(8, min(600, 250000 // hi))
@@ -44,12 +54,12 @@ for ci in range(ncfg):
         if w < 0 or w > 1000:
             w = int(rng.choice([200, 500, 1000, 3000]))
     try:
-        got = engine.extz2_batch(ps, mat, 40, 1, w, zd, flag)
+        got = engine.extz2_batch(ps, mat, go, ge, w, zd, flag)
     except engine.EngineError as ex:
         if ex.code == -5:
             continue                                   # too wide for the widest kernel: an explicit refusal, not a mismatch
         raise
-    _, fr, cr = chk.batch(ps, mat, 40, 1, w, zd, flag, nthreads=8)
+    _, fr, cr = chk.batch(ps, mat, go, ge, w, zd, flag, nthreads=8)
     nb = 0
     for i in range(ps.n):
         ok = got.fields(i) == fr[i] and ((flag & 1) or got.cigars[i].tolist() == cr[i])
@@ -59,7 +69,7 @@ for ci in range(ncfg):
         if not ok:
             nb += 1
             if nb <= 2:
-                print("  MISMATCH cfg", ci, kind, "w", w, "zd", zd, "flag", hex(flag), "seed", s, "pair", i, int(ps.qlen[i]), int(ps.tlen[i]))
+                print("  MISMATCH cfg", ci, kind, "w", w, "zd", zd, "flag", hex(flag), "seed", s, "scoring", mat[0], mat[1], mat[24], go, ge, "pair", i, int(ps.qlen[i]), int(ps.tlen[i]))
                 print("     got", got.fields(i)); print("     ref", fr[i])
     tot += ps.n; bad += nb
     if nb:

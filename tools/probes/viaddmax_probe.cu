@@ -1,6 +1,6 @@
 // Probe: does the fused VIADDMNMX.S16x2 (__viaddmax_s16x2) wrap its 16-bit add exactly like add.s16x2 followed by
 // max.s16x2 (the PTX it is defined as)?  The packed DP kernel relies on int8-in-the-top-byte wrap-around.
-// Also checks __dp4a byte extraction and the packed min/max/add primitives against scalar 16-bit code.
+// Also checks the unsigned __dp4a byte pick of the lazy-H update and the packed min/max/add primitives against scalar code.
 #include <cstdio>
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -23,10 +23,11 @@ __global__ void probe(unsigned long long *bad, uint32_t zr)
 		if (got != exp) atomicAdd(&bad[3], 1ull);
 		got = __vminu2(a, b); exp = (uint32_t)(ual < ubl ? ual : ubl) | ((uint32_t)(uah < ubh ? uah : ubh) << 16);
 		if (got != exp) atomicAdd(&bad[4], 1ull);
-		// dp4a: sign-extended byte 1 / byte 3 added to an accumulator
-		int acc = (int)(y * 2654435761u);
-		if (__dp4a((int)a, 0x00000100, acc) != acc + (int)(int8_t)(a >> 8)) atomicAdd(&bad[5], 1ull);
-		if (__dp4a((int)a, 0x01000000, acc) != acc + (int)(int8_t)(a >> 24)) atomicAdd(&bad[5], 1ull);
+		// unsigned dp4a: ZERO-extended byte 1 / byte 3 added to an accumulator (H[t] += v8[t], v8 = uint8_t*); the accumulator
+		// is a two's-complement int32 carried as uint32
+		const uint32_t acc = y * 2654435761u;
+		if (__dp4a(a, 0x00000100u, acc) != acc + ((a >> 8) & 0xffu)) atomicAdd(&bad[5], 1ull);
+		if (__dp4a(a, 0x01000000u, acc) != acc + (a >> 24)) atomicAdd(&bad[5], 1ull);
 	}
 }
 int main()

@@ -2,7 +2,9 @@
 maxima, class-boundary lengths) through the engine and the reference; every field and CIGAR must agree.
 usage: gpu_soak.py [n_configs] [seed] [scoring]   (developer tool; the fixed suites live in tests/)
 scoring = "rand": every configuration also draws match 1..12, mismatch -1..-12, gap open 1..60, gap extend 1..5 and sometimes
-a non-zero N row (fringe-cell wrap-around depends on the scoring; default is SEDEF's 5/-4/40/1)."""
+a non-zero N row (fringe-cell wrap-around depends on the scoring; default is SEDEF's 5/-4/40/1).
+scoring = "matrix": as "rand", plus alphabet sizes m in {5, 6, 8} (the wildcard is symbol m-1, so with m > 5 an N is an ordinary
+symbol) and, under KSW_EZ_GENERIC_SC, a fully random m x m matrix."""
 import sys, os, time
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -12,7 +14,8 @@ from sedef_b200 import engine, synth
 ncfg = int(sys.argv[1]) if len(sys.argv) > 1 else 200
 seed = int(sys.argv[2]) if len(sys.argv) > 2 else 12345
 rng = np.random.Generator(np.random.PCG64(seed))
-rand_scoring = len(sys.argv) > 3 and sys.argv[3] == "rand"
+rand_scoring = len(sys.argv) > 3 and sys.argv[3] in ("rand", "matrix")
+rand_matrix = len(sys.argv) > 3 and sys.argv[3] == "matrix"
 mat0 = synth.sedef_matrix()
 engine.init(0, 1)
 chk = oracle.ref() if oracle.have_ref() else oracle.port()
@@ -25,13 +28,22 @@ for ci in range(ncfg):
     zd = int(rng.choice([-1, -1, 10, 40, 100, 300, 1000]))
     flag = int(rng.choice(FLAGS))
     s = int(rng.integers(1, 1 << 30))
-    mat, go, ge = mat0, 40, 1
+    mat, go, ge, m = mat0, 40, 1, 5
     if rand_scoring:
         ma, mi = int(rng.integers(1, 13)), -int(rng.integers(1, 13))
         go, ge = int(rng.integers(1, 61)), int(rng.integers(1, 6))
         mat = synth.sedef_matrix(ma, mi)
         if rng.random() < 0.3:                          # N scores something (ksw2's sc_ambi style) instead of 0
             m5 = mat.reshape(5, 5).copy(); m5[4, :] = m5[:, 4] = -int(rng.integers(0, 4)); mat = m5.reshape(-1).copy()
+        if rand_matrix:
+            m = int(rng.choice([5, 5, 6, 8]))
+            if flag & 0x04:                             # GENERIC_SC: the whole matrix is used (:141)
+                mm = rng.integers(-12, 13, (m, m)).astype(np.int8)
+                mm[np.arange(m), np.arange(m)] = rng.integers(1, 13, m)
+                go = max(go, 7)                          # keep -min_sc <= 2(q+e): the early-out (:81) has its own test
+            else:                                       # only mat[0], mat[1] and the wildcard rule matter (:129-136)
+                mm = np.full((m, m), mi, np.int8); mm[np.arange(m), np.arange(m)] = ma
+            mat = mm.reshape(-1).copy()
     if kind == "mixed":
         hi = int(rng.choice([40, 150, 400, 700, 1100, 2200]))
         n = max(8, min(600, 250000 // hi))
@@ -54,12 +66,12 @@ for ci in range(ncfg):
         if w < 0 or w > 1000:
             w = int(rng.choice([200, 500, 1000, 3000]))
     try:
-        got = engine.extz2_batch(ps, mat, go, ge, w, zd, flag)
+        got = engine.extz2_batch(ps, mat, go, ge, w, zd, flag, m=m)
     except engine.EngineError as ex:
         if ex.code == -5:
             continue                                   # too wide for the widest kernel: an explicit refusal, not a mismatch
         raise
-    _, fr, cr = chk.batch(ps, mat, go, ge, w, zd, flag, nthreads=8)
+    _, fr, cr = chk.batch(ps, mat, go, ge, w, zd, flag, m=m, nthreads=8)
     nb = 0
     for i in range(ps.n):
         ok = got.fields(i) == fr[i] and ((flag & 1) or got.cigars[i].tolist() == cr[i])
@@ -69,7 +81,7 @@ for ci in range(ncfg):
         if not ok:
             nb += 1
             if nb <= 2:
-                print("  MISMATCH cfg", ci, kind, "w", w, "zd", zd, "flag", hex(flag), "seed", s, "scoring", mat[0], mat[1], mat[24], go, ge, "pair", i, int(ps.qlen[i]), int(ps.tlen[i]))
+                print("  MISMATCH cfg", ci, kind, "w", w, "zd", zd, "flag", hex(flag), "seed", s, "scoring m", m, mat[0], mat[1], go, ge, "pair", i, int(ps.qlen[i]), int(ps.tlen[i]))
                 print("     got", got.fields(i)); print("     ref", fr[i])
     tot += ps.n; bad += nb
     if nb:

@@ -141,21 +141,21 @@ __device__ __forceinline__ int32_t lane_cells(LaneState<S> &ls, const Band &b, i
 			// the block is the first of the rounded range (:117-121)
 			uint32_t xc = (sb == 0) ? xin : ls.X[sb * 16 - 1];
 			uint32_t vc = (sb == 0) ? vin : ls.V[sb * 16 - 1];
-			uint32_t orx = 0u, orv = 0u;
+			uint32_t orv = 0u;
 			if (tb0 == b.st) {
 				if (b.st > 0) { if (!(b.st > last_st)) xc = vc = 0u; }      // slot st-1 was not computed on the last diagonal
 				else { xc = 0u; vc = r ? sc.q_s : 0u; }
 				// x1 / v1 are int8_t and go through _mm_cvtsi32_si128() (:102,144-145): a carry byte >= 0x80 is sign-extended into
 				// lanes 1..3, and the _mm_or_si128 of the first block (:30,34) turns x[t-1] / v[t-1] of slots st+1..st+3 into 0xff
 				// (x is always in [0,127]; v reaches 128+ once 2(q+e) + match exceeds 127 -- never with SEDEF's scoring)
-				if (xc & 0x80000000u) orx = 0xff000000u;
+				// only v can trigger it: x = and(cmpgt(a, 0), a) is always in [0,127]
 				if (vc & 0x80000000u) orv = 0xff000000u;
 			}
 			uint32_t codes = 0;
 #pragma unroll
 			for (int ii = SUBW - 1; ii >= 0; --ii) {        // descending: slot i reads the OLD x,v of slot i-1
 				const int i = sb * 16 + ii;
-				uint32_t xt1 = (ii == 0) ? xc : (ls.X[i - 1] | ((ii <= 3) ? orx : 0u));
+				uint32_t xt1 = (ii == 0) ? xc : ls.X[i - 1];
 				uint32_t vt1 = (ii == 0) ? vc : (ls.V[i - 1] | ((ii <= 3) ? orv : 0u));
 				uint32_t c = cell<kRight, kCigar>(ls.Z[i], xt1, vt1, ls.U[i], ls.V[i], ls.X[i], ls.Y[i], sc);
 				if (kCigar) codes |= c << ((ii & 7) * 4);

@@ -213,7 +213,7 @@ __device__ __forceinline__ int32_t lane16_cells(Lane16 &ls, const Band &b, int r
                                                 uint4 *tb_dst, int4 *Hrow, uint4 *Urow, const Sc16 &sc)
 {
 	// carry into the first slot of a block that starts the rounded range (:117-121)
-	uint32_t orx = 0u, orv = 0u;
+	uint32_t orv = 0u;
 	if (ls.t0[0] == b.st || ls.t0[1] == b.st) {
 		const uint32_t keep = ls.t0[0] == b.st ? 0xffff0000u : 0x0000ffffu;
 		if (b.st > 0) { if (!(b.st > last_st)) { xin &= keep; vin &= keep; } }       // slot st-1 was not computed on the last diagonal
@@ -221,13 +221,12 @@ __device__ __forceinline__ int32_t lane16_cells(Lane16 &ls, const Band &b, int r
 		// x1 / v1 are int8_t and go through _mm_cvtsi32_si128() (:102,144-145): a carry byte >= 0x80 is sign-extended into lanes
 		// 1..3, and the _mm_or_si128 of the first block (:30,34) turns x[t-1] / v[t-1] of slots st+1..st+3 into 0xff.  (x is
 		// always in [0,127]; v reaches 128+ once 2(q+e) + match exceeds 127 -- never with SEDEF's scoring.)
-		const uint32_t sign = ~keep & 0x80008000u, ff = ~keep & 0xff00ff00u;
-		if (xin & sign) orx = ff;
-		if (vin & sign) orv = ff;
+		// Only v can trigger it: x = and(cmpgt(a, 0), a) (:187-188) is always in [0,127].
+		if (vin & ~keep & 0x80008000u) orv = ~keep & 0xff00ff00u;
 	}
 	uint32_t cw[4] = {0u, 0u, 0u, 0u};
 #define EXTZ_CELL2(ii) \
-	cell2<kRight, kCigar, 8 * ((ii) & 3)>(ls.Z[ii], (ii) ? (ls.X[(ii) ? (ii) - 1 : 0] | (((ii) >= 1 && (ii) <= 3) ? orx : 0u)) : xin, \
+	cell2<kRight, kCigar, 8 * ((ii) & 3)>(ls.Z[ii], (ii) ? ls.X[(ii) ? (ii) - 1 : 0] : xin, \
 	                                       (ii) ? (ls.V[(ii) ? (ii) - 1 : 0] | (((ii) >= 1 && (ii) <= 3) ? orv : 0u)) : vin, \
 	                                       ls.U[ii], ls.V[ii], ls.X[ii], ls.Y[ii], sc, cw[(ii) >> 2]);
 	// descending: register i reads the OLD x, v of register i-1

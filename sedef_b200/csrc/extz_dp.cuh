@@ -204,7 +204,8 @@ __device__ __forceinline__ uint32_t lane_argmax_count(const LaneState<S> &ls, in
 		if (h.z == gm) acc += base + 2;
 		if (h.w == gm) acc += base + 3;
 	}
-	return acc;
+	// only "count == 1" matters; clamp to 2 so that the group sum of up to 1024 equal maxima cannot wrap to 1 (extz_dp16.cuh)
+	return (acc >> 24) > 1u ? (2u << 24) : acc;
 }
 
 // arg-max, exact pass (only on real ties): smallest tie-break key among this lane's slots whose lazy H equals gm

@@ -255,6 +255,11 @@ __device__ __forceinline__ int32_t lane16_cells(Lane16 &ls, const Band &b, int r
 	return lane_max;
 }
 
+// The fast pass returns (count << 24) + sum of t.  Only "count == 1" matters, but a group can hold up to 1024 equal maxima
+// (degenerate scoring: match 1, mismatch -100 makes whole anti-diagonals tie) and 257 of them would wrap to 1.  Every lane
+// therefore reports a count of at most 2: the group sum stays below 2 * 32 and "exactly one" stays exact.
+__device__ __forceinline__ uint32_t clamp_tie_count(uint32_t acc) { return (acc >> 24) > 1u ? (2u << 24) : acc; }
+
 // arg-max, fast pass: (count << 24) + sum of t over this lane's slots whose lazy H equals gm
 template <int RS = 128>
 __device__ __forceinline__ uint32_t lane16_argmax_count(const Lane16 &ls, const int4 *Hrow, int32_t gm)
@@ -269,7 +274,7 @@ __device__ __forceinline__ uint32_t lane16_argmax_count(const Lane16 &ls, const 
 		if (h.z == gm) acc += base + 2;
 		if (h.w == gm) acc += base + 3;
 	}
-	return acc;
+	return clamp_tie_count(acc);
 }
 // the same count over the 8 rows of ONE lane (`wl`, group-relative), split between the G lanes of the group
 template <int G>
@@ -288,7 +293,7 @@ __device__ __forceinline__ uint32_t group_argmax_count(const int4 *Hgroup, int w
 		if (h.z == gm) acc += base + 2;
 		if (h.w == gm) acc += base + 3;
 	}
-	return acc;
+	return clamp_tie_count(acc);
 }
 // arg-max, exact pass (only on real ties): smallest tie-break key among this lane's slots whose lazy H equals gm
 // t0a / t0b: slot bases of the lane's two blocks ON THE DIAGONAL BEING SCANNED.  The pipelined kernels call this after

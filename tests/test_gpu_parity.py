@@ -297,6 +297,34 @@ def test_other_scoring_parameters(checker):
         assert got.fields(i) == fr[i] and got.cigars[i].tolist() == cr[i], i
 
 
+def test_degenerate_scoring_many_tied_maxima(checker):
+    """Match 1 / mismatch -100 with a large gap cost makes long stretches of an anti-diagonal tie for the maximum while the
+    z-drop test (which needs the exact arg-max slot) is armed.  The fast arg-max encodes (count << 24) + sum(t): 257 equal maxima
+    must not read as one.  Also gap costs of 0 and scores at the int8 limits: deterministic nonsense in the reference, to be matched."""
+    for (ma, mi, go, ge, w, zd, flag, seed, hi) in [(1, -100, 63, 5, 1000, 1000, 0x42, 668295684, 700), (1, -100, 63, 5, -1, 1000, 0, 5, 1100),
+                                                    (1, -128, 40, 1, -1, 300, 0, 6, 700), (5, -4, 0, 1, 50, 100, 0, 7, 400),
+                                                    (5, -4, 40, 0, -1, -1, 0x02, 8, 400), (127, -100, 120, 10, 100, 1000, 0, 9, 400),
+                                                    (100, -60, 90, 2, -1, -1, 0, 10, 400)]:
+        ps = synth.make_pairs_mixed(200, seed=seed, min_len=1, max_len=hi, div=0.4)
+        m = synth.sedef_matrix(ma, mi)
+        got = engine.extz2_batch(ps, m, go, ge, w, zd, flag)
+        _, fr, cr = checker.batch(ps, m, go, ge, w, zd, flag, nthreads=8)
+        for i in range(ps.n):
+            assert got.fields(i) == fr[i], (ma, mi, go, ge, w, zd, hex(flag), i)
+            assert got.cigars[i].tolist() == cr[i], (ma, mi, go, ge, i)
+    # the deterministic trigger: targets of exactly 257 / 513 bases under match 1 / mismatch -100 -- whole anti-diagonals tie, and
+    # a tie count of 257 or 513 is 1 modulo 256 (every pair a build without the clamp got wrong had tlen == 257)
+    ps = synth.make_pairs_small(8, length=640, div=0.4, seed=11)
+    ps.tlen[:] = np.minimum(ps.tlen, np.array([257, 257, 257, 257, 513, 513, 513, 513], np.int32))
+    ps.qlen[:] = np.minimum(ps.qlen, np.array([360, 364, 300, 620, 600, 640, 530, 514], np.int32))
+    m = synth.sedef_matrix(1, -100)
+    for (w, zd, flag) in [(-1, 300, 0), (-1, 1000, 0), (1000, 1000, 0x42)]:
+        got = engine.extz2_batch(ps, m, 63, 5, w, zd, flag)
+        _, fr, cr = checker.batch(ps, m, 63, 5, w, zd, flag, nthreads=8)
+        for i in range(ps.n):
+            assert got.fields(i) == fr[i] and got.cigars[i].tolist() == cr[i], (w, zd, hex(flag), i)
+
+
 def test_full_size_config2_properties(checker, mat):
     """BASELINE.json configs[1] at FULL size (100k x 1 kbp, w=100): size-independent properties for every pair
     (CIGAR consumes both sequences, stats are consistent with the CIGAR, idempotence across runs) and the

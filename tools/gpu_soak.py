@@ -14,7 +14,8 @@ from sedef_b200 import engine, synth
 ncfg = int(sys.argv[1]) if len(sys.argv) > 1 else 200
 seed = int(sys.argv[2]) if len(sys.argv) > 2 else 12345
 rng = np.random.Generator(np.random.PCG64(seed))
-rand_scoring = len(sys.argv) > 3 and sys.argv[3] in ("rand", "matrix")
+rand_scoring = len(sys.argv) > 3 and sys.argv[3] in ("rand", "matrix", "extreme")
+extreme = len(sys.argv) > 3 and sys.argv[3] == "extreme"       # match <= 100, mismatch >= -100, gap open 0..120, gap extend 0..10
 rand_matrix = len(sys.argv) > 3 and sys.argv[3] == "matrix"
 mat0 = synth.sedef_matrix()
 engine.init(0, 1)
@@ -32,6 +33,9 @@ for ci in range(ncfg):
     if rand_scoring:
         ma, mi = int(rng.integers(1, 13)), -int(rng.integers(1, 13))
         go, ge = int(rng.integers(1, 61)), int(rng.integers(1, 6))
+        if extreme:
+            ma, mi = int(rng.choice([1, 5, 20, 50, 100, 127])), -int(rng.choice([1, 4, 20, 60, 100, 128]))
+            go, ge = int(rng.choice([0, 1, 10, 40, 63, 64, 90, 120, 127])), int(rng.choice([0, 1, 2, 5, 10]))
         mat = synth.sedef_matrix(ma, mi)
         if rng.random() < 0.3:                          # N scores something (ksw2's sc_ambi style) instead of 0
             m5 = mat.reshape(5, 5).copy(); m5[4, :] = m5[:, 4] = -int(rng.integers(0, 4)); mat = m5.reshape(-1).copy()
@@ -68,8 +72,8 @@ for ci in range(ncfg):
     try:
         got = engine.extz2_batch(ps, mat, go, ge, w, zd, flag, m=m)
     except engine.EngineError as ex:
-        if ex.code == -5:
-            continue                                   # too wide for the widest kernel: an explicit refusal, not a mismatch
+        if ex.code in (-5, -3):
+            continue                                   # too wide / outside the scoring domain: an explicit refusal, not a mismatch
         raise
     _, fr, cr = chk.batch(ps, mat, go, ge, w, zd, flag, m=m, nthreads=8)
     nb = 0
@@ -85,5 +89,5 @@ for ci in range(ncfg):
                 print("     got", got.fields(i)); print("     ref", fr[i])
     tot += ps.n; bad += nb
     if nb:
-        print("cfg", ci, kind, "n", ps.n, "w", w, "zd", zd, "flag", hex(flag), "BAD", nb)
+        print("cfg", ci, kind, "n", ps.n, "w", w, "zd", zd, "flag", hex(flag), "scoring", int(mat[0]), int(mat[1]), go, ge, "BAD", nb)
 print("SOAK configs", ncfg, "pairs", tot, "BAD", bad, "secs %.1f" % (time.time() - t0), "seed", seed)

@@ -109,6 +109,30 @@ def test_port_vs_compiled_reference_scoring_regimes(built, ma, mi, go, ge):
         assert cr == cp, (w, flag)
 
 
+@pytest.mark.skipif(not oracle.have_ref(), reason="oracle/_ref not built (no /root/reference here)")
+def test_port_vs_compiled_reference_extreme_scoring_and_matrices(built):
+    """The port against the compiled reference where the reference's own arithmetic has overflowed (match up to 127, mismatch
+    down to -128, gap open 0..127, gap extend 0..10), with alphabet sizes 5 / 6 / 8 and fully random matrices under GENERIC_SC."""
+    rng = np.random.Generator(np.random.PCG64(20261017))
+    for k in range(40):
+        ma, mi = int(rng.choice([1, 5, 20, 50, 100, 127])), -int(rng.choice([1, 4, 20, 60, 100, 128]))
+        go, ge = int(rng.choice([0, 1, 10, 40, 63, 64, 90, 120, 127])), int(rng.choice([0, 1, 2, 5, 10]))
+        w, zd = int(rng.choice([-1, 16, 100, 1000])), int(rng.choice([-1, 100, 1000]))
+        flag = int(rng.choice([0, 0x02, 0x42, 0x40, 0x80, 0x04, 0x01]))
+        m = int(rng.choice([5, 5, 6, 8]))
+        if flag & 0x04:
+            mm = rng.integers(-12, 13, (m, m)).astype(np.int8); mm[np.arange(m), np.arange(m)] = rng.integers(1, 13, m); go = max(go, 7)
+        else:
+            mm = np.full((m, m), max(mi, -128), np.int8); mm[np.arange(m), np.arange(m)] = ma
+        mat = mm.reshape(-1).copy()
+        ps = synth.make_pairs_mixed(80, seed=int(rng.integers(1, 1 << 30)), min_len=1, max_len=int(rng.choice([150, 600])),
+                                    div=float(rng.choice([0.05, 0.2, 0.4])))
+        _, fr, cr = oracle.ref().batch(ps, mat, go, ge, w, zd, flag, m=m, nthreads=4)
+        _, fp, cp = oracle.port().batch(ps, mat, go, ge, w, zd, flag, m=m, nthreads=4)
+        assert fr == fp, (k, ma, mi, go, ge, w, zd, hex(flag), m)
+        assert cr == cp, (k, ma, mi, go, ge, w, zd, hex(flag), m)
+
+
 @pytest.mark.skipif(not oracle.have_ref(), reason="oracle/_ref not built")
 def test_region_golden_reproducible(built, golden_dir):
     """tests/golden/fast_align_golden.json is what the compiled reference align stage produces here (CPU, SSE kernel)."""

@@ -259,13 +259,23 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def host_cpu_threads(lib) -> int:
+    """Threads for the CPU reference: ALL host cores.  Launchers such as torchrun export OMP_NUM_THREADS=1, which made the
+    reference arm run single-threaded at N > 1 (1.25 instead of 19.9 GCUPS) -- the OpenMP default is therefore not trusted."""
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except AttributeError:
+        avail = os.cpu_count() or 1
+    return max(lib.max_threads(), avail, 1)
+
+
 def cpu_reference_run(ps, mat, W, ZD, FLAG, cells, best_of=2, sample_pairs=None, threads=0):
     """The reference's own ksw_extz2_sse (oracle/_ref, compiled from the untouched source) under an OpenMP
     parallel-for over pairs on all host cores; falls back to the scalar port if _ref is absent."""
     import oracle
     kind = "reference" if oracle.have_ref() else "port"
     lib = oracle.ref() if oracle.have_ref() else oracle.port()
-    nthreads = threads or lib.max_threads()
+    nthreads = threads or host_cpu_threads(lib)
     best = None
     for _ in range(best_of):
         s = lib.batch(ps, mat, 40, 1, W, ZD, FLAG, nthreads=nthreads, keep=False)
@@ -289,7 +299,7 @@ def run_reference(args):
     import oracle
     lib = oracle.ref() if oracle.have_ref() else oracle.port()
     kind = "reference" if oracle.have_ref() else "port"
-    nthreads = lib.max_threads()
+    nthreads = host_cpu_threads(lib)
     # exact in-band cell count of the sample (the oracle's own counter, oracle/ksw2_extz2_port.c)
     cnt = oracle.port().lib.oracle_count_cells
     cells = float(sum(int(cnt(int(q), int(t), W)) for q, t in zip(ps.qlen, ps.tlen)))

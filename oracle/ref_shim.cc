@@ -18,6 +18,18 @@
 std::vector<Anchor> generate_anchors(const std::string &query, const std::string &ref, const Hit &orig, const int kmer_size);
 std::pair<std::vector<int>, std::vector<std::pair<int, bool>>> chain_anchors(std::vector<Anchor> &anchors);
 
+// class Alignment declares `friend void test(int, char **argv);` (src/align.h) and none of the reference sources linked here
+// defines it.  The shim supplies it as a READ-ONLY window onto the private column strings: argv = {fa, fb, out_a, out_b, &rc}.
+void test(int cap, char **argv)
+{
+	Alignment a{std::string(argv[0]), std::string(argv[1])};
+	int *rc = reinterpret_cast<int *>(argv[4]);
+	if ((int)a.align_a.size() + 1 > cap || (int)a.align_b.size() + 1 > cap) { *rc = -1; return; }
+	memcpy(argv[2], a.align_a.c_str(), a.align_a.size() + 1);
+	memcpy(argv[3], a.align_b.c_str(), a.align_b.size() + 1);
+	*rc = (int)a.align_a.size();
+}
+
 extern "C" {
 // Alignment(fa, fb): reference src/align.cc:76-88 (align_dna + align_helper + populate_nice_alignment)
 int ref_alignment(const char *fa, const char *fb, char *cigar_out, int cigar_cap,
@@ -29,6 +41,15 @@ int ref_alignment(const char *fa, const char *fb, char *cigar_out, int cigar_cap
 	memcpy(cigar_out, c.c_str(), c.size() + 1);
 	*span = a.span(); *matches = a.matches(); *mismatches = a.mismatches(); *gaps = a.gaps(); *gap_bases = a.gap_bases();
 	return 0;
+}
+// The column strings the reference's Alignment(fa, fb) builds (populate_nice_alignment, src/align.cc:274-315; private
+// members align_a / align_b, src/align.h:39): the input of the BEDPE stat loop of src/stats_main.cc:244-271.
+int ref_alignment_strings(const char *fa, const char *fb, char *out_a, char *out_b, int cap)
+{
+	int rc = -1;
+	char *argv[5] = {const_cast<char *>(fa), const_cast<char *>(fb), out_a, out_b, reinterpret_cast<char *>(&rc)};
+	test(cap, argv);
+	return rc;
 }
 // Alignment(fa, fb, cigar): reference src/align.cc:90-105 ("from_cigar")
 int ref_alignment_from_cigar(const char *fa, const char *fb, const char *cigar,

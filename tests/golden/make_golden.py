@@ -50,6 +50,43 @@ def ref_alignment(lib, fa: str, fb: str):
                 gaps=v[3].value, gap_bases=v[4].value)
 
 
+def ref_alignment_strings(lib, fa: str, fb: str):
+    lib.ref_alignment_strings.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int]
+    cap = 2 * (len(fa) + len(fb)) + 64
+    oa, ob = C.create_string_buffer(cap), C.create_string_buffer(cap)
+    n = lib.ref_alignment_strings(fa.encode(), fb.encode(), oa, ob, cap)
+    assert n >= 0
+    return oa.value.decode(), ob.value.decode()
+
+
+def stat_loop(align_a: str, align_b: str) -> dict:
+    """LITERAL transcription of the BEDPE stat loop (reference src/stats_main.cc:244-271), run over the reference's own
+    align_a / align_b strings.  Deliberately not shared with any product or port code."""
+    d = dict(indel_a=0, indel_b=0, alnB=0, matchB=0, mismatchB=0, transitionsB=0, transversionsB=0,
+             uppercaseA=0, uppercaseB=0, uppercaseMatches=0)
+    assert len(align_a) == len(align_b)
+    for ca, cb in zip(align_a, align_b):
+        a, b = ca.upper(), cb.upper()
+        d["indel_a"] += a == "-"
+        d["indel_b"] += b == "-"
+        d["matchB"] += a != "-" and a == b
+        d["uppercaseA"] += ca != "-" and ca.upper() != "N" and ca.isupper()
+        d["uppercaseB"] += cb != "-" and cb.upper() != "N" and cb.isupper()
+        if a != "-" and b != "-":
+            d["alnB"] += 1
+            if a != b:
+                d["mismatchB"] += 1
+                if a == "A" or a == "G":
+                    d["transitionsB"] += b == "A" or b == "G"
+                    d["transversionsB"] += not (b == "A" or b == "G")
+                else:
+                    d["transitionsB"] += b == "C" or b == "T"
+                    d["transversionsB"] += not (b == "C" or b == "T")
+            elif ca.isupper() and cb.isupper():
+                d["uppercaseMatches"] += 1
+    return {k: int(v) for k, v in d.items()}
+
+
 def main():
     ref = oracle.ref()
     slib = sedef_ref()
@@ -99,8 +136,13 @@ def main():
     recs = []
     for i in range(pset.n):
         fa = "".join(map(chr, pset.raw_pair(i)[0])); fb = "".join(map(chr, pset.raw_pair(i)[1]))
-        recs.append(dict(a=fa, b=fb, **ref_alignment(slib, fa, fb)))
-    json.dump(dict(source="oracle/_ref/libsedef_ref.so: reference Alignment(fa, fb) (src/align.cc:76-88,274-315)",
+        rec = dict(a=fa, b=fb, **ref_alignment(slib, fa, fb))
+        aa, ab = ref_alignment_strings(slib, fa, fb)
+        assert len(aa) == rec["span"]
+        rec["stat_loop"] = stat_loop(aa, ab)             # the ten BEDPE integers from the reference's own column strings
+        recs.append(rec)
+    json.dump(dict(source="oracle/_ref/libsedef_ref.so: reference Alignment(fa, fb) (src/align.cc:76-88,274-315); stat_loop = "
+                          "src/stats_main.cc:244-271 applied to the reference's align_a / align_b",
                    records=recs), open(os.path.join(HERE, "sd_stats_golden.json"), "w"))
     # ---- region-level golden: the reference's whole fast_align() (every call site of the hot path) ----
     slib.ref_fast_align.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_char_p, C.c_int]

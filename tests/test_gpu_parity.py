@@ -64,6 +64,8 @@ def test_sedef_alignment_mirror(checker, golden_dir):
         assert a.cigar_string() == r["cigar"]
         assert (a.span(), a.matches(), a.mismatches(), a.gaps(), a.gap_bases()) == \
                (r["span"], r["matches"], r["mismatches"], r["gaps"], r["gap_bases"])
+        for k, v in r["stat_loop"].items():             # the BEDPE stat loop over the reference's own column strings
+            assert a.stats[k] == v, (k, r["cigar"])
     kat = load_json(golden_dir, "ksw2_kat.json")
     a = align.align(kat["seq1"], kat["seq2"])
     exp = kat["survey_stat_loop"]

@@ -52,6 +52,10 @@ def test_sd_stats_port_matches_reference_alignment_class(built, mat, golden_dir)
         st = oracle.sd_stats(cig, ps.q_raw, ps.t_raw)
         for k in ("span", "matches", "mismatches", "gaps", "gap_bases"):
             assert st[k] == rec[k], (k, rec["cigar"])
+        # the ten BEDPE integers: src/stats_main.cc:244-271 applied (by tests/golden/make_golden.py, literally) to the column
+        # strings the reference's own Alignment built for this pair
+        for k, v in rec["stat_loop"].items():
+            assert st[k] == v, (k, rec["cigar"])
 
 
 def test_sd_stats_port_matches_survey_stat_loop(built, mat, golden_dir):

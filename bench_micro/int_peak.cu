@@ -43,6 +43,14 @@ DEFKERNEL(vimnmx16x2, X = __vmaxs2(X, y))
 DEFKERNEL(vimnmx3_16x2, X = __vimax3_s16x2(X, y, z))
 DEFKERNEL(viaddmnmx16x2, X = __viaddmax_s16x2_relu(X, y, z))
 DEFKERNEL(viadd16x2,  X = __vadd2(X, y))
+// UN-FUSABLE 2-input chains: ptxas folds two dependent 2-input adds / max into ONE 3-input IADD3 / VIMNMX3 (SASS of k_iadd3,
+// k_vimnmx, k_vimnmx16x2: 512 instructions for 1024 PTX ops), which is what reads as "127 lanes/clk/SM" above.  Alternating a
+// 2-input op with an XOR (LOP3, same pipe, cannot be folded into either) shows the true issue rate of the 2-input forms.
+#define ALT2(OPA) do { if (u & 1) asm volatile("xor.b32 %0, %0, %1;" : "+r"(X) : "r"(z)); else { OPA; } } while (0)
+DEFKERNEL(iadd_nofuse,      ALT2(asm volatile("add.u32 %0, %0, %1;" : "+r"(X) : "r"(y))))
+DEFKERNEL(vimnmx_nofuse,    ALT2(asm volatile("max.s32 %0, %0, %1;" : "+r"(X) : "r"(y))))
+DEFKERNEL(vimnmx16x2_nofuse, ALT2(X = __vmaxs2(X, y)))
+DEFKERNEL(viadd16x2_nofuse, ALT2(X = __vadd2(X, y)))
 DEFKERNEL(imad,       asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(X) : "r"(y), "r"(z)))
 DEFKERNEL(imad_imm,   asm volatile("mad.lo.u32 %0, %0, 5, %1;" : "+r"(X) : "r"(y)))
 DEFKERNEL(imad_hi,    asm volatile("mad.hi.u32 %0, %1, 65536, %0;" : "+r"(X) : "r"(y)))
@@ -166,6 +174,7 @@ int main(int argc, char **argv) {
 #define RUN(NAME, MULT) rs.push_back(run(#NAME, k_##NAME, nsm, dout, OPS * (MULT)))
     RUN(iadd3, 1); RUN(iadd3_3in, 1); RUN(lop3, 1); RUN(shf, 1); RUN(prmt, 1);
     RUN(vimnmx, 1); RUN(vimnmx3, 1); RUN(vimnmx16x2, 1); RUN(vimnmx3_16x2, 1); RUN(viaddmnmx16x2, 1); RUN(viadd16x2, 1);
+    RUN(iadd_nofuse, 1); RUN(vimnmx_nofuse, 1); RUN(vimnmx16x2_nofuse, 1); RUN(viadd16x2_nofuse, 1);
     RUN(imad, 1); RUN(imad_imm, 1); RUN(imad_hi, 1); RUN(idp2a, 1); RUN(idp4a, 1);
     RUN(isetp_sel, 1); RUN(shfl, 1); RUN(redux, 1); RUN(vote, 1);
     RUN(mix_alu_fma, 1); RUN(mix_dpx_fma, 1); RUN(lds32, 1); RUN(lds128, 1);

@@ -8,8 +8,8 @@
  *
  * Everything here is plain C: pointers, sizes, POD structs. No torch / CUDA types.
  * All entry points need a CUDA device; there is NO CPU fallback. A call made without a
- * usable device returns KSW_B200_ERR_NO_DEVICE (batch API) or leaves `ez` reset and prints
- * to stderr (ksw2-compatible single-pair API, which has no error channel).
+ * usable device returns KSW_B200_ERR_NO_DEVICE (batch API) or is fatal (ksw2-compatible
+ * single-pair API, which has no error channel: see ksw_b200_set_fatal_handler).
  */
 #ifndef KSW2_B200_H_
 #define KSW2_B200_H_
@@ -30,7 +30,7 @@ extern "C" {
 #define KSW_EZ_SCORE_ONLY  0x01            /* extern/ksw2.h:8  : no traceback / CIGAR */
 #define KSW_EZ_RIGHT       0x02            /* extern/ksw2.h:9  : right-align gaps */
 #define KSW_EZ_GENERIC_SC  0x04            /* extern/ksw2.h:10 : full m*m matrix (m <= 8) */
-#define KSW_EZ_APPROX_MAX  0x08            /* extern/ksw2.h:11 : (NOT supported yet) */
+#define KSW_EZ_APPROX_MAX  0x08            /* extern/ksw2.h:11 : approximate max (one tracked H), no mqe/mte */
 #define KSW_EZ_APPROX_DROP 0x10            /* extern/ksw2.h:12 : only meaningful with APPROX_MAX */
 #define KSW_EZ_EXTZ_ONLY   0x40            /* extern/ksw2.h:13 : always trace back from (max_t,max_q) */
 #define KSW_EZ_REV_CIGAR   0x80            /* extern/ksw2.h:14 : emit the CIGAR end->start */
@@ -90,10 +90,11 @@ enum {
 	KSW_B200_ERR_CUDA        = -2,   /* a CUDA runtime call failed (see ksw_b200_last_error) */
 	KSW_B200_ERR_DOMAIN      = -3,   /* reserved: the kernels reproduce the reference's int8 wrap-around, so there is
 	                                    no scoring domain restriction */
-	KSW_B200_ERR_UNSUPPORTED = -4,   /* KSW_EZ_APPROX_MAX, or an alphabet with m > 8 */
+	KSW_B200_ERR_UNSUPPORTED = -4,   /* an alphabet with m > 8 */
 	KSW_B200_ERR_TOO_WIDE    = -5,   /* a pair needs more live slots per anti-diagonal than the widest kernel */
 	KSW_B200_ERR_NOMEM       = -6,   /* host or device allocation failed */
-	KSW_B200_ERR_ARG         = -7,   /* bad argument (n<0, NULL pointers, symbol >= m) */
+	KSW_B200_ERR_ARG         = -7,   /* bad argument: n<0, NULL pointers, a sequence symbol >= 8 (>= m with KSW_EZ_GENERIC_SC,
+	                                    where the reference would index past mat[]) */
 	KSW_B200_ERR_INEXACT     = -8    /* reserved */
 };
 const char *ksw_b200_strerror(int code);
@@ -112,9 +113,23 @@ void ksw_b200_set_host_threads(int n);
  * 16*n_col_, or 16*ceil(tlen/16) if smaller). */
 int  ksw_b200_max_slots(void);
 
+/* ---- page-locked host memory ---------------------------------------------------------------- */
+/* Sequence buffers that live in page-locked memory are copied to the device IN PLACE (no host pass over the bytes);
+ * pageable buffers are staged through the engine's own pinned buffers.  Allocate inputs here, or page-lock existing
+ * memory (e.g. the genome the caller already holds) once. */
+void *ksw_b200_host_alloc(size_t bytes);
+void  ksw_b200_host_free(void *p);
+int   ksw_b200_host_register(void *p, size_t bytes);
+int   ksw_b200_host_unregister(void *p);
+
 /* ---- single pair: identical signature and ownership to ksw_extz2_sse -------------------- */
 /* Replaces extern/ksw2.h:50 / extern/ksw2_extz2_sse.cc:23.  `km` is ignored, as in the
- * reference build (HAVE_KALLOC undefined, extern/ksw2.h:88-96). */
+ * reference build (HAVE_KALLOC undefined, extern/ksw2.h:88-96).
+ * ksw_extz2_sse has no error channel, so neither has this: a request the engine cannot serve (no device, a pair wider
+ * than ksw_b200_max_slots()) is FATAL -- reported on stderr, then abort() -- unless a handler is installed; if the handler
+ * returns, `ez` holds the reset record. */
+typedef void (*ksw_b200_fatal_fn)(int code, const char *detail);
+void ksw_b200_set_fatal_handler(ksw_b200_fatal_fn fn);     /* NULL restores the default (abort) */
 void ksw_extz2_b200(void *km, int qlen, const uint8_t *query, int tlen, const uint8_t *target,
                     int8_t m, const int8_t *mat, int8_t q, int8_t e, int w, int zdrop, int flag,
                     ksw_extz_t *ez);
@@ -136,6 +151,11 @@ int ksw_extz2_batch(int n, const int *qlen, const uint8_t *const *query,
                     ksw_extz_t *ez, sd_stats_t *stats,
                     const uint8_t *const *q_raw, const uint8_t *const *t_raw);
 
+/* Sequences as ORIGINAL-CASE BYTES ONLY: pass query = target = NULL (qbuf = tbuf = NULL in the flat forms) together with
+ * q_raw / t_raw and m = 5.  The codes are then derived ON THE DEVICE with SEDEF's align_dna (src/common.h:58-70,91:
+ * A C G T, either case -> 0..3, anything else -> 4), which is what Alignment(fa, fb) does before it calls ksw2
+ * (src/align.cc:79-82) -- one byte per base crosses PCIe instead of two. */
+
 /* H2D / D2H bytes and kernel launches of the last one-shot batch call made by this thread. */
 void ksw_b200_last_call_io(int64_t *h2d, int64_t *d2h, int *launches);
 
@@ -149,6 +169,30 @@ int ksw_extz2_batch_flat(int n, const int *qlen, const int64_t *qoff, const uint
                          int8_t m, const int8_t *mat, int8_t q, int8_t e, int w, int zdrop, int flag,
                          ksw_extz_t *ez, sd_stats_t *stats,
                          const uint8_t *q_raw_buf, const uint8_t *t_raw_buf);
+
+/* ---- arena output ("one arena + offsets with an explicit free") ------------------------------ */
+/* Same computation as ksw_extz2_batch_flat; the results stay in ONE page-locked arena owned by `*out`:
+ * ksw_b200_result_ez() is the ksw_extz_t array in the caller's order, every record exactly as ksw_extz2_sse fills it
+ * (m_cigar = the capacity ksw_push_cigar would have grown to), except that ez[i].cigar points INTO the arena -- do not
+ * free() or realloc() it; ksw_b200_result_free() releases everything at once.  The device writes the final records, so the
+ * host side of a call is three DMA copies and no per-pair work (no malloc, no gather loop). */
+typedef struct ksw_b200_result ksw_b200_result_t;
+int ksw_extz2_batch_arena(int n, const int *qlen, const int64_t *qoff, const uint8_t *qbuf,
+                          const int *tlen, const int64_t *toff, const uint8_t *tbuf,
+                          int8_t m, const int8_t *mat, int8_t q, int8_t e, int w, int zdrop, int flag,
+                          int want_stats, const uint8_t *q_raw_buf, const uint8_t *t_raw_buf,
+                          ksw_b200_result_t **out);
+const ksw_extz_t *ksw_b200_result_ez(const ksw_b200_result_t *r);        /* [n] */
+const sd_stats_t *ksw_b200_result_stats(const ksw_b200_result_t *r);     /* [n], or NULL when not requested / SCORE_ONLY */
+int  ksw_b200_result_count(const ksw_b200_result_t *r);
+void ksw_b200_result_io(const ksw_b200_result_t *r, int64_t *h2d, int64_t *d2h, int *launches);
+void ksw_b200_result_free(ksw_b200_result_t *r);
+/* Position-independent copy into CALLER-OWNED buffers (e.g. a shared-memory segment: the host-side gather of a
+ * one-process-per-GPU deployment).  Record i goes to ez_dst[index ? index[i] : i] (its statistics likewise, stats_dst may be
+ * NULL); CIGAR words are appended to cigar_dst in the arena's order and ez.cigar holds the WORD OFFSET cigar_base + position
+ * instead of a pointer.  Returns the CIGAR words written, or a negative error code (cigar_cap too small: nothing is copied). */
+int64_t ksw_b200_result_export(const ksw_b200_result_t *r, ksw_extz_t *ez_dst, sd_stats_t *stats_dst,
+                               uint32_t *cigar_dst, int64_t cigar_cap, int64_t cigar_base, const int64_t *index);
 
 /* ---- Alignment(fa, fb, cigar): statistics from existing CIGARs ------------------------------ */
 /* Replaces src/align.cc:90-105 + populate_nice_alignment + the stat loop for `sedef stats generate`
@@ -175,6 +219,7 @@ ksw_b200_batch_t *ksw_b200_batch_upload(int n, const int *qlen, const int64_t *q
                                         const uint8_t *q_raw_buf, const uint8_t *t_raw_buf, int *err);
 int  ksw_b200_batch_run(ksw_b200_batch_t *b, float *device_ms);
 int  ksw_b200_batch_fetch(ksw_b200_batch_t *b, ksw_extz_t *ez, sd_stats_t *stats);
+int  ksw_b200_batch_fetch_arena(ksw_b200_batch_t *b, int want_stats, ksw_b200_result_t **out);   /* no per-pair malloc */
 /* number of kernel launches issued by the last run, and per-kernel-class device ms */
 int  ksw_b200_batch_launches(const ksw_b200_batch_t *b);
 int  ksw_b200_batch_kernel_ms(const ksw_b200_batch_t *b, float *dp_ms, float *tb_ms, float *aux_ms);

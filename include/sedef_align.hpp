@@ -9,6 +9,7 @@
 // The difference is batching: requests are queued (AlignQueue) and flushed through ONE ksw_extz2_batch call, which is
 // what src/chain.cc, src/refine.cc and src/align.cc call sites do once they collect pairs per wave.
 #pragma once
+#include <stdint.h>
 #include <deque>
 #include <string>
 #include <utility>
@@ -38,6 +39,9 @@ public:
 	std::string cigar_string() const;                  // src/align.cc:614-621
 	sd_stats_fp_t bedpe_fp() const;                    // src/stats_main.cc:273-283,297-299
 };
+
+// Globals::Align::MAX_KSW_SEQ_LEN (src/globals.h:18,54: 60 * KB with KB = 1000): align_helper's chunk length
+int max_ksw_seq_len();
 
 // Batched Alignment(fa, fb) for every pair.  Throws std::runtime_error with the engine's message on failure.
 std::vector<Alignment> align_batch(const std::vector<std::pair<std::string, std::string>> &pairs, const AlignParams &p = AlignParams());
@@ -99,3 +103,7 @@ private:
 };
 
 } // namespace sedef_b200
+
+// The ksw_extz2 calls align_helper makes for one Alignment(fa, fb) with |fa| = alen, |fb| = blen (src/align.cc:46-53):
+// call k aligns (fa + sp[k], qlen[k]) against (fb + sp[k], tlen[k]).  Returns the number of calls (fills at most `cap`).
+extern "C" int sedef_b200_chunk_plan(int64_t alen, int64_t blen, int cap, int64_t *sp, int *qlen, int *tlen);

@@ -105,12 +105,31 @@ class _Lib:
         if not keep:
             return secs
         fields = [ez[i].fields() for i in range(n)]
+        self.last_m_cigar = [int(ez[i].m_cigar) for i in range(n)]     # capacity ksw_push_cigar grew the block to
         cigs = [np.ctypeslib.as_array(ez[i].cigar, shape=(int(ez[i].n_cigar),)).copy().tolist()
                 if ez[i].n_cigar else [] for i in range(n)]
         for i in range(n):
             if ez[i].cigar:
                 self.libc.free(ez[i].cigar)
         return secs, fields, cigs
+
+    def batch_records(self, ps, mat, q, e, w=-1, zdrop=-1, flag=0, m=5, nthreads=0):
+        """All pairs -> (seconds, numpy structured view of the ksw_extz_t records incl. live `cigar` pointers, keepalive).
+        For whole-benchmark parity checks (no per-pair Python objects); release with free_records(keepalive)."""
+        mat = np.ascontiguousarray(mat, np.int8)
+        n = ps.n
+        ez = (KswExtz * max(1, n))()
+        secs = self.lib.cpu_batch_run(n, ps.qlen.ctypes.data, ps.qoff.ctypes.data, ps.q.ctypes.data,
+                                      ps.tlen.ctypes.data, ps.toff.ctypes.data, ps.t.ctypes.data,
+                                      m, mat.ctypes.data, q, e, w, zdrop, flag, C.cast(ez, C.c_void_p), nthreads)
+        dt = np.dtype([("max_zd", "<u4"), ("max_q", "<i4"), ("max_t", "<i4"), ("mqe", "<i4"), ("mqe_t", "<i4"), ("mte", "<i4"),
+                       ("mte_q", "<i4"), ("score", "<i4"), ("cigar", "<u8"), ("m_cigar", "<i8"), ("n_cigar", "<i8")])
+        return secs, np.frombuffer(ez, dt, count=n), (ez, n)
+
+    def free_records(self, keepalive) -> None:
+        ez, n = keepalive
+        self.lib.cpu_batch_free_cigars.argtypes = [C.c_int, C.c_void_p]
+        self.lib.cpu_batch_free_cigars(n, C.cast(ez, C.c_void_p))
 
     def max_threads(self) -> int:
         return int(self.lib.cpu_batch_max_threads())

@@ -41,8 +41,11 @@ static int port_ceq(int a, int b)
 /*
  * cigar: raw ksw ops ((len<<4)|op, op 0=M, 1=I (query only), 2=D (target only)) in forward
  * order.  a = query original-case bytes, b = target original-case bytes.
- * Ops >= 3 are dropped like align_helper does (src/align.cc:61).
- * Returns 0, or -1 if the CIGAR overruns a sequence on an M column (the reference asserts).
+ * Op 3 stands for "any other op letter" of an Alignment(fa, fb, cigar) string: populate_nice_alignment treats it as
+ * not-M (a gap run), not-D and not-I (consumes both strings), src/align.cc:283-305.  (ksw_extz2 itself never emits
+ * ops >= 3, and align_helper would drop them, src/align.cc:61.)
+ * Returns 0, or -1 if the CIGAR overruns a sequence on an M column (the reference asserts) or on an op-3 column
+ * (where the reference reads past the string).
  */
 int oracle_sd_stats(const uint32_t *cigar, int64_t n_cigar, const uint8_t *a, int alen,
                     const uint8_t *b, int blen, sd_stats_t *s)
@@ -52,12 +55,11 @@ int oracle_sd_stats(const uint32_t *cigar, int64_t n_cigar, const uint8_t *a, in
 	for (k = 0; k < n_cigar; ++k) {
 		int op = cigar[k] & 0xf, len = (int)(cigar[k] >> 4), i;
 		char c;
-		if (op >= 3) continue;
-		c = "MDI"[op];                              /* ksw I -> 'D' (a only), ksw D -> 'I' (b only) */
+		c = op < 3 ? "MDI"[op] : 'X';               /* ksw I -> 'D' (a only), ksw D -> 'I' (b only) */
 		if (c != 'M') { s->gaps++; s->gap_bases += len; }      /* src/align.cc:300-305 */
 		for (i = 0; i < len; ++i) {
 			int ca, cb, ua, ub;
-			if (c == 'M' && (ia >= alen || ib >= blen)) return -1;
+			if ((c == 'M' || c == 'X') && (ia >= alen || ib >= blen)) return -1;
 			cb = (c != 'D') ? (ib < blen ? b[ib] : 0) : '-';
 			ca = (c != 'I') ? (ia < alen ? a[ia] : 0) : '-';
 			if (c != 'D') ib++;

@@ -23,7 +23,7 @@ import numpy as np
 
 from . import engine, synth
 
-MAX_KSW_SEQ_LEN = 60 * 1024        # src/globals.h:54  (60 * KB)
+MAX_KSW_SEQ_LEN = 60 * 1000        # src/globals.h:18,54: 60 * KB, and KB is 1000
 
 
 @dataclasses.dataclass
@@ -35,7 +35,7 @@ class Alignment:
     stats: dict                              # integer fields of sd_stats_t
 
     def cigar_string(self) -> str:           # src/align.cc:614-621
-        return "".join(f"{n}{op}" for op, n in self.cigar)
+        return "".join(f"{n}{op}" for op, n in self.cigar if n)     # zero-length runs are not printed (src/align.cc:617)
 
     def span(self) -> int: return self.stats["span"]
     def matches(self) -> int: return self.stats["matches"]
@@ -106,12 +106,17 @@ def align(fa: str, fb: str) -> Alignment:
 
 def from_cigars(pairs: Sequence[Tuple[str, str]], cigar_strings: Sequence[str]) -> List[Alignment]:
     """Batched `Alignment(fa, fb, cigar_string)` (src/align.cc:90-105): parse "\\d+[MID]" (';' skipped), statistics on the GPU."""
-    import re
     parsed, raw = [], []
     for cs in cigar_strings:
-        ops = [(m.group(2), int(m.group(1))) for m in re.finditer(r"(\d+)([A-Za-z])", cs.replace(";", ""))]
+        ops, num = [], 0
+        for ch in cs:                                            # the reference's own parser, src/align.cc:94-103
+            if ch.isdigit():
+                num = 10 * num + int(ch)
+            elif ch != ";":
+                ops.append((ch, num)); num = 0
         parsed.append(ops)
-        raw.append(np.array([(n << 4) | {"M": 0, "D": 1, "I": 2}.get(op, 3) for op, n in ops], np.uint32))   # SEDEF 'D' = a only = ksw I
+        # SEDEF 'D' = a only = ksw I; any other letter (code 3) consumes both strings and still counts as a gap run
+        raw.append(np.array([(n << 4) | {"M": 0, "D": 1, "I": 2}.get(op, 3) for op, n in ops], np.uint32))
     a_list = [np.frombuffer(fa.encode(), np.uint8) for fa, _ in pairs]
     b_list = [np.frombuffer(fb.encode(), np.uint8) for _, fb in pairs]
     st, status = engine.stats_from_cigars(raw, a_list, b_list)

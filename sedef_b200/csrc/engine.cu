@@ -29,10 +29,7 @@
 #include <condition_variable>
 
 #include "../../include/ksw2_b200.h"
-#include "extz_core.cuh"
-#include "extz_dp.cuh"
-#include "extz_dp16.cuh"
-#include "extz_tb.cuh"
+#include "kernels.h"
 
 using namespace extz;
 
@@ -51,7 +48,7 @@ extern "C" const char *ksw_b200_strerror(int code)
 	case KSW_B200_ERR_NO_DEVICE: return "no usable CUDA device (this engine has no CPU fallback)";
 	case KSW_B200_ERR_CUDA: return "CUDA runtime error";
 	case KSW_B200_ERR_DOMAIN: return "scoring parameters outside the supported domain";
-	case KSW_B200_ERR_UNSUPPORTED: return "unsupported flag or alphabet (KSW_EZ_APPROX_MAX, m > 8)";
+	case KSW_B200_ERR_UNSUPPORTED: return "unsupported flag or alphabet (m > 8)";
 	case KSW_B200_ERR_TOO_WIDE: return "pair needs more live slots per anti-diagonal than the widest kernel";
 	case KSW_B200_ERR_NOMEM: return "out of memory";
 	case KSW_B200_ERR_ARG: return "bad argument";
@@ -90,202 +87,34 @@ static inline int class_cluster(int c) { return class_packed(c) ? (class_ns(c) >
 static inline bool class_packed_wide(int c) { return class_packed(c) && class_ns(c) > 1024 && class_ns(c) <= 8192; }    // one CTA of NS/32 lanes per pair
 // one-slot lanes with S == 32 switch whole-lane (two 16-blocks at once), which costs 16 slots of window (extz_dp.cuh)
 static inline int class_capacity(int c) { return (kClasses[c].S > 16 && !class_packed(c)) ? class_ns(c) - 16 : class_ns(c); }
-static inline int class_threads(int c)
-{
-	if (class_cluster(c)) return 256;
-	if (class_packed(c)) return class_packed_wide(c) ? class_ns(c) / 32 : 128;
-	return kClasses[c].wide ? kClasses[c].G : 128;
-}
 static inline int class_pairs_per_block(int c)
 {
 	if (class_packed(c)) return class_ns(c) > 1024 ? 1 : 128 * 32 / class_ns(c);
 	return kClasses[c].wide ? 1 : 128 / kClasses[c].G;
 }
 
-// kernel selection: every (class, cigar, right) combination is a distinct instantiation
-template <int G, int S, bool W, bool C, bool R> struct KSel;
-template <int G, int S, bool C, bool R> struct KSel<G, S, false, C, R> { static constexpr auto fn = extz_dp_kernel<G, S, C, R>; };
-template <int G, int S, bool C, bool R> struct KSel<G, S, true, C, R> { static constexpr auto fn = extz_dp_wide_kernel<G, S, C, R>; };
-
-template <int G, int S, bool W>
-static cudaError_t launch_dp_gs(const DpLaunch &L, bool cigar, bool right, int grid, cudaStream_t st)
-{
-	constexpr int threads = W ? G : 128;
-	if (cigar) {
-		if (right) KSel<G, S, W, true, true>::fn<<<grid, threads, 0, st>>>(L);
-		else       KSel<G, S, W, true, false>::fn<<<grid, threads, 0, st>>>(L);
-	} else       KSel<G, S, W, false, false>::fn<<<grid, threads, 0, st>>>(L);
-	return cudaGetLastError();
-}
-template <int G, int S, bool W>
-static int dp_occupancy_gs(bool cigar, bool right, int)
-{
-	constexpr int threads = W ? G : 128;
-	int nb = 0;
-	if (cigar) {
-		if (right) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, KSel<G, S, W, true, true>::fn, threads, 0);
-		else       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, KSel<G, S, W, true, false>::fn, threads, 0);
-	} else       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, KSel<G, S, W, false, false>::fn, threads, 0);
-	return nb;
-}
-// cluster kernels: launched with a cluster dimension attribute; "occupancy" = co-resident clusters on the device
-template <int C, bool CG, bool R>
-static cudaError_t cluster_launch_one(const DpLaunch &L, int nclusters, cudaStream_t st, int *max_clusters)
-{
-	cudaLaunchConfig_t cfg = {};
-	cfg.gridDim = dim3((unsigned)(nclusters * C)); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = st;
-	cudaLaunchAttribute attr[1];
-	attr[0].id = cudaLaunchAttributeClusterDimension;
-	attr[0].val.clusterDim.x = C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-	cfg.attrs = attr; cfg.numAttrs = 1;
-	if (max_clusters) {
-		cfg.gridDim = dim3((unsigned)C);
-		return cudaOccupancyMaxActiveClusters(max_clusters, extz_dp_cluster_kernel<C, 16, CG, R>, &cfg);
-	}
-	return cudaLaunchKernelEx(&cfg, extz_dp_cluster_kernel<C, 16, CG, R>, L);
-}
-// packed cluster kernel (2 CTAs x 256 lanes x 32 slots = 16384 live slots): 48 KB of dynamic shared memory per CTA
-template <bool CG, bool R>
-static cudaError_t cluster16_launch_one(const DpLaunch &L, int nclusters, cudaStream_t st, int *max_clusters)
-{
-	constexpr int C = 2;
-	const size_t dyn = 256 * 192;
-	static cudaError_t once = cudaFuncSetAttribute(extz_dp16_cluster_kernel<C, CG, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-	if (once != cudaSuccess) return once;
-	cudaLaunchConfig_t cfg = {};
-	cfg.gridDim = dim3((unsigned)(nclusters * C)); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = dyn; cfg.stream = st;
-	cudaLaunchAttribute attr[1];
-	attr[0].id = cudaLaunchAttributeClusterDimension;
-	attr[0].val.clusterDim.x = C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-	cfg.attrs = attr; cfg.numAttrs = 1;
-	if (max_clusters) {
-		cfg.gridDim = dim3((unsigned)C);
-		return cudaOccupancyMaxActiveClusters(max_clusters, extz_dp16_cluster_kernel<C, CG, R>, &cfg);
-	}
-	return cudaLaunchKernelEx(&cfg, extz_dp16_cluster_kernel<C, CG, R>, L);
-}
-static cudaError_t cluster16_dispatch(const DpLaunch &L, bool cigar, bool right, int nclusters, cudaStream_t st, int *max_clusters)
-{
-	if (cigar) return right ? cluster16_launch_one<true, true>(L, nclusters, st, max_clusters)
-	                        : cluster16_launch_one<true, false>(L, nclusters, st, max_clusters);
-	return cluster16_launch_one<false, false>(L, nclusters, st, max_clusters);
-}
-template <int C>
-static cudaError_t cluster_dispatch(const DpLaunch &L, bool cigar, bool right, int nclusters, cudaStream_t st, int *max_clusters)
-{
-	if (cigar) return right ? cluster_launch_one<C, true, true>(L, nclusters, st, max_clusters)
-	                        : cluster_launch_one<C, true, false>(L, nclusters, st, max_clusters);
-	return cluster_launch_one<C, false, false>(L, nclusters, st, max_clusters);
-}
-// packed narrow kernels: G lanes x 32 slots
-template <int G>
-static cudaError_t launch_dp16(const DpLaunch &L, bool cigar, bool right, int grid, cudaStream_t st)
-{
-	if (cigar) {
-		if (right) extz_dp16_kernel<G, true, true><<<grid, 128, 0, st>>>(L);
-		else       extz_dp16_kernel<G, true, false><<<grid, 128, 0, st>>>(L);
-	} else       extz_dp16_kernel<G, false, false><<<grid, 128, 0, st>>>(L);
-	return cudaGetLastError();
-}
-template <int G>
-static int dp16_occupancy(bool cigar, bool right)
-{
-	int nb = 0;
-	if (cigar) {
-		if (right) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, extz_dp16_kernel<G, true, true>, 128, 0);
-		else       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, extz_dp16_kernel<G, true, false>, 128, 0);
-	} else       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, extz_dp16_kernel<G, false, false>, 128, 0);
-	return nb;
-}
-// packed CTA-wide kernels: 192 B of dynamic shared memory per lane (H and u' rows)
-template <int G, bool C, bool R>
-static cudaError_t dp16_wide_prepare()
-{
-	static cudaError_t once = cudaFuncSetAttribute(extz_dp16_wide_kernel<G, C, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, G * 192);
-	return once;
-}
-template <int G>
-static cudaError_t launch_dp16_wide(const DpLaunch &L, bool cigar, bool right, int grid, cudaStream_t st)
-{
-	const size_t dyn = (size_t)G * 192;
-	cudaError_t e;
-	if (cigar) {
-		if (right) { if ((e = dp16_wide_prepare<G, true, true>()) != cudaSuccess) return e; extz_dp16_wide_kernel<G, true, true><<<grid, G, dyn, st>>>(L); }
-		else       { if ((e = dp16_wide_prepare<G, true, false>()) != cudaSuccess) return e; extz_dp16_wide_kernel<G, true, false><<<grid, G, dyn, st>>>(L); }
-	} else         { if ((e = dp16_wide_prepare<G, false, false>()) != cudaSuccess) return e; extz_dp16_wide_kernel<G, false, false><<<grid, G, dyn, st>>>(L); }
-	return cudaGetLastError();
-}
-template <int G>
-static int dp16_wide_occupancy(bool cigar, bool right)
-{
-	int nb = 0;
-	const size_t dyn = (size_t)G * 192;
-	if (cigar) {
-		if (right) { dp16_wide_prepare<G, true, true>(); cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, extz_dp16_wide_kernel<G, true, true>, G, dyn); }
-		else       { dp16_wide_prepare<G, true, false>(); cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, extz_dp16_wide_kernel<G, true, false>, G, dyn); }
-	} else         { dp16_wide_prepare<G, false, false>(); cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, extz_dp16_wide_kernel<G, false, false>, G, dyn); }
-	return nb;
-}
-#define EXTZ_FOR_PACKED(ns, CALL) \
-	switch (ns) { \
-	case 32: return CALL(1); case 64: return CALL(2); case 128: return CALL(4); \
-	case 256: return CALL(8); case 512: return CALL(16); case 1024: return CALL(32); }
-#define EXTZ_FOR_CLASS(c, CALL) \
-	switch (c) { \
-	case 0: return CALL(2, 16, false); case 1: return CALL(4, 16, false); case 2: return CALL(8, 16, false); \
-	case 3: return CALL(16, 16, false); case 4: return CALL(32, 16, false); case 5: return CALL(32, 32, false); \
-	case 6: return CALL(64, 16, true); case 7: return CALL(128, 16, true); case 8: return CALL(256, 16, true); }
 // grid: CTAs for narrow / wide classes, clusters for cluster classes
 static cudaError_t launch_dp(int c, const DpLaunch &L, bool cigar, bool right, int grid, cudaStream_t st)
 {
-	if (class_packed_cluster(c)) return cluster16_dispatch(L, cigar, right, grid, st, nullptr);
-	if (class_cluster(c) == 2) return cluster_dispatch<2>(L, cigar, right, grid, st, nullptr);
-	if (class_cluster(c) == 4) return cluster_dispatch<4>(L, cigar, right, grid, st, nullptr);
-	if (class_packed_wide(c)) {
-		if (class_ns(c) == 2048) return launch_dp16_wide<64>(L, cigar, right, grid, st);
-		if (class_ns(c) == 4096) return launch_dp16_wide<128>(L, cigar, right, grid, st);
-		if (class_ns(c) == 8192) return launch_dp16_wide<256>(L, cigar, right, grid, st);
-		return cudaErrorInvalidValue;
-	}
-	if (class_packed(c)) {
-#define EXTZ_CALL16(G) launch_dp16<G>(L, cigar, right, grid, st)
-		EXTZ_FOR_PACKED(class_ns(c), EXTZ_CALL16)
-#undef EXTZ_CALL16
-		return cudaErrorInvalidValue;
-	}
-#define EXTZ_CALL(G, S, W) launch_dp_gs<G, S, W>(L, cigar, right, grid, st)
-	EXTZ_FOR_CLASS(c, EXTZ_CALL)
-#undef EXTZ_CALL
-	return cudaErrorInvalidValue;
+	if (class_packed_cluster(c)) return k_dp16_cluster_dispatch(L, cigar, right, grid, st, nullptr);
+	if (class_cluster(c)) return k_dp_cluster_dispatch(class_cluster(c), L, cigar, right, grid, st, nullptr);
+	if (class_packed_wide(c)) return k_dp16_wide_launch(class_ns(c) / 32, L, cigar, right, grid, st);
+	if (class_packed(c)) return k_dp16_launch(class_ns(c) / 32, L, cigar, right, grid, st);
+	return k_dp_launch(c, L, cigar, right, grid, st);
 }
-// resident CTAs per SM (narrow / wide) or co-resident clusters on the whole device (cluster classes)
-static int dp_occupancy(int c, bool cigar, bool right)
+// resident CTAs per SM (narrow / wide) or co-resident clusters on the whole device (cluster classes), on the CURRENT device
+static int dp_occupancy_query(int c, bool cigar, bool right)
 {
-	if (class_packed_cluster(c)) {
-		int n = 0; DpLaunch dummy = {};
-		if (cluster16_dispatch(dummy, cigar, right, 1, nullptr, &n) != cudaSuccess) { cudaGetLastError(); return 0; }
-		return n;
-	}
 	if (class_cluster(c)) {
 		int n = 0; DpLaunch dummy = {};
-		cudaError_t e = class_cluster(c) == 2 ? cluster_dispatch<2>(dummy, cigar, right, 1, nullptr, &n)
-		                                         : cluster_dispatch<4>(dummy, cigar, right, 1, nullptr, &n);
+		cudaError_t e = class_packed_cluster(c) ? k_dp16_cluster_dispatch(dummy, cigar, right, 1, nullptr, &n)
+		                                        : k_dp_cluster_dispatch(class_cluster(c), dummy, cigar, right, 1, nullptr, &n);
 		if (e != cudaSuccess) { cudaGetLastError(); return 0; }
 		return n;
 	}
-	if (class_packed_wide(c))
-		return class_ns(c) == 2048 ? dp16_wide_occupancy<64>(cigar, right)
-		     : class_ns(c) == 4096 ? dp16_wide_occupancy<128>(cigar, right) : dp16_wide_occupancy<256>(cigar, right);
-	if (class_packed(c)) {
-#define EXTZ_CALL16(G) dp16_occupancy<G>(cigar, right)
-		EXTZ_FOR_PACKED(class_ns(c), EXTZ_CALL16)
-#undef EXTZ_CALL16
-		return 0;
-	}
-#define EXTZ_CALL(G, S, W) dp_occupancy_gs<G, S, W>(cigar, right, 0)
-	EXTZ_FOR_CLASS(c, EXTZ_CALL)
-#undef EXTZ_CALL
-	return 0;
+	if (class_packed_wide(c)) return k_dp16_wide_occupancy(class_ns(c) / 32, cigar, right);
+	if (class_packed(c)) return k_dp16_occupancy(class_ns(c) / 32, cigar, right);
+	return k_dp_occupancy(c, cigar, right);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -298,7 +127,16 @@ struct DevCtx {
 	cudaStream_t tb_stream = nullptr;   // highest priority: a finished chunk's traceback must not queue behind the persistent
 	                                    // DP CTAs of the chunks launched after it (one-shot pipeline)
 	size_t tb_budget = 0;          // bytes of traceback memory one wave may use
+	int occ[kNumClasses][3];       // cached occupancy per (class, {score-only, cigar-left, cigar-right}); -1 = not asked yet
+	DevCtx() { for (auto &row : occ) for (int &v : row) v = -1; }
 };
+// occupancy of class c on device dc (which must be current): asked once per device
+static int dp_occupancy(DevCtx &dc, int c, bool cigar, bool right)
+{
+	int &slot = dc.occ[c][cigar ? (right ? 2 : 1) : 0];
+	if (slot < 0) slot = dp_occupancy_query(c, cigar, right);
+	return slot;
+}
 static std::mutex g_mu;
 static std::vector<DevCtx> g_devs;
 // host threads used for packing / gathering (0: OpenMP default).  Launchers such as torchrun export
@@ -345,6 +183,35 @@ extern "C" void ksw_b200_destroy(void)
 	g_devs.clear();
 }
 extern "C" int ksw_b200_num_devices(void) { return (int)g_devs.size(); }
+
+// ---- page-locked host memory for callers: sequences that live in pinned memory are copied to the device in place ----
+extern "C" void *ksw_b200_host_alloc(size_t bytes)
+{
+	void *p = nullptr;
+	if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+	return p;
+}
+extern "C" void ksw_b200_host_free(void *p) { if (p) cudaFreeHost(p); }
+extern "C" int ksw_b200_host_register(void *p, size_t bytes)
+{
+	if (!p || !bytes) return fail(KSW_B200_ERR_ARG, "null range");
+	CUDA_TRY(cudaHostRegister(p, bytes, cudaHostRegisterPortable));
+	return KSW_B200_OK;
+}
+extern "C" int ksw_b200_host_unregister(void *p)
+{
+	if (!p) return KSW_B200_OK;
+	CUDA_TRY(cudaHostUnregister(p));
+	return KSW_B200_OK;
+}
+// true when [p, p + bytes) can be the source / destination of an asynchronous DMA copy as it is
+static bool is_pinned(const void *p)
+{
+	if (!p) return false;
+	cudaPointerAttributes a;
+	if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+	return a.type == cudaMemoryTypeHost;
+}
 extern "C" int ksw_b200_max_slots(void) { return class_capacity(kNumSizedClasses - 1); }
 
 static int ensure_init()
@@ -448,22 +315,34 @@ struct SubBatch {
 	std::vector<PairDesc> pairs;        // grouped by class, each class sorted by descending work
 	std::vector<Wave> waves;
 	int class_first[kNumClasses + 1] = {0};
-	size_t arena_bytes = 0;
-	PinBuf h_arena, h_raw, h_results, h_cigar, h_stats, h_pairs;
-	DevBuf d_arena, d_raw, d_pairs, d_results, d_tb, d_cigar, d_stats, d_misc, d_table;
+	size_t arena_bytes = 0;             // bytes of one sequence plane on the device (codes; same size for the original-case plane)
+	PinBuf h_stage[2], h_recs, h_stats, h_pairs;
+	DevBuf d_arena, d_raw, d_pairs, d_results, d_tb, d_cigar, d_stats, d_misc, d_table, d_ez;
 	size_t cigar_cap = 0;               // entries
 	unsigned long long cigar_used = 0;
 	cudaStream_t stream = nullptr;      // every batch owns a stream so that the H2D of one batch overlaps the kernels of another
 	cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 	float dp_ms = 0, tb_ms = 0, total_ms = 0;
-	int launches = 0;
-	size_t h2d_bytes = 0, d2h_bytes = 0;
+	int launches = 0, aux_launches = 0;
+	int check_limit = 0;                // > 0: caller-supplied codes must be below this (checked on the device, first run only)
+	size_t h2d_seq_bytes = 0, h2d_desc_bytes = 0, d2h_bytes = 0;
 	std::vector<std::pair<cudaEvent_t, cudaEvent_t>> dp_ev, tb_ev;   // per-wave kernel timing events of the last launch
-	bool launched = false;
+	bool launched = false, touched = false;
+	void drop_events()
+	{
+		for (auto &p : dp_ev) cudaEventDestroy(p.first);
+		for (auto &p : tb_ev) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+		dp_ev.clear(); tb_ev.clear();
+	}
 	void release() {
-		h_arena.release(); h_raw.release(); h_results.release(); h_cigar.release(); h_stats.release(); h_pairs.release();
+		// kernels and copies of this batch may still be in flight on an error path: the buffers go back to a process-wide pool,
+		// so wait for the stream first (the traceback stream's work is ordered before it by events)
+		if (stream && touched) cudaStreamSynchronize(stream);
+		drop_events();
+		for (auto &b : h_stage) b.release();
+		h_recs.release(); h_stats.release(); h_pairs.release();
 		d_arena.release(); d_raw.release(); d_pairs.release(); d_results.release(); d_tb.release();
-		d_cigar.release(); d_stats.release(); d_misc.release(); d_table.release();
+		d_cigar.release(); d_stats.release(); d_misc.release(); d_table.release(); d_ez.release();
 		for (auto &e : ev) if (e) { cudaEventDestroy(e); e = nullptr; }
 		if (stream) { cudaStreamDestroy(stream); stream = nullptr; }
 	}
@@ -475,13 +354,28 @@ struct ksw_b200_batch {
 	int8_t mat[64];
 	bool early_out = false;             // -min_sc > 2(q+e): every pair returns the reset record (:81)
 	bool want_stats = false, have_raw = false;
+	bool encode_on_device = false;      // the caller passed original-case bytes only: codes = align_dna(bytes), computed on the device
+	int tb_budget_div = 1;              // batches in flight at once (one-shot pipeline): each gets this share of the traceback budget
 	Scoring sc;
 	uint32_t table[kTableStride * kTableStride];
 	std::vector<SubBatch> subs;
 	std::vector<uint8_t> is_empty;      // pairs with qlen<=0 || tlen<=0 (reset record)
+	int n_empty = 0;
 	int64_t cells = -1;                 // exact in-band cell count, computed on first request
 	std::vector<int> cq, ct;            // lengths kept for the lazy cell count
 	double t_plan = 0, t_pack = 0, t_h2d = 0, t_d2h = 0, t_gather = 0;   // host-side phase times (ms)
+};
+
+// Results of a batch in ONE arena: ksw_extz_t records in the caller's order whose `cigar` pointers point
+// into page-locked buffers owned by this object, and the statistics records.  Nothing here is malloc()'d per pair.
+struct ksw_b200_result {
+	int n = 0;
+	bool has_stats = false;
+	PinBuf ez, stats;
+	std::vector<PinBuf> cigars;         // one compact CIGAR arena per (chunk, device)
+	int64_t h2d = 0, d2h = 0;
+	int launches = 0;
+	void release() { ez.release(); stats.release(); for (auto &c : cigars) c.release(); cigars.clear(); }
 };
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -564,7 +458,65 @@ public:
 };
 static PipelineWorker g_worker;
 
+// One sequence plane (codes or original-case bytes) of one device's pairs goes to the device as
+//   [ query bytes | pad to 256 | target bytes | kArenaSlack ]
+// in one of two ways:
+//   dense   the pairs reference (almost) every byte of a contiguous range of the caller's flat buffers (the normal case:
+//           a batch built back to back, or windows of one genome): the two ranges are copied AS THEY ARE -- straight from
+//           the caller's memory when it is page-locked (no host pass over the sequences at all), through a pinned staging
+//           buffer in 8 MB blocks otherwise -- and a pair's offset is its caller offset minus the range start;
+//   sparse  otherwise every pair is packed back to back into the staging buffer first.
+struct PlanePlan {
+	bool dense = false;
+	int64_t qlo = 0, tlo = 0;           // start of the referenced ranges in the caller's buffers (dense)
+	size_t qspan = 0, tspan = 0;        // bytes per side on the device
+	size_t tbase = 0;                   // device offset of the target side
+};
+static int copy_plane(SubBatch &sb, const PlanePlan &pl, int slot, void *d_dst, const uint8_t *qsrc, const uint8_t *tsrc,
+                      const int64_t *qoff, const int64_t *toff, cudaStream_t st, double *t_pack)
+{
+	uint8_t *dst = (uint8_t *)d_dst;
+	if (pl.dense) {
+		const uint8_t *src[2] = {qsrc + pl.qlo, tsrc + pl.tlo};
+		const size_t len[2] = {pl.qspan, pl.tspan}, dofs[2] = {0, pl.tbase};
+		for (int side = 0; side < 2; ++side) {
+			if (!len[side]) continue;
+			if (is_pinned(src[side])) { CUDA_TRY(cudaMemcpyAsync(dst + dofs[side], src[side], len[side], cudaMemcpyHostToDevice, st)); continue; }
+			const double t0 = now_ms();
+			if (sb.h_stage[slot].ensure(sb.arena_bytes)) return fail(KSW_B200_ERR_NOMEM, "pinned staging allocation failed");
+			uint8_t *stage = (uint8_t *)sb.h_stage[slot].p + dofs[side];
+			const size_t blk = (size_t)8 << 20;
+			for (size_t o = 0; o < len[side]; o += blk) {                       // the DMA of block k overlaps the memcpy of block k+1
+				const size_t nb = std::min(blk, len[side] - o);
+				const int nt = (int)std::max<size_t>(1, std::min<size_t>(host_threads(), nb >> 18));
+#pragma omp parallel for num_threads(nt) schedule(static)
+				for (int t = 0; t < nt; ++t) {
+					const size_t a = nb * t / nt, b = nb * (t + 1) / nt;
+					memcpy(stage + o + a, src[side] + o + a, b - a);
+				}
+				CUDA_TRY(cudaMemcpyAsync(dst + dofs[side] + o, stage + o, nb, cudaMemcpyHostToDevice, st));
+			}
+			*t_pack += now_ms() - t0;
+		}
+		return 0;
+	}
+	const double t0 = now_ms();
+	if (sb.h_stage[slot].ensure(sb.arena_bytes)) return fail(KSW_B200_ERR_NOMEM, "pinned staging allocation failed");
+	uint8_t *stage = (uint8_t *)sb.h_stage[slot].p;
+	const int64_t np = (int64_t)sb.pairs.size();
+#pragma omp parallel for num_threads(host_threads()) schedule(static)
+	for (int64_t k = 0; k < np; ++k) {
+		const PairDesc &pd = sb.pairs[k];
+		memcpy(stage + pd.q_off, qsrc + qoff[pd.orig], pd.qlen);
+		memcpy(stage + pd.t_off, tsrc + toff[pd.orig], pd.tlen);
+	}
+	*t_pack += now_ms() - t0;
+	CUDA_TRY(cudaMemcpyAsync(dst, stage, pl.tbase + pl.tspan, cudaMemcpyHostToDevice, st));
+	return 0;
+}
+
 static thread_local bool tl_async_upload = false;      // set by the one-shot pipeline around its chunk uploads
+static thread_local int tl_pipeline_depth = 1;
 extern "C" ksw_b200_batch_t *ksw_b200_batch_upload(int n, const int *qlen, const int64_t *qoff, const uint8_t *qbuf,
                                                    const int *tlen, const int64_t *toff, const uint8_t *tbuf,
                                                    int8_t m, const int8_t *mat, int8_t q, int8_t e,
@@ -573,8 +525,11 @@ extern "C" ksw_b200_batch_t *ksw_b200_batch_upload(int n, const int *qlen, const
 {
 	auto bail = [&](int code) -> ksw_b200_batch_t * { if (err) *err = code; return nullptr; };
 	if (err) *err = KSW_B200_OK;
-	if (n < 0 || (n > 0 && (!qlen || !tlen || !qoff || !toff || !qbuf || !tbuf)) || (m > 0 && !mat))
+	const bool have_codes = qbuf && tbuf, have_raw = q_raw_buf && t_raw_buf;
+	if (n < 0 || (n > 0 && (!qlen || !tlen || !qoff || !toff || (!have_codes && !have_raw))) || (m > 0 && !mat))
 		return bail(fail(KSW_B200_ERR_ARG, "null pointer or negative count"));
+	if (!have_codes && m > 0 && m != 5)
+		return bail(fail(KSW_B200_ERR_ARG, "sequences given as original-case bytes only are encoded with align_dna (A C G T other -> 0..4): m must be 5"));
 	int nd = ensure_init();
 	if (nd <= 0) return bail(nd);
 
@@ -582,23 +537,29 @@ extern "C" ksw_b200_batch_t *ksw_b200_batch_upload(int n, const int *qlen, const
 	B->n = n; B->m = m; B->q = q; B->e = e; B->w = w; B->zdrop = zdrop; B->flag = flag;
 	memset(B->mat, 0, sizeof(B->mat));
 	if (m > 0 && m <= kTableStride) memcpy(B->mat, mat, (size_t)m * m);
-	B->have_raw = q_raw_buf && t_raw_buf;
+	B->have_raw = have_raw;
+	B->encode_on_device = !have_codes;
+	B->tb_budget_div = std::max(1, tl_pipeline_depth);
 	B->want_stats = !(flag & KSW_EZ_SCORE_ONLY) && !getenv("KSW_B200_NO_STATS");   // the fused K4 pass is on by default
 	int rc = build_scoring(*B);
 	if (rc) { delete B; return bail(rc); }
 	B->is_empty.assign(n, 0);
 	B->subs.resize(nd);
 	for (int d = 0; d < nd; ++d) B->subs[d].dc = &g_devs[d];
+	auto destroy = [&](int code) -> ksw_b200_batch_t * {
+		for (auto &s : B->subs) { if (s.dc) cudaSetDevice(s.dc->dev); s.release(); }
+		delete B; return bail(code);
+	};
 
 	const double t_start = now_ms();
 	// ---- classify + LPT partition ----
-	struct Item { int idx; int cls; int64_t work; };
+	struct Item { int cls; int64_t work; };
 	std::vector<Item> items(n);
 	const bool skip_s32 = getenv("KSW_B200_SKIP_S32") != nullptr;                       // A/B: 32 lanes x 32 slots vs 64-lane CTA
 	int too_wide = -1;
 #pragma omp parallel for num_threads(host_threads()) schedule(static) if (n >= 4096)
 	for (int i = 0; i < n; ++i) {
-		items[i].idx = i; items[i].cls = -1; items[i].work = 0;
+		items[i].cls = -1; items[i].work = 0;
 		if (m <= 0 || qlen[i] <= 0 || tlen[i] <= 0 || B->early_out) continue;           // empty record (:57,81)
 		int wi = w < 0 ? std::max(qlen[i], tlen[i]) : std::min(w, std::max(qlen[i], tlen[i]));
 		int need = slots_needed(qlen[i], tlen[i], wi);
@@ -620,7 +581,7 @@ extern "C" ksw_b200_batch_t *ksw_b200_batch_upload(int n, const int *qlen, const
 		                 " live slots; widest kernel holds " + std::to_string(class_capacity(kNumSizedClasses - 1))));
 	}
 	std::vector<int> order; order.reserve(n);
-	for (int i = 0; i < n; ++i) { if (items[i].cls < 0) B->is_empty[i] = 1; else order.push_back(i); }
+	for (int i = 0; i < n; ++i) { if (items[i].cls < 0) { B->is_empty[i] = 1; ++B->n_empty; } else order.push_back(i); }
 	std::vector<std::vector<int>> per_dev(nd);
 	if (nd == 1) {
 		// one device: the order the kernels want directly -- by class, descending work inside a class (the device-side
@@ -659,84 +620,83 @@ extern "C" ksw_b200_batch_t *ksw_b200_batch_upload(int n, const int *qlen, const
 	}
 
 	B->t_plan = now_ms() - t_start;
-	// ---- per device: group by class (descending work inside), pack, copy ----
+	// ---- per device: group by class (descending work inside), lay the sequence planes out, copy ----
 	for (int d = 0; d < nd; ++d) {
 		SubBatch &sb = B->subs[d];
 		auto &lst = per_dev[d];
 		if (nd > 1) std::stable_sort(lst.begin(), lst.end(), [&](int a, int b) { return items[a].cls < items[b].cls; });
-		size_t pos = 0;
 		sb.pairs.resize(lst.size());
 		for (int c = 0; c <= kNumClasses; ++c) {
 			int k = 0;
 			while (k < (int)lst.size() && items[lst[k]].cls < c) ++k;
 			sb.class_first[c] = k;                                                  // first pair of class >= c
 		}
-		for (size_t k = 0; k < lst.size(); ++k) {
-			const Item &it = items[lst[k]];
-			PairDesc &pd = sb.pairs[k];
-			const int i = it.idx;
-			pd.qlen = qlen[i]; pd.tlen = tlen[i];
-			pd.w = w < 0 ? std::max(qlen[i], tlen[i]) : std::min(w, std::max(qlen[i], tlen[i]));
-			pd.orig = i;
-			pd.q_off = (int64_t)(pos + kQPadL);
-			pos = align_up(pos + kQPadL + qlen[i], 16);
-			pd.t_off = (int64_t)pos;
-			pos = align_up(pos + tlen[i], 16);
-			pd.tb_off = 0;
-		}
-		sb.arena_bytes = pos + 128;   // the query window may read a few bytes past the last sequence
 		if (lst.empty()) continue;
-		if (cudaSetDevice(sb.dc->dev) != cudaSuccess) { delete B; return bail(fail(KSW_B200_ERR_CUDA, "cudaSetDevice")); }
-		if (sb.h_arena.ensure(sb.arena_bytes) || sb.d_arena.ensure(sb.arena_bytes) ||
-		    (B->have_raw && (sb.h_raw.ensure(sb.arena_bytes) || sb.d_raw.ensure(sb.arena_bytes)))) {
-			for (auto &s : B->subs) s.release();
-			delete B; return bail(fail(KSW_B200_ERR_NOMEM, "sequence arena allocation failed"));
-		}
-		const double t_pack0 = now_ms();
-		uint8_t *ha = (uint8_t *)sb.h_arena.p, *hr = (uint8_t *)sb.h_raw.p;
-		const int64_t np = (int64_t)sb.pairs.size();
-		int bad_symbol = 0;
-#pragma omp parallel for num_threads(host_threads()) schedule(static) reduction(| : bad_symbol)
+		// the ranges of the caller's buffers this device's pairs reference
+		const int64_t np = (int64_t)lst.size();
+		int64_t qlo = INT64_MAX, qhi = 0, tlo = INT64_MAX, thi = 0, qsum = 0, tsum = 0;
+#pragma omp parallel for num_threads(host_threads()) schedule(static) reduction(min : qlo, tlo) reduction(max : qhi, thi) reduction(+ : qsum, tsum) if (np >= 4096)
 		for (int64_t k = 0; k < np; ++k) {
-			const PairDesc &pd = sb.pairs[k];
-			const int i = pd.orig;
-			uint8_t *qd = ha + pd.q_off, *td = ha + pd.t_off;
-			memset(qd - kQPadL, 0, kQPadL);
-			memcpy(qd, qbuf + qoff[i], pd.qlen);
-			memset(qd + pd.qlen, 0, (size_t)(pd.t_off - pd.q_off) - pd.qlen);
-			memcpy(td, tbuf + toff[i], pd.tlen);
-			memset(td + pd.tlen, 0, align_up(pd.tlen, 16) - pd.tlen);
-			uint8_t acc = 0;
-			for (int x = 0; x < pd.qlen; ++x) acc |= qd[x];
-			for (int x = 0; x < pd.tlen; ++x) acc |= td[x];
-			if (acc >= kTableStride) bad_symbol |= 1;
-			if (hr) {
-				memcpy(hr + pd.q_off, q_raw_buf + qoff[i], pd.qlen);
-				memcpy(hr + pd.t_off, t_raw_buf + toff[i], pd.tlen);
+			const int i = lst[k];
+			qlo = std::min(qlo, qoff[i]); qhi = std::max(qhi, qoff[i] + qlen[i]); qsum += qlen[i];
+			tlo = std::min(tlo, toff[i]); thi = std::max(thi, toff[i] + tlen[i]); tsum += tlen[i];
+		}
+		PlanePlan pl;
+		pl.dense = qlo >= 0 && tlo >= 0 && !getenv("KSW_B200_FORCE_SPARSE") &&
+		           (uint64_t)(qhi - qlo) <= (uint64_t)qsum + (uint64_t)qsum / 2 + 65536 &&
+		           (uint64_t)(thi - tlo) <= (uint64_t)tsum + (uint64_t)tsum / 2 + 65536;
+		if (pl.dense) { pl.qlo = qlo; pl.tlo = tlo; pl.qspan = (size_t)(qhi - qlo); pl.tspan = (size_t)(thi - tlo); }
+		else { pl.qspan = (size_t)qsum; pl.tspan = (size_t)tsum; }
+		pl.tbase = align_up(pl.qspan, 256);
+		sb.arena_bytes = align_up(pl.tbase + pl.tspan + kArenaSlack, 256);
+		{
+			size_t qpos = 0, tpos = pl.tbase;
+			for (int64_t k = 0; k < np; ++k) {
+				PairDesc &pd = sb.pairs[k];
+				const int i = lst[k];
+				pd.qlen = qlen[i]; pd.tlen = tlen[i];
+				pd.w = w < 0 ? std::max(qlen[i], tlen[i]) : std::min(w, std::max(qlen[i], tlen[i]));
+				pd.orig = i; pd.tb_off = 0;
+				if (pl.dense) { pd.q_off = qoff[i] - qlo; pd.t_off = (int64_t)pl.tbase + (toff[i] - tlo); }
+				else { pd.q_off = (int64_t)qpos; pd.t_off = (int64_t)tpos; qpos += qlen[i]; tpos += tlen[i]; }
 			}
 		}
-		if (bad_symbol) {
-			for (auto &s : B->subs) s.release();
-			delete B; return bail(fail(KSW_B200_ERR_ARG, "sequence symbol >= 8"));
-		}
-		B->t_pack += now_ms() - t_pack0;
+		if (cudaSetDevice(sb.dc->dev) != cudaSuccess) return destroy(fail(KSW_B200_ERR_CUDA, "cudaSetDevice"));
+		if (sb.d_arena.ensure(sb.arena_bytes) || (B->have_raw && sb.d_raw.ensure(sb.arena_bytes)))
+			return destroy(fail(KSW_B200_ERR_NOMEM, "sequence arena allocation failed"));
 		if (!sb.stream && cudaStreamCreateWithFlags(&sb.stream, cudaStreamNonBlocking) != cudaSuccess) sb.stream = nullptr;
 		cudaStream_t st = sb.stream ? sb.stream : sb.dc->stream;
-		bool ok = cudaMemcpyAsync(sb.d_arena.p, ha, sb.arena_bytes, cudaMemcpyHostToDevice, st) == cudaSuccess;
-		if (ok && hr) ok = cudaMemcpyAsync(sb.d_raw.p, hr, sb.arena_bytes, cudaMemcpyHostToDevice, st) == cudaSuccess;
-		sb.h2d_bytes = sb.arena_bytes * (hr ? 2 : 1) + sizeof(B->table);
-		// per-pair descriptors, results, table
+		sb.touched = true;
 		const size_t pbytes = sb.pairs.size() * sizeof(PairDesc);
-		ok = ok && !sb.d_pairs.ensure(pbytes) && !sb.d_results.ensure(sb.pairs.size() * sizeof(PairResult)) &&
-		     !sb.d_table.ensure(sizeof(B->table)) && !sb.d_misc.ensure(4096) &&
-		     !sb.h_results.ensure(sb.pairs.size() * sizeof(PairResult));
-		if (ok) ok = cudaMemcpyAsync(sb.d_table.p, B->table, sizeof(B->table), cudaMemcpyHostToDevice, st) == cudaSuccess;
-		for (auto &e2 : sb.ev) if (ok) ok = cudaEventCreate(&e2) == cudaSuccess;
-		if (!ok) {
-			std::string msg = std::string("upload failed: ") + cudaGetErrorString(cudaGetLastError());
-			for (auto &s : B->subs) s.release();
-			delete B; return bail(fail(KSW_B200_ERR_CUDA, msg));
+		bool ok = !sb.d_pairs.ensure(pbytes) && !sb.d_results.ensure(sb.pairs.size() * sizeof(PairResult)) &&
+		          !sb.d_table.ensure(sizeof(B->table)) && !sb.d_misc.ensure(4096);
+		if (!ok) return destroy(fail(KSW_B200_ERR_NOMEM, "descriptor allocation failed"));
+		// misc: [0..2047] work counters (one per wave), [2048] cigar cursor (u64), [2112] CIGAR arena overflow, [2116] bad symbol
+		if (cudaMemsetAsync(sb.d_misc.p, 0, 4096, st) != cudaSuccess) return destroy(fail(KSW_B200_ERR_CUDA, "cudaMemsetAsync"));
+		// the slack behind the last sequence is read (never used): keep it defined
+		ok = cudaMemsetAsync((char *)sb.d_arena.p + sb.arena_bytes - kArenaSlack - 256, 0, kArenaSlack + 256, st) == cudaSuccess;
+		if (ok && B->have_raw) ok = cudaMemsetAsync((char *)sb.d_raw.p + sb.arena_bytes - kArenaSlack - 256, 0, kArenaSlack + 256, st) == cudaSuccess;
+		if (!ok) return destroy(fail(KSW_B200_ERR_CUDA, "cudaMemsetAsync"));
+		sb.h2d_seq_bytes = 0;
+		if (have_codes) {
+			if ((rc = copy_plane(sb, pl, 0, sb.d_arena.p, qbuf, tbuf, qoff, toff, st, &B->t_pack))) return destroy(rc);
+			sb.h2d_seq_bytes += pl.qspan + pl.tspan;
+			const int limit = (flag & KSW_EZ_GENERIC_SC) ? std::min<int>(m, kTableStride) : kTableStride;
+			sb.check_limit = limit;                             // checked per pair once the descriptors are on the device (launch_sub)
 		}
+		if (B->have_raw) {
+			if ((rc = copy_plane(sb, pl, 1, sb.d_raw.p, q_raw_buf, t_raw_buf, qoff, toff, st, &B->t_pack))) return destroy(rc);
+			sb.h2d_seq_bytes += pl.qspan + pl.tspan;
+			if (!have_codes) {
+				if (k_encode_launch((const uint8_t *)sb.d_raw.p, (uint8_t *)sb.d_arena.p, sb.arena_bytes, st) != cudaSuccess)
+					return destroy(fail(KSW_B200_ERR_CUDA, "encode launch failed"));
+				++sb.aux_launches;
+			}
+		}
+		ok = cudaMemcpyAsync(sb.d_table.p, B->table, sizeof(B->table), cudaMemcpyHostToDevice, st) == cudaSuccess;
+		sb.h2d_seq_bytes += sizeof(B->table);
+		for (auto &e2 : sb.ev) if (ok) ok = cudaEventCreate(&e2) == cudaSuccess;
+		if (!ok) return destroy(fail(KSW_B200_ERR_CUDA, std::string("upload failed: ") + cudaGetErrorString(cudaGetLastError())));
 	}
 	B->cq.assign(qlen, qlen + n); B->ct.assign(tlen, tlen + n);
 	if (!tl_async_upload) {           // resident API: the inputs are in HBM when this returns (the one-shot pipeline does not wait)
@@ -770,7 +730,7 @@ extern "C" int ksw_b200_batch_io_bytes(const ksw_b200_batch_t *b, int64_t *h2d, 
 {
 	if (!b) return KSW_B200_ERR_ARG;
 	int64_t a = 0, c = 0;
-	for (auto &sb : b->subs) { a += (int64_t)sb.h2d_bytes; c += (int64_t)sb.d2h_bytes; }
+	for (auto &sb : b->subs) { a += (int64_t)(sb.h2d_seq_bytes + sb.h2d_desc_bytes); c += (int64_t)sb.d2h_bytes; }
 	if (h2d) *h2d = a;
 	if (d2h) *d2h = c;
 	return 0;
@@ -784,6 +744,7 @@ static int plan_waves(ksw_b200_batch &B, SubBatch &sb, bool cigar)
 {
 	sb.waves.clear();
 	size_t max_tb = 0, max_cig = 0;
+	const size_t budget = std::max<size_t>(sb.dc->tb_budget / (size_t)B.tb_budget_div, (size_t)1 << 20);
 	for (int c = 0; c < kNumClasses; ++c) {
 		int first = sb.class_first[c], last = sb.class_first[c + 1];
 		if (first >= last) continue;
@@ -795,7 +756,7 @@ static int plan_waves(ksw_b200_batch &B, SubBatch &sb, bool cigar)
 			while (k < last) {
 				PairDesc &pd = sb.pairs[k];
 				size_t bytes = cigar ? align_up(((size_t)pd.qlen + pd.tlen) * rowB, 256) : 0;
-				if (wv.count > 0 && wv.tb_bytes + bytes > sb.dc->tb_budget) break;
+				if (wv.count > 0 && wv.tb_bytes + bytes > budget) break;
 				pd.tb_off = (int64_t)wv.tb_bytes;
 				wv.tb_bytes += bytes;
 				cig += (size_t)pd.qlen + pd.tlen + 2;
@@ -812,10 +773,13 @@ static int plan_waves(ksw_b200_batch &B, SubBatch &sb, bool cigar)
 		if (max_cig > 0x7fffffffull) max_cig = 0x7fffffffull;
 		sb.cigar_cap = max_cig;
 		if (sb.d_cigar.ensure(max_cig * 4 + 256)) return fail(KSW_B200_ERR_NOMEM, "CIGAR arena allocation failed");
-		if (B.want_stats && sb.d_stats.ensure(sb.pairs.size() * sizeof(sd_stats_t))) return fail(KSW_B200_ERR_NOMEM, "stats allocation failed");
 	}
 	return 0;
 }
+
+// the statistics records live in the caller's order when one device holds the whole batch (the traceback kernel scatters
+// them by PairDesc::orig and the host copies the array as it is); with several devices each keeps its own pairs' order
+static inline bool by_orig(const ksw_b200_batch &B) { return B.subs.size() == 1; }
 
 // asynchronous part of a run: plan waves and enqueue every kernel of this device on the batch's stream
 static int launch_sub(ksw_b200_batch &B, SubBatch &sb)
@@ -826,23 +790,35 @@ static int launch_sub(ksw_b200_batch &B, SubBatch &sb)
 	const bool right = (B.flag & KSW_EZ_RIGHT) != 0;
 	CUDA_TRY(cudaSetDevice(sb.dc->dev));
 	cudaStream_t st = sb.stream ? sb.stream : sb.dc->stream;
+	sb.touched = true;
 	int rc = plan_waves(B, sb, cigar);
 	if (rc) return rc;
+	if (sb.waves.size() > 500) return fail(KSW_B200_ERR_NOMEM, "too many waves; raise KSW_B200_TB_BUDGET_MB");
+	const bool stats_on = cigar && B.want_stats;
+	const size_t n_stats = by_orig(B) ? (size_t)B.n : sb.pairs.size();
+	if (stats_on) {
+		if (sb.d_stats.ensure(n_stats * sizeof(sd_stats_t))) return fail(KSW_B200_ERR_NOMEM, "stats allocation failed");
+		if (by_orig(B) && B.n_empty) CUDA_TRY(cudaMemsetAsync(sb.d_stats.p, 0, n_stats * sizeof(sd_stats_t), st));   // pairs no kernel sees
+	}
 	// descriptors carry tb offsets -> (re)upload
 	// (staged through pinned memory: a pageable source would make this call wait for the sequence copies queued before it)
-	if (sb.h_pairs.ensure(sb.pairs.size() * sizeof(PairDesc))) return fail(KSW_B200_ERR_NOMEM, "pinned descriptor allocation failed");
+	if (sb.h_pairs.ensure(std::max<size_t>(256, sb.pairs.size() * sizeof(PairDesc)))) return fail(KSW_B200_ERR_NOMEM, "pinned descriptor allocation failed");
 	memcpy(sb.h_pairs.p, sb.pairs.data(), sb.pairs.size() * sizeof(PairDesc));
 	CUDA_TRY(cudaMemcpyAsync(sb.d_pairs.p, sb.h_pairs.p, sb.pairs.size() * sizeof(PairDesc), cudaMemcpyHostToDevice, st));
-	sb.h2d_bytes += sb.pairs.size() * sizeof(PairDesc);
-	// misc: [0..63] work counters (one per wave, reused round-robin), [64] cigar cursor (u64 at byte 512), [66] overflow
-	CUDA_TRY(cudaMemsetAsync(sb.d_misc.p, 0, 4096, st));
+	sb.h2d_desc_bytes = sb.pairs.size() * sizeof(PairDesc);
 	int *d_counters = (int *)sb.d_misc.p;
 	unsigned long long *d_cursor = (unsigned long long *)((char *)sb.d_misc.p + 2048);
 	int *d_overflow = (int *)((char *)sb.d_misc.p + 2048 + 64);
+	CUDA_TRY(cudaMemsetAsync(sb.d_misc.p, 0, 2048 + 68, st));            // counters, cursor, overflow (not the bad-symbol flag of the upload)
+	if (sb.check_limit > 0) {
+		CUDA_TRY(k_check_symbols_launch((const PairDesc *)sb.d_pairs.p, (int)sb.pairs.size(), (const uint8_t *)sb.d_arena.p, sb.check_limit,
+		                                (int *)((char *)sb.d_misc.p + 2048 + 68), st));
+		sb.check_limit = 0; ++sb.aux_launches;
+	}
 	sb.launches = 0; sb.dp_ms = sb.tb_ms = 0;
 	CUDA_TRY(cudaEventRecord(sb.ev[0], st));
+	sb.drop_events();
 	auto &dp_ev = sb.dp_ev; auto &tb_ev = sb.tb_ev;
-	dp_ev.clear(); tb_ev.clear();
 	int wave_no = 0;
 	for (const Wave &wv : sb.waves) {
 		const int c = wv.cls;
@@ -852,28 +828,28 @@ static int launch_sub(ksw_b200_batch &B, SubBatch &sb)
 		L.seq = (const uint8_t *)sb.d_arena.p;
 		L.tb = (uint8_t *)sb.d_tb.p;
 		L.table = (const uint32_t *)sb.d_table.p;
-		if (wave_no >= 500) return fail(KSW_B200_ERR_NOMEM, "too many waves; raise KSW_B200_TB_BUDGET_MB");
 		L.work_counter = d_counters + wave_no;
 		L.n = wv.count; L.sc = B.sc;
-		int occ = dp_occupancy(c, cigar, right);
+		int occ = dp_occupancy(*sb.dc, c, cigar, right);
 		if (occ <= 0) return fail(KSW_B200_ERR_CUDA, "DP kernel cannot be resident (occupancy 0)");
 		const int groups_per_block = class_pairs_per_block(c);
 		int grid = class_cluster(c) ? std::min(wv.count, occ)                                 // clusters, one pair each
 		                               : std::min((wv.count + groups_per_block - 1) / groups_per_block, sb.dc->sms * occ);
 		cudaEvent_t a, b2, c2;
 		CUDA_TRY(cudaEventCreate(&a)); CUDA_TRY(cudaEventCreate(&b2)); CUDA_TRY(cudaEventCreate(&c2));
+		dp_ev.push_back({a, b2}); tb_ev.push_back({b2, c2});
 		CUDA_TRY(cudaEventRecord(a, st));
 		CUDA_TRY(launch_dp(c, L, cigar, right, grid, st));
 		CUDA_TRY(cudaEventRecord(b2, st));
 		++sb.launches;
-		dp_ev.push_back({a, b2});
 		if (cigar) {
 			TbLaunch TL;
 			TL.pairs = L.pairs; TL.results = L.results; TL.tb = L.tb;
 			TL.raw = B.have_raw ? (const uint8_t *)sb.d_raw.p : nullptr;
 			TL.seq = L.seq;
 			TL.cigar_arena = (uint32_t *)sb.d_cigar.p; TL.cigar_cursor = d_cursor; TL.cigar_capacity = sb.cigar_cap;
-			TL.stats = B.want_stats ? (sd_stats_t *)sb.d_stats.p + wv.first : nullptr;
+			TL.stats_by_orig = by_orig(B) ? 1 : 0;
+			TL.stats = stats_on ? (sd_stats_t *)sb.d_stats.p + (TL.stats_by_orig ? 0 : wv.first) : nullptr;
 			TL.overflow = d_overflow;
 			TL.n = wv.count; TL.NS = class_ns(c); TL.flag = B.flag; TL.packed = class_packed(c) ? 1 : 0;
 			cudaStream_t tbs = sb.dc->tb_stream;
@@ -882,22 +858,12 @@ static int launch_sub(ksw_b200_batch &B, SubBatch &sb)
 			int64_t steps = 0;
 			for (int k = wv.first; k < wv.first + wv.count; ++k) steps += (int64_t)sb.pairs[k].qlen + sb.pairs[k].tlen;
 			static const int warp_min_steps = [] { const char *e = getenv("KSW_B200_TB_WARP_MIN"); return e ? atoi(e) : 6000; }();
-			if (steps / std::max(1, wv.count) >= warp_min_steps) {
-				const int tgrid = (wv.count + 3) / 4;
-				if (B.want_stats) extz_traceback_warp_kernel<true><<<tgrid, 128, 0, tbs>>>(TL);
-				else extz_traceback_warp_kernel<false><<<tgrid, 128, 0, tbs>>>(TL);
-			} else {
-				const int tgrid = (wv.count + 127) / 128;
-				if (B.want_stats) extz_traceback_kernel<true><<<tgrid, 128, 0, tbs>>>(TL);
-				else extz_traceback_kernel<false><<<tgrid, 128, 0, tbs>>>(TL);
-			}
-			CUDA_TRY(cudaGetLastError());
+			CUDA_TRY(k_traceback_launch(TL, steps / std::max(1, wv.count) >= warp_min_steps, stats_on, tbs));
 			++sb.launches;
 			CUDA_TRY(cudaEventRecord(c2, tbs));
 			CUDA_TRY(cudaStreamWaitEvent(st, c2, 0));             // the next wave reuses the traceback arena
 		} else
 		CUDA_TRY(cudaEventRecord(c2, st));
-		tb_ev.push_back({b2, c2});
 		++wave_no;
 	}
 	CUDA_TRY(cudaEventRecord(sb.ev[1], st));
@@ -905,27 +871,27 @@ static int launch_sub(ksw_b200_batch &B, SubBatch &sb)
 	return 0;
 }
 
-// blocking part: wait for the stream, read the timers, the CIGAR cursor and the overflow flag
+// blocking part: wait for the stream, read the timers, the CIGAR cursor and the error flags
 static int finish_sub(ksw_b200_batch &B, SubBatch &sb)
 {
 	if (!sb.launched) return 0;
 	sb.launched = false;
 	CUDA_TRY(cudaSetDevice(sb.dc->dev));
 	cudaStream_t st = sb.stream ? sb.stream : sb.dc->stream;
-	auto &dp_ev = sb.dp_ev; auto &tb_ev = sb.tb_ev;
-	unsigned long long *d_cursor = (unsigned long long *)((char *)sb.d_misc.p + 2048);
-	int *d_overflow = (int *)((char *)sb.d_misc.p + 2048 + 64);
+	// cursor (8 bytes), overflow and bad-symbol flags in one small copy behind the kernels
+	struct Tail { unsigned long long cursor; int pad[14]; int overflow; int badsym; } tail;
+	static_assert(sizeof(Tail) == 72, "layout of the misc block");
+	if (sb.h_pairs.cap < sizeof(Tail)) return fail(KSW_B200_ERR_NOMEM, "pinned buffer");
+	CUDA_TRY(cudaMemcpyAsync(sb.h_pairs.p, (char *)sb.d_misc.p + 2048, sizeof(Tail), cudaMemcpyDeviceToHost, st));   // descriptors were consumed
 	CUDA_TRY(cudaStreamSynchronize(st));
+	memcpy(&tail, sb.h_pairs.p, sizeof(Tail));
 	CUDA_TRY(cudaEventElapsedTime(&sb.total_ms, sb.ev[0], sb.ev[1]));
-	for (auto &p : dp_ev) { float ms = 0; cudaEventElapsedTime(&ms, p.first, p.second); sb.dp_ms += ms; }
-	for (auto &p : tb_ev) { float ms = 0; cudaEventElapsedTime(&ms, p.first, p.second); sb.tb_ms += ms; }
-	for (auto &p : dp_ev) cudaEventDestroy(p.first);
-	for (auto &p : tb_ev) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
-	dp_ev.clear(); tb_ev.clear();
-	int ovf = 0;
-	CUDA_TRY(cudaMemcpy(&ovf, d_overflow, sizeof(int), cudaMemcpyDeviceToHost));
-	CUDA_TRY(cudaMemcpy(&sb.cigar_used, d_cursor, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-	if (ovf) return fail(KSW_B200_ERR_NOMEM, "compact CIGAR arena overflow");
+	for (auto &p : sb.dp_ev) { float ms = 0; cudaEventElapsedTime(&ms, p.first, p.second); sb.dp_ms += ms; }
+	for (auto &p : sb.tb_ev) { float ms = 0; cudaEventElapsedTime(&ms, p.first, p.second); sb.tb_ms += ms; }
+	sb.drop_events();
+	sb.cigar_used = tail.cursor;
+	if (tail.badsym) return fail(KSW_B200_ERR_ARG, (B.flag & KSW_EZ_GENERIC_SC) ? "sequence symbol >= m" : "sequence symbol >= 8");
+	if (tail.overflow) return fail(KSW_B200_ERR_NOMEM, "compact CIGAR arena overflow");
 	return 0;
 }
 
@@ -933,15 +899,16 @@ extern "C" int ksw_b200_batch_run(ksw_b200_batch_t *B, float *device_ms)
 {
 	if (!B) return fail(KSW_B200_ERR_ARG, "null batch");
 	float worst = 0;
-	// waves of different devices overlap: launches are asynchronous, run_sub only blocks on its own stream
-	// (one device per process is the scaling configuration; in-process multi-device runs them back to back
-	//  on the host side but concurrently on the devices when the batch fits one wave)
-	for (auto &sb : B->subs) { int rc = launch_sub(*B, sb); if (rc) return rc; }          // every device gets its work first
+	// waves of different devices overlap: launches are asynchronous, finish_sub only blocks on its own stream
+	int rc = 0;
+	for (auto &sb : B->subs) { rc = launch_sub(*B, sb); if (rc) break; }                 // every device gets its work first
 	for (auto &sb : B->subs) {
-		int rc = finish_sub(*B, sb);
-		if (rc) return rc;
+		// after a failure the devices that did launch are still waited for (their buffers may be released next)
+		int rc2 = finish_sub(*B, sb);
+		if (!rc) rc = rc2;
 		worst = std::max(worst, sb.total_ms);
 	}
+	if (rc) return rc;
 	if (device_ms) *device_ms = worst;
 	return KSW_B200_OK;
 }
@@ -974,62 +941,167 @@ static void reset_ez(ksw_extz_t *ez)                                            
 	ez->cigar = 0;
 }
 
-extern "C" int ksw_b200_batch_fetch(ksw_b200_batch_t *B, ksw_extz_t *ez, sd_stats_t *stats)
+// Results of a finished batch into records [s0, s0 + B.n) of the arena R (whose ez / stats arrays hold R.n records).
+//   one device    the gather kernel writes final ksw_extz_t records in the CALLER's order -- host CIGAR pointers included --
+//                 and the host side is three DMA copies into page-locked memory: no per-pair host work at all;
+//   n devices     every device gathers its own pairs (device order), the host permutes the records into place.
+static int fetch_into(ksw_b200_batch &B, ksw_b200_result &R, int s0)
 {
-	if (!B || (B->n > 0 && !ez)) return fail(KSW_B200_ERR_ARG, "null argument");
-	const bool cigar = !(B->flag & KSW_EZ_SCORE_ONLY);
-	B->t_d2h = B->t_gather = 0;
-	{ const double t0 = now_ms(); for (int i = 0; i < B->n; ++i) reset_ez(&ez[i]); B->t_gather += now_ms() - t0; }
-	if (stats) memset(stats, 0, sizeof(sd_stats_t) * (size_t)B->n);
-	int rc_all = 0;
-	for (auto &sb : B->subs) {
+	const bool cigar = !(B.flag & KSW_EZ_SCORE_ONLY);
+	const bool stats_on = cigar && B.want_stats && R.has_stats;
+	B.t_d2h = B.t_gather = 0;
+	ksw_extz_t *ez = (ksw_extz_t *)R.ez.p + s0;
+	sd_stats_t *stats = R.has_stats ? (sd_stats_t *)R.stats.p + s0 : nullptr;
+	const bool one = by_orig(B);
+	bool any = false;
+	for (auto &sb : B.subs) any = any || !sb.pairs.empty();
+	if (!one || !any) {                                                           // records no device will write
+		const double t0 = now_ms();
+		if (!any || B.n_empty) for (int i = 0; i < B.n; ++i) if (!any || B.is_empty[i]) reset_ez(&ez[i]);
+		if (stats && (!any || B.n_empty || !stats_on)) memset(stats, 0, sizeof(sd_stats_t) * (size_t)B.n);
+		B.t_gather += now_ms() - t0;
+	} else if (stats && !stats_on) memset(stats, 0, sizeof(sd_stats_t) * (size_t)B.n);
+	const double t_f0 = now_ms();
+	for (auto &sb : B.subs) {
 		if (sb.pairs.empty()) continue;
 		CUDA_TRY(cudaSetDevice(sb.dc->dev));
 		cudaStream_t st = sb.stream ? sb.stream : sb.dc->stream;
-		const size_t np = sb.pairs.size();
-		const double t_f0 = now_ms();
-		CUDA_TRY(cudaMemcpyAsync(sb.h_results.p, sb.d_results.p, np * sizeof(PairResult), cudaMemcpyDeviceToHost, st));
+		const size_t np = sb.pairs.size(), nrec = one ? (size_t)B.n : np;
+		if (sb.d_ez.ensure(nrec * sizeof(ksw_extz_t))) return fail(KSW_B200_ERR_NOMEM, "record buffer allocation failed");
+		uint64_t host_base = 0;
 		if (cigar && sb.cigar_used) {
-			if (sb.h_cigar.ensure(sb.cigar_used * 4)) return fail(KSW_B200_ERR_NOMEM, "pinned CIGAR buffer");
-			CUDA_TRY(cudaMemcpyAsync(sb.h_cigar.p, sb.d_cigar.p, sb.cigar_used * 4, cudaMemcpyDeviceToHost, st));
+			R.cigars.emplace_back();
+			if (R.cigars.back().ensure(sb.cigar_used * 4)) return fail(KSW_B200_ERR_NOMEM, "pinned CIGAR buffer");
+			host_base = (uint64_t)(uintptr_t)R.cigars.back().p;
+			CUDA_TRY(cudaMemcpyAsync(R.cigars.back().p, sb.d_cigar.p, sb.cigar_used * 4, cudaMemcpyDeviceToHost, st));
 		}
-		if (cigar && stats && B->want_stats) {
-			if (sb.h_stats.ensure(np * sizeof(sd_stats_t))) return fail(KSW_B200_ERR_NOMEM, "pinned stats buffer");
-			CUDA_TRY(cudaMemcpyAsync(sb.h_stats.p, sb.d_stats.p, np * sizeof(sd_stats_t), cudaMemcpyDeviceToHost, st));
-		}
-		CUDA_TRY(cudaStreamSynchronize(st));
-		B->t_d2h += now_ms() - t_f0;
-		const double t_g0 = now_ms();
-		sb.d2h_bytes = np * sizeof(PairResult) + (cigar ? sb.cigar_used * 4 : 0) + ((cigar && stats && B->want_stats) ? np * sizeof(sd_stats_t) : 0);
-		const PairResult *res = (const PairResult *)sb.h_results.p;
-		const uint32_t *carena = (const uint32_t *)sb.h_cigar.p;
-		const sd_stats_t *hst = (const sd_stats_t *)sb.h_stats.p;
-		int nomem = 0;
-#pragma omp parallel for num_threads(host_threads()) schedule(static) reduction(| : nomem)
-		for (int64_t k = 0; k < (int64_t)np; ++k) {
-			const PairResult &r = res[k];
-			ksw_extz_t *z = &ez[sb.pairs[k].orig];
-			z->max = (uint32_t)r.max; z->zdropped = (uint32_t)r.zdropped;
-			z->max_q = r.max_q; z->max_t = r.max_t; z->mqe = r.mqe; z->mqe_t = r.mqe_t;
-			z->mte = r.mte; z->mte_q = r.mte_q; z->score = r.score;
-			if (cigar && r.n_cigar > 0) {
-				int64_t cap = 4;                                                  // growth of ksw_push_cigar (extern/ksw2.h:101-105)
-				while (cap < r.n_cigar) cap <<= 1;
-				z->cigar = (uint32_t *)malloc((size_t)cap << 2);
-				if (!z->cigar) { nomem |= 1; continue; }
-				memcpy(z->cigar, carena + r.cigar_off, (size_t)r.n_cigar * 4);
-				z->n_cigar = r.n_cigar; z->m_cigar = cap;
+		if (one && B.n_empty) { CUDA_TRY(k_fill_reset_launch((uint64_t *)sb.d_ez.p, B.n, st)); ++sb.aux_launches; }
+		GatherLaunch G;
+		G.pairs = (const PairDesc *)sb.d_pairs.p; G.results = (const PairResult *)sb.d_results.p;
+		G.ez_out = (uint64_t *)sb.d_ez.p; G.host_cigar_base = host_base; G.n = (int)np; G.by_orig = one ? 1 : 0; G.with_cigar = cigar ? 1 : 0;
+		CUDA_TRY(k_gather_launch(G, st));
+		++sb.aux_launches;
+		sb.d2h_bytes = nrec * sizeof(ksw_extz_t) + (cigar ? sb.cigar_used * 4 : 0);
+		if (one) {
+			CUDA_TRY(cudaMemcpyAsync(ez, sb.d_ez.p, nrec * sizeof(ksw_extz_t), cudaMemcpyDeviceToHost, st));
+			if (stats_on) {
+				CUDA_TRY(cudaMemcpyAsync(stats, sb.d_stats.p, nrec * sizeof(sd_stats_t), cudaMemcpyDeviceToHost, st));
+				sb.d2h_bytes += nrec * sizeof(sd_stats_t);
 			}
-			if (cigar && stats && B->want_stats) stats[sb.pairs[k].orig] = hst[k];
+		} else {
+			if (sb.h_recs.ensure(np * sizeof(ksw_extz_t))) return fail(KSW_B200_ERR_NOMEM, "pinned record buffer");
+			CUDA_TRY(cudaMemcpyAsync(sb.h_recs.p, sb.d_ez.p, np * sizeof(ksw_extz_t), cudaMemcpyDeviceToHost, st));
+			if (stats_on) {
+				if (sb.h_stats.ensure(np * sizeof(sd_stats_t))) return fail(KSW_B200_ERR_NOMEM, "pinned stats buffer");
+				CUDA_TRY(cudaMemcpyAsync(sb.h_stats.p, sb.d_stats.p, np * sizeof(sd_stats_t), cudaMemcpyDeviceToHost, st));
+				sb.d2h_bytes += np * sizeof(sd_stats_t);
+			}
 		}
-		if (nomem) rc_all = KSW_B200_ERR_NOMEM;
-		B->t_gather += now_ms() - t_g0;
 	}
-	if (rc_all) {
-		for (int i = 0; i < B->n; ++i) { free(ez[i].cigar); ez[i].cigar = 0; ez[i].n_cigar = ez[i].m_cigar = 0; }
-		return fail(rc_all, "malloc of a CIGAR failed");
+	for (auto &sb : B.subs) {
+		if (sb.pairs.empty()) continue;
+		CUDA_TRY(cudaSetDevice(sb.dc->dev));
+		CUDA_TRY(cudaStreamSynchronize(sb.stream ? sb.stream : sb.dc->stream));
+	}
+	B.t_d2h += now_ms() - t_f0;
+	if (!one) {
+		const double t_g0 = now_ms();
+		for (auto &sb : B.subs) {
+			const int64_t np = (int64_t)sb.pairs.size();
+			const ksw_extz_t *rec = (const ksw_extz_t *)sb.h_recs.p;
+			const sd_stats_t *hst = (const sd_stats_t *)sb.h_stats.p;
+#pragma omp parallel for num_threads(host_threads()) schedule(static) if (np >= 4096)
+			for (int64_t k = 0; k < np; ++k) {
+				const int i = sb.pairs[k].orig;
+				ez[i] = rec[k];
+				if (stats_on) stats[i] = hst[k];
+			}
+		}
+		B.t_gather += now_ms() - t_g0;
 	}
 	return KSW_B200_OK;
+}
+
+static ksw_b200_result *result_new(int n, bool with_stats, int *err)
+{
+	ksw_b200_result *R = new ksw_b200_result();
+	R->n = n; R->has_stats = with_stats;
+	if (R->ez.ensure(std::max<size_t>(1, (size_t)n) * sizeof(ksw_extz_t)) ||
+	    (with_stats && R->stats.ensure(std::max<size_t>(1, (size_t)n) * sizeof(sd_stats_t)))) {
+		R->release(); delete R;
+		if (err) *err = fail(KSW_B200_ERR_NOMEM, "pinned result arena allocation failed");
+		return nullptr;
+	}
+	return R;
+}
+extern "C" void ksw_b200_result_free(ksw_b200_result_t *R) { if (R) { R->release(); delete R; } }
+extern "C" const ksw_extz_t *ksw_b200_result_ez(const ksw_b200_result_t *R) { return R ? (const ksw_extz_t *)R->ez.p : nullptr; }
+extern "C" const sd_stats_t *ksw_b200_result_stats(const ksw_b200_result_t *R) { return (R && R->has_stats) ? (const sd_stats_t *)R->stats.p : nullptr; }
+extern "C" int ksw_b200_result_count(const ksw_b200_result_t *R) { return R ? R->n : 0; }
+extern "C" void ksw_b200_result_io(const ksw_b200_result_t *R, int64_t *h2d, int64_t *d2h, int *launches)
+{
+	if (h2d) *h2d = R ? R->h2d : 0;
+	if (d2h) *d2h = R ? R->d2h : 0;
+	if (launches) *launches = R ? R->launches : 0;
+}
+
+// Position-independent copy of an arena into CALLER-OWNED buffers (e.g. a shared-memory segment another process reads: the
+// gather step of a one-process-per-GPU deployment).  Record i goes to ez_dst[index ? index[i] : i] (and its statistics
+// likewise); its CIGAR words are appended to cigar_dst in the arena's order and `cigar` becomes the WORD OFFSET
+// cigar_base + (position in cigar_dst) instead of a pointer.  Returns the number of CIGAR words written, or a negative
+// error code (KSW_B200_ERR_NOMEM when cigar_cap words are not enough).
+extern "C" int64_t ksw_b200_result_export(const ksw_b200_result_t *R, ksw_extz_t *ez_dst, sd_stats_t *stats_dst,
+                                          uint32_t *cigar_dst, int64_t cigar_cap, int64_t cigar_base, const int64_t *index)
+{
+	if (!R || (R->n > 0 && !ez_dst)) return fail(KSW_B200_ERR_ARG, "null argument");
+	const int n = R->n;
+	const ksw_extz_t *src = (const ksw_extz_t *)R->ez.p;
+	const sd_stats_t *sst = R->has_stats ? (const sd_stats_t *)R->stats.p : nullptr;
+	const int nt = std::max(1, host_threads());
+	std::vector<int64_t> part(nt + 1, 0);
+#pragma omp parallel num_threads(nt)
+	{
+		const int t = omp_get_thread_num(), T = omp_get_num_threads();
+		const int lo = (int)((int64_t)n * t / T), hi = (int)((int64_t)n * (t + 1) / T);
+		int64_t words = 0;
+		for (int i = lo; i < hi; ++i) words += src[i].n_cigar;
+		part[t + 1] = words;
+#pragma omp barrier
+#pragma omp single
+		for (int k = 0; k < T; ++k) part[k + 1] += part[k];
+		int64_t pos = part[t];
+		if (part[T] <= cigar_cap || !cigar_dst)
+			for (int i = lo; i < hi; ++i) {
+				const int64_t d = index ? index[i] : i;
+				ksw_extz_t z = src[i];
+				if (z.n_cigar > 0 && cigar_dst) memcpy(cigar_dst + pos, src[i].cigar, (size_t)z.n_cigar * 4);
+				z.cigar = (uint32_t *)(uintptr_t)(z.n_cigar > 0 ? cigar_base + pos : 0);
+				pos += z.n_cigar;
+				ez_dst[d] = z;
+				if (stats_dst) { if (sst) stats_dst[d] = sst[i]; else memset(&stats_dst[d], 0, sizeof(sd_stats_t)); }
+			}
+	}
+	int64_t total = 0;
+	for (int i = 0; i < n; ++i) total += src[i].n_cigar;
+	if (cigar_dst && total > cigar_cap) return fail(KSW_B200_ERR_NOMEM, "cigar_cap too small");
+	return total;
+}
+
+// arena records -> the ksw2 ownership contract: every CIGAR in its own malloc() block (caller free()s, src/align.cc:65)
+static int copy_out_malloc(const ksw_extz_t *src, const sd_stats_t *src_stats, int n, ksw_extz_t *ez, sd_stats_t *stats)
+{
+	int nomem = 0;
+#pragma omp parallel for num_threads(host_threads()) schedule(static) reduction(| : nomem) if (n >= 2048)
+	for (int i = 0; i < n; ++i) {
+		ez[i] = src[i];
+		if (src[i].n_cigar > 0) {
+			ez[i].cigar = (uint32_t *)malloc((size_t)src[i].m_cigar << 2);
+			if (!ez[i].cigar) { nomem |= 1; ez[i].n_cigar = ez[i].m_cigar = 0; continue; }
+			memcpy(ez[i].cigar, src[i].cigar, (size_t)src[i].n_cigar * 4);
+		}
+	}
+	if (stats) { if (src_stats) memcpy(stats, src_stats, sizeof(sd_stats_t) * (size_t)n); else memset(stats, 0, sizeof(sd_stats_t) * (size_t)n); }
+	return nomem ? fail(KSW_B200_ERR_NOMEM, "malloc of a CIGAR failed") : KSW_B200_OK;
 }
 
 extern "C" void ksw_b200_free_cigars(ksw_extz_t *ez, int n)
@@ -1038,6 +1110,39 @@ extern "C" void ksw_b200_free_cigars(ksw_extz_t *ez, int n)
 	// serial on purpose: the blocks were malloc'ed by the gather threads, so a parallel loop frees into foreign glibc arenas
 	// and contends on their locks (measured on the 32-thread host: 3.2 ms serial vs 4.7 ms parallel for 100k CIGARs)
 	for (int i = 0; i < n; ++i) { free(ez[i].cigar); ez[i].cigar = nullptr; ez[i].n_cigar = ez[i].m_cigar = 0; }
+}
+
+extern "C" int ksw_b200_batch_fetch(ksw_b200_batch_t *B, ksw_extz_t *ez, sd_stats_t *stats)
+{
+	if (!B || (B->n > 0 && !ez)) return fail(KSW_B200_ERR_ARG, "null argument");
+	for (int i = 0; i < B->n; ++i) reset_ez(&ez[i]);
+	int err = 0;
+	ksw_b200_result *R = result_new(B->n, stats != nullptr, &err);
+	if (!R) return err;
+	int rc = fetch_into(*B, *R, 0);
+	if (rc == 0) {
+		const double t0 = now_ms();
+		rc = copy_out_malloc((const ksw_extz_t *)R->ez.p, R->has_stats ? (const sd_stats_t *)R->stats.p : nullptr, B->n, ez, stats);
+		B->t_gather += now_ms() - t0;
+		if (rc) ksw_b200_free_cigars(ez, B->n);
+	}
+	ksw_b200_result_free(R);
+	return rc;
+}
+// the same without the per-pair malloc: records and CIGARs stay in the arena `*out` (ksw_b200_result_free)
+extern "C" int ksw_b200_batch_fetch_arena(ksw_b200_batch_t *B, int want_stats, ksw_b200_result_t **out)
+{
+	if (!B || !out) return fail(KSW_B200_ERR_ARG, "null argument");
+	*out = nullptr;
+	int err = 0;
+	ksw_b200_result *R = result_new(B->n, want_stats != 0, &err);
+	if (!R) return err;
+	int rc = fetch_into(*B, *R, 0);
+	if (rc) { ksw_b200_result_free(R); return rc; }
+	ksw_b200_batch_io_bytes(B, &R->h2d, &R->d2h);
+	R->launches = ksw_b200_batch_launches(B);
+	*out = R;
+	return KSW_B200_OK;
 }
 
 extern "C" void ksw_b200_batch_free(ksw_b200_batch_t *B)
@@ -1050,7 +1155,6 @@ extern "C" void ksw_b200_batch_free(ksw_b200_batch_t *B)
 // ------------------------------------------------------------------------------------------------
 // one-shot entry points
 // ------------------------------------------------------------------------------------------------
-extern "C" void ksw_b200_free_cigars(ksw_extz_t *ez, int n);
 // I/O accounting of the last one-shot call of this thread
 static thread_local int64_t g_last_h2d = 0, g_last_d2h = 0;
 static thread_local int g_last_launches = 0;
@@ -1061,17 +1165,17 @@ extern "C" void ksw_b200_last_call_io(int64_t *h2d, int64_t *d2h, int *launches)
 	if (launches) *launches = g_last_launches;
 }
 
-// One-shot batch.  Large batches are cut into chunks that flow through a two-stage software pipeline:
-// a producer thread packs chunk k+1 into pinned memory and copies it to the device (its own stream) while
-// this thread runs the kernels of chunk k and gathers its results -- H2D, kernels and D2H overlap.
-extern "C" int ksw_extz2_batch_flat(int n, const int *qlen, const int64_t *qoff, const uint8_t *qbuf,
-                                    const int *tlen, const int64_t *toff, const uint8_t *tbuf,
-                                    int8_t m, const int8_t *mat, int8_t q, int8_t e, int w, int zdrop, int flag,
-                                    ksw_extz_t *ez, sd_stats_t *stats,
-                                    const uint8_t *q_raw_buf, const uint8_t *t_raw_buf)
+struct BatchArgs {
+	int n; const int *qlen; const int64_t *qoff; const uint8_t *qbuf; const int *tlen; const int64_t *toff; const uint8_t *tbuf;
+	int8_t m; const int8_t *mat; int8_t q, e; int w, zdrop, flag; const uint8_t *q_raw_buf, *t_raw_buf;
+};
+
+// One-shot batch into the arena R.  Large batches are cut into chunks that flow through a software pipeline: a producer
+// thread plans chunk k+1, queues its copies and LAUNCHES its kernels (own stream) while this thread waits for chunk k and
+// fetches its results -- H2D, kernels and D2H overlap.  `on_chunk(s0, cnt)` runs after records [s0, s0 + cnt) are final.
+static int batch_core(const BatchArgs &A, ksw_b200_result &R, const std::function<int(int, int)> &on_chunk)
 {
-	g_last_h2d = g_last_d2h = 0; g_last_launches = 0;
-	if (n < 0) return fail(KSW_B200_ERR_ARG, "negative count");
+	const int n = A.n;
 	const char *env = getenv("KSW_B200_CHUNK_PAIRS");
 	const int chunk_pairs = env ? std::max(1, atoi(env)) : 25000;
 	// chunk sizes ramp up (1 : 2 : 4 : 4 ...) so that the first H2D copy -- the only one nothing can hide -- is short
@@ -1081,12 +1185,12 @@ extern "C" int ksw_extz2_batch_flat(int n, const int *qlen, const int64_t *qoff,
 		// each with a latency floor of one pair (1-2 ms) and a tail, so chunks of mid-size pairs that carry little work
 		// under-fill the GPU (100k pairs of <= 250 bp: 18 ms resident, 45 ms in six chunks; profiles/r01_tuning.md).  Keep
 		// at least ~2.5 G cells per chunk.  Batches of TINY pairs (< 2000 cells per pair) are host-bound instead -- there the
-		// pipeline exists to overlap packing with gathering, and many chunks stay the better choice.
+		// pipeline exists to overlap planning with fetching, and many chunks stay the better choice.
 		const int step = std::max(1, n / 512);
 		int64_t cells = 0; int cnt = 0;
 		for (int i = 0; i < n; i += step, ++cnt) {
-			const int ql = std::max(0, qlen[i]), tl = std::max(0, tlen[i]);
-			cells += est_cells(ql, tl, w < 0 ? std::max(ql, tl) : std::min(w, std::max(ql, tl)));
+			const int ql = std::max(0, A.qlen[i]), tl = std::max(0, A.tlen[i]);
+			cells += est_cells(ql, tl, A.w < 0 ? std::max(ql, tl) : std::min(A.w, std::max(ql, tl)));
 		}
 		const double avg = cnt ? (double)cells / cnt : 0.0;
 		if (avg >= 2000.0) nchunks = std::max(1, std::min(nchunks, (int)(avg * n / 2.5e9 + 0.5)));
@@ -1095,7 +1199,7 @@ extern "C" int ksw_extz2_batch_flat(int n, const int *qlen, const int64_t *qoff,
 	{
 		std::vector<double> wgt(nchunks, 4.0);
 		if (nchunks >= 3) { wgt[0] = 1.0; wgt[1] = 2.0; }
-		if (nchunks >= 5) wgt[nchunks - 1] = 2.0;                      // a short last chunk keeps the un-overlapped D2H + gather small
+		if (nchunks >= 5) wgt[nchunks - 1] = 2.0;                      // a short last chunk keeps the un-overlapped D2H small
 		double tot = 0; for (double x : wgt) tot += x;
 		double acc = 0;
 		for (int c = 0; c < nchunks; ++c) { acc += wgt[c]; start[c + 1] = (int)((double)n * acc / tot + 0.5); }
@@ -1108,22 +1212,28 @@ extern "C" int ksw_extz2_batch_flat(int n, const int *qlen, const int64_t *qoff,
 	auto upload_chunk = [&](int c, int *err) -> ksw_b200_batch_t * {
 		const int s0 = start[c], cnt = start[c + 1] - s0;
 		tl_async_upload = nchunks > 1;
-		struct Reset { ~Reset() { tl_async_upload = false; } } reset;
-		return ksw_b200_batch_upload(cnt, qlen + s0, qoff + s0, qbuf, tlen + s0, toff + s0, tbuf, m, mat, q, e, w, zdrop, flag,
-		                             q_raw_buf, t_raw_buf, err);
+		tl_pipeline_depth = nchunks > 1 ? 3 : 1;
+		struct Reset { ~Reset() { tl_async_upload = false; tl_pipeline_depth = 1; } } reset;
+		ksw_b200_batch_t *B = ksw_b200_batch_upload(cnt, A.qlen + s0, A.qoff + s0, A.qbuf, A.tlen + s0, A.toff + s0, A.tbuf, A.m, A.mat, A.q, A.e,
+		                                           A.w, A.zdrop, A.flag, A.q_raw_buf, A.t_raw_buf, err);
+		if (B && !R.has_stats) B->want_stats = false;
+		return B;
 	};
 	auto consume = [&](ksw_b200_batch_t *B, int c, bool launched) -> int {
 		const int s0 = start[c];
 		int rc = 0;
 		mark("wait", c);
-		if (!launched) { if (!stats) B->want_stats = false; rc = ksw_b200_batch_run(B, nullptr); }
-		else for (auto &sb : B->subs) { rc = finish_sub(*B, sb); if (rc) break; }
+		if (!launched) rc = ksw_b200_batch_run(B, nullptr);
+		else for (auto &sb : B->subs) { int rc2 = finish_sub(*B, sb); if (!rc) rc = rc2; }
 		mark("kernels done", c);
-		if (rc == 0) rc = ksw_b200_batch_fetch(B, ez + s0, stats ? stats + s0 : nullptr);
+		if (rc == 0) rc = fetch_into(*B, R, s0);
 		mark("fetched", c);
 		int64_t a = 0, d = 0; ksw_b200_batch_io_bytes(B, &a, &d);
-		g_last_h2d += a; g_last_d2h += d; g_last_launches += ksw_b200_batch_launches(B);
+		R.h2d += a; R.d2h += d; R.launches += ksw_b200_batch_launches(B);
+		if (trace) fprintf(stderr, "[ksw_b200]             chunk %d  d2h %.2f ms, gather %.2f ms\n", c, B->t_d2h, B->t_gather);
 		ksw_b200_batch_free(B);
+		if (rc == 0 && on_chunk) rc = on_chunk(s0, start[c + 1] - s0);
+		mark("handed over", c);
 		return rc;
 	};
 	if (nchunks == 1) {
@@ -1132,7 +1242,7 @@ extern "C" int ksw_extz2_batch_flat(int n, const int *qlen, const int64_t *qoff,
 		if (!B) return err;
 		return consume(B, 0, false);
 	}
-	// producer / consumer over chunks, one chunk of look-ahead
+	// producer / consumer over chunks
 	std::mutex mu; std::condition_variable cv;
 	std::vector<ksw_b200_batch_t *> ready(nchunks, nullptr);
 	std::vector<int> errs(nchunks, 0), done(nchunks, 0);
@@ -1151,9 +1261,8 @@ extern "C" int ksw_extz2_batch_flat(int n, const int *qlen, const int64_t *qoff,
 			mark("upload end", c);
 			if (trace && B) fprintf(stderr, "[ksw_b200]             chunk %d  plan %.2f ms, pack %.2f ms, %d pairs\n", c, B->t_plan, B->t_pack, B->n);
 			if (B) {                                                        // enqueue the kernels right behind the H2D copy
-				if (!stats) B->want_stats = false;
 				for (auto &sb : B->subs) { err = launch_sub(*B, sb); if (err) break; }
-				if (err) { ksw_b200_batch_free(B); B = nullptr; }
+				if (err) { std::string keep = g_last_error; ksw_b200_batch_free(B); B = nullptr; g_last_error = keep; }
 			}
 			mark("launched", c);
 			{
@@ -1169,6 +1278,7 @@ extern "C" int ksw_extz2_batch_flat(int n, const int *qlen, const int64_t *qoff,
 	std::thread producer;
 	if (own_worker) g_worker.start(producer_fn); else producer = std::thread(producer_fn);
 	int rc = 0;
+	std::string first_error;
 	for (int c = 0; c < nchunks && rc == 0; ++c) {
 		ksw_b200_batch_t *B = nullptr;
 		{
@@ -1178,6 +1288,7 @@ extern "C" int ksw_extz2_batch_flat(int n, const int *qlen, const int64_t *qoff,
 			if (!B) { rc = errs[c]; g_last_error = producer_error; }
 		}
 		if (B) rc = consume(B, c, true);
+		if (rc) first_error = g_last_error;
 		{
 			std::lock_guard<std::mutex> lk(mu);
 			consumed = c + 1;
@@ -1188,10 +1299,74 @@ extern "C" int ksw_extz2_batch_flat(int n, const int *qlen, const int64_t *qoff,
 	{ std::lock_guard<std::mutex> lk(mu); abort_all = abort_all || rc != 0; }
 	cv.notify_all();
 	if (own_worker) { g_worker.join(); g_worker.claim.unlock(); } else producer.join();
-	if (rc) {                                                           // leave nothing allocated on error
-		for (int c = 0; c < nchunks; ++c) if (ready[c] && c >= consumed) ksw_b200_batch_free(ready[c]);
-		ksw_b200_free_cigars(ez, n);
+	if (rc) {                                                           // chunks launched but not consumed: wait for them, then release
+		for (int c = consumed; c < nchunks; ++c) if (ready[c]) ksw_b200_batch_free(ready[c]);
+		g_last_error = first_error;
 	}
+	return rc;
+}
+
+static int check_batch_args(const BatchArgs &A)
+{
+	const bool have_codes = A.qbuf && A.tbuf, have_raw = A.q_raw_buf && A.t_raw_buf;
+	if (A.n < 0 || (A.n > 0 && (!A.qlen || !A.tlen || !A.qoff || !A.toff || (!have_codes && !have_raw))) || (A.m > 0 && !A.mat))
+		return fail(KSW_B200_ERR_ARG, "null pointer or negative count");
+	return 0;
+}
+
+extern "C" int ksw_extz2_batch_arena(int n, const int *qlen, const int64_t *qoff, const uint8_t *qbuf,
+                                     const int *tlen, const int64_t *toff, const uint8_t *tbuf,
+                                     int8_t m, const int8_t *mat, int8_t q, int8_t e, int w, int zdrop, int flag,
+                                     int want_stats, const uint8_t *q_raw_buf, const uint8_t *t_raw_buf,
+                                     ksw_b200_result_t **out)
+{
+	g_last_h2d = g_last_d2h = 0; g_last_launches = 0;
+	if (!out) return fail(KSW_B200_ERR_ARG, "null result pointer");
+	*out = nullptr;
+	const BatchArgs A{n, qlen, qoff, qbuf, tlen, toff, tbuf, m, mat, q, e, w, zdrop, flag, q_raw_buf, t_raw_buf};
+	int rc = check_batch_args(A);
+	if (rc) return rc;
+	int nd = ensure_init();
+	if (nd <= 0) return nd;
+	int err = 0;
+	ksw_b200_result *R = result_new(n, want_stats && !(flag & KSW_EZ_SCORE_ONLY), &err);
+	if (!R) return err;
+	rc = batch_core(A, *R, nullptr);
+	g_last_h2d = R->h2d; g_last_d2h = R->d2h; g_last_launches = R->launches;
+	if (rc) { std::string keep = g_last_error; ksw_b200_result_free(R); g_last_error = keep; return rc; }
+	*out = R;
+	return KSW_B200_OK;
+}
+
+extern "C" int ksw_extz2_batch_flat(int n, const int *qlen, const int64_t *qoff, const uint8_t *qbuf,
+                                    const int *tlen, const int64_t *toff, const uint8_t *tbuf,
+                                    int8_t m, const int8_t *mat, int8_t q, int8_t e, int w, int zdrop, int flag,
+                                    ksw_extz_t *ez, sd_stats_t *stats,
+                                    const uint8_t *q_raw_buf, const uint8_t *t_raw_buf)
+{
+	g_last_h2d = g_last_d2h = 0; g_last_launches = 0;
+	const BatchArgs A{n, qlen, qoff, qbuf, tlen, toff, tbuf, m, mat, q, e, w, zdrop, flag, q_raw_buf, t_raw_buf};
+	int rc = check_batch_args(A);
+	if (rc) return rc;
+	if (n > 0 && !ez) return fail(KSW_B200_ERR_ARG, "null result array");
+	// ez[] is the caller's storage and may be uninitialised (the ksw_extz2_sse contract: fully overwritten): reset it FIRST so
+	// that the error paths below only ever free() pointers this call allocated
+	for (int i = 0; i < n; ++i) reset_ez(&ez[i]);
+	if (stats) memset(stats, 0, sizeof(sd_stats_t) * (size_t)n);
+	int nd = ensure_init();
+	if (nd <= 0) return nd;
+	int err = 0;
+	ksw_b200_result *R = result_new(n, stats != nullptr && !(flag & KSW_EZ_SCORE_ONLY), &err);
+	if (!R) return err;
+	// every finished chunk is converted to the ksw2 ownership contract (one malloc() per CIGAR) while the next one computes
+	rc = batch_core(A, *R, [&](int s0, int cnt) {
+		return copy_out_malloc((const ksw_extz_t *)R->ez.p + s0, R->has_stats ? (const sd_stats_t *)R->stats.p + s0 : nullptr, cnt,
+		                       ez + s0, (stats && R->has_stats) ? stats + s0 : nullptr);
+	});
+	g_last_h2d = R->h2d; g_last_d2h = R->d2h; g_last_launches = R->launches;
+	std::string keep = g_last_error;
+	ksw_b200_result_free(R);
+	if (rc) { ksw_b200_free_cigars(ez, n); for (int i = 0; i < n; ++i) reset_ez(&ez[i]); g_last_error = keep; }
 	return rc;
 }
 
@@ -1217,6 +1392,18 @@ extern "C" int ksw_extz2_batch(int n, const int *qlen, const uint8_t *const *que
 	                            ez, stats, raw ? qr.data() : nullptr, raw ? tr.data() : nullptr);
 }
 
+// ksw_extz2_sse has no error channel (it exit()s when kmalloc fails); neither has its replacement.  A request the engine
+// cannot serve -- no device, a pair wider than the widest kernel -- must not come back looking like "no alignment", so the
+// default is to report and abort(); an integrator can install a handler instead (which may longjmp / throw / log and return,
+// in which case the caller sees the reset record).
+static void default_fatal(int code, const char *msg)
+{
+	fprintf(stderr, "[ksw_extz2_b200] fatal: %s: %s\n", ksw_b200_strerror(code), msg);
+	abort();
+}
+static ksw_b200_fatal_fn g_fatal = default_fatal;
+extern "C" void ksw_b200_set_fatal_handler(ksw_b200_fatal_fn fn) { g_fatal = fn ? fn : default_fatal; }
+
 extern "C" void ksw_extz2_b200(void *km, int qlen, const uint8_t *query, int tlen, const uint8_t *target,
                                int8_t m, const int8_t *mat, int8_t q, int8_t e, int w, int zdrop, int flag,
                                ksw_extz_t *ez)
@@ -1227,8 +1414,8 @@ extern "C" void ksw_extz2_b200(void *km, int qlen, const uint8_t *query, int tle
 	int64_t zero = 0;
 	int rc = ksw_extz2_batch_flat(1, &qlen, &zero, query, &tlen, &zero, target, m, mat, q, e, w, zdrop, flag, ez, nullptr, nullptr, nullptr);
 	if (rc) {
-		fprintf(stderr, "[ksw_extz2_b200] %s: %s\n", ksw_b200_strerror(rc), ksw_b200_last_error());
 		reset_ez(ez);
+		g_fatal(rc, ksw_b200_last_error());
 	}
 }
 
@@ -1278,8 +1465,7 @@ extern "C" int sd_stats_from_cigar_batch_flat(int n, const int64_t *cig_off, con
 	if (ok) {
 		CigarStatsLaunch L{(const uint32_t *)d_cig.p, m_coff, m_cn, (const uint8_t *)d_a.p, m_ao, m_al, (const uint8_t *)d_b.p, m_bo, m_bl,
 		                   d_stats, d_status, n};
-		sd_stats_from_cigar_kernel<<<(n + 127) / 128, 128, 0, st>>>(L);
-		ok = cudaGetLastError() == cudaSuccess &&
+		ok = k_stats_from_cigar_launch(L, st) == cudaSuccess &&
 		     cudaMemcpyAsync(out, d_stats, (size_t)n * sizeof(sd_stats_t), cudaMemcpyDeviceToHost, st) == cudaSuccess &&
 		     cudaMemcpyAsync(status, d_status, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, st) == cudaSuccess &&
 		     cudaStreamSynchronize(st) == cudaSuccess;

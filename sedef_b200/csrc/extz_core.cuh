@@ -37,7 +37,7 @@
 namespace extz {
 
 constexpr int kNegInf = -0x40000000;         // KSW_NEG_INF (extern/ksw2.h:6)
-constexpr int kQPadL = 16;                   // zero bytes in front of every packed query (j >= -15 is read)
+constexpr int kArenaSlack = 256;             // readable bytes behind the last sequence of an arena (the query window runs <= 15 bytes past a query)
 constexpr int kTableStride = 8;              // score table row stride (entries); symbols must be < 8
 
 enum : int {
@@ -59,7 +59,7 @@ struct Scoring {
 
 // One pair, as the DP kernel sees it.
 struct PairDesc {
-	int64_t q_off;         // byte offset of query[0] in the packed sequence arena (kQPadL zero bytes before it)
+	int64_t q_off;         // byte offset of query[0] in the sequence arena (no padding between sequences)
 	int64_t t_off;         // byte offset of target[0]
 	int64_t tb_off;        // byte offset of this pair's traceback rows in the wave's tb arena
 	int32_t qlen, tlen;

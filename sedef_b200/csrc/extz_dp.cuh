@@ -10,22 +10,13 @@
 #pragma once
 #include <cuda_runtime.h>
 #include "extz_core.cuh"
+#include "launch_structs.h"
 
 namespace extz {
 
-// Device-side view of one launch.
-struct DpLaunch {
-	const PairDesc *pairs;      // [n] sorted by descending work
-	PairResult *results;        // [n] (indexed like pairs)
-	const uint8_t *seq;         // packed sequence arena (codes)
-	uint8_t *tb;                // traceback arena of this wave (or nullptr when score-only)
-	const uint32_t *table;      // [kTableStride * kTableStride] (s + 2(q+e)) << 24 per (target, query) symbol
-	int *work_counter;          // dynamic work distribution
-	int n;
-	Scoring sc;
-};
-
-__device__ __forceinline__ uint32_t ld_u8(const uint8_t *p) { return (uint32_t)__ldg(p); }
+// sequence symbols are masked to 0..7: a byte the caller should not have passed (the engine reports KSW_B200_ERR_ARG for the
+// batch, engine.cu) must not index past the 8 x 8 score table meanwhile
+__device__ __forceinline__ uint32_t ld_u8(const uint8_t *p) { return (uint32_t)__ldg(p) & 7u; }
 __device__ __forceinline__ uint32_t lds_u32(uint32_t saddr)
 {
 	uint32_t v;
@@ -51,11 +42,12 @@ struct LaneState {
 	int t0;
 };
 
-// 4 * query[j], or 0 where the reference reads the zeroed tail of qr[] (j < 0, App. A.1); j may run a few bytes
-// past the query (values there are never used: the slot is below the band) but stays inside the arena
+// 4 * query[j], or 0 where the reference reads the zeroed tail of qr[] (j < 0, App. A.1).  j may run up to 15 bytes past
+// the query (values there are never used: the slot is below the band, its score is not refilled) but stays inside the
+// arena, which ends with 256 bytes of slack.
 __device__ __forceinline__ uint32_t qbyte4(const uint8_t *qseq, int j)
 {
-	return j >= -kQPadL ? ld_u8(qseq + j) << 2 : 0u;
+	return j >= 0 ? ld_u8(qseq + j) << 2 : 0u;
 }
 
 // (re)load the lane's slots for the window position t0, as seen at the START of anti-diagonal r (before its shift)
@@ -384,7 +376,7 @@ extz_dp_kernel(DpLaunch L)
 		const PairDesc pd = L.pairs[alive ? pi : base];
 		const int qlen = pd.qlen, tlen = pd.tlen, w = pd.w;
 		const int T = (tlen + 15) & ~15;
-		const uint8_t *qseq = L.seq + pd.q_off;                      // qseq[j], j in [-kQPadL, qlen) readable
+		const uint8_t *qseq = L.seq + pd.q_off;                      // qseq[j], j in [0, qlen + 15] is read
 		const uint8_t *tseq = L.seq + pd.t_off;
 		uint8_t *tbp = kCigar ? L.tb + pd.tb_off : nullptr;
 		const int R = alive ? qlen + tlen - 1 : 0;

@@ -382,7 +382,7 @@ extz_dp16_kernel(DpLaunch L)
 		const PairDesc pd = L.pairs[alive ? pi : base];
 		const int qlen = pd.qlen, tlen = pd.tlen, w = pd.w;
 		const int T = (tlen + 15) & ~15;
-		const uint8_t *qseq = L.seq + pd.q_off;                      // qseq[j], j in [-kQPadL, qlen) readable
+		const uint8_t *qseq = L.seq + pd.q_off;                      // qseq[j], j in [0, qlen + 15] is read
 		const uint8_t *tseq = L.seq + pd.t_off;
 		uint8_t *tbp = kCigar ? L.tb + pd.tb_off + gl * 16 : nullptr;
 		const int R = alive ? qlen + tlen - 1 : 0;

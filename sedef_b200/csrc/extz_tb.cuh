@@ -11,25 +11,11 @@
 #include <cuda_runtime.h>
 #include "extz_core.cuh"
 #include "../../include/ksw2_b200.h"
+#include "launch_structs.h"
 
 namespace extz {
 
 constexpr int kPrefetchRows = 16;
-
-struct TbLaunch {
-	const PairDesc *pairs;
-	PairResult *results;
-	uint8_t *tb;                 // traceback arena of the wave
-	const uint8_t *raw;          // arena of ORIGINAL-CASE bytes (same offsets as the code arena) or nullptr
-	const uint8_t *seq;          // code arena (used to synthesise "ACGTN" when raw == nullptr)
-	uint32_t *cigar_arena;       // compact output
-	unsigned long long *cigar_cursor;
-	unsigned long long cigar_capacity;
-	sd_stats_t *stats;           // [n] indexed like pairs, or nullptr
-	int *overflow;               // set to 1 when the compact arena is too small
-	int n, NS, flag;
-	int packed;                  // traceback rows written by the packed kernel (extz_dp16.cuh layout)
-};
 
 __device__ __forceinline__ int raw_byte(const TbLaunch &L, int64_t off, int idx)
 {
@@ -140,7 +126,7 @@ extz_traceback_kernel(TbLaunch L)
 		s.indel_a = sa.indel_a; s.indel_b = sa.indel_b; s.alnB = sa.alnB; s.matchB = sa.matchB; s.mismatchB = sa.mismatchB;
 		s.transitionsB = sa.transitionsB; s.transversionsB = sa.transversionsB;
 		s.uppercaseA = sa.uppercaseA; s.uppercaseB = sa.uppercaseB; s.uppercaseMatches = sa.uppercaseMatches; s.reserved = 0;
-		L.stats[pi] = s;
+		L.stats[L.stats_by_orig ? pd.orig : pi] = s;
 	}
 }
 
@@ -268,19 +254,13 @@ extz_traceback_warp_kernel(TbLaunch L)
 			s.indel_a = sa.indel_a; s.indel_b = sa.indel_b; s.alnB = sa.alnB; s.matchB = sa.matchB; s.mismatchB = sa.mismatchB;
 			s.transitionsB = sa.transitionsB; s.transversionsB = sa.transversionsB;
 			s.uppercaseA = sa.uppercaseA; s.uppercaseB = sa.uppercaseB; s.uppercaseMatches = sa.uppercaseMatches; s.reserved = 0;
-			L.stats[pi] = s;
+			L.stats[L.stats_by_orig ? pd.orig : pi] = s;
 		}
 	}
 }
 
 // ---- Alignment(fa, fb, cigar): SD statistics from an EXISTING CIGAR (src/align.cc:90-105,274-315; the consumer is
 // `sedef stats generate`, src/stats_main.cc:224).  One thread per alignment, forward walk over the raw ksw ops. ----
-struct CigarStatsLaunch {
-	const uint32_t *cig; const int64_t *cig_off; const int64_t *n_cig;
-	const uint8_t *a; const int64_t *a_off; const int *alen;
-	const uint8_t *b; const int64_t *b_off; const int *blen;
-	sd_stats_t *out; int *status; int n;
-};
 __global__ void __launch_bounds__(128)
 sd_stats_from_cigar_kernel(CigarStatsLaunch L)
 {
@@ -295,14 +275,20 @@ sd_stats_from_cigar_kernel(CigarStatsLaunch L)
 	int ia = 0, ib = 0, gaps = 0, bad = 0;
 	for (int64_t x = 0; x < L.n_cig[k] && !bad; ++x) {
 		const uint32_t op = c[x] & 0xfu; const int len = (int)(c[x] >> 4);
-		if (op >= 3) continue;                                        // align_helper drops them (src/align.cc:61)
 		if (op != 0) ++gaps;                                          // every non-M run counts, zero-length ones too (src/align.cc:300-305)
 		for (int y = 0; y < len; ++y) {
 			if (op == 0) {
 				if (ia >= alen || ib >= blen) { bad = 1; break; }     // the reference asserts (src/align.cc:281-282)
 				stat_match_col(sa, a[ia++], b[ib++]);
 			} else if (op == 1) { stat_qonly_col(sa, ia < alen ? a[ia] : 0); ++ia; }
-			else { stat_tonly_col(sa, ib < blen ? b[ib] : 0); ++ib; }
+			else if (op == 2) { stat_tonly_col(sa, ib < blen ? b[ib] : 0); ++ib; }
+			else {
+				// any other op letter: populate_nice_alignment (src/align.cc:283-297) consumes BOTH strings ("not D", "not I"), so
+				// the column is gap-free for the match / mismatch and BEDPE counters, while the run still counts as a gap run
+				if (ia >= alen || ib >= blen) { bad = 1; break; }     // (the reference reads past the string here: undefined)
+				stat_match_col(sa, a[ia++], b[ib++]);
+				sa.gap_bases++;
+			}
 		}
 	}
 	sd_stats_t s;

@@ -2,22 +2,12 @@
 #include "../../../include/sedef_align.hpp"
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 #include <stdexcept>
 
 namespace sedef_b200 {
 
-static const int kMaxKswSeqLen = 60 * 1024;            // Globals::Align::MAX_KSW_SEQ_LEN (src/globals.h:54)
-
-static inline uint8_t align_dna(char c)                // src/common.h:58-70,91
-{
-	switch (c) {
-	case 'A': case 'a': return 0;
-	case 'C': case 'c': return 1;
-	case 'G': case 'g': return 2;
-	case 'T': case 't': return 3;
-	default: return 4;
-	}
-}
+static const int kMaxKswSeqLen = 60 * 1000;            // Globals::Align::MAX_KSW_SEQ_LEN = 60 * KB, and KB is 1000 (src/globals.h:18,54)
 
 double Alignment::gap_error() const
 {
@@ -48,37 +38,60 @@ static void add_stats(sd_stats_t &d, const sd_stats_t &s)
 	for (size_t k = 0; k < sizeof(sd_stats_t) / sizeof(int32_t); ++k) dp[k] += sp[k];
 }
 
+static std::vector<sd_stats_t> stats_of(const std::vector<std::pair<std::string, std::string>> &pairs,
+                                        const std::vector<std::deque<std::pair<char, int>>> &cigars);
+
+int max_ksw_seq_len() { return kMaxKswSeqLen; }
+
+// align_helper's chunk loop (src/align.cc:46-53): for (SP = 0; SP < min(|t|, |q|); SP += MAX) one ksw call on
+// (q + SP, min(MAX, |q| - SP)) x (t + SP, min(MAX, |t| - SP))
+struct Chunk { size_t sp; int la, lb; };
+static inline void chunk_plan(size_t alen, size_t blen, std::vector<Chunk> &out)
+{
+	const size_t n = std::min(alen, blen);
+	for (size_t sp = 0; sp < n; sp += kMaxKswSeqLen)
+		out.push_back({sp, (int)std::min<size_t>(kMaxKswSeqLen, alen - sp), (int)std::min<size_t>(kMaxKswSeqLen, blen - sp)});
+}
+
 std::vector<Alignment> align_batch(const std::vector<std::pair<std::string, std::string>> &pairs, const AlignParams &p)
 {
 	// align_helper's matrix (src/align.cc:41-44)
 	const int8_t a = (int8_t)p.match, b = p.mismatch < 0 ? (int8_t)p.mismatch : (int8_t)(-p.mismatch);
 	const int8_t mat[25] = {a, b, b, b, 0, b, a, b, b, 0, b, b, a, b, 0, b, b, b, a, 0, 0, 0, 0, 0, 0};
-	// one flat buffer per side; pairs longer than MAX_KSW_SEQ_LEN are chunked with the same offset on both (src/align.cc:46-53)
+	// one flat buffer per side holding the ORIGINAL-CASE bytes (align_dna runs on the device); pairs longer than
+	// MAX_KSW_SEQ_LEN are chunked with the same offset on both strings (src/align.cc:46-53)
 	std::vector<int> ql, tl, owner;
 	std::vector<int64_t> qo, to;
-	std::vector<uint8_t> qcodes, tcodes, qraw, traw;
+	std::vector<Chunk> chunks;
+	size_t qtot = 0, ttot = 0;
 	for (size_t i = 0; i < pairs.size(); ++i) {
-		const std::string &fa = pairs[i].first, &fb = pairs[i].second;
-		const size_t n = std::min(fa.size(), fb.size());
-		for (size_t sp = 0; sp < n; sp += kMaxKswSeqLen) {
-			const size_t la = std::min<size_t>(kMaxKswSeqLen, fa.size() - sp), lb = std::min<size_t>(kMaxKswSeqLen, fb.size() - sp);
+		const size_t c0 = chunks.size();
+		chunk_plan(pairs[i].first.size(), pairs[i].second.size(), chunks);
+		for (size_t c = c0; c < chunks.size(); ++c) {
 			owner.push_back((int)i);
-			ql.push_back((int)la); tl.push_back((int)lb);
-			qo.push_back((int64_t)qcodes.size()); to.push_back((int64_t)tcodes.size());
-			for (size_t k = 0; k < la; ++k) { qraw.push_back((uint8_t)fa[sp + k]); qcodes.push_back(align_dna(fa[sp + k])); }
-			for (size_t k = 0; k < lb; ++k) { traw.push_back((uint8_t)fb[sp + k]); tcodes.push_back(align_dna(fb[sp + k])); }
+			ql.push_back(chunks[c].la); tl.push_back(chunks[c].lb);
+			qo.push_back((int64_t)qtot); to.push_back((int64_t)ttot);
+			qtot += chunks[c].la; ttot += chunks[c].lb;
 		}
 	}
+	std::vector<uint8_t> qraw(qtot + 1), traw(ttot + 1);                                   // never pass null buffers
+	for (size_t k = 0; k < chunks.size(); ++k) {
+		memcpy(&qraw[qo[k]], pairs[owner[k]].first.data() + chunks[k].sp, ql[k]);
+		memcpy(&traw[to[k]], pairs[owner[k]].second.data() + chunks[k].sp, tl[k]);
+	}
 	const int n = (int)owner.size();
-	std::vector<ksw_extz_t> ez(n);
-	std::vector<sd_stats_t> st(n);
-	qcodes.push_back(0); tcodes.push_back(0); qraw.push_back(0); traw.push_back(0);       // never pass null buffers
-	int rc = ksw_extz2_batch_flat(n, ql.data(), qo.data(), qcodes.data(), tl.data(), to.data(), tcodes.data(), 5, mat,
-	                              (int8_t)p.gap_open, (int8_t)p.gap_extend, p.bandwidth, -1, 0, ez.data(), st.data(),
-	                              qraw.data(), traw.data());
-	if (rc) throw std::runtime_error(std::string("ksw_extz2_batch_flat: ") + ksw_b200_strerror(rc) + " -- " + ksw_b200_last_error());
+	ksw_b200_result_t *res = nullptr;
+	int rc = ksw_extz2_batch_arena(n, ql.data(), qo.data(), nullptr, tl.data(), to.data(), nullptr, 5, mat,
+	                               (int8_t)p.gap_open, (int8_t)p.gap_extend, p.bandwidth, -1, 0, 1, qraw.data(), traw.data(), &res);
+	if (rc) throw std::runtime_error(std::string("ksw_extz2_batch_arena: ") + ksw_b200_strerror(rc) + " -- " + ksw_b200_last_error());
+	const ksw_extz_t *ez = ksw_b200_result_ez(res);
+	const sd_stats_t *st = ksw_b200_result_stats(res);
 	std::vector<Alignment> out(pairs.size());
 	for (size_t i = 0; i < pairs.size(); ++i) { out[i].a = pairs[i].first; out[i].b = pairs[i].second; }
+	// The statistics of a chunked pair are the sum of its chunks' statistics as long as every chunk but the last one is
+	// aligned end to end: the reference walks the CONCATENATED cigar from (0, 0) (populate_nice_alignment), so a chunk cut
+	// short by a band break (user-set bandwidth) shifts every later column.  Those pairs are re-walked below.
+	std::vector<char> rewalk(pairs.size(), 0);
 	for (int k = 0; k < n; ++k) {
 		Alignment &al = out[owner[k]];
 		for (int64_t c = 0; c < ez[k].n_cigar; ++c) {
@@ -86,7 +99,16 @@ std::vector<Alignment> align_batch(const std::vector<std::pair<std::string, std:
 			if (idx < 3) al.cigar.push_back({"MDI"[idx], len});                              // src/align.cc:58-63
 		}
 		add_stats(al.stats, st[k]);
-		free(ez[k].cigar);
+		if (ez[k].zdropped && k + 1 < n && owner[k + 1] == owner[k]) rewalk[owner[k]] = 1;
+	}
+	ksw_b200_result_free(res);
+	std::vector<std::pair<std::string, std::string>> rp;
+	std::vector<std::deque<std::pair<char, int>>> rc_;
+	std::vector<size_t> ri;
+	for (size_t i = 0; i < pairs.size(); ++i) if (rewalk[i]) { rp.push_back(pairs[i]); rc_.push_back(out[i].cigar); ri.push_back(i); }
+	if (!ri.empty()) {
+		std::vector<sd_stats_t> rs = stats_of(rp, rc_);
+		for (size_t k = 0; k < ri.size(); ++k) out[ri[k]].stats = rs[k];
 	}
 	return out;
 }
@@ -106,7 +128,7 @@ static std::vector<sd_stats_t> stats_of(const std::vector<std::pair<std::string,
 		coff[i] = (int64_t)cbuf.size();
 		for (auto &run : cigars[i]) {
 			const char ch = run.first;
-			uint32_t op = ch == 'M' ? 0u : (ch == 'D' ? 1u : (ch == 'I' ? 2u : (run.second == 0 ? 1u : 3u)));   // SEDEF 'D' = a only = ksw I
+			uint32_t op = ch == 'M' ? 0u : (ch == 'D' ? 1u : (ch == 'I' ? 2u : 3u));   // SEDEF 'D' = a only = ksw I; 3 = any other letter
 			cbuf.push_back((uint32_t)run.second << 4 | op);
 		}
 		cn[i] = (int64_t)cbuf.size() - coff[i];
@@ -503,3 +525,13 @@ std::vector<GuidedAlignment> merge_batch(const std::vector<MergeRequest> &reqs, 
 }
 
 } // namespace sedef_b200
+
+// C view of the chunk plan, for hosts that drive the C ABI themselves (and for the parity test of the chunk arithmetic)
+extern "C" int sedef_b200_chunk_plan(int64_t alen, int64_t blen, int cap, int64_t *sp, int *qlen, int *tlen)
+{
+	std::vector<sedef_b200::Chunk> c;
+	if (alen < 0 || blen < 0) return -1;
+	sedef_b200::chunk_plan((size_t)alen, (size_t)blen, c);
+	for (size_t k = 0; k < c.size() && (int)k < cap; ++k) { sp[k] = (int64_t)c[k].sp; qlen[k] = c[k].la; tlen[k] = c[k].lb; }
+	return (int)c.size();
+}

@@ -61,7 +61,12 @@ EXPORTS = ["ksw_b200_strerror", "ksw_b200_last_error", "ksw_b200_init", "ksw_b20
            "ksw_extz2_batch_flat", "ksw_b200_batch_upload", "ksw_b200_batch_run", "ksw_b200_batch_fetch",
            "ksw_b200_batch_launches", "ksw_b200_batch_kernel_ms", "ksw_b200_batch_cells",
            "ksw_b200_batch_free", "ksw_b200_count_cells", "sd_stats_derive_fp",
-           "ksw_b200_batch_io_bytes", "ksw_b200_batch_set_stats", "ksw_b200_free_cigars", "ksw_b200_batch_host_ms", "ksw_b200_last_call_io", "ksw_b200_set_host_threads", "sd_stats_from_cigar_batch_flat"]
+           "ksw_b200_batch_io_bytes", "ksw_b200_batch_set_stats", "ksw_b200_free_cigars", "ksw_b200_batch_host_ms",
+           "ksw_b200_last_call_io", "ksw_b200_set_host_threads", "sd_stats_from_cigar_batch_flat",
+           "ksw_b200_host_alloc", "ksw_b200_host_free", "ksw_b200_host_register", "ksw_b200_host_unregister",
+           "ksw_b200_set_fatal_handler", "ksw_extz2_batch_arena", "ksw_b200_result_ez", "ksw_b200_result_stats",
+           "ksw_b200_result_count", "ksw_b200_result_io", "ksw_b200_result_free", "ksw_b200_batch_fetch_arena",
+           "ksw_b200_result_export"]
 
 
 def load():
@@ -108,6 +113,29 @@ def load():
     lib.sd_stats_from_cigar_batch_flat.argtypes = [i32] + [vp] * 11
     lib.sd_stats_from_cigar_batch_flat.restype = i32
     lib.ksw_b200_last_call_io.argtypes = [C.POINTER(i64), C.POINTER(i64), C.POINTER(i32)]
+    lib.ksw_b200_host_alloc.argtypes = [C.c_size_t]
+    lib.ksw_b200_host_alloc.restype = vp
+    lib.ksw_b200_host_free.argtypes = [vp]
+    lib.ksw_b200_host_free.restype = None
+    lib.ksw_b200_host_register.argtypes = [vp, C.c_size_t]
+    lib.ksw_b200_host_unregister.argtypes = [vp]
+    lib.ksw_b200_set_fatal_handler.argtypes = [vp]
+    lib.ksw_b200_set_fatal_handler.restype = None
+    lib.ksw_extz2_batch_arena.argtypes = flat + [i32, vp, vp, C.POINTER(vp)]
+    lib.ksw_extz2_batch_arena.restype = i32
+    lib.ksw_b200_batch_fetch_arena.argtypes = [vp, i32, C.POINTER(vp)]
+    lib.ksw_b200_batch_fetch_arena.restype = i32
+    lib.ksw_b200_result_ez.argtypes = [vp]
+    lib.ksw_b200_result_ez.restype = vp
+    lib.ksw_b200_result_stats.argtypes = [vp]
+    lib.ksw_b200_result_stats.restype = vp
+    lib.ksw_b200_result_count.argtypes = [vp]
+    lib.ksw_b200_result_io.argtypes = [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i32)]
+    lib.ksw_b200_result_io.restype = None
+    lib.ksw_b200_result_free.argtypes = [vp]
+    lib.ksw_b200_result_free.restype = None
+    lib.ksw_b200_result_export.argtypes = [vp, vp, vp, vp, i64, i64, vp]
+    lib.ksw_b200_result_export.restype = i64
     lib.sd_stats_derive_fp.argtypes = [C.POINTER(SdStats), C.POINTER(SdStatsFp)]
     lib.free = C.CDLL(None).free
     lib.free.argtypes = [vp]
@@ -170,19 +198,119 @@ def _ptr(a):
 
 
 def extz2_batch(ps, mat, q: int, e: int, w: int = -1, zdrop: int = -1, flag: int = 0, m: int = 5,
-                want_stats: bool = True, use_raw: bool = True, keep_cigars: bool = True) -> BatchResult:
-    """One-shot batch through `ksw_extz2_batch_flat` with HOST buffers (H2D + kernels + D2H)."""
+                want_stats: bool = True, use_raw: bool = True, keep_cigars: bool = True, raw_only: bool = False) -> BatchResult:
+    """One-shot batch through `ksw_extz2_batch_flat` with HOST buffers (H2D + kernels + D2H); every CIGAR is malloc()'d by
+    the library like ksw2 does.  raw_only: pass the original-case bytes alone (codes derived on the device)."""
     lib = load()
     mat = np.ascontiguousarray(mat, np.int8)
     n = ps.n
     ez = np.zeros(n, EZ_DTYPE)
     stats = np.zeros(n, STATS_DTYPE) if want_stats else None
-    rc = lib.ksw_extz2_batch_flat(n, _ptr(ps.qlen), _ptr(ps.qoff), _ptr(ps.q), _ptr(ps.tlen), _ptr(ps.toff), _ptr(ps.t),
+    use_raw = use_raw or raw_only
+    rc = lib.ksw_extz2_batch_flat(n, _ptr(ps.qlen), _ptr(ps.qoff), None if raw_only else _ptr(ps.q), _ptr(ps.tlen), _ptr(ps.toff),
+                                  None if raw_only else _ptr(ps.t),
                                   m, _ptr(mat), q, e, w, zdrop, flag, _ptr(ez), _ptr(stats),
                                   _ptr(ps.q_raw) if use_raw else None, _ptr(ps.t_raw) if use_raw else None)
     _check(rc)
     cigs = _collect(lib, ez, keep_cigars)
     return BatchResult(ez, cigs, stats)
+
+
+class ArenaResult:
+    """Results of `ksw_extz2_batch_arena` / `ksw_b200_batch_fetch_arena`: numpy VIEWS of the library's page-locked arena
+    (no copies); `ez[i]["cigar"]` is a pointer into the arena.  Valid until free()."""
+
+    def __init__(self, lib, handle):
+        self.lib, self.h = lib, handle
+        n = int(lib.ksw_b200_result_count(handle))
+        self.n = n
+        pe = lib.ksw_b200_result_ez(handle)
+        self.ez = np.frombuffer((C.c_char * (n * EZ_DTYPE.itemsize)).from_address(pe), EZ_DTYPE) if n else np.zeros(0, EZ_DTYPE)
+        pst = lib.ksw_b200_result_stats(handle)
+        self.stats = (np.frombuffer((C.c_char * (n * STATS_DTYPE.itemsize)).from_address(pst), STATS_DTYPE) if (pst and n) else None)
+
+    def cigar(self, i: int) -> np.ndarray:
+        n, p = int(self.ez[i]["n_cigar"]), int(self.ez[i]["cigar"])
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint32)), shape=(n,)).copy() if n else np.zeros(0, np.uint32)
+
+    def io(self):
+        a, b, c = C.c_int64(0), C.c_int64(0), C.c_int(0)
+        self.lib.ksw_b200_result_io(self.h, C.byref(a), C.byref(b), C.byref(c))
+        return int(a.value), int(b.value), int(c.value)
+
+    def export(self, ez_dst: np.ndarray, stats_dst, cigar_dst: np.ndarray, cigar_base: int = 0, index=None) -> int:
+        """`ksw_b200_result_export`: position-independent copy into caller-owned (e.g. shared-memory) arrays."""
+        n = self.lib.ksw_b200_result_export(self.h, _ptr(ez_dst), _ptr(stats_dst), _ptr(cigar_dst), int(cigar_dst.shape[0]),
+                                            int(cigar_base), _ptr(index))
+        if n < 0:
+            _check(int(n))
+        return int(n)
+
+    def to_batch_result(self) -> BatchResult:
+        """Deep copy into the BatchResult form the tests compare (the arena can be freed afterwards)."""
+        ez = self.ez.copy()
+        cigs = [self.cigar(i) for i in range(self.n)]
+        return BatchResult(ez, cigs, None if self.stats is None else self.stats.copy())
+
+    def free(self):
+        if self.h:
+            self.ez = self.stats = None
+            self.lib.ksw_b200_result_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def extz2_batch_arena(ps, mat, q: int, e: int, w: int = -1, zdrop: int = -1, flag: int = 0, m: int = 5,
+                      want_stats: bool = True, raw_only: bool = True, use_raw: bool = True) -> ArenaResult:
+    """One-shot batch through `ksw_extz2_batch_arena`: host buffers in, one result arena out (no per-pair malloc).
+    raw_only (default): the sequences go in as original-case bytes alone, SEDEF's Alignment(fa, fb) call shape."""
+    lib = load()
+    mat = np.ascontiguousarray(mat, np.int8)
+    out = C.c_void_p(None)
+    use_raw = use_raw or raw_only
+    rc = lib.ksw_extz2_batch_arena(ps.n, _ptr(ps.qlen), _ptr(ps.qoff), None if raw_only else _ptr(ps.q), _ptr(ps.tlen), _ptr(ps.toff),
+                                   None if raw_only else _ptr(ps.t), m, _ptr(mat), q, e, w, zdrop, flag, int(want_stats),
+                                   _ptr(ps.q_raw) if use_raw else None, _ptr(ps.t_raw) if use_raw else None, C.byref(out))
+    _check(rc)
+    return ArenaResult(lib, out.value)
+
+
+class PinnedArray:
+    """A numpy view of page-locked host memory from `ksw_b200_host_alloc` (inputs there are DMA-copied in place)."""
+
+    def __init__(self, src: np.ndarray):
+        lib = load()
+        self.lib = lib
+        nbytes = max(1, src.nbytes)
+        self.ptr = lib.ksw_b200_host_alloc(nbytes)
+        if not self.ptr:
+            raise MemoryError("ksw_b200_host_alloc failed")
+        self.array = np.frombuffer((C.c_char * nbytes).from_address(self.ptr), src.dtype, count=src.size).reshape(src.shape)
+        self.array[...] = src
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            self.lib.ksw_b200_host_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def pin_pairset(ps):
+    """Copy of a PairSet whose sequence buffers live in page-locked memory.  Returns (pinned PairSet, keepalive list)."""
+    import dataclasses
+    keep = {k: PinnedArray(getattr(ps, k)) for k in ("q", "t", "q_raw", "t_raw")}
+    return dataclasses.replace(ps, **{k: v.array for k, v in keep.items()}), list(keep.values())
 
 
 def last_call_io():
@@ -207,13 +335,14 @@ def extz2(query, target, mat, q: int, e: int, w: int = -1, zdrop: int = -1, flag
 class ResidentBatch:
     """Inputs resident in HBM (`ksw_b200_batch_upload`); `run()` times the device path only."""
 
-    def __init__(self, ps, mat, q, e, w=-1, zdrop=-1, flag=0, m=5, use_raw=True):
+    def __init__(self, ps, mat, q, e, w=-1, zdrop=-1, flag=0, m=5, use_raw=True, raw_only=False):
         lib = load()
         self.lib, self.n = lib, ps.n
         self._keep = (ps, np.ascontiguousarray(mat, np.int8))
         err = C.c_int(0)
-        self.h = lib.ksw_b200_batch_upload(ps.n, _ptr(ps.qlen), _ptr(ps.qoff), _ptr(ps.q), _ptr(ps.tlen), _ptr(ps.toff),
-                                           _ptr(ps.t), m, _ptr(self._keep[1]), q, e, w, zdrop, flag,
+        use_raw = use_raw or raw_only
+        self.h = lib.ksw_b200_batch_upload(ps.n, _ptr(ps.qlen), _ptr(ps.qoff), None if raw_only else _ptr(ps.q), _ptr(ps.tlen), _ptr(ps.toff),
+                                           None if raw_only else _ptr(ps.t), m, _ptr(self._keep[1]), q, e, w, zdrop, flag,
                                            _ptr(ps.q_raw) if use_raw else None, _ptr(ps.t_raw) if use_raw else None,
                                            C.byref(err))
         if not self.h:
@@ -247,6 +376,11 @@ class ResidentBatch:
 
     def set_stats(self, on: bool):
         self.lib.ksw_b200_batch_set_stats(self.h, int(on))
+
+    def fetch_arena(self, want_stats=True) -> ArenaResult:
+        out = C.c_void_p(None)
+        _check(self.lib.ksw_b200_batch_fetch_arena(self.h, int(want_stats), C.byref(out)))
+        return ArenaResult(self.lib, out.value)
 
     def fetch(self, want_stats=True, keep_cigars=True) -> BatchResult:
         ez = np.zeros(self.n, EZ_DTYPE)

@@ -67,13 +67,29 @@ class PairSet:
         if len(idx):
             qo[1:] = np.cumsum(ql[:-1]); to[1:] = np.cumsum(tl[:-1])
         def gather(buf, off, ln, noff):
-            out = np.empty(int(ln.sum()), np.uint8)
-            for k, i in enumerate(idx):
-                out[noff[k]:noff[k] + ln[k]] = buf[off[i]:off[i] + ln[k]]
-            return out
+            # vectorised: source position of every output byte
+            tot = int(ln.sum())
+            if tot == 0:
+                return np.empty(0, np.uint8)
+            src = np.repeat(off[idx] - noff, ln) + np.arange(tot, dtype=np.int64)
+            return buf[src]
         return PairSet(ql.copy(), qo, gather(self.q, self.qoff, ql, qo), tl.copy(), to,
                        gather(self.t, self.toff, tl, to),
                        gather(self.q_raw, self.qoff, ql, qo), gather(self.t_raw, self.toff, tl, to))
+
+
+def concat_pairsets(parts) -> "PairSet":
+    """Concatenation of PairSets (pairs keep their order; offsets are rebased)."""
+    parts = list(parts)
+    if len(parts) == 1:
+        return parts[0]
+    qlen = np.concatenate([p.qlen for p in parts]).astype(np.int32)
+    tlen = np.concatenate([p.tlen for p in parts]).astype(np.int32)
+    qbase = np.cumsum([0] + [p.q.shape[0] for p in parts[:-1]]).astype(np.int64)
+    tbase = np.cumsum([0] + [p.t.shape[0] for p in parts[:-1]]).astype(np.int64)
+    return PairSet(qlen, np.concatenate([p.qoff + b for p, b in zip(parts, qbase)]), np.concatenate([p.q for p in parts]),
+                   tlen, np.concatenate([p.toff + b for p, b in zip(parts, tbase)]), np.concatenate([p.t for p in parts]),
+                   np.concatenate([p.q_raw for p in parts]), np.concatenate([p.t_raw for p in parts]))
 
 
 def encode(ascii_bytes: np.ndarray) -> np.ndarray:

@@ -94,26 +94,26 @@ static inline int class_pairs_per_block(int c)
 }
 
 // grid: CTAs for narrow / wide classes, clusters for cluster classes
-static cudaError_t launch_dp(int c, const DpLaunch &L, bool cigar, bool right, int grid, cudaStream_t st)
+static cudaError_t launch_dp(int c, const DpLaunch &L, bool cigar, bool right, bool approx, int grid, cudaStream_t st)
 {
-	if (class_packed_cluster(c)) return k_dp16_cluster_dispatch(L, cigar, right, grid, st, nullptr);
+	if (class_packed_cluster(c)) return k_dp16_cluster_dispatch(L, cigar, right, approx, grid, st, nullptr);
 	if (class_cluster(c)) return k_dp_cluster_dispatch(class_cluster(c), L, cigar, right, grid, st, nullptr);
-	if (class_packed_wide(c)) return k_dp16_wide_launch(class_ns(c) / 32, L, cigar, right, grid, st);
-	if (class_packed(c)) return k_dp16_launch(class_ns(c) / 32, L, cigar, right, grid, st);
+	if (class_packed_wide(c)) return k_dp16_wide_launch(class_ns(c) / 32, L, cigar, right, approx, grid, st);
+	if (class_packed(c)) return k_dp16_launch(class_ns(c) / 32, L, cigar, right, approx, grid, st);
 	return k_dp_launch(c, L, cigar, right, grid, st);
 }
 // resident CTAs per SM (narrow / wide) or co-resident clusters on the whole device (cluster classes), on the CURRENT device
-static int dp_occupancy_query(int c, bool cigar, bool right)
+static int dp_occupancy_query(int c, bool cigar, bool right, bool approx)
 {
 	if (class_cluster(c)) {
 		int n = 0; DpLaunch dummy = {};
-		cudaError_t e = class_packed_cluster(c) ? k_dp16_cluster_dispatch(dummy, cigar, right, 1, nullptr, &n)
+		cudaError_t e = class_packed_cluster(c) ? k_dp16_cluster_dispatch(dummy, cigar, right, approx, 1, nullptr, &n)
 		                                        : k_dp_cluster_dispatch(class_cluster(c), dummy, cigar, right, 1, nullptr, &n);
 		if (e != cudaSuccess) { cudaGetLastError(); return 0; }
 		return n;
 	}
-	if (class_packed_wide(c)) return k_dp16_wide_occupancy(class_ns(c) / 32, cigar, right);
-	if (class_packed(c)) return k_dp16_occupancy(class_ns(c) / 32, cigar, right);
+	if (class_packed_wide(c)) return k_dp16_wide_occupancy(class_ns(c) / 32, cigar, right, approx);
+	if (class_packed(c)) return k_dp16_occupancy(class_ns(c) / 32, cigar, right, approx);
 	return k_dp_occupancy(c, cigar, right);
 }
 
@@ -127,14 +127,14 @@ struct DevCtx {
 	cudaStream_t tb_stream = nullptr;   // highest priority: a finished chunk's traceback must not queue behind the persistent
 	                                    // DP CTAs of the chunks launched after it (one-shot pipeline)
 	size_t tb_budget = 0;          // bytes of traceback memory one wave may use
-	int occ[kNumClasses][3];       // cached occupancy per (class, {score-only, cigar-left, cigar-right}); -1 = not asked yet
+	int occ[kNumClasses][6];       // cached occupancy per (class, {score-only, cigar-left, cigar-right} x {exact, approx max}); -1 = not asked yet
 	DevCtx() { for (auto &row : occ) for (int &v : row) v = -1; }
 };
 // occupancy of class c on device dc (which must be current): asked once per device
-static int dp_occupancy(DevCtx &dc, int c, bool cigar, bool right)
+static int dp_occupancy(DevCtx &dc, int c, bool cigar, bool right, bool approx)
 {
-	int &slot = dc.occ[c][cigar ? (right ? 2 : 1) : 0];
-	if (slot < 0) slot = dp_occupancy_query(c, cigar, right);
+	int &slot = dc.occ[c][(cigar ? (right ? 2 : 1) : 0) + (approx ? 3 : 0)];
+	if (slot < 0) slot = dp_occupancy_query(c, cigar, right, approx);
 	return slot;
 }
 static std::mutex g_mu;
@@ -386,7 +386,8 @@ static int build_scoring(ksw_b200_batch &B)
 	const int m = B.m, q = B.q, e = B.e;
 	if (m <= 0) return 0;   // every pair is reset (:57)
 	if (m > kTableStride) return fail(KSW_B200_ERR_UNSUPPORTED, "alphabet size m > 8 is not supported");
-	if (B.flag & KSW_EZ_APPROX_MAX) return fail(KSW_B200_ERR_UNSUPPORTED, "KSW_EZ_APPROX_MAX is not supported");
+	if ((B.flag & KSW_EZ_APPROX_MAX) && !packed_enabled())
+		return fail(KSW_B200_ERR_UNSUPPORTED, "KSW_EZ_APPROX_MAX is implemented by the packed kernels only (unset KSW_B200_PACKED=0)");
 	int max_sc = B.mat[0], min_sc = B.mat[1];
 	for (int t = 1; t < m * m; ++t) { max_sc = std::max<int>(max_sc, B.mat[t]); min_sc = std::min<int>(min_sc, B.mat[t]); }
 	B.early_out = (-min_sc > 2 * (q + e));                                          // :81
@@ -788,6 +789,7 @@ static int launch_sub(ksw_b200_batch &B, SubBatch &sb)
 	if (sb.pairs.empty()) { sb.total_ms = sb.dp_ms = sb.tb_ms = 0; sb.launches = 0; return 0; }
 	const bool cigar = !(B.flag & KSW_EZ_SCORE_ONLY);
 	const bool right = (B.flag & KSW_EZ_RIGHT) != 0;
+	const bool approx = (B.flag & KSW_EZ_APPROX_MAX) != 0;
 	CUDA_TRY(cudaSetDevice(sb.dc->dev));
 	cudaStream_t st = sb.stream ? sb.stream : sb.dc->stream;
 	sb.touched = true;
@@ -830,7 +832,7 @@ static int launch_sub(ksw_b200_batch &B, SubBatch &sb)
 		L.table = (const uint32_t *)sb.d_table.p;
 		L.work_counter = d_counters + wave_no;
 		L.n = wv.count; L.sc = B.sc;
-		int occ = dp_occupancy(*sb.dc, c, cigar, right);
+		int occ = dp_occupancy(*sb.dc, c, cigar, right, approx);
 		if (occ <= 0) return fail(KSW_B200_ERR_CUDA, "DP kernel cannot be resident (occupancy 0)");
 		const int groups_per_block = class_pairs_per_block(c);
 		int grid = class_cluster(c) ? std::min(wv.count, occ)                                 // clusters, one pair each
@@ -839,7 +841,7 @@ static int launch_sub(ksw_b200_batch &B, SubBatch &sb)
 		CUDA_TRY(cudaEventCreate(&a)); CUDA_TRY(cudaEventCreate(&b2)); CUDA_TRY(cudaEventCreate(&c2));
 		dp_ev.push_back({a, b2}); tb_ev.push_back({b2, c2});
 		CUDA_TRY(cudaEventRecord(a, st));
-		CUDA_TRY(launch_dp(c, L, cigar, right, grid, st));
+		CUDA_TRY(launch_dp(c, L, cigar, right, approx, grid, st));
 		CUDA_TRY(cudaEventRecord(b2, st));
 		++sb.launches;
 		if (cigar) {

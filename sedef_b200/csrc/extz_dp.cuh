@@ -232,8 +232,33 @@ struct Leader {
 	int exit_slot; int32_t exit_H;          // most recently exited slot and its TRUE H (stale reads of :228)
 	int32_t Hprev_true;                     // H[en0-1] of the previous diagonal
 	int32_t Hen0_lazy, gmax;
+	int32_t H0, last_H0_t;                  // KSW_EZ_APPROX_MAX: the one tracked score and its slot (:51,268-284)
 
-	__device__ __forceinline__ void reset() { ez_reset(ez); st0_prev = 0; exit_slot = -2; exit_H = kNegInf; Hprev_true = kNegInf; Hen0_lazy = gmax = kNegInf; }
+	__device__ __forceinline__ void reset() { ez_reset(ez); st0_prev = 0; exit_slot = -2; exit_H = kNegInf; Hprev_true = kNegInf; Hen0_lazy = gmax = kNegInf; H0 = 0; last_H0_t = 0; }
+
+	// KSW_EZ_APPROX_MAX (:268-284): instead of the exact maximum over the anti-diagonal, ONE score H0 is walked along the
+	// locally better of the two moves (stay on slot t: + v[t] - qe; step to slot t+1: + u[t+1] - qe).  Every slot it reads is
+	// in band: last_H0_t never exceeds en0 (en0 is non-decreasing) and falls at most one slot behind st0, where the third arm
+	// steps it back to st0.  mqe / mte are never updated; max / z-drop only with KSW_EZ_APPROX_DROP.  `A` additionally gives
+	// a.v(c), the v' of the current diagonal.  Returns stop.
+	template <class A>
+	__device__ __forceinline__ int approx(const A &acc, const Band &b, int r, int qe, uint32_t v0_r0, int qlen, int tlen, int zdrop, int e, bool drop)
+	{
+		if (r > 0) {
+			const bool in0 = last_H0_t >= b.st0 && last_H0_t <= b.en0;
+			const bool in1 = last_H0_t + 1 >= b.st0 && last_H0_t + 1 <= b.en0;
+			if (in0 && in1) {
+				const int32_t d0 = (int32_t)(acc.v(last_H0_t & A::kMask) >> 24) - qe;
+				const int32_t d1 = (int32_t)(acc.u((last_H0_t + 1) & A::kMask) >> 24) - qe;
+				if (d0 > d1) H0 += d0;
+				else { H0 += d1; ++last_H0_t; }
+			} else if (in0) H0 += (int32_t)(acc.v(last_H0_t & A::kMask) >> 24) - qe;
+			else { ++last_H0_t; H0 += (int32_t)(acc.u(last_H0_t & A::kMask) >> 24) - qe; }
+			if (drop && ez_apply_zdrop(ez, H0, r, last_H0_t, zdrop, e)) return 1;
+		} else { H0 = (int32_t)(v0_r0 >> 24) - 2 * qe; last_H0_t = 0; }
+		if (r == qlen + tlen - 2 && b.en0 == tlen - 1) ez.score = H0;
+		return 0;
+	}
 
 	// `A` gives access to the H / u' rows by circular slot index: a.h(c) (int32_t&), a.u(c) (uint32_t), A::kMask.
 	// before the cells: remember/knock out slots that must not take part in the regular H update

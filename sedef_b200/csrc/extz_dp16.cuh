@@ -208,7 +208,9 @@ __device__ __forceinline__ void lane16_prepare(Lane16 &ls, const Band &b, int r,
 // Hrow / Urow point at this thread's column of the CTA-wide row arrays: row k of the thread is Hrow[k * RS]
 // (RS = threads per CTA).
 // H rows 2j / 2j+1 hold slots 4j..4j+3 of block A / block B; U row j holds registers 4j..4j+3.
-template <bool kCigar, bool kRight, int RS = 128>
+// kApprox (KSW_EZ_APPROX_MAX): no H row at all -- the lane dumps v' next to u' (into the first four H rows, which are unused
+// then) for the leader's one tracked score.
+template <bool kCigar, bool kRight, int RS = 128, bool kApprox = false>
 __device__ __forceinline__ int32_t lane16_cells(Lane16 &ls, const Band &b, int r, int last_st, uint32_t xin, uint32_t vin,
                                                 uint4 *tb_dst, int4 *Hrow, uint4 *Urow, const Sc16 &sc)
 {
@@ -235,6 +237,15 @@ __device__ __forceinline__ int32_t lane16_cells(Lane16 &ls, const Band &b, int r
 #undef EXTZ_CELL2
 	if (kCigar) *tb_dst = make_uint4(cw[0], cw[1], cw[2], cw[3]);
 	int32_t lane_max = kNegInf;
+	if (kApprox) {
+		uint4 *Vrow = reinterpret_cast<uint4 *>(Hrow);
+#pragma unroll
+		for (int j = 0; j < 4; ++j) {
+			Urow[j * RS] = make_uint4(ls.U[4 * j], ls.U[4 * j + 1], ls.U[4 * j + 2], ls.U[4 * j + 3]);
+			Vrow[j * RS] = make_uint4(ls.V[4 * j], ls.V[4 * j + 1], ls.V[4 * j + 2], ls.V[4 * j + 3]);
+		}
+		return lane_max;
+	}
 #pragma unroll
 	for (int j = 0; j < 4; ++j) {
 		// H += v8[t] (extern/ksw2_extz2_sse.cc:103,255: v8 is uint8_t*, the byte is ZERO-extended): the UNSIGNED IDP.4A against a
@@ -336,6 +347,12 @@ struct PackedRows {
 		const uint32_t w = Us[((((i >> 2) * RS) + (vl >> 1)) << 2) | (i & 3)];
 		return (vl & 1) ? (w & 0xffff0000u) : (w << 16);
 	}
+	__device__ __forceinline__ uint32_t v(int c) const          // v' dump of the approx-max variant: same layout, in the H rows' storage
+	{
+		const int vl = c >> 4, i = c & 15;
+		const uint32_t w = reinterpret_cast<const uint32_t *>(H)[((((i >> 2) * RS) + (vl >> 1)) << 2) | (i & 3)];
+		return (vl & 1) ? (w & 0xffff0000u) : (w << 16);
+	}
 };
 
 // =====================================================================================================
@@ -344,7 +361,7 @@ struct PackedRows {
 #ifndef EXTZ_MIN_BLOCKS_P
 #define EXTZ_MIN_BLOCKS_P 3
 #endif
-template <int G, bool kCigar, bool kRight>
+template <int G, bool kCigar, bool kRight, bool kApprox = false>
 __global__ void __launch_bounds__(128, EXTZ_MIN_BLOCKS_P)
 extz_dp16_kernel(DpLaunch L)
 {
@@ -416,6 +433,20 @@ extz_dp16_kernel(DpLaunch L)
 				xin = __byte_perm(__shfl_sync(FULL, ls.X[15], pred_lane, G), ls.X[15], 0x5432);
 				vin = __byte_perm(__shfl_sync(FULL, ls.V[15], pred_lane, G), ls.V[15], 0x5432);
 			}
+			if (kApprox) {
+				// KSW_EZ_APPROX_MAX: no H row, no maximum, no arg-max -- the leader walks its one score over the u' / v' dumps
+				if (act) {
+					lane16_prepare<NS>(ls, b, r, last_en, qseq, tseq, tlen, table_saddr, sc16);
+					lane16_cells<kCigar, kRight, 128, true>(ls, b, r, last_st, xin, vin, (uint4 *)(tbp + (int64_t)r * (NS >> 1)), Hrow, Urow, sc16);
+				}
+				__syncwarp();
+				int stop = 0;
+				if (act && gl == 0) stop = ld.approx(rows, b, r, qe, ls.V[0] << 16, qlen, tlen, sc.zdrop, sc.e, (sc.flag & kFlagApproxDrop) != 0);
+				stop = __shfl_sync(FULL, stop, 0, G);
+				if (act) { n_diag = r + 1; last_st = b.st; last_en = b.en; if (stop) alive = false; }
+				__syncwarp();            // the leader read the dumps; the next diagonal overwrites them
+				continue;
+			}
 			if (act) {
 				lane16_prepare<NS>(ls, b, r, last_en, qseq, tseq, tlen, table_saddr, sc16);
 				if (gl == 0) ld.pre(rows, b, r, qe);
@@ -483,7 +514,7 @@ extz_dp16_kernel(DpLaunch L)
 // fills of a few kbp).  Carries between warps and the per-diagonal reductions go through shared memory, ordering by __syncthreads;
 // otherwise the per-lane code of the narrow kernel.
 // =====================================================================================================
-template <int G, bool kCigar, bool kRight>
+template <int G, bool kCigar, bool kRight, bool kApprox = false>
 __global__ void __launch_bounds__(G, G == 128 ? 3 : 1)       // 128 lanes: 3 CTAs/SM at <= 170 registers; 64: 5 fit anyway; 256: 1
 extz_dp16_wide_kernel(DpLaunch L)
 {
@@ -548,15 +579,35 @@ extz_dp16_wide_kernel(DpLaunch L)
 		bool okb = band_of(0, qlen, tlen, w, T, generic, b);
 		if (okb) {
 			lane16_prepare<NS>(ls, b, 0, -1, qseq, tseq, tlen, table_saddr, sc16);
-			if (gl == 0) ld.pre(rows, b, 0, qe);
+			if (!kApprox && gl == 0) ld.pre(rows, b, 0, qe);
 		} else zdropped_band = 1;
 		uint32_t xp = 0u, vp = 0u;                                    // OLD x,v of the register below (zero state at r = 0)
 		__syncthreads();
 		for (int r = 0; okb && r < R; ++r) {
 			// cells of diagonal r
 			const uint32_t xin = __byte_perm(xp, ls.X[15], 0x5432), vin = __byte_perm(vp, ls.V[15], 0x5432);
-			const int32_t lane_max = lane16_cells<kCigar, kRight, G>(ls, b, r, last_st, xin, vin, (uint4 *)(tbp + (int64_t)r * (NS >> 1)),
-			                                                         Hrow, Urow, sc16);
+			const int32_t lane_max = lane16_cells<kCigar, kRight, G, kApprox>(ls, b, r, last_st, xin, vin, (uint4 *)(tbp + (int64_t)r * (NS >> 1)),
+			                                                                  Hrow, Urow, sc16);
+			if (kApprox) {
+				// KSW_EZ_APPROX_MAX: the leader walks its one score over the u' / v' dumps of diagonal r while the other lanes
+				// run prepare(r+1); two barriers per diagonal
+				if (lane == 31) { sCarryX[wid] = ls.X[15]; sCarryV[wid] = ls.V[15]; }
+				xp = __shfl_up_sync(0xffffffffu, ls.X[15], 1);
+				vp = __shfl_up_sync(0xffffffffu, ls.V[15], 1);
+				Band bn;
+				const bool okn = (r + 1 < R) && band_of(r + 1, qlen, tlen, w, T, generic, bn);
+				__syncthreads();
+				if (lane == 0) { const int pw = (wid + NW - 1) % NW; xp = sCarryX[pw]; vp = sCarryV[pw]; }
+				if (gl == 0) sStop = ld.approx(rows, b, r, qe, ls.V[0] << 16, qlen, tlen, sc.zdrop, sc.e, (sc.flag & kFlagApproxDrop) != 0);
+				if (okn) lane16_prepare<NS>(ls, bn, r + 1, b.en, qseq, tseq, tlen, table_saddr, sc16);
+				__syncthreads();
+				n_diag = r + 1;
+				last_st = b.st; last_en = b.en;
+				if (sStop) break;
+				if (r + 1 < R && !okn) { zdropped_band = 1; break; }
+				b = bn;
+				continue;
+			}
 			const int32_t wmax = __reduce_max_sync(0xffffffffu, lane_max);
 			if (lane == 0) sWarpMax[wid] = wmax;
 			if (lane == 31) { sCarryX[wid] = ls.X[15]; sCarryV[wid] = ls.V[15]; }      // OLD values for diagonal r+1
@@ -632,9 +683,16 @@ struct ClusterRows16 {
 		const uint32_t w = cl.map_shared_rank(Us, gl / GC)[((((i >> 2) * GC) + (gl % GC)) << 2) | (i & 3)];
 		return half ? (w & 0xffff0000u) : (w << 16);
 	}
+	__device__ __forceinline__ uint32_t v(int c) const
+	{
+		cg::cluster_group cl = cg::this_cluster();
+		const int gl = c >> 5, half = (c >> 4) & 1, i = c & 15;
+		const uint32_t w = cl.map_shared_rank(reinterpret_cast<uint32_t *>(H), gl / GC)[((((i >> 2) * GC) + (gl % GC)) << 2) | (i & 3)];
+		return half ? (w & 0xffff0000u) : (w << 16);
+	}
 };
 
-template <int C, bool kCigar, bool kRight>
+template <int C, bool kCigar, bool kRight, bool kApprox = false>
 __global__ void __launch_bounds__(256, 1)
 extz_dp16_cluster_kernel(DpLaunch L)
 {
@@ -707,14 +765,43 @@ extz_dp16_cluster_kernel(DpLaunch L)
 		bool okb = band_of(0, qlen, tlen, w, T, generic, b);
 		if (okb) {
 			lane16_prepare<NS>(ls, b, 0, -1, qseq, tseq, tlen, table_saddr, sc16);
-			if (leader) ld.pre(rows, b, 0, qe);
+			if (!kApprox && leader) ld.pre(rows, b, 0, qe);
 		} else zdropped_band = 1;
 		uint32_t xp = 0u, vp = 0u;
 		cluster.sync();
 		for (int r = 0; okb && r < R; ++r) {
 			const uint32_t xin = __byte_perm(xp, ls.X[15], 0x5432), vin = __byte_perm(vp, ls.V[15], 0x5432);
-			const int32_t lane_max = lane16_cells<kCigar, kRight, GC>(ls, b, r, last_st, xin, vin, (uint4 *)(tbp + (int64_t)r * (NS >> 1)),
-			                                                          Hrow, Urow, sc16);
+			const int32_t lane_max = lane16_cells<kCigar, kRight, GC, kApprox>(ls, b, r, last_st, xin, vin, (uint4 *)(tbp + (int64_t)r * (NS >> 1)),
+			                                                                   Hrow, Urow, sc16);
+			if (kApprox) {
+				// KSW_EZ_APPROX_MAX, as in extz_dp16_wide_kernel; the leader reads the dumps of other CTAs through DSMEM
+				if (lane == 31) { sCarryX[wid] = ls.X[15]; sCarryV[wid] = ls.V[15]; }
+				xp = __shfl_up_sync(0xffffffffu, ls.X[15], 1);
+				vp = __shfl_up_sync(0xffffffffu, ls.V[15], 1);
+				Band bn;
+				const bool okn = (r + 1 < R) && band_of(r + 1, qlen, tlen, w, T, generic, bn);
+				cluster.sync();
+				if (lane == 0) {
+					if (wid > 0) { xp = sCarryX[wid - 1]; vp = sCarryV[wid - 1]; }
+					else {
+						const int pr = (rank + C - 1) % C;
+						xp = cluster.map_shared_rank(sCarryX, pr)[NW - 1];
+						vp = cluster.map_shared_rank(sCarryV, pr)[NW - 1];
+					}
+				}
+				if (leader) {
+					const int stop = ld.approx(rows, b, r, qe, ls.V[0] << 16, qlen, tlen, sc.zdrop, sc.e, (sc.flag & kFlagApproxDrop) != 0);
+					for (int k = 0; k < C; ++k) *cluster.map_shared_rank(&sStop, k) = stop;
+				}
+				if (okn) lane16_prepare<NS>(ls, bn, r + 1, b.en, qseq, tseq, tlen, table_saddr, sc16);
+				cluster.sync();
+				n_diag = r + 1;
+				last_st = b.st; last_en = b.en;
+				if (sStop) break;
+				if (r + 1 < R && !okn) { zdropped_band = 1; break; }
+				b = bn;
+				continue;
+			}
 			const int32_t wmax = __reduce_max_sync(0xffffffffu, lane_max);
 			if (lane == 0) max0[rank * NW + wid] = wmax;
 			if (lane == 31) { sCarryX[wid] = ls.X[15]; sCarryV[wid] = ls.V[15]; }      // OLD values for diagonal r+1

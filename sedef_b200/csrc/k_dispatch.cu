@@ -3,47 +3,42 @@
 
 namespace extz {
 
-cudaError_t k_dp16_launch(int G, const DpLaunch &L, bool cigar, bool right, int grid, cudaStream_t st)
+#define EXTZ_G_SWITCH(G, CALL) \
+	switch (G) { case 1: return CALL(1); case 2: return CALL(2); case 4: return CALL(4); case 8: return CALL(8); case 16: return CALL(16); case 32: return CALL(32); }
+#define EXTZ_GW_SWITCH(G, CALL) \
+	switch (G) { case 64: return CALL(64); case 128: return CALL(128); case 256: return CALL(256); }
+cudaError_t k_dp16_launch(int G, const DpLaunch &L, bool cigar, bool right, bool approx, int grid, cudaStream_t st)
 {
-	switch (G) {
-	case 1: return dp16_launch_g<1>(L, cigar, right, grid, st);
-	case 2: return dp16_launch_g<2>(L, cigar, right, grid, st);
-	case 4: return dp16_launch_g<4>(L, cigar, right, grid, st);
-	case 8: return dp16_launch_g<8>(L, cigar, right, grid, st);
-	case 16: return dp16_launch_g<16>(L, cigar, right, grid, st);
-	case 32: return dp16_launch_g<32>(L, cigar, right, grid, st);
-	}
+#define EXTZ_CALL(g) (approx ? dp16_launch_g<g, true>(L, cigar, right, grid, st) : dp16_launch_g<g, false>(L, cigar, right, grid, st))
+	EXTZ_G_SWITCH(G, EXTZ_CALL)
+#undef EXTZ_CALL
 	return cudaErrorInvalidValue;
 }
-int k_dp16_occupancy(int G, bool cigar, bool right)
+int k_dp16_occupancy(int G, bool cigar, bool right, bool approx)
 {
-	switch (G) {
-	case 1: return dp16_occupancy_g<1>(cigar, right);
-	case 2: return dp16_occupancy_g<2>(cigar, right);
-	case 4: return dp16_occupancy_g<4>(cigar, right);
-	case 8: return dp16_occupancy_g<8>(cigar, right);
-	case 16: return dp16_occupancy_g<16>(cigar, right);
-	case 32: return dp16_occupancy_g<32>(cigar, right);
-	}
+#define EXTZ_CALL(g) (approx ? dp16_occupancy_g<g, true>(cigar, right) : dp16_occupancy_g<g, false>(cigar, right))
+	EXTZ_G_SWITCH(G, EXTZ_CALL)
+#undef EXTZ_CALL
 	return 0;
 }
-cudaError_t k_dp16_wide_launch(int G, const DpLaunch &L, bool cigar, bool right, int grid, cudaStream_t st)
+cudaError_t k_dp16_wide_launch(int G, const DpLaunch &L, bool cigar, bool right, bool approx, int grid, cudaStream_t st)
 {
-	switch (G) {
-	case 64: return dp16_wide_launch_g<64>(L, cigar, right, grid, st);
-	case 128: return dp16_wide_launch_g<128>(L, cigar, right, grid, st);
-	case 256: return dp16_wide_launch_g<256>(L, cigar, right, grid, st);
-	}
+#define EXTZ_CALL(g) (approx ? dp16_wide_launch_g<g, true>(L, cigar, right, grid, st) : dp16_wide_launch_g<g, false>(L, cigar, right, grid, st))
+	EXTZ_GW_SWITCH(G, EXTZ_CALL)
+#undef EXTZ_CALL
 	return cudaErrorInvalidValue;
 }
-int k_dp16_wide_occupancy(int G, bool cigar, bool right)
+int k_dp16_wide_occupancy(int G, bool cigar, bool right, bool approx)
 {
-	switch (G) {
-	case 64: return dp16_wide_occupancy_g<64>(cigar, right);
-	case 128: return dp16_wide_occupancy_g<128>(cigar, right);
-	case 256: return dp16_wide_occupancy_g<256>(cigar, right);
-	}
+#define EXTZ_CALL(g) (approx ? dp16_wide_occupancy_g<g, true>(cigar, right) : dp16_wide_occupancy_g<g, false>(cigar, right))
+	EXTZ_GW_SWITCH(G, EXTZ_CALL)
+#undef EXTZ_CALL
 	return 0;
+}
+cudaError_t k_dp16_cluster_dispatch(const DpLaunch &L, bool cigar, bool right, bool approx, int nclusters, cudaStream_t st, int *max_clusters)
+{
+	return approx ? dp16_cluster_dispatch_a<true>(L, cigar, right, nclusters, st, max_clusters)
+	              : dp16_cluster_dispatch_a<false>(L, cigar, right, nclusters, st, max_clusters);
 }
 #define EXTZ_FOR_CLASS(c, CALL) \
 	switch (c) { \

@@ -1,6 +1,6 @@
 // packed narrow kernel, G = 1 and 2 lanes per pair (see k_dp16_narrow.cuh)
 #include "k_dp16_narrow.cuh"
 namespace extz {
-EXTZ_INSTANTIATE_DP16(1)
-EXTZ_INSTANTIATE_DP16(2)
+EXTZ_INSTANTIATE_DP16(1, false)
+EXTZ_INSTANTIATE_DP16(2, false)
 }

@@ -5,27 +5,27 @@
 
 namespace extz {
 
-template <int G>
+template <int G, bool A>
 cudaError_t dp16_launch_g(const DpLaunch &L, bool cigar, bool right, int grid, cudaStream_t st)
 {
 	if (cigar) {
-		if (right) extz_dp16_kernel<G, true, true><<<grid, 128, 0, st>>>(L);
-		else       extz_dp16_kernel<G, true, false><<<grid, 128, 0, st>>>(L);
-	} else       extz_dp16_kernel<G, false, false><<<grid, 128, 0, st>>>(L);
+		if (right) extz_dp16_kernel<G, true, true, A><<<grid, 128, 0, st>>>(L);
+		else       extz_dp16_kernel<G, true, false, A><<<grid, 128, 0, st>>>(L);
+	} else       extz_dp16_kernel<G, false, false, A><<<grid, 128, 0, st>>>(L);
 	return cudaGetLastError();
 }
-template <int G>
+template <int G, bool A>
 int dp16_occupancy_g(bool cigar, bool right)
 {
 	int nb = 0;
 	if (cigar) {
-		if (right) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, extz_dp16_kernel<G, true, true>, 128, 0);
-		else       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, extz_dp16_kernel<G, true, false>, 128, 0);
-	} else       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, extz_dp16_kernel<G, false, false>, 128, 0);
+		if (right) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, extz_dp16_kernel<G, true, true, A>, 128, 0);
+		else       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, extz_dp16_kernel<G, true, false, A>, 128, 0);
+	} else       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, extz_dp16_kernel<G, false, false, A>, 128, 0);
 	return nb;
 }
-#define EXTZ_INSTANTIATE_DP16(G) \
-	template cudaError_t dp16_launch_g<G>(const DpLaunch &, bool, bool, int, cudaStream_t); \
-	template int dp16_occupancy_g<G>(bool, bool);
+#define EXTZ_INSTANTIATE_DP16(G, A) \
+	template cudaError_t dp16_launch_g<G, A>(const DpLaunch &, bool, bool, int, cudaStream_t); \
+	template int dp16_occupancy_g<G, A>(bool, bool);
 
 } // namespace extz

@@ -1,0 +1,5 @@
+// packed CTA-wide + cluster kernels, KSW_EZ_APPROX_MAX variant (see k_dp16_wide.cuh)
+#include "k_dp16_wide.cuh"
+namespace extz {
+EXTZ_INSTANTIATE_DP16_WIDE(true)
+}

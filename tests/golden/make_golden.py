@@ -95,7 +95,8 @@ def main():
     q, t = ps.pair(0)
     rows = []
     for w, zd, flag in [(-1, -1, 0), (100, -1, 0), (20, -1, 0), (10, -1, 0), (-1, -1, 0x02), (-1, -1, 0x01),
-                        (-1, -1, 0x80), (100, 50, 0), (100, 50, 0x40), (10, -1, 0x40), (10, -1, 0x42)]:
+                        (-1, -1, 0x80), (100, 50, 0), (100, 50, 0x40), (10, -1, 0x40), (10, -1, 0x42),
+                        (-1, -1, 0x08), (100, 50, 0x18), (10, -1, 0x08), (100, 50, 0x19)]:      # SURVEY App. B.3 approx-max rows
         f, c = ref.extz2(q, t, mat, 40, 1, w, zd, flag)
         rows.append(dict(w=w, zdrop=zd, flag=flag, fields=f, cigar=oracle.cigar_str(c)))
     kat = dict(source="reference python/simulations.py:6-7 (seq1, seq2); outputs of the compiled reference",

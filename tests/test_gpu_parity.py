@@ -104,6 +104,33 @@ def test_fuzz_vs_oracle(checker, mat, w, zdrop, flag, kw):
     compare(ps, mat, checker, w, zdrop, flag)
 
 
+@pytest.mark.parametrize("w,zdrop,flag,kw", [
+    (-1, -1, 0x08, dict(min_len=1, max_len=300, div=0.12)),           # KSW_EZ_APPROX_MAX: score only from the tracked H0, CIGAR end to end
+    (30, 80, 0x08, dict(min_len=1, max_len=700, div=0.2)),
+    (30, 80, 0x18, dict(min_len=1, max_len=700, div=0.2)),            # + APPROX_DROP: z-drop on the tracked score
+    (30, 80, 0x19, dict(min_len=1, max_len=700, div=0.2)),            # score-only
+    (30, 60, 0x5a, dict(min_len=1, max_len=700, div=0.3)),            # + RIGHT + EXTZ_ONLY
+    (100, 200, 0x98, dict(min_len=500, max_len=1300, div=0.15)),      # + REV_CIGAR, 128-slot class
+    (5, 20, 0x18, dict(min_len=1, max_len=600, div=0.3)),
+    (-1, 150, 0x18, dict(min_len=300, max_len=1000, div=0.35, burst=100)),   # 1024-slot class
+    (-1, 50, 0x1c, dict(min_len=1, max_len=400, div=0.2)),            # + GENERIC_SC
+])
+def test_approx_max_vs_oracle(checker, mat, w, zdrop, flag, kw):
+    """KSW_EZ_APPROX_MAX / KSW_EZ_APPROX_DROP (extern/ksw2_extz2_sse.cc:268-284): one tracked score instead of the exact
+    maximum; no mqe / mte; z-drop only with APPROX_DROP."""
+    ps = synth.make_pairs_mixed(250, seed=8800 + 7 * (w + 2) + flag, **kw)
+    compare(ps, mat, checker, w, zdrop, flag)
+
+
+def test_approx_max_wide_kernels(checker, mat):
+    """The approx-max variant on the CTA-wide (2048 / 4096 / 8192 slots) and cluster (16384 slots) kernels."""
+    for (cnt, length, seed) in [(4, 1500, 21), (3, 3000, 22), (2, 6000, 23), (2, 9500, 24)]:
+        ps = synth.make_pairs_small(cnt, length=length, div=0.1, seed=seed)
+        compare(ps, mat, checker, -1, -1, 0x08)
+        compare(ps, mat, checker, -1, 300, 0x18)
+        compare(ps, mat, checker, -1, 300, 0x1a)
+
+
 def test_config2_shape_vs_oracle(checker, mat):
     """BASELINE.json configs[1] shape (1 kbp pairs, w=100, 5 % divergence) at a size the oracle finishes in seconds."""
     ps = synth.make_pairs_small(3000, length=1000, div=0.05, seed=0x5EDEF002)
@@ -174,9 +201,6 @@ def test_widest_pair_and_too_wide(checker, mat):
     with pytest.raises(engine.EngineError) as ei:
         engine.extz2_batch(big, mat, 40, 1, -1, -1, 0)
     assert ei.value.code == -5
-    with pytest.raises(engine.EngineError) as ei:
-        engine.extz2_batch(ps, mat, 40, 1, -1, -1, engine.KSW_EZ_APPROX_MAX)
-    assert ei.value.code == -4
 
 
 def test_packed_class_boundaries(checker, mat):

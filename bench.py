@@ -289,10 +289,15 @@ def run_ours(args):
     # ---- end-to-end arm: host buffers in, ksw_extz_t + CIGARs + stats on the host (rank 0's, at N > 1) out -----------
     gather = None
 
+    phase = [0.0, 0.0]
+
     def e2e_once():
+        t_a = time.perf_counter()
         res = engine.extz2_batch_arena(ps_pinned, mat, synth.SEDEF_GAPO, synth.SEDEF_GAPE, W, ZD, FLAG, want_stats=True, raw_only=True)
+        t_b = time.perf_counter()
         if gather is not None:
             res.export(gather.ez, gather.stats, gather.mine, cigar_base=rank * gather.cap, index=gidx)
+        phase[0] += t_b - t_a; phase[1] += time.perf_counter() - t_b
         return res
     warm = e2e_once()
     words = int(warm.ez["n_cigar"].sum())
@@ -306,6 +311,7 @@ def run_ours(args):
     t0 = time.perf_counter()
     e2e_steps = max(1, min(args.steps, 5))
     res = None
+    phase[0] = phase[1] = 0.0
     for _ in range(e2e_steps):
         if res is not None:
             res.free()
@@ -313,6 +319,8 @@ def run_ours(args):
     barrier_sync(dist, local)
     e2e_ms = allreduce(dist, local, (time.perf_counter() - t0) * 1e3, "max") / e2e_steps
     e2e_gcups = cells_total / (e2e_ms * 1e-3) / 1e9
+    call_ms = allreduce(dist, local, phase[0] * 1e3 / e2e_steps, "max")
+    gather_ms = allreduce(dist, local, phase[1] * 1e3 / e2e_steps, "max")
     io = res.io()
     io = (int(allreduce(dist, local, float(io[0]), "sum")), int(allreduce(dist, local, float(io[1]), "sum")),
           int(allreduce(dist, local, float(io[2]), "sum")))
@@ -371,6 +379,7 @@ def run_ours(args):
             "e2e": {"value": round(e2e_gcups, 2), "unit": "GCUPS", "h2d_bytes_per_step": int(io[0]), "d2h_bytes_per_step": int(io[1]),
                     "ms_per_step": round(e2e_ms, 3), "pairs_per_s": round(pairs_total / (e2e_ms * 1e-3), 1),
                     "gpu_launches_per_step": int(io[2]),
+                    "call_ms_max": round(call_ms, 3), "gather_ms_max": round(gather_ms, 3),
                     "api": "ksw_extz2_batch_arena: one call per rank, sequences as original-case bytes in page-locked host memory "
                            "(align_dna on the device), ksw_extz_t + CIGARs + sd_stats_t back in one page-locked arena"
                            + ("; ksw_b200_result_export gathers every rank's records into one shared host segment" if n_gpus > 1 else ""),

@@ -143,6 +143,10 @@ static std::vector<DevCtx> g_devs;
 // OMP_NUM_THREADS=1, which would serialise the host side of every rank; callers can override it here.
 static int g_host_threads = 0;
 static inline int host_threads() { return g_host_threads > 0 ? g_host_threads : omp_get_max_threads(); }
+// threads worth waking for a loop over n items of ~`grain` items per thread-millisecond: the host side of a batch is a few
+// hundred microseconds of work, and an OpenMP team that is larger than the work only adds wake-up latency and spinning
+// (with one process per GPU the ranks share the cores)
+static inline int threads_for(int64_t n, int64_t grain) { return (int)std::max<int64_t>(1, std::min<int64_t>(host_threads(), n / grain)); }
 extern "C" void ksw_b200_set_host_threads(int n) { g_host_threads = n > 0 ? n : 0; }
 
 extern "C" int ksw_b200_init(int first_dev, int ndev)
@@ -558,7 +562,7 @@ extern "C" ksw_b200_batch_t *ksw_b200_batch_upload(int n, const int *qlen, const
 	std::vector<Item> items(n);
 	const bool skip_s32 = getenv("KSW_B200_SKIP_S32") != nullptr;                       // A/B: 32 lanes x 32 slots vs 64-lane CTA
 	int too_wide = -1;
-#pragma omp parallel for num_threads(host_threads()) schedule(static) if (n >= 4096)
+#pragma omp parallel for num_threads(threads_for(n, 32768)) schedule(static)
 	for (int i = 0; i < n; ++i) {
 		items[i].cls = -1; items[i].work = 0;
 		if (m <= 0 || qlen[i] <= 0 || tlen[i] <= 0 || B->early_out) continue;           // empty record (:57,81)
@@ -636,7 +640,7 @@ extern "C" ksw_b200_batch_t *ksw_b200_batch_upload(int n, const int *qlen, const
 		// the ranges of the caller's buffers this device's pairs reference
 		const int64_t np = (int64_t)lst.size();
 		int64_t qlo = INT64_MAX, qhi = 0, tlo = INT64_MAX, thi = 0, qsum = 0, tsum = 0;
-#pragma omp parallel for num_threads(host_threads()) schedule(static) reduction(min : qlo, tlo) reduction(max : qhi, thi) reduction(+ : qsum, tsum) if (np >= 4096)
+#pragma omp parallel for num_threads(threads_for(np, 65536)) schedule(static) reduction(min : qlo, tlo) reduction(max : qhi, thi) reduction(+ : qsum, tsum)
 		for (int64_t k = 0; k < np; ++k) {
 			const int i = lst[k];
 			qlo = std::min(qlo, qoff[i]); qhi = std::max(qhi, qoff[i] + qlen[i]); qsum += qlen[i];
@@ -1059,7 +1063,7 @@ extern "C" int64_t ksw_b200_result_export(const ksw_b200_result_t *R, ksw_extz_t
 	const int n = R->n;
 	const ksw_extz_t *src = (const ksw_extz_t *)R->ez.p;
 	const sd_stats_t *sst = R->has_stats ? (const sd_stats_t *)R->stats.p : nullptr;
-	const int nt = std::max(1, host_threads());
+	const int nt = threads_for(n, 8192);
 	std::vector<int64_t> part(nt + 1, 0);
 #pragma omp parallel num_threads(nt)
 	{

@@ -317,6 +317,24 @@ struct Leader {
 		st0_prev = b.st0;
 		return stop;
 	}
+	// end scores and z-drop as in fin(), for the leaderless kernels: every lane of the group runs it on identical inputs.
+	// Hst0_lazy: lazy H[st0] (only read on diagonals that end on the last query row).
+	__device__ __forceinline__ int fin_local(const Band &b, int r, int qe, int max_t, int32_t Hst0_lazy, int qlen, int tlen, int zdrop, int e)
+	{
+		const int R = qlen + tlen - 1;
+		const int32_t Hen0_true = Hen0_lazy - qe * r;
+		const int32_t maxH_true = gmax - qe * r;
+		if (b.en0 == tlen - 1 && Hen0_true > ez.mte) { ez.mte = Hen0_true; ez.mte_q = r - b.en; }          // :261-262
+		if (r - b.st0 == qlen - 1) {                                                                      // :263-264
+			const int32_t Hst0 = (b.st0 == b.en0) ? Hen0_true : Hst0_lazy - qe * r;
+			if (Hst0 > ez.mqe) { ez.mqe = Hst0; ez.mqe_t = b.st0; }
+		}
+		int stop = 0;
+		if (ez_apply_zdrop(ez, maxH_true, r, max_t, zdrop, e)) stop = 1;                                  // :265
+		else if (r == R - 1 && b.en0 == tlen - 1) ez.score = Hen0_true;                                   // :266-267
+		st0_prev = b.st0;
+		return stop;
+	}
 	__device__ __forceinline__ void store(PairResult *out, int n_diag) const
 	{
 		PairResult pr;

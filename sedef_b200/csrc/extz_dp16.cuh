@@ -447,6 +447,119 @@ extz_dp16_kernel(DpLaunch L)
 				__syncwarp();            // the leader read the dumps; the next diagonal overwrites them
 				continue;
 			}
+#ifndef EXTZ_NARROW_LEADER
+			// ---- exact maximum, LEADERLESS ----------------------------------------------------------------------------------
+			// The scalar bookkeeping of a pair (ez, the special H entries) is not done by one leader lane reaching into the
+			// other lanes' shared-memory rows between __syncwarp()s: every lane of the group keeps an IDENTICAL copy of the scalar
+			// state (same issue slots under SIMT), and the three H entries that need dynamic slot addressing -- H[en0], the old
+			// H[en0-1] it is computed from, the exited H[st0-1] -- are handled by the lane that OWNS the slot, on its own rows
+			// (program order, no barrier).  What crosses lanes travels in registers: the diagonal maximum (xor-reduction), H[en0]
+			// (one shuffle from its owner) and the old top H of the predecessor lane (one shuffle).  The only cross-lane
+			// shared-memory reads left are the arg-max passes.
+			const int en_c = b.en0 & (NS - 1);
+			const int en_owner = en_c >> 5;                                 // group-relative lane that owns slot en0
+			// old H of my block-B top slot as the reference reads it on this diagonal: the lazy row entry, or -- if that slot has
+			// left the band -- its TRUE H frozen at exit (stale read of :228), moved into the lazy domain of diagonal r-1
+			int32_t htop;
+			{
+				const int ttop = ls.t0[1] + 15;
+				htop = (ttop == ld.exit_slot) ? ld.exit_H + qe * (r - 1) : reinterpret_cast<const int32_t *>(Hrow)[((7 * 128) << 2) | 3];
+			}
+			const int32_t hcar = G == 1 ? htop : __shfl_sync(FULL, htop, pred_lane, G);
+			int32_t Hen0 = kNegInf;
+			int32_t lane_max = kNegInf;
+			if (act) {
+				auto hptr = [&](int t) -> int32_t * {                       // lazy-H entry of a slot THIS lane owns
+					const int i = t & 15, half = (t >> 4) & 1;
+					return reinterpret_cast<int32_t *>(Hrow) + ((((((i >> 2) << 1) | half) * 128) << 2) | (i & 3));
+				};
+				auto owns = [&](int t) { return G == 1 || ((t & (NS - 1)) >> 5) == gl; };
+				lane16_prepare<NS>(ls, b, r, last_en, qseq, tseq, tlen, table_saddr, sc16);
+				int32_t hprev = kNegInf;
+				if (r > 0) {
+					if (b.st0 > ld.st0_prev) {                              // slot st0-1 left the band: freeze its TRUE H, drop it from the max
+						const int xs = b.st0 - 1;
+						ld.exit_slot = xs;
+						if (owns(xs)) { int32_t *px = hptr(xs); ld.exit_H = *px - qe * (r - 1); *px = kNegInf; }
+					}
+					if (b.en0 > 0 && en_owner == gl) {                      // H[en0] is recomputed from the OLD H[en0-1] (:228)
+						const int ps = b.en0 - 1;
+						if ((en_c & 31) == 0) hprev = hcar;                 // en0 starts my block A: en0-1 is the predecessor lane's top slot
+						else hprev = (ps == ld.exit_slot) ? ld.exit_H + qe * (r - 1) : *hptr(ps);
+						*hptr(b.en0) = kNegInf;                             // the regular update below must not count for slot en0
+					}
+				}
+				lane_max = lane16_cells<kCigar, kRight>(ls, b, r, last_st, xin, vin, (uint4 *)(tbp + (int64_t)r * (NS >> 1)), Hrow, Urow, sc16);
+				if (en_owner == gl) {
+					if (r == 0) Hen0 = (int32_t)((ls.V[0] >> 8) & 0xffu) - 2 * qe;                        // :259
+					else if (b.en0 > 0) {
+						const int i = b.en0 & 15;
+						const uint32_t uw = reinterpret_cast<const uint32_t *>(Urow)[(((i >> 2) * 128) << 2) | (i & 3)];   // my own u' dump
+						Hen0 = hprev + (int32_t)(((b.en0 >> 4) & 1) ? (uw >> 24) : ((uw >> 8) & 0xffu));   // :228 in the lazy domain
+					} else Hen0 = *hptr(0);                                 // en0 == 0: the regular update (:228 else-arm)
+					if (r == 0 || b.en0 > 0) *hptr(b.en0) = Hen0;
+					lane_max = lane_max > Hen0 ? lane_max : Hen0;
+				}
+			}
+			ld.gmax = group_max<G>(lane_max);
+			ld.Hen0_lazy = G == 1 ? Hen0 : __shfl_sync(FULL, Hen0, en_owner, G);
+			int need = 0;
+			if (act) {
+				const int32_t maxH_true = ld.gmax - qe * r;
+				need = (maxH_true > ld.ez.max) || (sc.zdrop >= 0 && ld.ez.max - maxH_true > sc.zdrop);
+			}
+			const int32_t gm = ld.gmax;
+			int max_t = b.en0;
+			if (__any_sync(FULL, need)) {
+				__syncwarp();                                               // the passes below read other lanes' rows
+				uint32_t cnt = 0;
+				if (G == 1) { if (need) cnt = lane16_argmax_count(ls, Hrow, gm); }
+				else {
+					// Only a lane whose own maximum reaches gm can hold the arg-max.  With ONE such lane (the rule) the G lanes
+					// of the group split ITS 8 rows between them instead of every lane scanning its own 32 entries.
+					const bool cand = need && lane_max == gm;
+					const unsigned bal = __ballot_sync(FULL, cand);
+					const unsigned gmask = G == 32 ? bal : ((bal >> (lane_w & ~(G - 1))) & ((1u << (G & 31)) - 1u));
+					const int wl = gmask ? __ffs(gmask) - 1 : 0;
+					const int wt0a = __shfl_sync(FULL, ls.t0[0], wl, G), wt0b = __shfl_sync(FULL, ls.t0[1], wl, G);
+					if (need) {
+						if (__popc(gmask) == 1) cnt = group_argmax_count<G>(Hrow - gl, wl, wt0a, wt0b, gl, gm);
+						else cnt = lane16_argmax_count(ls, Hrow, gm);
+					}
+				}
+				cnt = group_sum_u<G>(cnt);
+				max_t = (int)(cnt & 0x00ffffffu);
+				const int tie = need && (cnt >> 24) != 1u;
+				if (__any_sync(FULL, tie)) {                                                      // real ties: exact 4-lane rule
+					uint32_t key = 0xffffffffu;
+					if (tie) {
+						key = lane16_argmax_key(b, Hrow, gm, ls.t0[0], ls.t0[1]);
+						if (gl == 0) { uint32_t k0 = ld.en0_key(b, r); key = k0 < key ? k0 : key; }
+					}
+					key = group_min_u<G>(key);
+					if (tie) max_t = tie_key_slot(key, b.en0);
+				}
+				__syncwarp();                                               // ... before the owners overwrite them on the next diagonal
+			}
+			// H[st0] when the diagonal ends on the last query row (:263-264): from its owner
+			const bool want_q = act && (r - b.st0 == qlen - 1) && b.st0 != b.en0;
+			int32_t Hst0_lazy = ld.Hen0_lazy;
+			if (__any_sync(FULL, want_q)) {
+				int32_t hs = 0;
+				if (want_q && (G == 1 || ((b.st0 & (NS - 1)) >> 5) == gl)) {
+					const int i = b.st0 & 15, half = (b.st0 >> 4) & 1;
+					hs = reinterpret_cast<const int32_t *>(Hrow)[(((((i >> 2) << 1) | half) * 128) << 2) | (i & 3)];
+				}
+				hs = G == 1 ? hs : __shfl_sync(FULL, hs, (b.st0 & (NS - 1)) >> 5, G);
+				if (want_q) Hst0_lazy = hs;
+			}
+			if (act) {
+				const int stop = ld.fin_local(b, r, qe, max_t, Hst0_lazy, qlen, tlen, sc.zdrop, sc.e);
+				n_diag = r + 1; last_st = b.st; last_en = b.en;
+				if (stop) alive = false;
+			}
+#else
+			// ---- exact maximum, one LEADER lane per group (the round-1 formulation; -DEXTZ_NARROW_LEADER for A/B builds) ----
 			if (act) {
 				lane16_prepare<NS>(ls, b, r, last_en, qseq, tseq, tlen, table_saddr, sc16);
 				if (gl == 0) ld.pre(rows, b, r, qe);
@@ -503,6 +616,7 @@ extz_dp16_kernel(DpLaunch L)
 			stop = __shfl_sync(FULL, stop, 0, G);
 			if (act) { n_diag = r + 1; last_st = b.st; last_en = b.en; if (stop) alive = false; }
 			__syncwarp();            // the arg-max passes read H; the next diagonal's leader writes it
+#endif
 		}
 		if (pi < L.n && gl == 0) { if (zdropped_band) ld.ez.zdropped = 1; ld.store(&L.results[pi], n_diag); }
 		__syncwarp();

@@ -462,8 +462,10 @@ extz_dp16_kernel(DpLaunch L)
 			// left the band -- its TRUE H frozen at exit (stale read of :228), moved into the lazy domain of diagonal r-1
 			int32_t htop;
 			{
+				// (the block may already have moved NS further up -- it slides on the diagonal its top slot exits -- hence both tests)
 				const int ttop = ls.t0[1] + 15;
-				htop = (ttop == ld.exit_slot) ? ld.exit_H + qe * (r - 1) : reinterpret_cast<const int32_t *>(Hrow)[((7 * 128) << 2) | 3];
+				htop = (ttop == ld.exit_slot || ttop - NS == ld.exit_slot) ? ld.exit_H + qe * (r - 1)
+				                                                            : reinterpret_cast<const int32_t *>(Hrow)[((7 * 128) << 2) | 3];
 			}
 			const int32_t hcar = G == 1 ? htop : __shfl_sync(FULL, htop, pred_lane, G);
 			int32_t Hen0 = kNegInf;

@@ -477,30 +477,34 @@ extz_dp16_kernel(DpLaunch L)
 				};
 				auto owns = [&](int t) { return G == 1 || ((t & (NS - 1)) >> 5) == gl; };
 				lane16_prepare<NS>(ls, b, r, last_en, qseq, tseq, tlen, table_saddr, sc16);
-				int32_t hprev = kNegInf;
+				// (written branch-free where it can be: the owner-only steps are predicated loads / stores on the lane's own rows)
+				const bool own_en = en_owner == gl;
+				const int ps = b.en0 - 1;
+				int32_t hprev = hcar;                                       // en0 starts my block A: en0-1 is the predecessor lane's top slot
 				if (r > 0) {
 					if (b.st0 > ld.st0_prev) {                              // slot st0-1 left the band: freeze its TRUE H, drop it from the max
 						const int xs = b.st0 - 1;
 						ld.exit_slot = xs;
 						if (owns(xs)) { int32_t *px = hptr(xs); ld.exit_H = *px - qe * (r - 1); *px = kNegInf; }
 					}
-					if (b.en0 > 0 && en_owner == gl) {                      // H[en0] is recomputed from the OLD H[en0-1] (:228)
-						const int ps = b.en0 - 1;
-						if ((en_c & 31) == 0) hprev = hcar;                 // en0 starts my block A: en0-1 is the predecessor lane's top slot
-						else hprev = (ps == ld.exit_slot) ? ld.exit_H + qe * (r - 1) : *hptr(ps);
+					if (own_en && b.en0 > 0) {                              // H[en0] is recomputed from the OLD H[en0-1] (:228)
+						if ((en_c & 31) != 0) hprev = (ps == ld.exit_slot) ? ld.exit_H + qe * (r - 1) : *hptr(ps);
 						*hptr(b.en0) = kNegInf;                             // the regular update below must not count for slot en0
 					}
 				}
 				lane_max = lane16_cells<kCigar, kRight>(ls, b, r, last_st, xin, vin, (uint4 *)(tbp + (int64_t)r * (NS >> 1)), Hrow, Urow, sc16);
-				if (en_owner == gl) {
-					if (r == 0) Hen0 = (int32_t)((ls.V[0] >> 8) & 0xffu) - 2 * qe;                        // :259
-					else if (b.en0 > 0) {
-						const int i = b.en0 & 15;
-						const uint32_t uw = reinterpret_cast<const uint32_t *>(Urow)[(((i >> 2) * 128) << 2) | (i & 3)];   // my own u' dump
-						Hen0 = hprev + (int32_t)(((b.en0 >> 4) & 1) ? (uw >> 24) : ((uw >> 8) & 0xffu));   // :228 in the lazy domain
-					} else Hen0 = *hptr(0);                                 // en0 == 0: the regular update (:228 else-arm)
-					if (r == 0 || b.en0 > 0) *hptr(b.en0) = Hen0;
-					lane_max = lane_max > Hen0 ? lane_max : Hen0;
+				{
+					const int i = b.en0 & 15;
+					const uint32_t uw = reinterpret_cast<const uint32_t *>(Urow)[(((i >> 2) * 128) << 2) | (i & 3)];       // my own u' dump
+					const int32_t ub = (int32_t)(((b.en0 >> 4) & 1) ? (uw >> 24) : ((uw >> 8) & 0xffu));
+					int32_t hen = hprev + ub;                                                              // :228 in the lazy domain
+					if (r == 0) hen = (int32_t)((ls.V[0] >> 8) & 0xffu) - 2 * qe;                          // :259
+					else if (b.en0 == 0) hen = *hptr(0);                    // en0 == 0: the regular update (:228 else-arm)
+					if (own_en) {
+						*hptr(b.en0) = hen;
+						Hen0 = hen;
+						lane_max = lane_max > hen ? lane_max : hen;
+					}
 				}
 			}
 			ld.gmax = group_max<G>(lane_max);

@@ -89,6 +89,28 @@ void trim_back(GuidedAlignment &g, const AlignParams &p = AlignParams());
 struct MergeRequest { GuidedAlignment prev, cur; const std::string *qstr, *rstr; };
 std::vector<GuidedAlignment> merge_batch(const std::vector<MergeRequest> &reqs, const AlignParams &p = AlignParams());
 
+// ---- the region-level driver ----------------------------------------------------------------
+// Everything fast_align does AFTER anchoring and chaining (src/chain.cc:249-265 + refine_chains, src/refine.cc:23-193), for MANY
+// regions at once, driven as WAVES of batched ksw_extz2 calls instead of one synchronous call per gap:
+//   wave 0      every chain of every region:   Alignment(query, ref, anchors, guide_idx)         (align_chains_batch)
+//   host        per region: sort, the refine DP over chain alignments, path extraction            (src/refine.cc:27-118)
+//   wave k      per region the next step of its current path: one Alignment::merge of two overlapping chain alignments
+//               (merge_batch) or the final Alignment(qstr, rstr, guide, SIDE_ALIGN) (align_hit_guides_batch); the steps of
+//               one region are sequential (a path's filters look at the hits accepted before it), regions advance together.
+// Anchors and chains come from the caller (SEDEF's own generate_anchors / chain_anchors, src/chain.cc:24-199): `guides` are the
+// chains that passed the filter of src/chain.cc:222-247, anchors in query order.  Results: per region the refined hits in the
+// order refine_chains leaves them, bit-identical to the reference.
+struct RegionTask {
+	const std::string *qstr, *rstr;
+	const std::vector<Anchor> *anchors;
+	std::vector<std::vector<int>> guides;
+	bool same_chr = false;                              // orig.query->name == orig.ref->name && same strand (src/refine.cc:29-30)
+	int orig_query_start = 0, orig_ref_start = 0;       // of the seed hit the region was cut from
+};
+struct RefineStats { int rounds = 0; long long batch_calls = 0, ksw_requests = 0; };
+std::vector<std::vector<GuidedAlignment>> refine_regions_batch(const std::vector<RegionTask> &regions, const AlignParams &p = AlignParams(),
+                                                              RefineStats *stats = nullptr);
+
 // Deferred-alignment queue: call sites push requests, the driver flushes a whole wave at once.
 class AlignQueue {
 public:

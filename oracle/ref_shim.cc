@@ -118,6 +118,44 @@ int ref_chain_guides(const char *query, const char *ref, int kmer_size, char *ou
 	memcpy(out, sres.c_str(), sres.size() + 1);
 	return n;
 }
+// One region as the region-level driver sees it: the reference's own anchors and (filtered) chains for a seed hit `orig`
+// (same chromosome or not, with its start coordinates), followed by what the reference's fast_align makes of the same region.
+//   "A q r l"                    one line per anchor (index = line order)
+//   "C n i0 i1 ..."              one line per chain that passes the filter of src/chain.cc:222-247: anchor indices in query order
+//   "H qs qe rs re cigar span matches mismatches gaps gap_bases"      one line per hit fast_align returns
+int ref_region(const char *query, const char *ref, int kmer_size, int same_chr, int orig_qs, int orig_rs, char *out, int cap)
+{
+	std::string q(query), r(ref);
+	auto qp = std::make_shared<Sequence>(same_chr ? "CHR" : "QRY", q);
+	auto rp = std::make_shared<Sequence>(same_chr ? "CHR" : "REF", r);
+	Hit orig{qp, orig_qs, orig_qs + (int)q.size(), rp, orig_rs, orig_rs + (int)r.size()};
+	auto anchors = generate_anchors(q, r, orig, kmer_size);
+	auto chains_init = chain_anchors(anchors);
+	auto &bounds = chains_init.second;
+	auto &chain = chains_init.first;
+	std::ostringstream os;
+	for (auto &a : anchors) os << "A " << a.q << ' ' << a.r << ' ' << a.l << '\n';
+	for (int bi = 1; bi < (int)bounds.size(); bi++) {                   // the loop of src/chain.cc:222-247, called, not changed
+		bool has_u = bounds[bi].second;
+		int be = bounds[bi].first, bs = bounds[bi - 1].first;
+		int qlo = anchors[chain[be - 1]].q, qhi = anchors[chain[bs]].q + anchors[chain[bs]].l;
+		int rlo = anchors[chain[be - 1]].r, rhi = anchors[chain[bs]].r + anchors[chain[bs]].l;
+		int span = std::max(rhi - rlo, qhi - qlo);
+		if ((!has_u || span < Globals::Chain::MIN_UPPERCASE_MATCH) &&
+		    span < Globals::Search::MIN_READ_SIZE * (1 - Globals::Search::MAX_ERROR)) continue;
+		os << "C " << (be - bs);
+		for (int k = be - 1; k >= bs; k--) os << ' ' << chain[k];
+		os << '\n';
+	}
+	std::vector<Hit> hits = fast_align(q, r, orig, kmer_size);
+	for (auto &h : hits)
+		os << "H " << h.query_start << ' ' << h.query_end << ' ' << h.ref_start << ' ' << h.ref_end << ' ' << h.aln.cigar_string() << ' '
+		   << h.aln.span() << ' ' << h.aln.matches() << ' ' << h.aln.mismatches() << ' ' << h.aln.gaps() << ' ' << h.aln.gap_bases() << '\n';
+	std::string sres = os.str();
+	if ((int)sres.size() + 1 > cap) return -1;
+	memcpy(out, sres.c_str(), sres.size() + 1);
+	return (int)hits.size();
+}
 // The final constructor of the refine wave: Alignment(qstr, rstr, vector<Hit> guide, side) (src/align.cc:107-197:
 // gap fills between consecutive hits, +-side extensions with trim_front / trim_back, src/align.cc:343-456), run on a
 // guide made of the reference's own chain alignments: the chains of the chain wave, sorted, greedily thinned to a

@@ -1,6 +1,8 @@
 // sedef_align.cc -- see include/sedef_align.hpp.  Host C++ on top of the C ABI; compiled into libsedef_b200.so.
 #include "../../../include/sedef_align.hpp"
 #include <algorithm>
+#include <functional>
+#include <tuple>
 #include <cstdlib>
 #include <cstring>
 #include <stdexcept>
@@ -521,6 +523,176 @@ std::vector<GuidedAlignment> merge_batch(const std::vector<MergeRequest> &reqs, 
 	}
 	std::vector<sd_stats_t> st = stats_of(finals, final_cigars);
 	for (size_t k = 0; k < reqs.size(); ++k) out[k].stats = st[k];
+	return out;
+}
+
+// ---- region-level driver ------------------------------------------------------------------------------------------
+namespace {
+// Globals::Chain::Refine (src/globals.h:80-86)
+const double kRefMatch = 10, kRefMismatch = 1, kRefGap = 0.5, kRefGapOpen = 100;
+const int kRefMinRead = 900, kRefSideAlign = 500, kRefMaxGap = 10 * 1000;
+
+struct RegionState {
+	std::vector<GuidedAlignment> anc;                   // chain alignments, sorted like refine_chains sorts its hits
+	std::vector<int> prev;
+	std::vector<std::pair<int, int>> order;             // (dp, index), descending: the `maxes` set of src/refine.cc:39
+	size_t mpos = 0;
+	std::vector<char> used;
+	std::vector<GuidedAlignment> accepted;
+	std::deque<int> path;
+	size_t pi = 0;
+	int prev_idx = -1;
+	std::vector<GuidedAlignment> guide;
+	enum Phase { NEXT_PATH, WALK, WAIT_MERGE, WAIT_GUIDE, DONE } phase = NEXT_PATH;
+};
+
+inline bool hit_less(const GuidedAlignment &a, const GuidedAlignment &b)        // Hit::operator< (src/hit.h:44-47)
+{
+	return std::tie(a.start_a, a.end_a, a.start_b, a.end_b) < std::tie(b.start_a, b.end_a, b.start_b, b.end_b);
+}
+
+// the dynamic program of refine_chains over one region's chain alignments (src/refine.cc:27-98)
+void refine_dp(const RegionTask &t, RegionState &st)
+{
+	std::sort(st.anc.begin(), st.anc.end(), hit_less);
+	const int n = (int)st.anc.size();
+	std::vector<int> score(n);
+	for (int i = 0; i < n; ++i)
+		score[i] = (int)(+kRefMatch * st.anc[i].matches() - kRefMismatch * st.anc[i].mismatches() - kRefGap * st.anc[i].gap_bases());
+	std::vector<int> dp(n, 0);
+	st.prev.assign(n, -1);
+	st.used.assign(n, 0);
+	for (int ai = 0; ai < n; ++ai) {
+		const GuidedAlignment &c = st.anc[ai];
+		if (t.same_chr) {
+			const int qlo = c.start_a, qhi = c.end_a, rlo = c.start_b, rhi = c.end_b;
+			const int qo = std::max(0, std::min(t.orig_query_start + qhi, t.orig_ref_start + rhi) - std::max(t.orig_query_start + qlo, t.orig_ref_start + rlo));
+			if ((rhi - rlo) - qo < kRefSideAlign && (qhi - qlo) - qo < kRefSideAlign) continue;       // no gap between
+		}
+		dp[ai] = score[ai];
+		for (int aj = ai - 1; aj >= 0; --aj) {
+			const GuidedAlignment &pv = st.anc[aj];
+			int cqs = c.start_a; if (cqs < pv.end_a) cqs = pv.end_a;
+			int crs = c.start_b; if (crs < pv.end_b) crs = pv.end_b;
+			if (pv.end_a >= c.end_a || pv.end_b >= c.end_b) continue;
+			if (pv.start_b >= c.start_b) continue;
+			const int ma = std::max(cqs - pv.end_a, crs - pv.end_b), mi = std::min(cqs - pv.end_a, crs - pv.end_b);
+			if (ma >= kRefMaxGap) continue;
+			if (t.same_chr) {
+				const int qlo = pv.end_a, qhi = cqs, rlo = pv.end_b, rhi = crs;
+				const int qo = std::max(0, std::min(t.orig_query_start + qhi, t.orig_ref_start + rhi) - std::max(t.orig_query_start + qlo, t.orig_ref_start + rlo));
+				if (qo >= 1) continue;
+			}
+			const int mis = (int)(kRefMismatch * mi), gap = (int)(kRefGapOpen + kRefGap * (ma - mi));
+			const int sco = dp[aj] + score[ai] - mis - gap;
+			if (sco >= dp[ai]) { dp[ai] = sco; st.prev[ai] = aj; }
+		}
+		st.order.push_back({dp[ai], ai});
+	}
+	std::sort(st.order.begin(), st.order.end(), std::greater<std::pair<int, int>>());    // set<..., greater<>>: keys are unique (index)
+}
+
+// advance one region until it needs an alignment (returns true and fills the request) or is done
+struct Request { int kind; MergeRequest merge; HitGuide hg; };     // kind 1 = merge, 2 = final guide constructor
+bool advance(const RegionTask &t, RegionState &st, Request &rq)
+{
+	for (;;) {
+		if (st.phase == RegionState::DONE) return false;
+		if (st.phase == RegionState::NEXT_PATH) {
+			if (st.mpos >= st.order.size() || st.order[st.mpos].first == 0) { st.phase = RegionState::DONE; return false; }   // src/refine.cc:104-105
+			int maxi = st.order[st.mpos++].second;
+			if (st.used[maxi]) continue;
+			st.path.clear();
+			while (maxi != -1 && !st.used[maxi]) { st.path.push_front(maxi); st.used[maxi] = 1; maxi = st.prev[maxi]; }
+			const int qlo = st.anc[st.path.front()].start_a, qhi = st.anc[st.path.back()].end_a;
+			const int rlo = st.anc[st.path.front()].start_b, rhi = st.anc[st.path.back()].end_b;
+			int est_size = st.anc[st.path[0]].span();
+			for (size_t i = 1; i < st.path.size(); ++i) {
+				est_size += st.anc[st.path[i]].span();
+				est_size += std::max(st.anc[st.path[i]].start_a - st.anc[st.path[i - 1]].end_a, st.anc[st.path[i]].start_b - st.anc[st.path[i - 1]].end_b);
+			}
+			if (est_size < kRefMinRead - kRefSideAlign) continue;                                        // src/refine.cc:142-146
+			bool overlap = false;
+			for (auto &h : st.accepted) {                                                                 // src/refine.cc:148-160
+				const int qo = std::max(0, std::min(qhi, h.end_a) - std::max(qlo, h.start_a));
+				const int ro = std::max(0, std::min(rhi, h.end_b) - std::max(rlo, h.start_b));
+				if (qhi - qlo - qo < kRefSideAlign && rhi - rlo - ro < kRefSideAlign) { overlap = true; break; }
+			}
+			if (overlap) continue;
+			st.guide.clear();
+			st.prev_idx = st.path[0]; st.pi = 1;
+			st.phase = RegionState::WALK;
+		}
+		if (st.phase == RegionState::WALK) {                                                              // src/refine.cc:167-179
+			while (st.pi < st.path.size()) {
+				const GuidedAlignment &cur = st.anc[st.path[st.pi]];
+				const GuidedAlignment &pv = st.anc[st.prev_idx];
+				if (cur.start_a < pv.end_a || cur.start_b < pv.end_b) {
+					rq.kind = 1; rq.merge = MergeRequest{pv, cur, t.qstr, t.rstr};
+					st.phase = RegionState::WAIT_MERGE;
+					return true;
+				}
+				st.guide.push_back(pv);
+				st.prev_idx = st.path[st.pi++];
+			}
+			st.guide.push_back(st.anc[st.prev_idx]);
+			rq.kind = 2; rq.hg = HitGuide{t.qstr, t.rstr, st.guide, kRefSideAlign};
+			st.phase = RegionState::WAIT_GUIDE;
+			return true;
+		}
+		return false;   // WAIT_*: the caller has not delivered the result yet
+	}
+}
+} // namespace
+
+std::vector<std::vector<GuidedAlignment>> refine_regions_batch(const std::vector<RegionTask> &regions, const AlignParams &p, RefineStats *stats)
+{
+	RefineStats rs;
+	// wave 0: every chain of every region through one batched call
+	std::vector<ChainGuide> chains;
+	std::vector<size_t> owner;
+	for (size_t ri = 0; ri < regions.size(); ++ri)
+		for (auto &g : regions[ri].guides) { chains.push_back(ChainGuide{regions[ri].qstr, regions[ri].rstr, regions[ri].anchors, g}); owner.push_back(ri); }
+	std::vector<GuidedAlignment> wave0 = align_chains_batch(chains, p);
+	rs.batch_calls += 2; rs.ksw_requests += (long long)chains.size(); rs.rounds = 1;
+	std::vector<RegionState> st(regions.size());
+	for (size_t k = 0; k < wave0.size(); ++k) st[owner[k]].anc.push_back(std::move(wave0[k]));
+	for (size_t ri = 0; ri < regions.size(); ++ri) refine_dp(regions[ri], st[ri]);
+	// waves 1..: every region contributes the next step of its current path
+	for (;;) {
+		std::vector<MergeRequest> merges; std::vector<size_t> merge_owner;
+		std::vector<HitGuide> guides; std::vector<size_t> guide_owner;
+		for (size_t ri = 0; ri < regions.size(); ++ri) {
+			Request rq;
+			if (!advance(regions[ri], st[ri], rq)) continue;
+			if (rq.kind == 1) { merges.push_back(std::move(rq.merge)); merge_owner.push_back(ri); }
+			else { guides.push_back(std::move(rq.hg)); guide_owner.push_back(ri); }
+		}
+		if (merges.empty() && guides.empty()) break;
+		++rs.rounds;
+		if (!merges.empty()) {
+			std::vector<GuidedAlignment> done = merge_batch(merges, p);
+			rs.batch_calls += 2; rs.ksw_requests += (long long)merges.size();
+			for (size_t k = 0; k < done.size(); ++k) {
+				RegionState &s = st[merge_owner[k]];
+				s.anc[s.prev_idx] = std::move(done[k]);                                                   // prev->aln.merge(...); update_from_alignment(*prev)
+				++s.pi;
+				s.phase = RegionState::WALK;
+			}
+		}
+		if (!guides.empty()) {
+			std::vector<GuidedAlignment> done = align_hit_guides_batch(guides, p);
+			rs.batch_calls += 2; rs.ksw_requests += (long long)guides.size();
+			for (size_t k = 0; k < done.size(); ++k) {
+				RegionState &s = st[guide_owner[k]];
+				if (done[k].span() >= kRefMinRead) s.accepted.push_back(std::move(done[k]));                  // src/refine.cc:186-191
+				s.phase = RegionState::NEXT_PATH;
+			}
+		}
+	}
+	std::vector<std::vector<GuidedAlignment>> out(regions.size());
+	for (size_t ri = 0; ri < regions.size(); ++ri) out[ri] = std::move(st[ri].accepted);
+	if (stats) *stats = rs;
 	return out;
 }
 

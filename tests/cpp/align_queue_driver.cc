@@ -33,6 +33,42 @@ static int run_chains()
 	return 0;
 }
 
+// mode "regions": any number of regions, each: "R same_chr orig_qs orig_rs" / query / reference / "A q r l" anchor lines /
+// "C n i0 i1 ..." chain lines / "E".  ALL regions go through ONE refine_regions_batch call.  Output per region: "R k" then one
+// "H qs qe rs re cigar span matches mismatches gaps gap_bases" line per refined hit; last line "S rounds batch_calls requests".
+static int run_regions()
+{
+	struct Reg { std::string q, r; std::vector<sedef_b200::Anchor> anchors; sedef_b200::RegionTask t; };
+	std::vector<Reg *> regs;
+	std::string line;
+	Reg *cur = nullptr;
+	while (std::getline(std::cin, line)) {
+		if (line.empty()) continue;
+		std::istringstream is(line);
+		char tag; is >> tag;
+		if (tag == 'R') {
+			cur = new Reg(); regs.push_back(cur);
+			int sc; is >> sc >> cur->t.orig_query_start >> cur->t.orig_ref_start; cur->t.same_chr = sc != 0;
+			std::getline(std::cin, cur->q); std::getline(std::cin, cur->r);
+		} else if (tag == 'A') { sedef_b200::Anchor a{}; is >> a.q >> a.r >> a.l; cur->anchors.push_back(a); }
+		else if (tag == 'C') { int n; is >> n; std::vector<int> g(n); for (int &x : g) is >> x; cur->t.guides.push_back(g); }
+	}
+	std::vector<sedef_b200::RegionTask> tasks;
+	for (Reg *r : regs) { r->t.qstr = &r->q; r->t.rstr = &r->r; r->t.anchors = &r->anchors; tasks.push_back(r->t); }
+	sedef_b200::RefineStats st;
+	std::vector<std::vector<sedef_b200::GuidedAlignment>> res;
+	try { res = sedef_b200::refine_regions_batch(tasks, sedef_b200::AlignParams(), &st); }
+	catch (const std::exception &e) { fprintf(stderr, "error: %s\n", e.what()); return 2; }
+	for (size_t k = 0; k < res.size(); ++k) {
+		printf("R %zu\n", k);
+		for (auto &a : res[k])
+			printf("H %d %d %d %d %s %d %d %d %d %d\n", a.start_a, a.end_a, a.start_b, a.end_b, a.cigar_string().c_str(), a.span(), a.matches(),
+			       a.mismatches(), a.gaps(), a.gap_bases());
+	}
+	printf("S %d %lld %lld\n", st.rounds, st.batch_calls, st.ksw_requests);
+	return 0;
+}
+
 // mode "hitguide": line 1 = query region, line 2 = reference region, line 3 = side, then one guide hit per line:
 // query_start query_end ref_start ref_end cigar
 static int run_hitguide()
@@ -89,6 +125,7 @@ static int run_merge()
 
 int main(int argc, char **argv)
 {
+	if (argc > 1 && std::string(argv[1]) == "regions") return run_regions();
 	if (argc > 1 && std::string(argv[1]) == "merge") return run_merge();
 	if (argc > 1 && std::string(argv[1]) == "chains") return run_chains();
 	if (argc > 1 && std::string(argv[1]) == "hitguide") return run_hitguide();

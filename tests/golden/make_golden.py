@@ -190,7 +190,23 @@ def main():
         mregs.append(dict(length=L, div=div, seed=seed, n_merges=n, text=buf.value.decode()))
     json.dump(dict(source="oracle/_ref/libsedef_ref.so: reference Alignment::merge (src/align.cc:505-610); per pair: P prev, C cur, M merged",
                    regions=mregs), open(os.path.join(HERE, "merge_golden.json"), "w"))
-    for f in ("ksw2_kat.json", "ksw2_golden.json", "sd_stats_golden.json", "fast_align_golden.json", "chain_wave_golden.json",
+    # ---- region golden: the reference's anchors + filtered chains (the region-level driver's input) and its fast_align hits ----
+    slib.ref_region.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int]
+    rregs = []
+    for (L, div, seed, same, qs0, rs0) in [(2500, 0.03, 11, 0, 0, 0), (6000, 0.06, 12, 0, 0, 0), (9000, 0.10, 13, 0, 0, 0), (5000, 0.2, 14, 0, 0, 0),
+                                           (7000, 0.3, 16, 0, 0, 0), (12000, 0.15, 18, 0, 0, 0), (20000, 0.08, 19, 0, 0, 0),
+                                           (6000, 0.06, 12, 1, 100000, 140000), (9000, 0.10, 13, 1, 5000, 9000), (12000, 0.15, 18, 1, 0, 6000),
+                                           (8000, 0.05, 21, 1, 1000, 1400), (15000, 0.12, 22, 0, 0, 0), (4000, 0.25, 23, 0, 0, 0)]:
+        qs, ts = synth.make_region_pair(L, div, seed=seed)
+        buf = C.create_string_buffer(1 << 24)
+        n = slib.ref_region(qs.encode(), ts.encode(), 11, same, qs0, rs0, buf, len(buf))
+        assert n >= 0
+        rregs.append(dict(length=L, div=div, seed=seed, same_chr=same, orig_qs=qs0, orig_rs=rs0, n_hits=n, text=buf.value.decode()))
+    json.dump(dict(source="oracle/_ref/libsedef_ref.so: reference generate_anchors + chain_anchors (+ the chain filter of src/chain.cc:222-247) "
+                          "and fast_align (src/chain.cc:203-268) on synth.make_region_pair(length, div, seed=seed) for a seed hit with the given "
+                          "same_chr / origin; lines: 'A q r l' anchors, 'C n i...' chains (anchor indices), 'H ...' hits",
+                   regions=rregs), open(os.path.join(HERE, "region_golden.json"), "w"))
+    for f in ("region_golden.json", "ksw2_kat.json", "ksw2_golden.json", "sd_stats_golden.json", "fast_align_golden.json", "chain_wave_golden.json",
               "hit_guide_golden.json", "merge_golden.json"):
         print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")
 

@@ -1,7 +1,10 @@
 // tests/cpp/align_queue_driver.cc -- exercises the C++ host layer (include/sedef_align.hpp) from C++, no Python:
 // reads "fa fb [cigar]" lines on stdin, pushes them through AlignQueue / from_cigar_batch, prints one line per
 // request: cigar span matches mismatches gaps gap_bases indel_a indel_b alnB matchB mismatchB ts tv upA upB upM total_error(.1f)
+#include <chrono>
 #include <cstdio>
+#include <cstdlib>
+#include <algorithm>
 #include <iostream>
 #include <sstream>
 #include <string>
@@ -57,8 +60,18 @@ static int run_regions()
 	for (Reg *r : regs) { r->t.qstr = &r->q; r->t.rstr = &r->r; r->t.anchors = &r->anchors; tasks.push_back(r->t); }
 	sedef_b200::RefineStats st;
 	std::vector<std::vector<sedef_b200::GuidedAlignment>> res;
-	try { res = sedef_b200::refine_regions_batch(tasks, sedef_b200::AlignParams(), &st); }
+	double best_ms = 1e30;
+	const char *reps_env = getenv("REGIONS_REPS");
+	const int reps = reps_env ? atoi(reps_env) : 1;
+	try {
+		for (int rep = 0; rep < reps; ++rep) {
+			auto t0 = std::chrono::steady_clock::now();
+			res = sedef_b200::refine_regions_batch(tasks, sedef_b200::AlignParams(), &st);
+			best_ms = std::min(best_ms, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+		}
+	}
 	catch (const std::exception &e) { fprintf(stderr, "error: %s\n", e.what()); return 2; }
+	fprintf(stderr, "refine_regions_batch: %zu regions, best of %d: %.2f ms\n", tasks.size(), reps, best_ms);
 	for (size_t k = 0; k < res.size(); ++k) {
 		printf("R %zu\n", k);
 		for (auto &a : res[k])

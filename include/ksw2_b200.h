@@ -184,6 +184,13 @@ int ksw_extz2_batch_arena(int n, const int *qlen, const int64_t *qoff, const uin
                           ksw_b200_result_t **out);
 const ksw_extz_t *ksw_b200_result_ez(const ksw_b200_result_t *r);        /* [n] */
 const sd_stats_t *ksw_b200_result_stats(const ksw_b200_result_t *r);     /* [n], or NULL when not requested / SCORE_ONLY */
+/* Per pair two ints computed on the same traceback walk as the statistics: the maximum-suffix / maximum-prefix scans of
+ * Alignment::trim_front / trim_back (src/align.cc:343-456) with the ALIGNMENT scoring (mat[0], mat[1], gap open, gap extend):
+ *   [2i]   trim_front's max_i = leading alignment columns to drop; -1 when no suffix scores >= 0 (the reference then keeps its
+ *          initial max_i = a.size(), sic)
+ *   [2i+1] columns trim_back keeps (its max_i + 1); -1 when no prefix scores >= 0 (the alignment is cleared)
+ * NULL when statistics were not requested. */
+const int32_t *ksw_b200_result_trims(const ksw_b200_result_t *r);
 int  ksw_b200_result_count(const ksw_b200_result_t *r);
 void ksw_b200_result_io(const ksw_b200_result_t *r, int64_t *h2d, int64_t *d2h, int *launches);
 void ksw_b200_result_free(ksw_b200_result_t *r);

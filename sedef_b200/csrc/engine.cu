@@ -320,8 +320,8 @@ struct SubBatch {
 	std::vector<Wave> waves;
 	int class_first[kNumClasses + 1] = {0};
 	size_t arena_bytes = 0;             // bytes of one sequence plane on the device (codes; same size for the original-case plane)
-	PinBuf h_stage[2], h_recs, h_stats, h_pairs;
-	DevBuf d_arena, d_raw, d_pairs, d_results, d_tb, d_cigar, d_stats, d_misc, d_table, d_ez;
+	PinBuf h_stage[2], h_recs, h_stats, h_trims, h_pairs;
+	DevBuf d_arena, d_raw, d_pairs, d_results, d_tb, d_cigar, d_stats, d_trims, d_misc, d_table, d_ez;
 	size_t cigar_cap = 0;               // entries
 	unsigned long long cigar_used = 0;
 	cudaStream_t stream = nullptr;      // every batch owns a stream so that the H2D of one batch overlaps the kernels of another
@@ -344,9 +344,9 @@ struct SubBatch {
 		if (stream && touched) cudaStreamSynchronize(stream);
 		drop_events();
 		for (auto &b : h_stage) b.release();
-		h_recs.release(); h_stats.release(); h_pairs.release();
+		h_recs.release(); h_stats.release(); h_trims.release(); h_pairs.release();
 		d_arena.release(); d_raw.release(); d_pairs.release(); d_results.release(); d_tb.release();
-		d_cigar.release(); d_stats.release(); d_misc.release(); d_table.release(); d_ez.release();
+		d_cigar.release(); d_stats.release(); d_trims.release(); d_misc.release(); d_table.release(); d_ez.release();
 		for (auto &e : ev) if (e) { cudaEventDestroy(e); e = nullptr; }
 		if (stream) { cudaStreamDestroy(stream); stream = nullptr; }
 	}
@@ -375,11 +375,11 @@ struct ksw_b200_batch {
 struct ksw_b200_result {
 	int n = 0;
 	bool has_stats = false;
-	PinBuf ez, stats;
+	PinBuf ez, stats, trims;            // trims: {trim_front max_i | -1, trim_back kept columns | -1} per pair, with the statistics
 	std::vector<PinBuf> cigars;         // one compact CIGAR arena per (chunk, device)
 	int64_t h2d = 0, d2h = 0;
 	int launches = 0;
-	void release() { ez.release(); stats.release(); for (auto &c : cigars) c.release(); cigars.clear(); }
+	void release() { ez.release(); stats.release(); trims.release(); for (auto &c : cigars) c.release(); cigars.clear(); }
 };
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -803,8 +803,11 @@ static int launch_sub(ksw_b200_batch &B, SubBatch &sb)
 	const bool stats_on = cigar && B.want_stats;
 	const size_t n_stats = by_orig(B) ? (size_t)B.n : sb.pairs.size();
 	if (stats_on) {
-		if (sb.d_stats.ensure(n_stats * sizeof(sd_stats_t))) return fail(KSW_B200_ERR_NOMEM, "stats allocation failed");
-		if (by_orig(B) && B.n_empty) CUDA_TRY(cudaMemsetAsync(sb.d_stats.p, 0, n_stats * sizeof(sd_stats_t), st));   // pairs no kernel sees
+		if (sb.d_stats.ensure(n_stats * sizeof(sd_stats_t)) || sb.d_trims.ensure(n_stats * 8)) return fail(KSW_B200_ERR_NOMEM, "stats allocation failed");
+		if (by_orig(B) && B.n_empty) {                                          // pairs no kernel sees
+			CUDA_TRY(cudaMemsetAsync(sb.d_stats.p, 0, n_stats * sizeof(sd_stats_t), st));
+			CUDA_TRY(cudaMemsetAsync(sb.d_trims.p, 0xff, n_stats * 8, st));
+		}
 	}
 	// descriptors carry tb offsets -> (re)upload
 	// (staged through pinned memory: a pageable source would make this call wait for the sequence copies queued before it)
@@ -856,6 +859,8 @@ static int launch_sub(ksw_b200_batch &B, SubBatch &sb)
 			TL.cigar_arena = (uint32_t *)sb.d_cigar.p; TL.cigar_cursor = d_cursor; TL.cigar_capacity = sb.cigar_cap;
 			TL.stats_by_orig = by_orig(B) ? 1 : 0;
 			TL.stats = stats_on ? (sd_stats_t *)sb.d_stats.p + (TL.stats_by_orig ? 0 : wv.first) : nullptr;
+			TL.trims = stats_on ? (int32_t *)sb.d_trims.p + 2 * (size_t)(TL.stats_by_orig ? 0 : wv.first) : nullptr;
+			TL.t_match = B.mat[0]; TL.t_mismatch = B.mat[1]; TL.t_gapo = B.q; TL.t_gape = B.e;
 			TL.overflow = d_overflow;
 			TL.n = wv.count; TL.NS = class_ns(c); TL.flag = B.flag; TL.packed = class_packed(c) ? 1 : 0;
 			cudaStream_t tbs = sb.dc->tb_stream;
@@ -958,15 +963,16 @@ static int fetch_into(ksw_b200_batch &B, ksw_b200_result &R, int s0)
 	B.t_d2h = B.t_gather = 0;
 	ksw_extz_t *ez = (ksw_extz_t *)R.ez.p + s0;
 	sd_stats_t *stats = R.has_stats ? (sd_stats_t *)R.stats.p + s0 : nullptr;
+	int32_t *trims = R.has_stats ? (int32_t *)R.trims.p + 2 * (size_t)s0 : nullptr;
 	const bool one = by_orig(B);
 	bool any = false;
 	for (auto &sb : B.subs) any = any || !sb.pairs.empty();
 	if (!one || !any) {                                                           // records no device will write
 		const double t0 = now_ms();
 		if (!any || B.n_empty) for (int i = 0; i < B.n; ++i) if (!any || B.is_empty[i]) reset_ez(&ez[i]);
-		if (stats && (!any || B.n_empty || !stats_on)) memset(stats, 0, sizeof(sd_stats_t) * (size_t)B.n);
+		if (stats && (!any || B.n_empty || !stats_on)) { memset(stats, 0, sizeof(sd_stats_t) * (size_t)B.n); memset(trims, 0xff, 8 * (size_t)B.n); }
 		B.t_gather += now_ms() - t0;
-	} else if (stats && !stats_on) memset(stats, 0, sizeof(sd_stats_t) * (size_t)B.n);
+	} else if (stats && !stats_on) { memset(stats, 0, sizeof(sd_stats_t) * (size_t)B.n); memset(trims, 0xff, 8 * (size_t)B.n); }
 	const double t_f0 = now_ms();
 	for (auto &sb : B.subs) {
 		if (sb.pairs.empty()) continue;
@@ -992,15 +998,17 @@ static int fetch_into(ksw_b200_batch &B, ksw_b200_result &R, int s0)
 			CUDA_TRY(cudaMemcpyAsync(ez, sb.d_ez.p, nrec * sizeof(ksw_extz_t), cudaMemcpyDeviceToHost, st));
 			if (stats_on) {
 				CUDA_TRY(cudaMemcpyAsync(stats, sb.d_stats.p, nrec * sizeof(sd_stats_t), cudaMemcpyDeviceToHost, st));
-				sb.d2h_bytes += nrec * sizeof(sd_stats_t);
+				CUDA_TRY(cudaMemcpyAsync(trims, sb.d_trims.p, nrec * 8, cudaMemcpyDeviceToHost, st));
+				sb.d2h_bytes += nrec * (sizeof(sd_stats_t) + 8);
 			}
 		} else {
 			if (sb.h_recs.ensure(np * sizeof(ksw_extz_t))) return fail(KSW_B200_ERR_NOMEM, "pinned record buffer");
 			CUDA_TRY(cudaMemcpyAsync(sb.h_recs.p, sb.d_ez.p, np * sizeof(ksw_extz_t), cudaMemcpyDeviceToHost, st));
 			if (stats_on) {
-				if (sb.h_stats.ensure(np * sizeof(sd_stats_t))) return fail(KSW_B200_ERR_NOMEM, "pinned stats buffer");
+				if (sb.h_stats.ensure(np * sizeof(sd_stats_t)) || sb.h_trims.ensure(np * 8)) return fail(KSW_B200_ERR_NOMEM, "pinned stats buffer");
 				CUDA_TRY(cudaMemcpyAsync(sb.h_stats.p, sb.d_stats.p, np * sizeof(sd_stats_t), cudaMemcpyDeviceToHost, st));
-				sb.d2h_bytes += np * sizeof(sd_stats_t);
+				CUDA_TRY(cudaMemcpyAsync(sb.h_trims.p, sb.d_trims.p, np * 8, cudaMemcpyDeviceToHost, st));
+				sb.d2h_bytes += np * (sizeof(sd_stats_t) + 8);
 			}
 		}
 	}
@@ -1016,11 +1024,12 @@ static int fetch_into(ksw_b200_batch &B, ksw_b200_result &R, int s0)
 			const int64_t np = (int64_t)sb.pairs.size();
 			const ksw_extz_t *rec = (const ksw_extz_t *)sb.h_recs.p;
 			const sd_stats_t *hst = (const sd_stats_t *)sb.h_stats.p;
+			const int64_t *htr = (const int64_t *)sb.h_trims.p;
 #pragma omp parallel for num_threads(host_threads()) schedule(static) if (np >= 4096)
 			for (int64_t k = 0; k < np; ++k) {
 				const int i = sb.pairs[k].orig;
 				ez[i] = rec[k];
-				if (stats_on) stats[i] = hst[k];
+				if (stats_on) { stats[i] = hst[k]; ((int64_t *)trims)[i] = htr[k]; }
 			}
 		}
 		B.t_gather += now_ms() - t_g0;
@@ -1033,7 +1042,7 @@ static ksw_b200_result *result_new(int n, bool with_stats, int *err)
 	ksw_b200_result *R = new ksw_b200_result();
 	R->n = n; R->has_stats = with_stats;
 	if (R->ez.ensure(std::max<size_t>(1, (size_t)n) * sizeof(ksw_extz_t)) ||
-	    (with_stats && R->stats.ensure(std::max<size_t>(1, (size_t)n) * sizeof(sd_stats_t)))) {
+	    (with_stats && (R->stats.ensure(std::max<size_t>(1, (size_t)n) * sizeof(sd_stats_t)) || R->trims.ensure(std::max<size_t>(1, (size_t)n) * 8)))) {
 		R->release(); delete R;
 		if (err) *err = fail(KSW_B200_ERR_NOMEM, "pinned result arena allocation failed");
 		return nullptr;
@@ -1043,6 +1052,7 @@ static ksw_b200_result *result_new(int n, bool with_stats, int *err)
 extern "C" void ksw_b200_result_free(ksw_b200_result_t *R) { if (R) { R->release(); delete R; } }
 extern "C" const ksw_extz_t *ksw_b200_result_ez(const ksw_b200_result_t *R) { return R ? (const ksw_extz_t *)R->ez.p : nullptr; }
 extern "C" const sd_stats_t *ksw_b200_result_stats(const ksw_b200_result_t *R) { return (R && R->has_stats) ? (const sd_stats_t *)R->stats.p : nullptr; }
+extern "C" const int32_t *ksw_b200_result_trims(const ksw_b200_result_t *R) { return (R && R->has_stats) ? (const int32_t *)R->trims.p : nullptr; }
 extern "C" int ksw_b200_result_count(const ksw_b200_result_t *R) { return R ? R->n : 0; }
 extern "C" void ksw_b200_result_io(const ksw_b200_result_t *R, int64_t *h2d, int64_t *d2h, int *launches)
 {

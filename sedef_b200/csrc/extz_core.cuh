@@ -217,7 +217,8 @@ struct StatAcc {
 EXTZ_HD int up(int c) { return (c >= 'a' && c <= 'z') ? c - 32 : c; }          // toupper, C locale
 EXTZ_HD bool isup(int c) { return c >= 'A' && c <= 'Z'; }                       // isupper, C locale
 // one gap-free column (a = query byte, b = target byte, original case)
-EXTZ_HD void stat_match_col(StatAcc &s, int ca, int cb)
+// returns ceq(a, b): the column is a '|' of Alignment::alignment
+EXTZ_HD bool stat_match_col(StatAcc &s, int ca, int cb)
 {
 	int ua = up(ca), ub = up(cb);
 	s.span++; s.alnB++;
@@ -232,6 +233,7 @@ EXTZ_HD void stat_match_col(StatAcc &s, int ca, int cb)
 		if (ua == 'A' || ua == 'G') { s.transitionsB += bpur; s.transversionsB += !bpur; }
 		else { bool bpyr = (ub == 'C' || ub == 'T'); s.transitionsB += bpyr; s.transversionsB += !bpyr; }
 	} else if (isup(ca) && isup(cb)) s.uppercaseMatches++;           // :267-269
+	return ceq;
 }
 // column consuming only the query (ksw I, SEDEF 'D': align_b = '-')
 EXTZ_HD void stat_qonly_col(StatAcc &s, int ca)
@@ -245,6 +247,46 @@ EXTZ_HD void stat_tonly_col(StatAcc &s, int cb)
 {
 	s.span++; s.gap_bases++; s.indel_a++;
 	s.uppercaseB += (up(cb) != 'N' && isup(cb));
+}
+
+// ---- Alignment::trim_front / trim_back (src/align.cc:343-456) fused into the traceback walk ------------------------------
+// Both are maximum-prefix scans over the alignment's columns with the ALIGNMENT scoring (match, mismatch; a gap run pays
+// `open` once plus `ext` per column).  The traceback visits the columns from the LAST to the first, which is trim_front's own
+// scan order.  trim_back scans forward; its prefix score up to column i is total - S(i+1), where S(j) = forward score of columns
+// j..n-1 -- accumulated on the same backward walk, with the open of a gap run added when the walk LEAVES the run (forward, the
+// open belongs to the run's first column) -- so the best prefix is the smallest S, at the largest j on ties.
+struct TrimAcc {
+	int32_t score_f, max_f, kf;      // trim_front: running score, best score, visit number of the best column (-1: never)
+	int32_t S, minS, kmin;           // trim_back: S(j) for j = n - k, its minimum and where
+	int32_t prev, k;                 // type of the previously visited column (0 M, 1 a-gap, 2 b-gap, -1 none), columns visited
+	int32_t match, mismatch, open, ext;
+};
+EXTZ_HD void trim_reset(TrimAcc &t, int match, int mismatch, int gap_open, int gap_extend)
+{
+	t.score_f = 0; t.max_f = 0; t.kf = -1; t.S = 0; t.minS = 0x7fffffff; t.kmin = 0; t.prev = -1; t.k = 0;
+	t.match = match; t.mismatch = mismatch; t.open = -gap_open; t.ext = -gap_extend;
+}
+// one visited column: type 0 = both bases (is_match = ceq), 1 = align_a is '-' (target only), 2 = align_b is '-' (query only)
+EXTZ_HD void trim_col(TrimAcc &t, int type, bool is_match)
+{
+	// trim_back: the column to the right closed a gap run if this one is of another type -> its open is now known
+	if (t.prev > 0 && type != t.prev) t.S += t.open;
+	if (t.S < t.minS) { t.minS = t.S; t.kmin = t.k; }                  // candidate j = n - k (k = 0: keep everything)
+	const int32_t own = type == 0 ? (is_match ? t.match : t.mismatch) : t.ext;
+	t.S += own;
+	// trim_front (src/align.cc:347-365): a gap column pays the open when the column to its right is not the same kind of gap
+	t.score_f += own + ((type != 0 && type != t.prev) ? t.open : 0);
+	if (t.score_f >= t.max_f) { t.max_f = t.score_f; t.kf = t.k; }
+	t.prev = type; ++t.k;
+}
+// front: max_i of trim_front (leading columns to drop), or -1 when no suffix scores >= 0 (the reference then keeps its
+//        initial max_i = a.size(), sic); back: columns trim_back keeps (max_i + 1), or -1 when no prefix scores >= 0
+EXTZ_HD void trim_finish(TrimAcc &t, int32_t &front, int32_t &back)
+{
+	if (t.prev > 0) t.S += t.open;                                      // column 0 starts its run (i == 0)
+	const int32_t n = t.k;
+	front = t.kf < 0 ? -1 : n - 1 - t.kf;
+	back = (n > 0 && t.S - t.minS >= 0) ? n - t.kmin : -1;
 }
 
 } // namespace extz

@@ -39,6 +39,8 @@ extz_traceback_kernel(TbLaunch L)
 	StatAcc sa;
 	sa.span = sa.gap_bases = sa.matches = sa.mismatches = sa.indel_a = sa.indel_b = sa.alnB = sa.matchB = 0;
 	sa.mismatchB = sa.transitionsB = sa.transversionsB = sa.uppercaseA = sa.uppercaseB = sa.uppercaseMatches = 0;
+	TrimAcc ta;                                                     // trim_front / trim_back scans ride on the same walk
+	trim_reset(ta, L.t_match, L.t_mismatch, L.t_gapo, L.t_gape);
 
 	int i0, j0; bool run = true;                                   // extern/ksw2_extz2_sse.cc:290-295
 	if (!pr.zdropped && !(L.flag & kFlagExtzOnly)) { i0 = tlen - 1; j0 = qlen - 1; }
@@ -83,25 +85,25 @@ extz_traceback_kernel(TbLaunch L)
 			if (force >= 0) state = force;
 			if (state == 0) {
 				push(0, 1);
-				if (kStats) stat_match_col(sa, raw_byte(L, pd.q_off, j), raw_byte(L, pd.t_off, i));
+				if (kStats) trim_col(ta, 0, stat_match_col(sa, raw_byte(L, pd.q_off, j), raw_byte(L, pd.t_off, i)));
 				--i; --j;
 			} else if (state == 1) {
 				push(2, 1);                                          // ksw D: consumes the target
-				if (kStats) stat_tonly_col(sa, raw_byte(L, pd.t_off, i));
+				if (kStats) { stat_tonly_col(sa, raw_byte(L, pd.t_off, i)); trim_col(ta, 1, false); }
 				--i;
 			} else {
 				push(1, 1);                                          // ksw I: consumes the query
-				if (kStats) stat_qonly_col(sa, raw_byte(L, pd.q_off, j));
+				if (kStats) { stat_qonly_col(sa, raw_byte(L, pd.q_off, j)); trim_col(ta, 2, false); }
 				--j;
 			}
 		}
 		if (i >= 0) {                                               // extern/ksw2.h:145
 			push(2, i + 1);
-			if (kStats) for (int k = i; k >= 0; --k) stat_tonly_col(sa, raw_byte(L, pd.t_off, k));
+			if (kStats) for (int k = i; k >= 0; --k) { stat_tonly_col(sa, raw_byte(L, pd.t_off, k)); trim_col(ta, 1, false); }
 		}
 		if (j >= 0) {                                               // extern/ksw2.h:146
 			push(1, j + 1);
-			if (kStats) for (int k = j; k >= 0; --k) stat_qonly_col(sa, raw_byte(L, pd.q_off, k));
+			if (kStats) for (int k = j; k >= 0; --k) { stat_qonly_col(sa, raw_byte(L, pd.q_off, k)); trim_col(ta, 2, false); }
 		}
 		if (n) cend[-n] = last;
 	}
@@ -127,6 +129,11 @@ extz_traceback_kernel(TbLaunch L)
 		s.transitionsB = sa.transitionsB; s.transversionsB = sa.transversionsB;
 		s.uppercaseA = sa.uppercaseA; s.uppercaseB = sa.uppercaseB; s.uppercaseMatches = sa.uppercaseMatches; s.reserved = 0;
 		L.stats[L.stats_by_orig ? pd.orig : pi] = s;
+		if (L.trims) {
+			int32_t tf, tb2;
+			trim_finish(ta, tf, tb2);
+			reinterpret_cast<int2 *>(L.trims)[L.stats_by_orig ? pd.orig : pi] = make_int2(tf, tb2);
+		}
 	}
 }
 
@@ -155,6 +162,8 @@ extz_traceback_warp_kernel(TbLaunch L)
 	StatAcc sa;
 	sa.span = sa.gap_bases = sa.matches = sa.mismatches = sa.indel_a = sa.indel_b = sa.alnB = sa.matchB = 0;
 	sa.mismatchB = sa.transitionsB = sa.transversionsB = sa.uppercaseA = sa.uppercaseB = sa.uppercaseMatches = 0;
+	TrimAcc ta;                                                     // trim_front / trim_back scans ride on the same walk
+	trim_reset(ta, L.t_match, L.t_mismatch, L.t_gapo, L.t_gape);
 
 	int i0, j0; bool run = true;                                   // extern/ksw2_extz2_sse.cc:290-295
 	if (!pr.zdropped && !(L.flag & kFlagExtzOnly)) { i0 = tlen - 1; j0 = qlen - 1; }
@@ -204,15 +213,15 @@ extz_traceback_warp_kernel(TbLaunch L)
 				if (force >= 0) state = force;
 				if (state == 0) {
 					push(0, 1);
-					if (kStats) stat_match_col(sa, raw_byte(L, pd.q_off, j), raw_byte(L, pd.t_off, i));
+					if (kStats) trim_col(ta, 0, stat_match_col(sa, raw_byte(L, pd.q_off, j), raw_byte(L, pd.t_off, i)));
 					--i; --j;
 				} else if (state == 1) {
 					push(2, 1);
-					if (kStats) stat_tonly_col(sa, raw_byte(L, pd.t_off, i));
+					if (kStats) { stat_tonly_col(sa, raw_byte(L, pd.t_off, i)); trim_col(ta, 1, false); }
 					--i;
 				} else {
 					push(1, 1);
-					if (kStats) stat_qonly_col(sa, raw_byte(L, pd.q_off, j));
+					if (kStats) { stat_qonly_col(sa, raw_byte(L, pd.q_off, j)); trim_col(ta, 2, false); }
 					--j;
 				}
 			}
@@ -224,11 +233,11 @@ extz_traceback_warp_kernel(TbLaunch L)
 	if (lane == 0 && run) {
 		if (i >= 0) {                                               // extern/ksw2.h:145
 			push(2, i + 1);
-			if (kStats) for (int k = i; k >= 0; --k) stat_tonly_col(sa, raw_byte(L, pd.t_off, k));
+			if (kStats) for (int k = i; k >= 0; --k) { stat_tonly_col(sa, raw_byte(L, pd.t_off, k)); trim_col(ta, 1, false); }
 		}
 		if (j >= 0) {                                               // extern/ksw2.h:146
 			push(1, j + 1);
-			if (kStats) for (int k = j; k >= 0; --k) stat_qonly_col(sa, raw_byte(L, pd.q_off, k));
+			if (kStats) for (int k = j; k >= 0; --k) { stat_qonly_col(sa, raw_byte(L, pd.q_off, k)); trim_col(ta, 2, false); }
 		}
 		if (n) cend[-n] = last;
 	}
@@ -255,6 +264,11 @@ extz_traceback_warp_kernel(TbLaunch L)
 			s.transitionsB = sa.transitionsB; s.transversionsB = sa.transversionsB;
 			s.uppercaseA = sa.uppercaseA; s.uppercaseB = sa.uppercaseB; s.uppercaseMatches = sa.uppercaseMatches; s.reserved = 0;
 			L.stats[L.stats_by_orig ? pd.orig : pi] = s;
+		if (L.trims) {
+			int32_t tf, tb2;
+			trim_finish(ta, tf, tb2);
+			reinterpret_cast<int2 *>(L.trims)[L.stats_by_orig ? pd.orig : pi] = make_int2(tf, tb2);
+		}
 		}
 	}
 }

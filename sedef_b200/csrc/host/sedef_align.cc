@@ -55,7 +55,16 @@ static inline void chunk_plan(size_t alen, size_t blen, std::vector<Chunk> &out)
 		out.push_back({sp, (int)std::min<size_t>(kMaxKswSeqLen, alen - sp), (int)std::min<size_t>(kMaxKswSeqLen, blen - sp)});
 }
 
+// device-side results of the trim scans of one request: valid only for requests aligned in a single ksw call
+struct TrimScan { bool valid = false; int front = -1, back = -1; };
+static std::vector<Alignment> align_batch_impl(const std::vector<std::pair<std::string, std::string>> &pairs, const AlignParams &p,
+                                               std::vector<TrimScan> *trims);
 std::vector<Alignment> align_batch(const std::vector<std::pair<std::string, std::string>> &pairs, const AlignParams &p)
+{
+	return align_batch_impl(pairs, p, nullptr);
+}
+static std::vector<Alignment> align_batch_impl(const std::vector<std::pair<std::string, std::string>> &pairs, const AlignParams &p,
+                                               std::vector<TrimScan> *trims)
 {
 	// align_helper's matrix (src/align.cc:41-44)
 	const int8_t a = (int8_t)p.match, b = p.mismatch < 0 ? (int8_t)p.mismatch : (int8_t)(-p.mismatch);
@@ -88,6 +97,14 @@ std::vector<Alignment> align_batch(const std::vector<std::pair<std::string, std:
 	if (rc) throw std::runtime_error(std::string("ksw_extz2_batch_arena: ") + ksw_b200_strerror(rc) + " -- " + ksw_b200_last_error());
 	const ksw_extz_t *ez = ksw_b200_result_ez(res);
 	const sd_stats_t *st = ksw_b200_result_stats(res);
+	if (trims) {
+		const int32_t *tr = ksw_b200_result_trims(res);
+		trims->assign(pairs.size(), TrimScan());
+		for (int k = 0; k < n; ++k) {
+			const bool single = (k == 0 || owner[k - 1] != owner[k]) && (k + 1 == n || owner[k + 1] != owner[k]);
+			if (single && tr) (*trims)[owner[k]] = TrimScan{true, tr[2 * k], tr[2 * k + 1]};
+		}
+	}
 	std::vector<Alignment> out(pairs.size());
 	for (size_t i = 0; i < pairs.size(); ++i) { out[i].a = pairs[i].first; out[i].b = pairs[i].second; }
 	// The statistics of a chunked pair are the sum of its chunks' statistics as long as every chunk but the last one is
@@ -280,11 +297,12 @@ static std::vector<uint8_t> columns_of(const GuidedAlignment &g)
 }
 static void clear_alignment(GuidedAlignment &g) { g.a.clear(); g.b.clear(); g.cigar.clear(); }
 
-void trim_front(GuidedAlignment &g, const AlignParams &p)              // src/align.cc:343-398   ABCD -> --CD
+// maximum-suffix scan of trim_front over the columns (src/align.cc:345-365): max_i, or -1 when no suffix scores >= 0
+static int scan_trim_front(const GuidedAlignment &g, const AlignParams &p)
 {
 	const std::vector<uint8_t> col = columns_of(g);
 	const int n = (int)col.size();
-	int max_score = 0, max_i = (int)g.a.size(), score = 0;            // (sic) initialised with the SEQUENCE length
+	int max_score = 0, max_i = -1, score = 0;
 	for (int i = n - 1; i >= 0; --i) {
 		if (col[i] == 0) score += p.match;
 		else if (col[i] == 1) score += p.mismatch;
@@ -294,6 +312,29 @@ void trim_front(GuidedAlignment &g, const AlignParams &p)              // src/al
 		}
 		if (score >= max_score) { max_score = score; max_i = i; }
 	}
+	return max_i;
+}
+// maximum-prefix scan of trim_back (src/align.cc:402-420): columns kept (max_i + 1), or -1 when no prefix scores >= 0
+static int scan_trim_back(const GuidedAlignment &g, const AlignParams &p)
+{
+	const std::vector<uint8_t> col = columns_of(g);
+	const int n = (int)col.size();
+	int max_score = 0, max_i = -1, score = 0;
+	for (int i = 0; i < n; ++i) {
+		if (col[i] == 0) score += p.match;
+		else if (col[i] == 1) score += p.mismatch;
+		else {
+			if (i == 0 || (col[i] == 2 && col[i - 1] != 2) || (col[i] == 3 && col[i - 1] != 3)) score += -p.gap_open;
+			score += -p.gap_extend;
+		}
+		if (score >= max_score) { max_score = score; max_i = i; }
+	}
+	return max_i < 0 ? -1 : max_i + 1;
+}
+// the CIGAR surgery of trim_front for a given scan result (src/align.cc:366-397)
+static void apply_trim_front(GuidedAlignment &g, int scan)
+{
+	const int max_i = scan < 0 ? (int)g.a.size() : scan;              // (sic) the reference initialises max_i with the SEQUENCE length
 	if (max_i == (int)g.a.size()) { clear_alignment(g); g.start_a = g.end_a; g.start_b = g.end_b; return; }
 	for (int ci = 0, cur_len = 0; ci < (int)g.cigar.size(); ++ci) {
 		if (g.cigar[ci].second + cur_len > max_i) {
@@ -311,23 +352,11 @@ void trim_front(GuidedAlignment &g, const AlignParams &p)              // src/al
 	g.a = g.a.substr(g.start_a, g.end_a - g.start_a);
 	g.b = g.b.substr(g.start_b, g.end_b - g.start_b);
 }
-
-void trim_back(GuidedAlignment &g, const AlignParams &p)               // src/align.cc:400-456   ABCD -> AB--
+// the CIGAR surgery of trim_back for a given scan result (src/align.cc:421-455)
+static void apply_trim_back(GuidedAlignment &g, int keep)
 {
-	const std::vector<uint8_t> col = columns_of(g);
-	const int n = (int)col.size();
-	int max_score = 0, max_i = -1, score = 0;
-	for (int i = 0; i < n; ++i) {
-		if (col[i] == 0) score += p.match;
-		else if (col[i] == 1) score += p.mismatch;
-		else {
-			if (i == 0 || (col[i] == 2 && col[i - 1] != 2) || (col[i] == 3 && col[i - 1] != 3)) score += -p.gap_open;
-			score += -p.gap_extend;
-		}
-		if (score >= max_score) { max_score = score; max_i = i; }
-	}
-	if (max_i == -1) { clear_alignment(g); g.end_a = g.start_a; g.end_b = g.start_b; return; }
-	++max_i;
+	if (keep < 0) { clear_alignment(g); g.end_a = g.start_a; g.end_b = g.start_b; return; }
+	const int max_i = keep;
 	g.end_a = g.start_a; g.end_b = g.start_b;
 	for (int ci = 0, cur_len = 0; ci < (int)g.cigar.size(); ++ci) {
 		if (g.cigar[ci].second + cur_len >= max_i) {
@@ -345,6 +374,8 @@ void trim_back(GuidedAlignment &g, const AlignParams &p)               // src/al
 	g.a = g.a.substr(g.start_a, g.end_a - g.start_a);
 	g.b = g.b.substr(g.start_b, g.end_b - g.start_b);
 }
+void trim_front(GuidedAlignment &g, const AlignParams &p) { apply_trim_front(g, scan_trim_front(g, p)); }   // src/align.cc:343-398   ABCD -> --CD
+void trim_back(GuidedAlignment &g, const AlignParams &p) { apply_trim_back(g, scan_trim_back(g, p)); }      // src/align.cc:400-456   ABCD -> AB--
 
 std::vector<GuidedAlignment> align_hit_guides_batch(const std::vector<HitGuide> &guides, const AlignParams &p)
 {
@@ -378,7 +409,9 @@ std::vector<GuidedAlignment> align_hit_guides_batch(const std::vector<HitGuide> 
 			if (qhi_n - qhi && rhi_n - rhi) { reqs.emplace_back(qstr.substr(qhi, qhi_n - qhi), rstr.substr(rhi, rhi_n - rhi)); meta.push_back({gi, RIGHT, 0, 0}); }
 		}
 	}
-	std::vector<Alignment> done = align_batch(reqs, p);                                 // ONE batched ksw_extz2 call
+	// ONE batched ksw_extz2 call; the trim scans of the side extensions come back with it (computed on the traceback walk)
+	std::vector<TrimScan> scans;
+	std::vector<Alignment> done = align_batch_impl(reqs, p, &scans);
 	std::vector<GuidedAlignment> out(guides.size());
 	std::vector<std::pair<std::string, std::string>> finals(guides.size());
 	std::vector<std::deque<std::pair<char, int>>> final_cigars(guides.size());
@@ -407,7 +440,7 @@ std::vector<GuidedAlignment> align_hit_guides_batch(const std::vector<HitGuide> 
 			if (pos < meta.size() && meta[pos].guide == gi && meta[pos].kind == LEFT) {
 				GuidedAlignment gap; gap.a = done[pos].a; gap.b = done[pos].b; gap.cigar = done[pos].cigar;
 				gap.start_a = gap.start_b = 0; gap.end_a = (int)gap.a.size(); gap.end_b = (int)gap.b.size();
-				trim_front(gap, p);
+				apply_trim_front(gap, scans[pos].valid ? scans[pos].front : scan_trim_front(gap, p));
 				qlo -= gap.end_a - gap.start_a; rlo -= gap.end_b - gap.start_b;
 				prepend_cigar(al.cigar, gap.cigar);
 				++pos;
@@ -415,7 +448,7 @@ std::vector<GuidedAlignment> align_hit_guides_batch(const std::vector<HitGuide> 
 			if (pos < meta.size() && meta[pos].guide == gi && meta[pos].kind == RIGHT) {
 				GuidedAlignment gap; gap.a = done[pos].a; gap.b = done[pos].b; gap.cigar = done[pos].cigar;
 				gap.start_a = gap.start_b = 0; gap.end_a = (int)gap.a.size(); gap.end_b = (int)gap.b.size();
-				trim_back(gap, p);
+				apply_trim_back(gap, scans[pos].valid ? scans[pos].back : scan_trim_back(gap, p));
 				qhi += gap.end_a; rhi += gap.end_b;
 				append_cigar(al.cigar, gap.cigar);
 				++pos;

@@ -32,6 +32,9 @@ struct TbLaunch {
 	int *overflow;               // set to 1 when the compact arena is too small
 	int n, NS, flag;
 	int packed;                  // traceback rows written by the packed kernel (extz_dp16.cuh layout)
+	int32_t *trims;              // per pair {trim_front max_i | -1, trim_back kept columns | -1} (extz_core.cuh TrimAcc), indexed like
+	                             // stats; nullptr: not wanted
+	int t_match, t_mismatch, t_gapo, t_gape;   // alignment scoring of the trim scans (Globals::Align, src/align.cc:343-456)
 	int stats_by_orig;           // 1: stats[] is indexed by PairDesc::orig (the caller's order), `stats` = base of the whole
 	                             //    batch; 0: indexed like pairs, `stats` = base of this wave
 };

@@ -66,7 +66,7 @@ EXPORTS = ["ksw_b200_strerror", "ksw_b200_last_error", "ksw_b200_init", "ksw_b20
            "ksw_b200_host_alloc", "ksw_b200_host_free", "ksw_b200_host_register", "ksw_b200_host_unregister",
            "ksw_b200_set_fatal_handler", "ksw_extz2_batch_arena", "ksw_b200_result_ez", "ksw_b200_result_stats",
            "ksw_b200_result_count", "ksw_b200_result_io", "ksw_b200_result_free", "ksw_b200_batch_fetch_arena",
-           "ksw_b200_result_export"]
+           "ksw_b200_result_export", "ksw_b200_result_trims"]
 
 
 def load():
@@ -129,6 +129,8 @@ def load():
     lib.ksw_b200_result_ez.restype = vp
     lib.ksw_b200_result_stats.argtypes = [vp]
     lib.ksw_b200_result_stats.restype = vp
+    lib.ksw_b200_result_trims.argtypes = [vp]
+    lib.ksw_b200_result_trims.restype = vp
     lib.ksw_b200_result_count.argtypes = [vp]
     lib.ksw_b200_result_io.argtypes = [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i32)]
     lib.ksw_b200_result_io.restype = None
@@ -228,6 +230,8 @@ class ArenaResult:
         self.ez = np.frombuffer((C.c_char * (n * EZ_DTYPE.itemsize)).from_address(pe), EZ_DTYPE) if n else np.zeros(0, EZ_DTYPE)
         pst = lib.ksw_b200_result_stats(handle)
         self.stats = (np.frombuffer((C.c_char * (n * STATS_DTYPE.itemsize)).from_address(pst), STATS_DTYPE) if (pst and n) else None)
+        ptr = lib.ksw_b200_result_trims(handle)
+        self.trims = (np.frombuffer((C.c_char * (n * 8)).from_address(ptr), np.int32).reshape(n, 2) if (ptr and n) else None)
 
     def cigar(self, i: int) -> np.ndarray:
         n, p = int(self.ez[i]["n_cigar"]), int(self.ez[i]["cigar"])
@@ -254,7 +258,7 @@ class ArenaResult:
 
     def free(self):
         if self.h:
-            self.ez = self.stats = None
+            self.ez = self.stats = self.trims = None
             self.lib.ksw_b200_result_free(self.h)
             self.h = None
 

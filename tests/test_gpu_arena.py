@@ -220,3 +220,56 @@ def test_from_cigar_other_ops(checker):
         v = [C.c_int(0) for _ in range(5)]
         lib.ref_alignment_from_cigar(fa.encode(), fb.encode(), cig.encode(), *[C.byref(x) for x in v])
         assert [x.value for x in v] == [a.span(), a.matches(), a.mismatches(), a.gaps(), a.gap_bases()], cig
+
+
+def _trim_scans(cigar, qa, ta, match=5, mismatch=-4, gapo=40, gape=1):
+    """Alignment::trim_front / trim_back scans (reference src/align.cc:345-365, 402-420) restated over the columns of one
+    alignment: returns (trim_front max_i or -1 when never updated, columns trim_back keeps or -1)."""
+    up = lambda c: c - 32 if 97 <= c <= 122 else c
+    cols, ia, ib = [], 0, 0                       # 0 = '|', 1 = mismatch, 2 = align_a is '-', 3 = align_b is '-'
+    for c in cigar:
+        op, ln = c & 0xF, c >> 4
+        for _ in range(ln):
+            if op == 0:
+                a, b = up(int(qa[ia])), up(int(ta[ib])); ia += 1; ib += 1
+                cols.append(0 if (a == b and a != ord("N") and b != ord("N")) else 1)
+            elif op == 1:
+                cols.append(3); ia += 1           # ksw I: query only -> align_b is '-'
+            else:
+                cols.append(2); ib += 1
+    n = len(cols)
+    score, best, front = 0, 0, -1
+    for i in range(n - 1, -1, -1):
+        if cols[i] == 0: score += match
+        elif cols[i] == 1: score += mismatch
+        else:
+            if i == n - 1 or cols[i + 1] != cols[i]: score -= gapo
+            score -= gape
+        if score >= best: best, front = score, i
+    score, best, back = 0, 0, -1
+    for i in range(n):
+        if cols[i] == 0: score += match
+        elif cols[i] == 1: score += mismatch
+        else:
+            if i == 0 or cols[i - 1] != cols[i]: score -= gapo
+            score -= gape
+        if score >= best: best, back = score, i
+    return front, (back + 1 if back >= 0 else -1)
+
+
+@pytest.mark.parametrize("kw,w,zd", [(dict(min_len=1, max_len=120, div=0.3), -1, -1), (dict(min_len=200, max_len=520, div=0.15, burst=40), -1, -1),
+                                     (dict(min_len=5000, max_len=7000, div=0.1), 300, -1), (dict(min_len=1, max_len=400, div=0.45), 30, 60)])
+def test_trim_scans_on_the_traceback_walk(checker, mat, kw, w, zd):
+    """the maximum-suffix / maximum-prefix scans of trim_front / trim_back computed on the device during the
+    traceback (thread-per-pair and warp-per-pair kernels), against the reference's loops over the same columns."""
+    ps = synth.make_pairs_mixed(300 if kw["max_len"] < 2000 else 12, seed=515 + w, **kw)
+    res = engine.extz2_batch_arena(ps, mat, 40, 1, w, zd, 0)
+    assert res.trims is not None and res.trims.shape == (ps.n, 2)
+    n_trimmed = 0
+    for i in range(ps.n):
+        qa, ta = ps.raw_pair(i)
+        f, b = _trim_scans(res.cigar(i).tolist(), qa, ta)
+        assert (int(res.trims[i, 0]), int(res.trims[i, 1])) == (f, b), (i, res.trims[i].tolist(), (f, b))
+        n_trimmed += (f > 0) + (0 <= b < int(res.stats[i]["span"]))
+    assert n_trimmed > 0
+    res.free()

@@ -654,7 +654,17 @@ extern "C" ksw_b200_batch_t *ksw_b200_batch_upload(int n, const int *qlen, const
 		else { pl.qspan = (size_t)qsum; pl.tspan = (size_t)tsum; }
 		pl.tbase = align_up(pl.qspan, 256);
 		sb.arena_bytes = align_up(pl.tbase + pl.tspan + kArenaSlack, 256);
-		{
+		if (pl.dense) {
+#pragma omp parallel for num_threads(threads_for(np, 8192)) schedule(static)
+			for (int64_t k = 0; k < np; ++k) {              // a gather over the caller's arrays in kernel order: worth several threads
+				PairDesc &pd = sb.pairs[k];
+				const int i = lst[k];
+				pd.qlen = qlen[i]; pd.tlen = tlen[i];
+				pd.w = w < 0 ? std::max(qlen[i], tlen[i]) : std::min(w, std::max(qlen[i], tlen[i]));
+				pd.orig = i; pd.tb_off = 0;
+				pd.q_off = qoff[i] - qlo; pd.t_off = (int64_t)pl.tbase + (toff[i] - tlo);
+			}
+		} else {
 			size_t qpos = 0, tpos = pl.tbase;
 			for (int64_t k = 0; k < np; ++k) {
 				PairDesc &pd = sb.pairs[k];
@@ -662,8 +672,7 @@ extern "C" ksw_b200_batch_t *ksw_b200_batch_upload(int n, const int *qlen, const
 				pd.qlen = qlen[i]; pd.tlen = tlen[i];
 				pd.w = w < 0 ? std::max(qlen[i], tlen[i]) : std::min(w, std::max(qlen[i], tlen[i]));
 				pd.orig = i; pd.tb_off = 0;
-				if (pl.dense) { pd.q_off = qoff[i] - qlo; pd.t_off = (int64_t)pl.tbase + (toff[i] - tlo); }
-				else { pd.q_off = (int64_t)qpos; pd.t_off = (int64_t)tpos; qpos += qlen[i]; tpos += tlen[i]; }
+				pd.q_off = (int64_t)qpos; pd.t_off = (int64_t)tpos; qpos += qlen[i]; tpos += tlen[i];
 			}
 		}
 		if (cudaSetDevice(sb.dc->dev) != cudaSuccess) return destroy(fail(KSW_B200_ERR_CUDA, "cudaSetDevice"));
@@ -1200,8 +1209,7 @@ static int batch_core(const BatchArgs &A, ksw_b200_result &R, const std::functio
 		// A chunk also has to be worth a set of kernel launches.  Every chunk runs one DP + one traceback kernel PER CLASS,
 		// each with a latency floor of one pair (1-2 ms) and a tail, so chunks of mid-size pairs that carry little work
 		// under-fill the GPU (100k pairs of <= 250 bp: 18 ms resident, 45 ms in six chunks; profiles/r01_tuning.md).  Keep
-		// at least ~2.5 G cells per chunk.  Batches of TINY pairs (< 2000 cells per pair) are host-bound instead -- there the
-		// pipeline exists to overlap planning with fetching, and many chunks stay the better choice.
+		// at least ~2.5 G cells per chunk.
 		const int step = std::max(1, n / 512);
 		int64_t cells = 0; int cnt = 0;
 		for (int i = 0; i < n; i += step, ++cnt) {
@@ -1210,6 +1218,9 @@ static int batch_core(const BatchArgs &A, ksw_b200_result &R, const std::functio
 		}
 		const double avg = cnt ? (double)cells / cnt : 0.0;
 		if (avg >= 2000.0) nchunks = std::max(1, std::min(nchunks, (int)(avg * n / 2.5e9 + 0.5)));
+		// tiny pairs: the kernels need ~5 ns per pair and the host 40-50 ns to plan and describe it (the producer thread is
+		// the bottleneck), plus ~0.4 ms of fixed cost per chunk (stream, events, small copies): chunks of >= 50k pairs
+		else nchunks = std::max(1, std::min(nchunks, n / 50000));
 	}
 	std::vector<int> start(nchunks + 1, 0);
 	{

@@ -56,6 +56,44 @@ def test_fp_fields_match_reference_kat(built, golden_dir):
     assert "%.1f" % fp["total_error"] == "4.0"          # BED score column of the KAT
 
 
+def test_fp_fields_are_the_reference_expressions_bit_for_bit(built, golden_dir):
+    """The floating-point BEDPE fields are derived on the host from the integer record with the reference's own double-precision
+    expressions (src/stats_main.cc:273-283,297-299; src/align.h:84-92).  Over the integers of all golden records (produced by the
+    reference's own Alignment class) the C results must equal an independent IEEE-754 double evaluation of the same expressions
+    BIT FOR BIT -- not just to the 6 digits the reference prints."""
+    import math, struct
+    from helpers import load_json
+    recs = load_json(golden_dir, "sd_stats_golden.json")["records"]
+    assert len(recs) >= 50
+    n_checked = 0
+    for r in recs:
+        row = {n: 0 for n in engine.STAT_FIELDS}
+        row.update(r["stat_loop"]); row.update({k: r[k] for k in ("span", "matches", "mismatches", "gaps", "gap_bases")})
+        if row["alnB"] == 0:
+            continue
+        fp = engine.derive_fp(row)
+        exp = {}
+        exp["fracMatch"] = float(row["matchB"]) / row["alnB"]
+        exp["fracMatchIndel"] = float(row["matchB"]) / row["span"]
+        jcp = float(row["mismatchB"]) / row["alnB"]
+        p = float(row["transitionsB"]) / row["alnB"]; q = float(row["transversionsB"]) / row["alnB"]
+        try:
+            exp["jcK"] = -0.75 * math.log(1.0 - 4.0 / 3 * jcp)
+            exp["k2K"] = 0.5 * math.log(1.0 / (1 - 2.0 * p - q)) + 0.25 * math.log(1.0 / (1 - 2.0 * q))
+        except ValueError:
+            continue                                    # log of a non-positive number: nan in C, an exception in Python
+        exp["errorScaled"] = (row["gaps"] + row["mismatches"]) / float(row["gaps"] + row["mismatches"] + row["matches"])
+        exp["filter_score"] = 1 - exp["errorScaled"]
+        tot = float(row["matches"] + row["gap_bases"] + row["mismatches"])
+        exp["gap_error"] = 100.0 * row["gap_bases"] / tot
+        exp["mismatch_error"] = 100.0 * row["mismatches"] / tot
+        exp["total_error"] = exp["mismatch_error"] + exp["gap_error"]
+        for k, v in exp.items():
+            assert struct.pack("<d", fp[k]) == struct.pack("<d", v), (k, fp[k], v)
+        n_checked += 1
+    assert n_checked >= 50
+
+
 def _has_gpu():
     try:
         import torch

@@ -273,3 +273,30 @@ def test_trim_scans_on_the_traceback_walk(checker, mat, kw, w, zd):
         n_trimmed += (f > 0) + (0 <= b < int(res.stats[i]["span"]))
     assert n_trimmed > 0
     res.free()
+
+
+def test_result_export_into_caller_memory(checker, mat):
+    """`ksw_b200_result_export`: position-independent copy of an arena into caller-owned arrays at given indices (the host-side
+    gather of a one-process-per-GPU deployment): records land at index[i], `cigar` becomes a word offset into the caller's buffer."""
+    ps = synth.make_pairs_mixed(500, seed=99, min_len=1, max_len=300, div=0.1)
+    res = engine.extz2_batch_arena(ps, mat, 40, 1, 30, 50, 0)
+    rng = np.random.default_rng(1)
+    index = rng.permutation(800)[:ps.n].astype(np.int64)
+    ez = np.zeros(800, engine.EZ_DTYPE); st = np.zeros(800, engine.STATS_DTYPE)
+    words = int(res.ez["n_cigar"].sum())
+    cig = np.zeros(words + 10, np.uint32)
+    assert res.export(ez, st, cig, cigar_base=1000, index=index) == words
+    for i in range(ps.n):
+        d = int(index[i])
+        for k in ("max_zd", "max_q", "max_t", "mqe", "mqe_t", "mte", "mte_q", "score", "n_cigar", "m_cigar"):
+            assert ez[d][k] == res.ez[i][k], (i, k)
+        n = int(ez[d]["n_cigar"])
+        if n:
+            o = int(ez[d]["cigar"]) - 1000
+            assert np.array_equal(cig[o:o + n], res.cigar(i)), i
+        else:
+            assert int(ez[d]["cigar"]) == 0
+        assert st[d] == res.stats[i]
+    with pytest.raises(engine.EngineError):
+        res.export(ez, st, cig[:max(1, words // 2)], index=index)
+    res.free()

@@ -20,7 +20,7 @@ rand_matrix = len(sys.argv) > 3 and sys.argv[3] == "matrix"
 mat0 = synth.sedef_matrix()
 engine.init(0, 1)
 chk = oracle.ref() if oracle.have_ref() else oracle.port()
-FLAGS = [0, 0, 0, 0, 0x02, 0x01, 0x40, 0x80, 0x42, 0xc2, 0x04]
+FLAGS = [0, 0, 0, 0, 0x02, 0x01, 0x40, 0x80, 0x42, 0xc2, 0x04, 0x08, 0x18, 0x1a, 0x58]
 tot = bad = 0
 t0 = time.time()
 for ci in range(ncfg):

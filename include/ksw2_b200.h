@@ -211,6 +211,19 @@ int sd_stats_from_cigar_batch_flat(int n, const int64_t *cig_off, const int64_t 
                                    const int *blen, const int64_t *boff, const uint8_t *bbuf,
                                    sd_stats_t *out, int *status);
 
+/* ---- anchors ------------------------------------------------------------- */
+/* SEDEF's generate_anchors (src/chain.cc:24-101) for n region pairs at once, on the GPU: the maximal exact-match runs
+ * (case-insensitive; N ends a run) of length >= kmer_size on every diagonal, each started at its first k-mer that occurs fewer
+ * than 1000 times in the reference region, with the same-chromosome diagonal exclusion (same_chr[i] != 0: diagonals within
+ * kmer_size of orig_ref_start[i] + r == orig_query_start[i] + q are dropped).  q/r buffers hold ORIGINAL-CASE bytes.
+ * Output: one malloc()'d array (caller free()s) with the anchors of region i at [anchor_off[i], anchor_off[i+1]), in the order
+ * the reference emits them (by q, then r); has_u = 1 when the match holds an upper-case base (Anchor, src/align.h:25-28). */
+typedef struct { int32_t q, r, l, has_u; } sedef_anchor_t;
+int sedef_anchors_batch(int n, const int *qlen, const int64_t *qoff, const uint8_t *qbuf,
+                        const int *rlen, const int64_t *roff, const uint8_t *rbuf, int kmer_size,
+                        const uint8_t *same_chr, const int64_t *orig_query_start, const int64_t *orig_ref_start,
+                        sedef_anchor_t **anchors_out, int64_t *anchor_off /* [n + 1] */);
+
 /* ---- resident batches (measurement + pipelined callers) -------------------------------- */
 /*
  * A resident batch keeps the encoded inputs in HBM so that repeated runs time the device

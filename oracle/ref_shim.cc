@@ -156,6 +156,21 @@ int ref_region(const char *query, const char *ref, int kmer_size, int same_chr, 
 	memcpy(out, sres.c_str(), sres.size() + 1);
 	return (int)hits.size();
 }
+// generate_anchors alone (src/chain.cc:24-101): one line "q r l has_u" per anchor, in the order the reference emits them.
+int ref_region_anchors(const char *query, const char *ref, int kmer_size, int same_chr, int orig_qs, int orig_rs, char *out, int cap)
+{
+	std::string q(query), r(ref);
+	auto qp = std::make_shared<Sequence>(same_chr ? "CHR" : "QRY", q);
+	auto rp = std::make_shared<Sequence>(same_chr ? "CHR" : "REF", r);
+	Hit orig{qp, orig_qs, orig_qs + (int)q.size(), rp, orig_rs, orig_rs + (int)r.size()};
+	auto anchors = generate_anchors(q, r, orig, kmer_size);
+	std::ostringstream os;
+	for (auto &a : anchors) os << a.q << ' ' << a.r << ' ' << a.l << ' ' << (a.has_u ? 1 : 0) << '\n';
+	std::string sres = os.str();
+	if ((int)sres.size() + 1 > cap) return -1;
+	memcpy(out, sres.c_str(), sres.size() + 1);
+	return (int)anchors.size();
+}
 // The final constructor of the refine wave: Alignment(qstr, rstr, vector<Hit> guide, side) (src/align.cc:107-197:
 // gap fills between consecutive hits, +-side extensions with trim_front / trim_back, src/align.cc:343-456), run on a
 // guide made of the reference's own chain alignments: the chains of the chain wave, sorted, greedily thinned to a

@@ -66,7 +66,7 @@ EXPORTS = ["ksw_b200_strerror", "ksw_b200_last_error", "ksw_b200_init", "ksw_b20
            "ksw_b200_host_alloc", "ksw_b200_host_free", "ksw_b200_host_register", "ksw_b200_host_unregister",
            "ksw_b200_set_fatal_handler", "ksw_extz2_batch_arena", "ksw_b200_result_ez", "ksw_b200_result_stats",
            "ksw_b200_result_count", "ksw_b200_result_io", "ksw_b200_result_free", "ksw_b200_batch_fetch_arena",
-           "ksw_b200_result_export", "ksw_b200_result_trims"]
+           "ksw_b200_result_export", "ksw_b200_result_trims", "sedef_anchors_batch"]
 
 
 def load():
@@ -138,6 +138,8 @@ def load():
     lib.ksw_b200_result_free.restype = None
     lib.ksw_b200_result_export.argtypes = [vp, vp, vp, vp, i64, i64, vp]
     lib.ksw_b200_result_export.restype = i64
+    lib.sedef_anchors_batch.argtypes = [i32, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, C.POINTER(vp), vp]
+    lib.sedef_anchors_batch.restype = i32
     lib.sd_stats_derive_fp.argtypes = [C.POINTER(SdStats), C.POINTER(SdStatsFp)]
     lib.free = C.CDLL(None).free
     lib.free.argtypes = [vp]
@@ -420,6 +422,31 @@ def stats_from_cigars(cigars, a_list, b_list):
     _check(lib.sd_stats_from_cigar_batch_flat(n, _ptr(coff), _ptr(cn), _ptr(cbuf), _ptr(al), _ptr(ao), _ptr(ab),
                                               _ptr(bl), _ptr(bo), _ptr(bb), _ptr(out), _ptr(status)))
     return out, status
+
+
+def anchors_batch(regions, kmer_size: int = 11, same_chr=None, orig_query_start=None, orig_ref_start=None):
+    """`sedef_anchors_batch`: generate_anchors (src/chain.cc:24-101) for a list of (query, ref) original-case str / bytes pairs on
+    the GPU.  Returns one int32 array [k, 4] = (q, r, l, has_u) per region, in the reference's order."""
+    lib = load()
+    n = len(regions)
+    qs = [x[0].encode() if isinstance(x[0], str) else bytes(x[0]) for x in regions]
+    rs = [x[1].encode() if isinstance(x[1], str) else bytes(x[1]) for x in regions]
+    ql = np.array([len(x) for x in qs], np.int32); rl = np.array([len(x) for x in rs], np.int32)
+    qo = np.zeros(n, np.int64); ro = np.zeros(n, np.int64)
+    if n > 1:
+        qo[1:] = np.cumsum(ql[:-1]); ro[1:] = np.cumsum(rl[:-1])
+    qb = np.frombuffer(b"".join(qs) + b"\0", np.uint8); rb = np.frombuffer(b"".join(rs) + b"\0", np.uint8)
+    sc = None if same_chr is None else np.ascontiguousarray(same_chr, np.uint8)
+    oq = None if orig_query_start is None else np.ascontiguousarray(orig_query_start, np.int64)
+    orr = None if orig_ref_start is None else np.ascontiguousarray(orig_ref_start, np.int64)
+    out = C.c_void_p(None); off = np.zeros(n + 1, np.int64)
+    _check(lib.sedef_anchors_batch(n, _ptr(ql), _ptr(qo), _ptr(qb), _ptr(rl), _ptr(ro), _ptr(rb), kmer_size, _ptr(sc), _ptr(oq), _ptr(orr),
+                                   C.byref(out), _ptr(off)))
+    tot = int(off[n])
+    flat = np.ctypeslib.as_array(C.cast(out.value, C.POINTER(C.c_int32)), shape=(max(tot, 1), 4))[:tot].copy() if out.value else np.zeros((0, 4), np.int32)
+    if out.value:
+        lib.free(out.value)
+    return [flat[int(off[i]):int(off[i + 1])] for i in range(n)]
 
 
 def derive_fp(stats_row) -> dict:

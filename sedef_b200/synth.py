@@ -327,3 +327,34 @@ def make_region_pair(length: int = 8000, div: float = 0.06, flank: int = 1500, s
     qs = np.concatenate([flank_seq(flank), q, flank_seq(flank)])
     ts = np.concatenate([flank_seq(flank), t, flank_seq(flank)])
     return qs.tobytes().decode(), ts.tobytes().decode()
+
+
+def make_genome_with_dups(length: int = 2_000_000, n_dups: int = 40, min_len: int = 5000, max_len: int = 20000,
+                          min_div: float = 0.02, max_div: float = 0.10, seed: int = 0x5EDEF001):
+    """BASELINE.json configs[0] shape: one soft-masked chromosome with planted segmental duplications (a source segment copied to
+    a disjoint place with makeSmall divergence plus a few longer indels).  Returns (genome bytes as np.uint8 ASCII,
+    [(src_start, src_end, dst_start, dst_end, div)]) -- the planted catalog, in genome coordinates."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    codes = rng.integers(0, 4, length).astype(np.uint8)
+    codes[rng.random(length) < 0.0005] = 4
+    g = _to_ascii(codes, _softmask(rng, length, mean_run=400))
+    # disjoint slots: 2 * n_dups windows of max_len on a grid, shuffled; sources from the first half, destinations from the second
+    grid = length // (2 * n_dups + 1)
+    assert grid > max_len + 2000, "genome too short for the catalog"
+    slots = rng.permutation(2 * n_dups)
+    catalog = []
+    for k in range(n_dups):
+        L = int(rng.integers(min_len, max_len + 1)); div = float(rng.uniform(min_div, max_div))
+        s0 = int(slots[2 * k]) * grid + int(rng.integers(500, grid - max_len - 500))
+        d0 = int(slots[2 * k + 1]) * grid + int(rng.integers(500, grid - max_len - 500))
+        src = g[s0:s0 + L]
+        pair = pairs_from_strings([(src.tobytes().decode(), "A")])
+        cp, cl, _ = _mutate_small(rng, pair.q[:L], src >= ord("a"), div)
+        copy = _to_ascii(cp, cl)
+        for _ in range(2):                                   # a few longer indels (the makeLarge idea)
+            p = int(rng.integers(200, max(201, len(copy) - 200))); kk = int(rng.integers(20, 120))
+            copy = np.concatenate([copy[:p], copy[p + kk:]]) if rng.random() < 0.5 else np.concatenate([copy[:p], ASCII[rng.integers(0, 4, kk)], copy[p:]])
+        copy = copy[:max_len + 400]
+        g[d0:d0 + len(copy)] = copy
+        catalog.append((s0, s0 + L, d0, d0 + len(copy), div))
+    return g, catalog

@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def declared_functions():
     src = open(os.path.join(ROOT, "include", "ksw2_b200.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    names = re.findall(r"\b(ksw_[a-z0-9_]+|sd_stats_[a-z0-9_]+)\s*\(", src)
+    names = re.findall(r"\b(ksw_[a-z0-9_]+|sd_stats_[a-z0-9_]+|sedef_[a-z0-9_]+)\s*\(", src)
     return sorted(set(n for n in names if not n.endswith("_t")))
 
 

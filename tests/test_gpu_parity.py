@@ -611,3 +611,51 @@ def test_region_driver_matches_fast_align(checker, golden_dir):
         assert a == b, (k, g["regions"][k]["seed"], g["regions"][k]["same_chr"])
     # all 13 regions shared their waves: far fewer batched calls than the ~700 synchronous kernel calls of one region alone
     assert rounds <= 40 and calls <= 2 * rounds + 2 and reqs >= 100, (rounds, calls, reqs)
+
+
+def test_config1_genome_align_stage(checker):
+    """BASELINE.json configs[0] shape at the align stage: a 2 Mbp soft-masked chromosome with 40 planted 5-20 kbp duplications at
+    2-10 % divergence; one seed hit per planted copy (windows with slop, same chromosome, real coordinates) -> the reference's own
+    anchors and chains (live, through oracle/_ref/libsedef_ref.so) -> `refine_regions_batch` with ALL regions in one call.  The
+    hits must equal the reference's fast_align hits region by region, and in genome coordinates recover the planted catalog."""
+    import ctypes as C, os, subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    path = os.path.join(root, "oracle", "_ref", "libsedef_ref.so")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref/libsedef_ref.so not built")
+    slib = C.CDLL(path)
+    slib.ref_region.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int]
+    g, catalog = synth.make_genome_with_dups()
+    rng = np.random.default_rng(17)
+    buf = C.create_string_buffer(1 << 24)
+    text, want, origin = [], [], []
+    for (s0, s1, d0, d1, div) in catalog:
+        qs, qe = max(0, s0 - int(rng.integers(300, 900))), min(len(g), s1 + int(rng.integers(300, 900)))
+        rs, re_ = max(0, d0 - int(rng.integers(300, 900))), min(len(g), d1 + int(rng.integers(300, 900)))
+        q, r = g[qs:qe].tobytes(), g[rs:re_].tobytes()
+        n = slib.ref_region(q, r, 11, 1, qs, rs, buf, len(buf))
+        assert n >= 0
+        lines = [ln for ln in buf.value.decode().split("\n") if ln.strip()]
+        text.append("R 1 %d %d\n%s\n%s\n" % (qs, rs, q.decode(), r.decode()) + "\n".join(ln for ln in lines if ln[0] in "AC") + "\nE\n")
+        want.append([ln for ln in lines if ln[0] == "H"])
+        origin.append((qs, rs))
+    drv = os.path.join(root, "tests", "cpp", "align_queue_driver")
+    out = subprocess.run([drv, "regions"], input="".join(text), capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stderr
+    got, cur = [], None
+    for ln in out.stdout.split("\n"):
+        if ln.startswith("R "):
+            cur = []; got.append(cur)
+        elif ln.startswith("H "):
+            cur.append(ln)
+    assert len(got) == len(want) == 40
+    recovered = 0
+    for k, (a, b) in enumerate(zip(got, want)):
+        assert a == b, (k, catalog[k])
+        s0, s1, d0, d1, _ = catalog[k]
+        for ln in a:                                                    # genome coordinates, as align_main prints them
+            f = ln.split()
+            hq0, hq1, hr0, hr1 = origin[k][0] + int(f[1]), origin[k][0] + int(f[2]), origin[k][1] + int(f[3]), origin[k][1] + int(f[4])
+            if hq0 <= s0 + 50 and hq1 >= s1 - 50 and hr0 <= d0 + 50 and hr1 >= d1 - 50:
+                recovered += 1
+    assert recovered >= 38, recovered

@@ -66,15 +66,20 @@ extern "C" const char *ksw_b200_last_error(void) { return g_last_error.c_str(); 
 //   * packed (default, extz_dp16.cuh; two slots per register, NS / 32 lanes per pair):
 //       NS <= 1024           extz_dp16_kernel<NS/32>          128-thread CTAs, 32 / (NS/32) pairs per warp in lock-step
 //       NS = 2048/4096/8192  extz_dp16_wide_kernel<NS/32>     one CTA of 64 / 128 / 256 lanes per pair
-//       NS = 16384           extz_dp16_cluster_kernel<2>      one cluster of 2 CTAs x 256 lanes per pair (DSMEM)
+//       NS = 16384 ... 65536 extz_dp16_cluster_kernel<C>      one cluster of C = 2 / 4 / 8 CTAs x 256 lanes per pair (DSMEM); 65536
+//                                                             live slots hold the largest call the reference makes (60 000 per chunk)
 //   * one slot per register (KSW_B200_PACKED=0, extz_dp.cuh; the table below: G lanes x S slots), kept for A/B runs and
 //     under test: narrow (G <= 32), CTA-wide (one CTA of G lanes), cluster (`cluster` CTAs x 256 lanes).
 struct KClass { int G, S; bool wide; int cluster; };
 static const KClass kClasses[] = { {2, 16, false, 0}, {4, 16, false, 0}, {8, 16, false, 0}, {16, 16, false, 0}, {32, 16, false, 0},
                                    {32, 32, false, 0}, {64, 16, true, 0}, {128, 16, true, 0}, {256, 16, true, 0},
-                                   {512, 16, true, 2}, {1024, 16, true, 4} };
+                                   {512, 16, true, 2}, {1024, 16, true, 4},
+                                   {2048, 16, true, 0}, {4096, 16, true, 0} };       // packed only: clusters of 4 / 8 CTAs (32768 / 65536 slots)
 static const int kNumClasses = sizeof(kClasses) / sizeof(kClasses[0]);
-static const int kNumSizedClasses = kNumClasses;                        // all classes are ordered by capacity
+static inline bool class_packed(int c);
+// all classes are ordered by capacity; the last two exist in packed form only
+static inline int num_sized_classes() { return class_packed(0) ? kNumClasses : kNumClasses - 2; }
+#define kNumSizedClasses num_sized_classes()
 static inline int class_ns(int c) { return kClasses[c].G * kClasses[c].S; }
 static inline bool packed_enabled()
 {
@@ -83,7 +88,7 @@ static inline bool packed_enabled()
 }
 static inline bool class_packed(int c) { return packed_enabled(); }                              // every class has a packed kernel
 static inline bool class_packed_cluster(int c) { return class_packed(c) && class_ns(c) > 8192; } // 2 CTAs x 256 lanes x 32 slots
-static inline int class_cluster(int c) { return class_packed(c) ? (class_ns(c) > 8192 ? 2 : 0) : kClasses[c].cluster; }
+static inline int class_cluster(int c) { return class_packed(c) ? (class_ns(c) > 8192 ? class_ns(c) / 8192 : 0) : kClasses[c].cluster; }
 static inline bool class_packed_wide(int c) { return class_packed(c) && class_ns(c) > 1024 && class_ns(c) <= 8192; }    // one CTA of NS/32 lanes per pair
 // one-slot lanes with S == 32 switch whole-lane (two 16-blocks at once), which costs 16 slots of window (extz_dp.cuh)
 static inline int class_capacity(int c) { return (kClasses[c].S > 16 && !class_packed(c)) ? class_ns(c) - 16 : class_ns(c); }
@@ -96,7 +101,7 @@ static inline int class_pairs_per_block(int c)
 // grid: CTAs for narrow / wide classes, clusters for cluster classes
 static cudaError_t launch_dp(int c, const DpLaunch &L, bool cigar, bool right, bool approx, int grid, cudaStream_t st)
 {
-	if (class_packed_cluster(c)) return k_dp16_cluster_dispatch(L, cigar, right, approx, grid, st, nullptr);
+	if (class_packed_cluster(c)) return k_dp16_cluster_dispatch(class_cluster(c), L, cigar, right, approx, grid, st, nullptr);
 	if (class_cluster(c)) return k_dp_cluster_dispatch(class_cluster(c), L, cigar, right, grid, st, nullptr);
 	if (class_packed_wide(c)) return k_dp16_wide_launch(class_ns(c) / 32, L, cigar, right, approx, grid, st);
 	if (class_packed(c)) return k_dp16_launch(class_ns(c) / 32, L, cigar, right, approx, grid, st);
@@ -107,7 +112,7 @@ static int dp_occupancy_query(int c, bool cigar, bool right, bool approx)
 {
 	if (class_cluster(c)) {
 		int n = 0; DpLaunch dummy = {};
-		cudaError_t e = class_packed_cluster(c) ? k_dp16_cluster_dispatch(dummy, cigar, right, approx, 1, nullptr, &n)
+		cudaError_t e = class_packed_cluster(c) ? k_dp16_cluster_dispatch(class_cluster(c), dummy, cigar, right, approx, 1, nullptr, &n)
 		                                        : k_dp_cluster_dispatch(class_cluster(c), dummy, cigar, right, 1, nullptr, &n);
 		if (e != cudaSuccess) { cudaGetLastError(); return 0; }
 		return n;

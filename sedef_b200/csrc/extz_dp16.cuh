@@ -781,7 +781,8 @@ extz_dp16_wide_kernel(DpLaunch L)
 
 // =====================================================================================================
 // packed cluster kernel: one thread-block CLUSTER of C CTAs x 256 lanes x 32 slots per pair (C = 2: 16384 live slots, the
-// unbanded <= 10 kbp gap fills of src/align.cc:130-139).  Every CTA keeps the H / u' rows of its own lanes; the carry
+// unbanded <= 10 kbp gap fills of src/align.cc:130-139; C = 4 / 8: 32768 / 65536 live slots, which covers the largest call
+// the reference can make -- 60 000 x 60 000 per align_helper chunk, src/align.cc:46-53).  Every CTA keeps the H / u' rows of its own lanes; the carry
 // between CTAs, the leader's accesses to arbitrary slots and the per-diagonal reductions go through DISTRIBUTED SHARED
 // MEMORY (cluster.map_shared_rank), ordering by cluster.sync() -- the choreography of extz_dp_cluster_kernel with the
 // packed lane code.
@@ -817,7 +818,7 @@ __global__ void __launch_bounds__(256, 1)
 extz_dp16_cluster_kernel(DpLaunch L)
 {
 	constexpr int GC = 256, G = GC * C, NS = G * 32, NW = GC / 32;
-	static_assert(C == 2 || C == 4, "packed cluster kernel: 2 or 4 CTAs");
+	static_assert(C == 2 || C == 4 || C == 8, "packed cluster kernel: 2, 4 or 8 CTAs (8 = the portable cluster limit)");
 	cg::cluster_group cluster = cg::this_cluster();
 	const int rank = (int)cluster.block_rank();
 
@@ -826,8 +827,8 @@ extz_dp16_cluster_kernel(DpLaunch L)
 	uint4 (*sU)[GC] = reinterpret_cast<uint4 (*)[GC]>(extz_dyn_smem + sizeof(int4) * 8 * GC);
 	__shared__ uint32_t sTable[kTableStride * kTableStride];
 	__shared__ uint32_t sCarryX[NW], sCarryV[NW];       // OLD x,v (packed) of every warp's top register
-	__shared__ int32_t sAllMax[4 * NW];                 // [rank][warp], only CTA 0's copy is used
-	__shared__ uint32_t sAllKey[4 * NW];
+	__shared__ int32_t sAllMax[8 * NW];                 // [rank][warp], only CTA 0's copy is used
+	__shared__ uint32_t sAllKey[8 * NW];
 	__shared__ int sPair, sNeedArg, sStop;              // written into EVERY CTA's copy by the leader
 	__shared__ int32_t sGmax;
 

@@ -35,10 +35,10 @@ int k_dp16_wide_occupancy(int G, bool cigar, bool right, bool approx)
 #undef EXTZ_CALL
 	return 0;
 }
-cudaError_t k_dp16_cluster_dispatch(const DpLaunch &L, bool cigar, bool right, bool approx, int nclusters, cudaStream_t st, int *max_clusters)
+cudaError_t k_dp16_cluster_dispatch(int C, const DpLaunch &L, bool cigar, bool right, bool approx, int nclusters, cudaStream_t st, int *max_clusters)
 {
-	return approx ? dp16_cluster_dispatch_a<true>(L, cigar, right, nclusters, st, max_clusters)
-	              : dp16_cluster_dispatch_a<false>(L, cigar, right, nclusters, st, max_clusters);
+	return approx ? dp16_cluster_dispatch_a<true>(C, L, cigar, right, nclusters, st, max_clusters)
+	              : dp16_cluster_dispatch_a<false>(C, L, cigar, right, nclusters, st, max_clusters);
 }
 #define EXTZ_FOR_CLASS(c, CALL) \
 	switch (c) { \

@@ -34,11 +34,10 @@ int dp16_wide_occupancy_g(bool cigar, bool right)
 	} else         { dp16_wide_prepare<G, false, false, A>(); cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, extz_dp16_wide_kernel<G, false, false, A>, G, dyn); }
 	return nb;
 }
-// packed cluster kernel (2 CTAs x 256 lanes x 32 slots = 16384 live slots): 48 KB of dynamic shared memory per CTA
-template <bool CG, bool R, bool A>
+// packed cluster kernels (C = 2 / 4 / 8 CTAs x 256 lanes x 32 slots = 16384 / 32768 / 65536 live slots): 48 KB of dynamic shared memory per CTA
+template <int C, bool CG, bool R, bool A>
 static cudaError_t cluster16_launch_one(const DpLaunch &L, int nclusters, cudaStream_t st, int *max_clusters)
 {
-	constexpr int C = 2;
 	const size_t dyn = 256 * 192;
 	cudaError_t e = cudaFuncSetAttribute(extz_dp16_cluster_kernel<C, CG, R, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
 	if (e != cudaSuccess) return e;
@@ -54,12 +53,20 @@ static cudaError_t cluster16_launch_one(const DpLaunch &L, int nclusters, cudaSt
 	}
 	return cudaLaunchKernelEx(&cfg, extz_dp16_cluster_kernel<C, CG, R, A>, L);
 }
-template <bool A>
-cudaError_t dp16_cluster_dispatch_a(const DpLaunch &L, bool cigar, bool right, int nclusters, cudaStream_t st, int *max_clusters)
+template <int C, bool A>
+static cudaError_t dp16_cluster_dispatch_ca(const DpLaunch &L, bool cigar, bool right, int nclusters, cudaStream_t st, int *max_clusters)
 {
-	if (cigar) return right ? cluster16_launch_one<true, true, A>(L, nclusters, st, max_clusters)
-	                        : cluster16_launch_one<true, false, A>(L, nclusters, st, max_clusters);
-	return cluster16_launch_one<false, false, A>(L, nclusters, st, max_clusters);
+	if (cigar) return right ? cluster16_launch_one<C, true, true, A>(L, nclusters, st, max_clusters)
+	                        : cluster16_launch_one<C, true, false, A>(L, nclusters, st, max_clusters);
+	return cluster16_launch_one<C, false, false, A>(L, nclusters, st, max_clusters);
+}
+template <bool A>
+cudaError_t dp16_cluster_dispatch_a(int C, const DpLaunch &L, bool cigar, bool right, int nclusters, cudaStream_t st, int *max_clusters)
+{
+	if (C == 2) return dp16_cluster_dispatch_ca<2, A>(L, cigar, right, nclusters, st, max_clusters);
+	if (C == 4) return dp16_cluster_dispatch_ca<4, A>(L, cigar, right, nclusters, st, max_clusters);
+	if (C == 8) return dp16_cluster_dispatch_ca<8, A>(L, cigar, right, nclusters, st, max_clusters);
+	return cudaErrorInvalidValue;
 }
 #define EXTZ_INSTANTIATE_DP16_WIDE(A) \
 	template cudaError_t dp16_wide_launch_g<64, A>(const DpLaunch &, bool, bool, int, cudaStream_t); \
@@ -68,6 +75,6 @@ cudaError_t dp16_cluster_dispatch_a(const DpLaunch &L, bool cigar, bool right, i
 	template int dp16_wide_occupancy_g<64, A>(bool, bool); \
 	template int dp16_wide_occupancy_g<128, A>(bool, bool); \
 	template int dp16_wide_occupancy_g<256, A>(bool, bool); \
-	template cudaError_t dp16_cluster_dispatch_a<A>(const DpLaunch &, bool, bool, int, cudaStream_t, int *);
+	template cudaError_t dp16_cluster_dispatch_a<A>(int, const DpLaunch &, bool, bool, int, cudaStream_t, int *);
 
 } // namespace extz

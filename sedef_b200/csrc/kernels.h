@@ -18,8 +18,8 @@ int k_dp16_occupancy(int G, bool cigar, bool right, bool approx);
 // CTA-wide: G in {64,128,256} lanes per pair
 cudaError_t k_dp16_wide_launch(int G, const DpLaunch &L, bool cigar, bool right, bool approx, int grid, cudaStream_t st);
 int k_dp16_wide_occupancy(int G, bool cigar, bool right, bool approx);
-// cluster of 2 CTAs x 256 lanes; max_clusters != nullptr: occupancy query only
-cudaError_t k_dp16_cluster_dispatch(const DpLaunch &L, bool cigar, bool right, bool approx, int nclusters, cudaStream_t st, int *max_clusters);
+// cluster of C = 2 / 4 / 8 CTAs x 256 lanes; max_clusters != nullptr: occupancy query only
+cudaError_t k_dp16_cluster_dispatch(int C, const DpLaunch &L, bool cigar, bool right, bool approx, int nclusters, cudaStream_t st, int *max_clusters);
 
 // ---- one-slot kernels (extz_dp.cuh; KSW_B200_PACKED=0 A/B path) ----------------------------------------------------------
 // c: index into the one-slot class table of engine.cu (0..8); cluster classes go through k_dp_cluster_dispatch

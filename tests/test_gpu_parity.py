@@ -197,7 +197,17 @@ def test_widest_pair_and_too_wide(checker, mat):
     compare(synth.make_pairs_small(2, length=10000, div=0.08, seed=10), mat, checker, -1, -1, 0)      # cluster of 4 CTAs
     compare(synth.make_pairs_small(2, length=9000, div=0.3, seed=11), mat, checker, -1, 500, 0x42)    # z-drop, right, extz-only
     compare(synth.make_pairs_large(3, min_len=12000, max_len=20000, seed=12), mat, checker, 5000, 600, 0)   # banded, 5 k wide
-    big = synth.make_pairs_small(2, length=17000, div=0.05, seed=4)
+
+
+def test_largest_reference_call_sizes(checker, mat):
+    """Unbanded pairs beyond 16384 live slots run on clusters of 4 and 8 CTAs (32768 / 65536 slots, DSMEM): the engine now covers
+    the largest call the reference can make (align_helper chunks at 60 000 bases, src/align.cc:46-53).  One pair per cluster
+    size against the compiled reference (the 33 kbp pair is 1.1 G cells and 2.2 GB of reference traceback), and the refusal above."""
+    assert engine.load().ksw_b200_max_slots() == 65536
+    compare(synth.make_pairs_small(2, length=17000, div=0.05, seed=4), mat, checker, -1, -1, 0)          # cluster of 4 CTAs
+    compare(synth.make_pairs_small(1, length=33000, div=0.08, seed=5), mat, checker, -1, 2000, 0x02)     # cluster of 8 CTAs, z-drop, right
+    compare(synth.make_pairs_large(2, min_len=40000, max_len=60000, seed=6), mat, checker, 20000, -1, 0) # banded but wider than 16384 slots
+    big = synth.make_pairs_small(1, length=66000, div=0.02, seed=7)
     with pytest.raises(engine.EngineError) as ei:
         engine.extz2_batch(big, mat, 40, 1, -1, -1, 0)
     assert ei.value.code == -5

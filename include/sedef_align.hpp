@@ -111,6 +111,23 @@ struct RefineStats { int rounds = 0; long long batch_calls = 0, ksw_requests = 0
 std::vector<std::vector<GuidedAlignment>> refine_regions_batch(const std::vector<RegionTask> &regions, const AlignParams &p = AlignParams(),
                                                               RefineStats *stats = nullptr);
 
+// ---- anchoring + chaining: with these the region-level driver is a complete fast_align ---------------------------------------
+// generate_anchors (src/chain.cc:24-101) for many region pairs on the GPU (sedef_anchors_batch, include/ksw2_b200.h)
+struct RegionSeed {
+	const std::string *qstr, *rstr;                     // the two region strings (original case)
+	bool same_chr = false; int orig_query_start = 0, orig_ref_start = 0;
+};
+std::vector<std::vector<Anchor>> anchors_batch(const std::vector<RegionSeed> &regions, int kmer_size = 11);
+// chain_anchors (src/chain.cc:103-199) on the host: the chaining DP over the anchors of ONE region (sweep over anchor start / end
+// events in query order, best predecessor by a range-maximum query over reference end coordinates within MAX_CHAIN_GAP), then the
+// chain extraction in score order.  Returns the chains that pass the filter of src/chain.cc:222-247 (an upper-case anchor and a
+// span of at least MIN_UPPERCASE_MATCH, or a span of at least 490), anchors in query order -- the `guides` of RegionTask.
+std::vector<std::vector<int>> chain_anchors(const std::vector<Anchor> &anchors);
+// fast_align (src/chain.cc:203-268) for many regions: anchors on the GPU, chaining on the host (one region per host thread), then
+// refine_regions_batch.  Hits per region, in the order the reference returns them.
+std::vector<std::vector<GuidedAlignment>> fast_align_batch(const std::vector<RegionSeed> &regions, int kmer_size = 11,
+                                                           const AlignParams &p = AlignParams(), RefineStats *stats = nullptr);
+
 // Deferred-alignment queue: call sites push requests, the driver flushes a whole wave at once.
 class AlignQueue {
 public:

@@ -120,7 +120,7 @@ int ref_chain_guides(const char *query, const char *ref, int kmer_size, char *ou
 }
 // One region as the region-level driver sees it: the reference's own anchors and (filtered) chains for a seed hit `orig`
 // (same chromosome or not, with its start coordinates), followed by what the reference's fast_align makes of the same region.
-//   "A q r l"                    one line per anchor (index = line order)
+//   "A q r l has_u"              one line per anchor (index = line order)
 //   "C n i0 i1 ..."              one line per chain that passes the filter of src/chain.cc:222-247: anchor indices in query order
 //   "H qs qe rs re cigar span matches mismatches gaps gap_bases"      one line per hit fast_align returns
 int ref_region(const char *query, const char *ref, int kmer_size, int same_chr, int orig_qs, int orig_rs, char *out, int cap)
@@ -134,7 +134,7 @@ int ref_region(const char *query, const char *ref, int kmer_size, int same_chr, 
 	auto &bounds = chains_init.second;
 	auto &chain = chains_init.first;
 	std::ostringstream os;
-	for (auto &a : anchors) os << "A " << a.q << ' ' << a.r << ' ' << a.l << '\n';
+	for (auto &a : anchors) os << "A " << a.q << ' ' << a.r << ' ' << a.l << ' ' << (a.has_u ? 1 : 0) << '\n';
 	for (int bi = 1; bi < (int)bounds.size(); bi++) {                   // the loop of src/chain.cc:222-247, called, not changed
 		bool has_u = bounds[bi].second;
 		int be = bounds[bi].first, bs = bounds[bi - 1].first;

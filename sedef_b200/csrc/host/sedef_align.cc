@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <functional>
 #include <tuple>
+#include <climits>
 #include <cstdlib>
 #include <cstring>
 #include <stdexcept>
@@ -729,7 +730,215 @@ std::vector<std::vector<GuidedAlignment>> refine_regions_batch(const std::vector
 	return out;
 }
 
+// ---- anchoring + chaining -----------------------------------------------------------------------------------------------
+std::vector<std::vector<Anchor>> anchors_batch(const std::vector<RegionSeed> &regions, int kmer_size)
+{
+	const int n = (int)regions.size();
+	std::vector<int> ql(n), rl(n);
+	std::vector<int64_t> qo(n), ro(n), oq(n), orr(n);
+	std::vector<uint8_t> same(n);
+	std::string qbuf, rbuf;
+	for (int i = 0; i < n; ++i) {
+		ql[i] = (int)regions[i].qstr->size(); rl[i] = (int)regions[i].rstr->size();
+		qo[i] = (int64_t)qbuf.size(); ro[i] = (int64_t)rbuf.size();
+		qbuf += *regions[i].qstr; rbuf += *regions[i].rstr;
+		same[i] = regions[i].same_chr; oq[i] = regions[i].orig_query_start; orr[i] = regions[i].orig_ref_start;
+	}
+	qbuf.push_back('\0'); rbuf.push_back('\0');
+	sedef_anchor_t *flat = nullptr;
+	std::vector<int64_t> off(n + 1, 0);
+	int rc = sedef_anchors_batch(n, ql.data(), qo.data(), (const uint8_t *)qbuf.data(), rl.data(), ro.data(), (const uint8_t *)rbuf.data(), kmer_size,
+	                             same.data(), oq.data(), orr.data(), &flat, off.data());
+	if (rc) throw std::runtime_error(std::string("sedef_anchors_batch: ") + ksw_b200_strerror(rc) + " -- " + ksw_b200_last_error());
+	std::vector<std::vector<Anchor>> out(n);
+	for (int i = 0; i < n; ++i)
+		for (int64_t k = off[i]; k < off[i + 1]; ++k) out[i].push_back(Anchor{flat[k].q, flat[k].r, flat[k].l, flat[k].has_u});
+	free(flat);
+	return out;
+}
+
+namespace {
+// Globals::Chain / Globals::Search (src/globals.h:71-75, src/globals.cc:20-30)
+const int kMatchChainScore = 4, kMaxChainGap = 210, kMinUppercaseMatch = 90;
+const double kMinChainSpan = 700 * (1 - 0.30);             // MIN_READ_SIZE * (1 - MAX_ERROR), evaluated in double like the reference
+
+// The reference's range structure (src/segment.h, src/segment.tpp): a static binary tree over the points sorted by key; every
+// node additionally holds the best ACTIVE point of its subtree that no ancestor holds (a priority search tree).  Ties are part
+// of the contract -- chains are extracted by following `prev[]` -- so the same rules are kept: on activation an equal score
+// displaces the resident point (>=), a range query prefers the LEFT subtree on equal scores (>=), a removal promotes the right
+// child's point only when it is strictly better.
+struct PointTree {
+	typedef std::pair<int, int> Key;
+	struct Node { int best = -1, leaf = -1; Key hi; };     // best: node index of the held leaf; leaf: index into pts (-1: internal)
+	struct Pt { Key x; int score, pos; };
+	static const int kMin = INT_MIN;
+	std::vector<Node> t;
+	std::vector<Pt> &pts;
+	explicit PointTree(std::vector<Pt> &p) : pts(p)
+	{
+		std::sort(pts.begin(), pts.end(), [](const Pt &a, const Pt &b) { return a.x < b.x; });
+		int size = 1;
+		while (size < (int)pts.size()) size <<= 1;
+		if (pts.size() <= 1) size = 1;
+		t.resize((size_t)size << 1);
+		int next = 0;
+		build(0, 0, (int)pts.size(), next);
+	}
+	void build(int i, int s, int e, int &next)
+	{
+		if (i >= (int)t.size() || s >= e) return;
+		if (s + 1 == e) { t[i].leaf = next; t[i].hi = pts[next].x; pts[next].score = kMin; ++next; return; }
+		const int mid = (s + e + 1) / 2;
+		build(2 * i + 1, s, mid, next);
+		build(2 * i + 2, mid, e, next);
+		t[i].hi = t[2 * i + 1 + (2 * i + 2 < (int)t.size())].hi;
+	}
+	int find_leaf(const Key &q) const
+	{
+		int i = 0;
+		while (i < (int)t.size() && (t[i].leaf == -1 || q != pts[t[i].leaf].x)) i = 2 * i + 1 + (q > t[2 * i + 1].hi);
+		return i;
+	}
+	int score_of(int node) const { return pts[t[node].leaf].score; }
+	void activate(const Key &q, int score)
+	{
+		int carry = find_leaf(q);
+		pts[t[carry].leaf].score = score;
+		for (int i = 0; i < (int)t.size();) {
+			if (t[i].best == -1 || score_of(carry) >= score_of(t[i].best)) std::swap(t[i].best, carry);
+			if (carry == -1) break;
+			i = 2 * i + 1 + (pts[t[carry].leaf].x > t[2 * i + 1].hi);
+		}
+	}
+	void deactivate(const Key &q)
+	{
+		int gone = find_leaf(q);
+		pts[t[gone].leaf].score = kMin;
+		for (int i = 0; i < (int)t.size();) {
+			if (t[i].best == -1) break;
+			if (t[i].best == gone) {
+				if (t[i].leaf != -1) t[i].best = -1;
+				else {
+					const int l = 2 * i + 1, r = 2 * i + 2;
+					if (r < (int)t.size() && t[r].best != -1 && (t[l].best == -1 || score_of(t[r].best) > score_of(t[l].best))) { t[i].best = gone = t[r].best; i = r; }
+					else { t[i].best = gone = t[l].best; i = l; }
+				}
+			} else i = 2 * i + 1 + (q > t[2 * i + 1].hi);
+		}
+	}
+	int query(const Key &lo, const Key &hi, int i) const      // node index of the best point with lo <= key <= hi, or -1
+	{
+		if (i >= (int)t.size()) return -1;
+		if (t[i].leaf != -1) return (lo <= pts[t[i].leaf].x && pts[t[i].leaf].x <= hi) ? i : -1;
+		const int b = t[i].best;
+		if (b == -1) return -1;
+		if (lo <= pts[t[b].leaf].x && pts[t[b].leaf].x <= hi) return b;
+		if (hi <= t[2 * i + 1].hi) return query(lo, hi, 2 * i + 1);
+		if (lo > t[2 * i + 1].hi) return query(lo, hi, 2 * i + 2);
+		const int m1 = query(lo, hi, 2 * i + 1), m2 = query(lo, hi, 2 * i + 2);
+		if (m1 == -1) return m2;
+		if (m2 == -1) return m1;
+		return score_of(m1) >= score_of(m2) ? m1 : m2;
+	}
+	int query(const Key &lo, const Key &hi) const { const int i = query(lo, hi, 0); return i == -1 ? -1 : t[i].leaf; }
+};
+} // namespace
+
+std::vector<std::vector<int>> chain_anchors(const std::vector<Anchor> &anchors)
+{
+	const int n = (int)anchors.size();
+	std::vector<std::vector<int>> guides;
+	if (n == 0) return guides;
+	struct Ev { std::pair<int, int> x; };
+	std::vector<Ev> xs; xs.reserve(2 * (size_t)n);
+	std::vector<PointTree::Pt> ys; ys.reserve(n);
+	int max_q = 0, max_r = 0;
+	for (int i = 0; i < n; ++i) {
+		const Anchor &a = anchors[i];
+		xs.push_back({{a.q, i}}); xs.push_back({{a.q + a.l, i}});
+		ys.push_back({{a.r + a.l - 1, i}, PointTree::kMin, i});
+		max_q = std::max(max_q, a.q + a.l); max_r = std::max(max_r, a.r + a.l);
+	}
+	std::sort(xs.begin(), xs.end(), [](const Ev &a, const Ev &b) { return a.x < b.x; });
+	PointTree tree(ys);
+	std::vector<int> prev(n, -1);
+	std::vector<std::pair<int, int>> dp(n);
+	for (int i = 0; i < n; ++i) dp[i] = {0, i};
+	size_t bound = 0;
+	for (size_t xi = 0; xi < xs.size(); ++xi) {
+		const int i = xs[xi].x.second;
+		const Anchor &a = anchors[i];
+		if (xs[xi].x.first == a.q) {                                                      // the anchor starts: pick its predecessor
+			while (bound < xi) {                                                        // retire end points that are too far behind
+				const int t = xs[bound].x.second;
+				if (xs[bound].x.first == anchors[t].q + anchors[t].l) {
+					if (a.q - (anchors[t].q + anchors[t].l) <= kMaxChainGap) break;
+					tree.deactivate({anchors[t].r + anchors[t].l - 1, t});
+				}
+				++bound;
+			}
+			const int w = kMatchChainScore * a.has_u + (kMatchChainScore / 2) * (a.l - a.has_u);
+			int j = tree.query({a.r - kMaxChainGap, 0}, {a.r - 1, n});
+			if (j != -1 && ys[j].score != PointTree::kMin) {
+				j = ys[j].pos;
+				const Anchor &pv = anchors[j];
+				const int gap = a.q - (pv.q + pv.l) + a.r - (pv.r + pv.l);
+				if (w + dp[j].first - gap > 0) { dp[i].first = w + dp[j].first - gap; prev[i] = j; }
+				else dp[i].first = w;
+			} else dp[i].first = w;
+		} else {                                                                            // the anchor ends: it becomes a candidate
+			const int gap = max_q + 1 - (a.q + a.l) + max_r + 1 - (a.r + a.l);
+			tree.activate({a.r + a.l - 1, i}, dp[i].first - gap);
+		}
+	}
+	std::sort(dp.begin(), dp.end(), std::greater<std::pair<int, int>>());
+	std::vector<char> used(n, 0);
+	for (auto &m : dp) {                                                                    // chains in score order (chain.cc:181-197)
+		int at = m.second;
+		if (used[at]) continue;
+		std::vector<int> path;                                                              // from the chain's LAST anchor back to its first
+		int has_u = 0;
+		while (at != -1 && !used[at]) { path.push_back(at); has_u += anchors[at].has_u; used[at] = 1; at = prev[at]; }
+		// the filter of fast_align (chain.cc:222-247)
+		const Anchor &first = anchors[path.back()], &last = anchors[path.front()];
+		const int span = std::max(last.r + last.l - first.r, last.q + last.l - first.q);
+		if ((!(has_u != 0) || span < kMinUppercaseMatch) && span < kMinChainSpan) continue;
+		guides.emplace_back(path.rbegin(), path.rend());
+	}
+	return guides;
+}
+
+std::vector<std::vector<GuidedAlignment>> fast_align_batch(const std::vector<RegionSeed> &regions, int kmer_size, const AlignParams &p,
+                                                           RefineStats *stats)
+{
+	std::vector<std::vector<Anchor>> anchors = anchors_batch(regions, kmer_size);
+	std::vector<RegionTask> tasks(regions.size());
+#pragma omp parallel for schedule(dynamic, 1)
+	for (long ri = 0; ri < (long)regions.size(); ++ri) {
+		RegionTask &t = tasks[ri];
+		t.qstr = regions[ri].qstr; t.rstr = regions[ri].rstr; t.anchors = &anchors[ri];
+		t.same_chr = regions[ri].same_chr; t.orig_query_start = regions[ri].orig_query_start; t.orig_ref_start = regions[ri].orig_ref_start;
+		t.guides = chain_anchors(anchors[ri]);
+	}
+	return refine_regions_batch(tasks, p, stats);
+}
+
 } // namespace sedef_b200
+
+// chains of one region for callers without C++ (and the CPU parity test): anchors as (q, r, l, has_u) rows; chain k holds
+// chain_len[k] anchor indices, concatenated in chain_idx.  Returns the number of chains (fills at most cap_* entries).
+extern "C" int sedef_b200_chain_anchors(int n, const int32_t *anchors4, int cap_chains, int *chain_len, int cap_idx, int *chain_idx)
+{
+	std::vector<sedef_b200::Anchor> a(n < 0 ? 0 : n);
+	for (int i = 0; i < n; ++i) a[i] = sedef_b200::Anchor{anchors4[4 * i], anchors4[4 * i + 1], anchors4[4 * i + 2], anchors4[4 * i + 3]};
+	std::vector<std::vector<int>> g = sedef_b200::chain_anchors(a);
+	int pos = 0;
+	for (size_t k = 0; k < g.size(); ++k) {
+		if ((int)k < cap_chains) chain_len[k] = (int)g[k].size();
+		for (int v : g[k]) { if (pos < cap_idx) chain_idx[pos] = v; ++pos; }
+	}
+	return (int)g.size();
+}
 
 // C view of the chunk plan, for hosts that drive the C ABI themselves (and for the parity test of the chunk arithmetic)
 extern "C" int sedef_b200_chunk_plan(int64_t alen, int64_t blen, int cap, int64_t *sp, int *qlen, int *tlen)

@@ -53,7 +53,7 @@ static int run_regions()
 			cur = new Reg(); regs.push_back(cur);
 			int sc; is >> sc >> cur->t.orig_query_start >> cur->t.orig_ref_start; cur->t.same_chr = sc != 0;
 			std::getline(std::cin, cur->q); std::getline(std::cin, cur->r);
-		} else if (tag == 'A') { sedef_b200::Anchor a{}; is >> a.q >> a.r >> a.l; cur->anchors.push_back(a); }
+		} else if (tag == 'A') { sedef_b200::Anchor a{}; is >> a.q >> a.r >> a.l >> a.has_u; cur->anchors.push_back(a); }
 		else if (tag == 'C') { int n; is >> n; std::vector<int> g(n); for (int &x : g) is >> x; cur->t.guides.push_back(g); }
 	}
 	std::vector<sedef_b200::RegionTask> tasks;
@@ -72,6 +72,47 @@ static int run_regions()
 	}
 	catch (const std::exception &e) { fprintf(stderr, "error: %s\n", e.what()); return 2; }
 	fprintf(stderr, "refine_regions_batch: %zu regions, best of %d: %.2f ms\n", tasks.size(), reps, best_ms);
+	for (size_t k = 0; k < res.size(); ++k) {
+		printf("R %zu\n", k);
+		for (auto &a : res[k])
+			printf("H %d %d %d %d %s %d %d %d %d %d\n", a.start_a, a.end_a, a.start_b, a.end_b, a.cigar_string().c_str(), a.span(), a.matches(),
+			       a.mismatches(), a.gaps(), a.gap_bases());
+	}
+	printf("S %d %lld %lld\n", st.rounds, st.batch_calls, st.ksw_requests);
+	return 0;
+}
+
+// mode "fastalign": any number of regions, each: "R same_chr orig_qs orig_rs" / query / reference.  ALL regions go through ONE
+// fast_align_batch call (anchors on the GPU, chaining on the host, the region-level driver).  Output as in mode "regions".
+static int run_fastalign()
+{
+	struct Reg { std::string q, r; sedef_b200::RegionSeed s; };
+	std::vector<Reg *> regs;
+	std::string line;
+	while (std::getline(std::cin, line)) {
+		if (line.empty() || line[0] != 'R') continue;
+		std::istringstream is(line);
+		char tag; int sc;
+		Reg *cur = new Reg(); regs.push_back(cur);
+		is >> tag >> sc >> cur->s.orig_query_start >> cur->s.orig_ref_start; cur->s.same_chr = sc != 0;
+		std::getline(std::cin, cur->q); std::getline(std::cin, cur->r);
+	}
+	std::vector<sedef_b200::RegionSeed> seeds;
+	for (Reg *r : regs) { r->s.qstr = &r->q; r->s.rstr = &r->r; seeds.push_back(r->s); }
+	sedef_b200::RefineStats st;
+	std::vector<std::vector<sedef_b200::GuidedAlignment>> res;
+	double best_ms = 1e30;
+	const char *reps_env = getenv("REGIONS_REPS");
+	const int reps = reps_env ? atoi(reps_env) : 1;
+	try {
+		for (int rep = 0; rep < reps; ++rep) {
+			auto t0 = std::chrono::steady_clock::now();
+			res = sedef_b200::fast_align_batch(seeds, 11, sedef_b200::AlignParams(), &st);
+			best_ms = std::min(best_ms, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+		}
+	}
+	catch (const std::exception &e) { fprintf(stderr, "error: %s\n", e.what()); return 2; }
+	fprintf(stderr, "fast_align_batch: %zu regions, best of %d: %.2f ms\n", seeds.size(), reps, best_ms);
 	for (size_t k = 0; k < res.size(); ++k) {
 		printf("R %zu\n", k);
 		for (auto &a : res[k])
@@ -139,6 +180,7 @@ static int run_merge()
 int main(int argc, char **argv)
 {
 	if (argc > 1 && std::string(argv[1]) == "regions") return run_regions();
+	if (argc > 1 && std::string(argv[1]) == "fastalign") return run_fastalign();
 	if (argc > 1 && std::string(argv[1]) == "merge") return run_merge();
 	if (argc > 1 && std::string(argv[1]) == "chains") return run_chains();
 	if (argc > 1 && std::string(argv[1]) == "hitguide") return run_hitguide();

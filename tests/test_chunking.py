@@ -91,3 +91,26 @@ def test_single_pair_api_is_fatal_without_device(built):
         lib.ksw_b200_set_fatal_handler(None)
     assert seen and seen[0][0] == -1
     assert fields["score"] == engine.KSW_NEG_INF and fields["max"] == 0 and fields["max_q"] == -1 and cig == []
+
+
+def test_chain_anchors_matches_reference(built, golden_dir):
+    """The host chaining DP (`chain_anchors`, mirror of src/chain.cc:103-199 incl. the tie rules of its range structure,
+    src/segment.tpp) and the chain filter of src/chain.cc:222-247: on the reference's own anchors of 13 regions it must return
+    exactly the reference's chains (tests/golden/region_golden.json, 'A q r l has_u' -> 'C n i0 i1 ...')."""
+    from helpers import load_json
+    so = C.CDLL(engine.LIB_PATH)
+    so.sedef_b200_chain_anchors.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+    g = load_json(golden_dir, "region_golden.json")
+    total = 0
+    for reg in g["regions"]:
+        lines = [ln for ln in reg["text"].split("\n") if ln.strip()]
+        anchors = np.array([[int(x) for x in ln.split()[1:5]] for ln in lines if ln[0] == "A"], np.int32)
+        want = [[int(x) for x in ln.split()[2:]] for ln in lines if ln[0] == "C"]
+        clen = np.zeros(4096, np.int32); cidx = np.zeros(len(anchors) + 16, np.int32)
+        n = so.sedef_b200_chain_anchors(len(anchors), anchors.ctypes.data, len(clen), clen.ctypes.data, len(cidx), cidx.ctypes.data)
+        got, pos = [], 0
+        for k in range(n):
+            got.append(cidx[pos:pos + int(clen[k])].tolist()); pos += int(clen[k])
+        assert got == want, (reg["seed"], reg["same_chr"], n, len(want))
+        total += n
+    assert total >= 80

@@ -669,3 +669,62 @@ def test_config1_genome_align_stage(checker):
             if hq0 <= s0 + 50 and hq1 >= s1 - 50 and hr0 <= d0 + 50 and hr1 >= d1 - 50:
                 recovered += 1
     assert recovered >= 38, recovered
+
+
+def _run_fastalign(text):
+    import os, subprocess
+    drv = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "cpp", "align_queue_driver")
+    out = subprocess.run([drv, "fastalign"], input=text, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stderr
+    got, cur = [], None
+    for ln in out.stdout.split("\n"):
+        if ln.startswith("R "):
+            cur = []; got.append(cur)
+        elif ln.startswith("H "):
+            cur.append(ln)
+    return got
+
+
+def test_fast_align_batch_complete_path(checker, golden_dir):
+    """The COMPLETE align-stage path without any reference code underneath: `fast_align_batch` = anchors on the GPU
+    (sedef_anchors_batch) + chaining on the host (chain_anchors) + the region-level driver, given nothing but the region strings
+    and the seed's origin.  Hits must equal the reference's fast_align (src/chain.cc:203-268) on the 13 golden regions."""
+    g = load_json(golden_dir, "region_golden.json")
+    text, want = [], []
+    for reg in g["regions"]:
+        q, t = synth.make_region_pair(reg["length"], reg["div"], seed=reg["seed"])
+        text.append("R %d %d %d\n%s\n%s\n" % (reg["same_chr"], reg["orig_qs"], reg["orig_rs"], q, t))
+        want.append([ln for ln in reg["text"].split("\n") if ln.startswith("H ")])
+    got = _run_fastalign("".join(text))
+    assert len(got) == len(want)
+    for k, (a, b) in enumerate(zip(got, want)):
+        assert a == b, (k, g["regions"][k]["seed"], g["regions"][k]["same_chr"])
+
+
+def test_config1_genome_complete_path(checker):
+    """BASELINE.json configs[0] shape through the complete path: 2 Mbp chromosome, 40 planted duplications, one seed window per
+    copy -> `fast_align_batch` -> hits; compared with the reference's fast_align on the same windows (live, oracle/_ref) and with
+    the planted catalog in genome coordinates."""
+    import ctypes as C, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    path = os.path.join(root, "oracle", "_ref", "libsedef_ref.so")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref/libsedef_ref.so not built")
+    slib = C.CDLL(path)
+    slib.ref_region.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int]
+    g, catalog = synth.make_genome_with_dups(seed=0x5EDEF011)
+    rng = np.random.default_rng(23)
+    buf = C.create_string_buffer(1 << 24)
+    text, want = [], []
+    for (s0, s1, d0, d1, div) in catalog:
+        qs, qe = max(0, s0 - int(rng.integers(300, 900))), min(len(g), s1 + int(rng.integers(300, 900)))
+        rs, re_ = max(0, d0 - int(rng.integers(300, 900))), min(len(g), d1 + int(rng.integers(300, 900)))
+        q, r = g[qs:qe].tobytes(), g[rs:re_].tobytes()
+        assert slib.ref_region(q, r, 11, 1, qs, rs, buf, len(buf)) >= 0
+        want.append([ln for ln in buf.value.decode().split("\n") if ln.startswith("H ")])
+        text.append("R 1 %d %d\n%s\n%s\n" % (qs, rs, q.decode(), r.decode()))
+    got = _run_fastalign("".join(text))
+    assert len(got) == 40
+    for k, (a, b) in enumerate(zip(got, want)):
+        assert a == b, (k, catalog[k])
+    assert sum(len(a) for a in got) >= 38

@@ -3,7 +3,9 @@
 #include <algorithm>
 #include <functional>
 #include <tuple>
+#include <chrono>
 #include <climits>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <stdexcept>
@@ -34,6 +36,9 @@ sd_stats_fp_t Alignment::bedpe_fp() const
 	return o;
 }
 
+static inline double wall_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+static inline bool region_trace() { static const bool on = getenv("SEDEF_B200_TRACE") != nullptr; return on; }   // developer aid: phase times on stderr
+
 static void add_stats(sd_stats_t &d, const sd_stats_t &s)
 {
 	int32_t *dp = reinterpret_cast<int32_t *>(&d);
@@ -41,8 +46,8 @@ static void add_stats(sd_stats_t &d, const sd_stats_t &s)
 	for (size_t k = 0; k < sizeof(sd_stats_t) / sizeof(int32_t); ++k) dp[k] += sp[k];
 }
 
-static std::vector<sd_stats_t> stats_of(const std::vector<std::pair<std::string, std::string>> &pairs,
-                                        const std::vector<std::deque<std::pair<char, int>>> &cigars);
+struct StrPair { const std::string *a, *b; };
+static std::vector<sd_stats_t> stats_of(const std::vector<StrPair> &pairs, const std::vector<const std::deque<std::pair<char, int>> *> &cigars);
 
 int max_ksw_seq_len() { return kMaxKswSeqLen; }
 
@@ -87,15 +92,18 @@ static std::vector<Alignment> align_batch_impl(const std::vector<std::pair<std::
 		}
 	}
 	std::vector<uint8_t> qraw(qtot + 1), traw(ttot + 1);                                   // never pass null buffers
-	for (size_t k = 0; k < chunks.size(); ++k) {
+#pragma omp parallel for schedule(static) if (chunks.size() >= 512)
+	for (long k = 0; k < (long)chunks.size(); ++k) {
 		memcpy(&qraw[qo[k]], pairs[owner[k]].first.data() + chunks[k].sp, ql[k]);
 		memcpy(&traw[to[k]], pairs[owner[k]].second.data() + chunks[k].sp, tl[k]);
 	}
 	const int n = (int)owner.size();
 	ksw_b200_result_t *res = nullptr;
+	const double t_call = wall_ms();
 	int rc = ksw_extz2_batch_arena(n, ql.data(), qo.data(), nullptr, tl.data(), to.data(), nullptr, 5, mat,
 	                               (int8_t)p.gap_open, (int8_t)p.gap_extend, p.bandwidth, -1, 0, 1, qraw.data(), traw.data(), &res);
 	if (rc) throw std::runtime_error(std::string("ksw_extz2_batch_arena: ") + ksw_b200_strerror(rc) + " -- " + ksw_b200_last_error());
+	if (region_trace()) fprintf(stderr, "[regions]     ksw_extz2_batch_arena: %d pairs, %.1f ms\n", n, wall_ms() - t_call);
 	const ksw_extz_t *ez = ksw_b200_result_ez(res);
 	const sd_stats_t *st = ksw_b200_result_stats(res);
 	if (trims) {
@@ -107,25 +115,31 @@ static std::vector<Alignment> align_batch_impl(const std::vector<std::pair<std::
 		}
 	}
 	std::vector<Alignment> out(pairs.size());
-	for (size_t i = 0; i < pairs.size(); ++i) { out[i].a = pairs[i].first; out[i].b = pairs[i].second; }
 	// The statistics of a chunked pair are the sum of its chunks' statistics as long as every chunk but the last one is
 	// aligned end to end: the reference walks the CONCATENATED cigar from (0, 0) (populate_nice_alignment), so a chunk cut
 	// short by a band break (user-set bandwidth) shifts every later column.  Those pairs are re-walked below.
 	std::vector<char> rewalk(pairs.size(), 0);
-	for (int k = 0; k < n; ++k) {
-		Alignment &al = out[owner[k]];
-		for (int64_t c = 0; c < ez[k].n_cigar; ++c) {
-			const int idx = ez[k].cigar[c] & 0xf, len = (int)(ez[k].cigar[c] >> 4);
-			if (idx < 3) al.cigar.push_back({"MDI"[idx], len});                              // src/align.cc:58-63
+	std::vector<int> first(pairs.size() + 1, n);                                           // first chunk of every pair
+	for (int k = n - 1; k >= 0; --k) first[owner[k]] = k;
+	for (long i = (long)pairs.size() - 1; i >= 0; --i) if (first[i] == n || first[i] > first[i + 1]) first[i] = first[i + 1];   // pairs without chunks
+#pragma omp parallel for schedule(static) if (pairs.size() >= 512)
+	for (long i = 0; i < (long)pairs.size(); ++i) {
+		Alignment &al = out[i];
+		al.a = pairs[i].first; al.b = pairs[i].second;
+		for (int k = first[i]; k < first[i + 1]; ++k) {
+			for (int64_t c = 0; c < ez[k].n_cigar; ++c) {
+				const int idx = ez[k].cigar[c] & 0xf, len = (int)(ez[k].cigar[c] >> 4);
+				if (idx < 3) al.cigar.push_back({"MDI"[idx], len});                          // src/align.cc:58-63
+			}
+			add_stats(al.stats, st[k]);
+			if (ez[k].zdropped && k + 1 < first[i + 1]) rewalk[i] = 1;
 		}
-		add_stats(al.stats, st[k]);
-		if (ez[k].zdropped && k + 1 < n && owner[k + 1] == owner[k]) rewalk[owner[k]] = 1;
 	}
 	ksw_b200_result_free(res);
-	std::vector<std::pair<std::string, std::string>> rp;
-	std::vector<std::deque<std::pair<char, int>>> rc_;
+	std::vector<StrPair> rp;
+	std::vector<const std::deque<std::pair<char, int>> *> rc_;
 	std::vector<size_t> ri;
-	for (size_t i = 0; i < pairs.size(); ++i) if (rewalk[i]) { rp.push_back(pairs[i]); rc_.push_back(out[i].cigar); ri.push_back(i); }
+	for (size_t i = 0; i < pairs.size(); ++i) if (rewalk[i]) { rp.push_back({&pairs[i].first, &pairs[i].second}); rc_.push_back(&out[i].cigar); ri.push_back(i); }
 	if (!ri.empty()) {
 		std::vector<sd_stats_t> rs = stats_of(rp, rc_);
 		for (size_t k = 0; k < ri.size(); ++k) out[ri[k]].stats = rs[k];
@@ -136,28 +150,31 @@ static std::vector<Alignment> align_batch_impl(const std::vector<std::pair<std::
 // statistics of alignments given as SEDEF-alphabet run lists (populate_nice_alignment, src/align.cc:274-315).
 // Zero-length runs are kept: the reference counts every non-M run in `gaps`, also the ('\0', 0) run that
 // cigar_from_alignment leaves for an alignment trimmed to nothing (src/align.cc:300-305,479-501).
-static std::vector<sd_stats_t> stats_of(const std::vector<std::pair<std::string, std::string>> &pairs,
-                                        const std::vector<std::deque<std::pair<char, int>>> &cigars)
+static std::vector<sd_stats_t> stats_of(const std::vector<StrPair> &pairs, const std::vector<const std::deque<std::pair<char, int>> *> &cigars)
 {
 	const int n = (int)pairs.size();
 	std::vector<int64_t> coff(n), cn(n), ao(n), bo(n);
 	std::vector<int> al(n), bl(n);
-	std::vector<uint32_t> cbuf;
-	std::vector<uint8_t> abuf, bbuf;
+	int64_t ctot = 0, atot = 0, btot = 0;
 	for (int i = 0; i < n; ++i) {
-		coff[i] = (int64_t)cbuf.size();
-		for (auto &run : cigars[i]) {
+		coff[i] = ctot; cn[i] = (int64_t)cigars[i]->size(); ctot += cn[i];
+		ao[i] = atot; bo[i] = btot;
+		al[i] = (int)pairs[i].a->size(); bl[i] = (int)pairs[i].b->size();
+		atot += al[i]; btot += bl[i];
+	}
+	std::vector<uint32_t> cbuf(ctot + 1);
+	std::vector<uint8_t> abuf(atot + 1), bbuf(btot + 1);
+#pragma omp parallel for schedule(static) if (n >= 256)
+	for (int i = 0; i < n; ++i) {
+		int64_t c = coff[i];
+		for (auto &run : *cigars[i]) {
 			const char ch = run.first;
 			uint32_t op = ch == 'M' ? 0u : (ch == 'D' ? 1u : (ch == 'I' ? 2u : 3u));   // SEDEF 'D' = a only = ksw I; 3 = any other letter
-			cbuf.push_back((uint32_t)run.second << 4 | op);
+			cbuf[c++] = (uint32_t)run.second << 4 | op;
 		}
-		cn[i] = (int64_t)cbuf.size() - coff[i];
-		ao[i] = (int64_t)abuf.size(); bo[i] = (int64_t)bbuf.size();
-		al[i] = (int)pairs[i].first.size(); bl[i] = (int)pairs[i].second.size();
-		abuf.insert(abuf.end(), pairs[i].first.begin(), pairs[i].first.end());
-		bbuf.insert(bbuf.end(), pairs[i].second.begin(), pairs[i].second.end());
+		memcpy(&abuf[ao[i]], pairs[i].a->data(), al[i]);
+		memcpy(&bbuf[bo[i]], pairs[i].b->data(), bl[i]);
 	}
-	cbuf.push_back(0); abuf.push_back(0); bbuf.push_back(0);
 	std::vector<sd_stats_t> st(n);
 	std::vector<int> status(n);
 	int rc = sd_stats_from_cigar_batch_flat(n, coff.data(), cn.data(), cbuf.data(), al.data(), ao.data(), abuf.data(),
@@ -185,7 +202,10 @@ std::vector<Alignment> from_cigar_batch(const std::vector<std::pair<std::string,
 		}
 		out[i].cigar = runs[i];
 	}
-	std::vector<sd_stats_t> st = stats_of(pairs, runs);
+	std::vector<StrPair> sp(n);
+	std::vector<const std::deque<std::pair<char, int>> *> cp(n);
+	for (int i = 0; i < n; ++i) { sp[i] = {&pairs[i].first, &pairs[i].second}; cp[i] = &runs[i]; }
+	std::vector<sd_stats_t> st = stats_of(sp, cp);
 	for (int i = 0; i < n; ++i) out[i].stats = st[i];
 	return out;
 }
@@ -206,9 +226,11 @@ std::vector<GuidedAlignment> align_chains_batch(const std::vector<ChainGuide> &c
 	struct Fill { size_t chain; size_t step; char tail_op; int tail_len; };   // fill result is spliced in at `step`
 	std::vector<std::pair<std::string, std::string>> reqs;
 	std::vector<Fill> fills;
+	std::vector<size_t> fill_first(chains.size() + 1, 0);                       // first fill of every chain: the stitch pass runs in parallel
 	for (size_t ci = 0; ci < chains.size(); ++ci) {
 		const ChainGuide &cg = chains[ci];
 		const std::vector<Anchor> &g = *cg.anchors;
+		fill_first[ci] = fills.size();
 		for (size_t k = 1; k < cg.guide_idx.size(); ++k) {
 			const Anchor &pv = g[cg.guide_idx[k - 1]], &cu = g[cg.guide_idx[k]];
 			const int qpe = pv.q + pv.l, rpe = pv.r + pv.l, qs = cu.q, rs = cu.r;
@@ -225,15 +247,18 @@ std::vector<GuidedAlignment> align_chains_batch(const std::vector<ChainGuide> &c
 			}
 		}
 	}
+	fill_first[chains.size()] = fills.size();
 	std::vector<Alignment> filled = align_batch(reqs, p);                              // ONE batched ksw_extz2 call
-	// pass 2: stitch
+	// pass 2: stitch (chains are independent)
 	std::vector<GuidedAlignment> out(chains.size());
-	std::vector<std::pair<std::string, std::string>> finals(chains.size());
-	std::vector<std::deque<std::pair<char, int>>> final_cigars(chains.size());
-	size_t fpos = 0;
-	for (size_t ci = 0; ci < chains.size(); ++ci) {
+	std::vector<StrPair> finals(chains.size());
+	std::vector<const std::deque<std::pair<char, int>> *> final_cigars(chains.size());
+#pragma omp parallel for schedule(dynamic, 16) if (chains.size() >= 64)
+	for (long ci = 0; ci < (long)chains.size(); ++ci) {
 		const ChainGuide &cg = chains[ci];
 		GuidedAlignment &al = out[ci];
+		size_t fpos = fill_first[ci];
+		finals[ci] = {&al.a, &al.b}; final_cigars[ci] = &al.cigar;
 		if (cg.guide_idx.empty()) continue;                                             // src/align.cc:202-205
 		const std::vector<Anchor> &g = *cg.anchors;
 		const Anchor &a0 = g[cg.guide_idx[0]];
@@ -256,8 +281,6 @@ std::vector<GuidedAlignment> align_chains_batch(const std::vector<ChainGuide> &c
 		}
 		al.a = cg.qstr->substr(al.start_a, al.end_a - al.start_a);
 		al.b = cg.rstr->substr(al.start_b, al.end_b - al.start_b);
-		finals[ci] = {al.a, al.b};
-		final_cigars[ci] = al.cigar;
 	}
 	// populate_nice_alignment for every stitched alignment: one statistics-from-CIGAR call
 	std::vector<sd_stats_t> st = stats_of(finals, final_cigars);
@@ -384,8 +407,10 @@ std::vector<GuidedAlignment> align_hit_guides_batch(const std::vector<HitGuide> 
 	struct Req { size_t guide; int kind; char tail_op; int tail_len; };
 	std::vector<std::pair<std::string, std::string>> reqs;
 	std::vector<Req> meta;
+	std::vector<size_t> req_first(guides.size() + 1, 0);                         // first request of every guide
 	for (size_t gi = 0; gi < guides.size(); ++gi) {
 		const HitGuide &hg = guides[gi];
+		req_first[gi] = meta.size();
 		if (hg.guide.empty()) continue;
 		const std::string &qstr = *hg.qstr, &rstr = *hg.rstr;
 		for (size_t k = 1; k < hg.guide.size(); ++k) {
@@ -411,15 +436,20 @@ std::vector<GuidedAlignment> align_hit_guides_batch(const std::vector<HitGuide> 
 		}
 	}
 	// ONE batched ksw_extz2 call; the trim scans of the side extensions come back with it (computed on the traceback walk)
+	req_first[guides.size()] = meta.size();
+	const double t_req = wall_ms();
 	std::vector<TrimScan> scans;
 	std::vector<Alignment> done = align_batch_impl(reqs, p, &scans);
+	const double t_aln = wall_ms();
 	std::vector<GuidedAlignment> out(guides.size());
-	std::vector<std::pair<std::string, std::string>> finals(guides.size());
-	std::vector<std::deque<std::pair<char, int>>> final_cigars(guides.size());
-	size_t pos = 0;
-	for (size_t gi = 0; gi < guides.size(); ++gi) {
+	std::vector<StrPair> finals(guides.size());
+	std::vector<const std::deque<std::pair<char, int>> *> final_cigars(guides.size());
+#pragma omp parallel for schedule(dynamic, 8) if (guides.size() >= 32)
+	for (long gi = 0; gi < (long)guides.size(); ++gi) {
 		const HitGuide &hg = guides[gi];
 		GuidedAlignment &al = out[gi];
+		size_t pos = req_first[gi];
+		finals[gi] = {&al.a, &al.b}; final_cigars[gi] = &al.cigar;
 		if (hg.guide.empty()) continue;
 		const std::string &qstr = *hg.qstr, &rstr = *hg.rstr;
 		al.cigar = hg.guide.front().cigar;
@@ -438,7 +468,7 @@ std::vector<GuidedAlignment> align_hit_guides_batch(const std::vector<HitGuide> 
 		int qlo = hg.guide.front().start_a, rlo = hg.guide.front().start_b;
 		int qhi = hg.guide.back().end_a, rhi = hg.guide.back().end_b;
 		if (hg.side) {
-			if (pos < meta.size() && meta[pos].guide == gi && meta[pos].kind == LEFT) {
+			if (pos < meta.size() && meta[pos].guide == (size_t)gi && meta[pos].kind == LEFT) {
 				GuidedAlignment gap; gap.a = done[pos].a; gap.b = done[pos].b; gap.cigar = done[pos].cigar;
 				gap.start_a = gap.start_b = 0; gap.end_a = (int)gap.a.size(); gap.end_b = (int)gap.b.size();
 				apply_trim_front(gap, scans[pos].valid ? scans[pos].front : scan_trim_front(gap, p));
@@ -446,7 +476,7 @@ std::vector<GuidedAlignment> align_hit_guides_batch(const std::vector<HitGuide> 
 				prepend_cigar(al.cigar, gap.cigar);
 				++pos;
 			}
-			if (pos < meta.size() && meta[pos].guide == gi && meta[pos].kind == RIGHT) {
+			if (pos < meta.size() && meta[pos].guide == (size_t)gi && meta[pos].kind == RIGHT) {
 				GuidedAlignment gap; gap.a = done[pos].a; gap.b = done[pos].b; gap.cigar = done[pos].cigar;
 				gap.start_a = gap.start_b = 0; gap.end_a = (int)gap.a.size(); gap.end_b = (int)gap.b.size();
 				apply_trim_back(gap, scans[pos].valid ? scans[pos].back : scan_trim_back(gap, p));
@@ -457,10 +487,10 @@ std::vector<GuidedAlignment> align_hit_guides_batch(const std::vector<HitGuide> 
 		}
 		al.start_a = qlo; al.end_a = qhi; al.start_b = rlo; al.end_b = rhi;
 		al.a = qstr.substr(qlo, qhi - qlo); al.b = rstr.substr(rlo, rhi - rlo);
-		finals[gi] = {al.a, al.b};
-		final_cigars[gi] = al.cigar;
 	}
+	const double t_st = wall_ms();
 	std::vector<sd_stats_t> st = stats_of(finals, final_cigars);
+	if (region_trace()) fprintf(stderr, "[regions]   guides: %zu requests, align %.1f ms, stitch %.1f ms, statistics %.1f ms\n", reqs.size(), t_aln - t_req, t_st - t_aln, wall_ms() - t_st);
 	for (size_t gi = 0; gi < guides.size(); ++gi) out[gi].stats = st[gi];
 	return out;
 }
@@ -507,10 +537,11 @@ static void cut_head(std::vector<char> &ops, int lim, bool by_a, int &q, int &r)
 
 std::vector<GuidedAlignment> merge_batch(const std::vector<MergeRequest> &reqs, const AlignParams &p)
 {
-	struct Work { GuidedAlignment prev, cur; int fill = -1; char tail_op = 0; int tail_len = 0; int qgap = 0, rgap = 0; };
+	struct Work { GuidedAlignment prev, cur; int fill = -1; char tail_op = 0; int tail_len = 0; int qgap = 0, rgap = 0; std::string fa, fb; bool want = false; };
 	std::vector<Work> work(reqs.size());
 	std::vector<std::pair<std::string, std::string>> fills;
-	for (size_t k = 0; k < reqs.size(); ++k) {
+#pragma omp parallel for schedule(dynamic, 8) if (reqs.size() >= 32)
+	for (long k = 0; k < (long)reqs.size(); ++k) {
 		Work &w = work[k];
 		w.prev = reqs[k].prev; w.cur = reqs[k].cur;
 		const std::string &qstr = *reqs[k].qstr, &rstr = *reqs[k].rstr;
@@ -525,22 +556,26 @@ std::vector<GuidedAlignment> merge_batch(const std::vector<MergeRequest> &reqs, 
 		w.prev.cigar = cigar_from_ops(po); w.cur.cigar = cigar_from_ops(co);               // src/align.cc:570-571
 		w.qgap = w.cur.start_a - w.prev.end_a; w.rgap = w.cur.start_b - w.prev.end_b;
 		if (w.qgap && w.rgap) {                                                            // src/align.cc:579-594
-			w.fill = (int)fills.size();
-			if (w.qgap <= 1000 && w.rgap <= 1000) fills.emplace_back(qstr.substr(w.prev.end_a, w.qgap), rstr.substr(w.prev.end_b, w.rgap));
+			w.want = true;
+			if (w.qgap <= 1000 && w.rgap <= 1000) { w.fa = qstr.substr(w.prev.end_a, w.qgap); w.fb = rstr.substr(w.prev.end_b, w.rgap); }
 			else {
 				const int ma = std::max(w.qgap, w.rgap), mi = std::min(w.qgap, w.rgap);
-				fills.emplace_back(qstr.substr(w.prev.end_a, mi), rstr.substr(w.prev.end_b, mi));
+				w.fa = qstr.substr(w.prev.end_a, mi); w.fb = rstr.substr(w.prev.end_b, mi);
 				w.tail_op = w.qgap == mi ? 'I' : 'D'; w.tail_len = ma - mi;
 			}
 		}
 	}
+	for (size_t k = 0; k < reqs.size(); ++k)
+		if (work[k].want) { work[k].fill = (int)fills.size(); fills.emplace_back(std::move(work[k].fa), std::move(work[k].fb)); }
 	std::vector<Alignment> done = align_batch(fills, p);                                  // ONE batched ksw_extz2 call
 	std::vector<GuidedAlignment> out(reqs.size());
-	std::vector<std::pair<std::string, std::string>> finals(reqs.size());
-	std::vector<std::deque<std::pair<char, int>>> final_cigars(reqs.size());
-	for (size_t k = 0; k < reqs.size(); ++k) {
+	std::vector<StrPair> finals(reqs.size());
+	std::vector<const std::deque<std::pair<char, int>> *> final_cigars(reqs.size());
+#pragma omp parallel for schedule(dynamic, 8) if (reqs.size() >= 32)
+	for (long k = 0; k < (long)reqs.size(); ++k) {
 		Work &w = work[k];
 		GuidedAlignment &al = out[k];
+		finals[k] = {&al.a, &al.b}; final_cigars[k] = &al.cigar;
 		al = w.prev;
 		if (w.fill >= 0) {
 			std::deque<std::pair<char, int>> gc = done[w.fill].cigar;
@@ -552,8 +587,6 @@ std::vector<GuidedAlignment> merge_batch(const std::vector<MergeRequest> &reqs, 
 		append_cigar(al.cigar, w.cur.cigar);
 		al.a = reqs[k].qstr->substr(al.start_a, al.end_a - al.start_a);
 		al.b = reqs[k].rstr->substr(al.start_b, al.end_b - al.start_b);
-		finals[k] = {al.a, al.b};
-		final_cigars[k] = al.cigar;
 	}
 	std::vector<sd_stats_t> st = stats_of(finals, final_cigars);
 	for (size_t k = 0; k < reqs.size(); ++k) out[k].stats = st[k];
@@ -579,6 +612,15 @@ struct RegionState {
 	std::vector<GuidedAlignment> guide;
 	enum Phase { NEXT_PATH, WALK, WAIT_MERGE, WAIT_GUIDE, DONE } phase = NEXT_PATH;
 };
+
+// a guide / merge request needs the coordinates, the CIGAR and the counters of a chain alignment, not its two strings
+inline GuidedAlignment light(const GuidedAlignment &g)
+{
+	GuidedAlignment o;
+	o.cigar = g.cigar; o.stats = g.stats;
+	o.start_a = g.start_a; o.end_a = g.end_a; o.start_b = g.start_b; o.end_b = g.end_b;
+	return o;
+}
 
 inline bool hit_less(const GuidedAlignment &a, const GuidedAlignment &b)        // Hit::operator< (src/hit.h:44-47)
 {
@@ -662,15 +704,16 @@ bool advance(const RegionTask &t, RegionState &st, Request &rq)
 				const GuidedAlignment &cur = st.anc[st.path[st.pi]];
 				const GuidedAlignment &pv = st.anc[st.prev_idx];
 				if (cur.start_a < pv.end_a || cur.start_b < pv.end_b) {
-					rq.kind = 1; rq.merge = MergeRequest{pv, cur, t.qstr, t.rstr};
+					rq.kind = 1; rq.merge = MergeRequest{light(pv), light(cur), t.qstr, t.rstr};
 					st.phase = RegionState::WAIT_MERGE;
 					return true;
 				}
-				st.guide.push_back(pv);
+				st.guide.push_back(light(pv));
 				st.prev_idx = st.path[st.pi++];
 			}
-			st.guide.push_back(st.anc[st.prev_idx]);
-			rq.kind = 2; rq.hg = HitGuide{t.qstr, t.rstr, st.guide, kRefSideAlign};
+			st.guide.push_back(light(st.anc[st.prev_idx]));
+			rq.kind = 2; rq.hg = HitGuide{t.qstr, t.rstr, std::move(st.guide), kRefSideAlign};
+			st.guide.clear();
 			st.phase = RegionState::WAIT_GUIDE;
 			return true;
 		}
@@ -682,6 +725,7 @@ bool advance(const RegionTask &t, RegionState &st, Request &rq)
 std::vector<std::vector<GuidedAlignment>> refine_regions_batch(const std::vector<RegionTask> &regions, const AlignParams &p, RefineStats *stats)
 {
 	RefineStats rs;
+	const double t_begin = wall_ms();
 	// wave 0: every chain of every region through one batched call
 	std::vector<ChainGuide> chains;
 	std::vector<size_t> owner;
@@ -689,21 +733,27 @@ std::vector<std::vector<GuidedAlignment>> refine_regions_batch(const std::vector
 		for (auto &g : regions[ri].guides) { chains.push_back(ChainGuide{regions[ri].qstr, regions[ri].rstr, regions[ri].anchors, g}); owner.push_back(ri); }
 	std::vector<GuidedAlignment> wave0 = align_chains_batch(chains, p);
 	rs.batch_calls += 2; rs.ksw_requests += (long long)chains.size(); rs.rounds = 1;
+	if (region_trace()) fprintf(stderr, "[regions] chain wave: %zu chains, %.1f ms\n", chains.size(), wall_ms() - t_begin);
 	std::vector<RegionState> st(regions.size());
 	for (size_t k = 0; k < wave0.size(); ++k) st[owner[k]].anc.push_back(std::move(wave0[k]));
-	for (size_t ri = 0; ri < regions.size(); ++ri) refine_dp(regions[ri], st[ri]);
+#pragma omp parallel for schedule(dynamic, 4) if (regions.size() >= 16)
+	for (long ri = 0; ri < (long)regions.size(); ++ri) refine_dp(regions[ri], st[ri]);
 	// waves 1..: every region contributes the next step of its current path
 	for (;;) {
 		std::vector<MergeRequest> merges; std::vector<size_t> merge_owner;
 		std::vector<HitGuide> guides; std::vector<size_t> guide_owner;
+		std::vector<Request> rqs(regions.size());
+		std::vector<char> has(regions.size(), 0);
+#pragma omp parallel for schedule(dynamic, 4) if (regions.size() >= 16)
+		for (long ri = 0; ri < (long)regions.size(); ++ri) has[ri] = advance(regions[ri], st[ri], rqs[ri]) ? 1 : 0;
 		for (size_t ri = 0; ri < regions.size(); ++ri) {
-			Request rq;
-			if (!advance(regions[ri], st[ri], rq)) continue;
-			if (rq.kind == 1) { merges.push_back(std::move(rq.merge)); merge_owner.push_back(ri); }
-			else { guides.push_back(std::move(rq.hg)); guide_owner.push_back(ri); }
+			if (!has[ri]) continue;
+			if (rqs[ri].kind == 1) { merges.push_back(std::move(rqs[ri].merge)); merge_owner.push_back(ri); }
+			else { guides.push_back(std::move(rqs[ri].hg)); guide_owner.push_back(ri); }
 		}
 		if (merges.empty() && guides.empty()) break;
 		++rs.rounds;
+		const double t_round = wall_ms();
 		if (!merges.empty()) {
 			std::vector<GuidedAlignment> done = merge_batch(merges, p);
 			rs.batch_calls += 2; rs.ksw_requests += (long long)merges.size();
@@ -723,6 +773,7 @@ std::vector<std::vector<GuidedAlignment>> refine_regions_batch(const std::vector
 				s.phase = RegionState::NEXT_PATH;
 			}
 		}
+		if (region_trace()) fprintf(stderr, "[regions] round %d: %zu merges, %zu guides, %.1f ms\n", rs.rounds, merges.size(), guides.size(), wall_ms() - t_round);
 	}
 	std::vector<std::vector<GuidedAlignment>> out(regions.size());
 	for (size_t ri = 0; ri < regions.size(); ++ri) out[ri] = std::move(st[ri].accepted);
@@ -911,7 +962,9 @@ std::vector<std::vector<int>> chain_anchors(const std::vector<Anchor> &anchors)
 std::vector<std::vector<GuidedAlignment>> fast_align_batch(const std::vector<RegionSeed> &regions, int kmer_size, const AlignParams &p,
                                                            RefineStats *stats)
 {
+	const double t0 = wall_ms();
 	std::vector<std::vector<Anchor>> anchors = anchors_batch(regions, kmer_size);
+	const double t1 = wall_ms();
 	std::vector<RegionTask> tasks(regions.size());
 #pragma omp parallel for schedule(dynamic, 1)
 	for (long ri = 0; ri < (long)regions.size(); ++ri) {
@@ -920,6 +973,7 @@ std::vector<std::vector<GuidedAlignment>> fast_align_batch(const std::vector<Reg
 		t.same_chr = regions[ri].same_chr; t.orig_query_start = regions[ri].orig_query_start; t.orig_ref_start = regions[ri].orig_ref_start;
 		t.guides = chain_anchors(anchors[ri]);
 	}
+	if (region_trace()) fprintf(stderr, "[regions] anchors %.1f ms, chaining %.1f ms\n", t1 - t0, wall_ms() - t1);
 	return refine_regions_batch(tasks, p, stats);
 }
 

@@ -27,7 +27,8 @@ for k in range(n):
     text.append("R 0 0 0\n%s\n%s\n" % (q, t) + "\n".join(ln for ln in lines if ln[0] in "AC") + "\nE\n")
     want.append([ln for ln in lines if ln[0] == "H"])
 drv = os.path.join(root, "tests", "cpp", "align_queue_driver")
-out = subprocess.run([drv, "regions"], input="".join(text), capture_output=True, text=True, env=dict(os.environ, REGIONS_REPS="3"))
+mode = sys.argv[2] if len(sys.argv) > 2 else "fastalign"          # "fastalign": the complete path; "regions": the driver on the reference's anchors + chains
+out = subprocess.run([drv, mode], input="".join(text), capture_output=True, text=True, env=dict(os.environ, REGIONS_REPS="3"))
 assert out.returncode == 0, out.stderr
 got, cur = [], None
 for ln in out.stdout.split("\n"):
@@ -39,6 +40,13 @@ for ln in out.stdout.split("\n"):
         stats = ln
 ok = sum(a == b for a, b in zip(got, want))
 ms = float(out.stderr.strip().split()[-2])
+trace = [ln for ln in out.stderr.split("\n") if ln.startswith("[regions]")]
+if trace:
+    per_rep = len(trace) // 3
+    print("\n".join(trace[-per_rep:]))
 print("regions %d, identical to fast_align: %d" % (n, ok))
 print("reference fast_align (1 core, incl. anchoring + chaining): %.1f ms total, %.2f ms per region" % (t_total * 1e3, t_total * 1e3 / n))
-print("refine_regions_batch (all regions in flight, excl. anchoring + chaining): %.1f ms total, %.3f ms per region; %s" % (ms, ms / n, stats))
+what = "fast_align_batch (GPU anchors + host chaining + region driver, all regions in flight)" if mode == "fastalign" else \
+       "refine_regions_batch (all regions in flight, excl. anchoring + chaining)"
+print("%s: %.1f ms total, %.3f ms per region; %s" % (what, ms, ms / n, stats))
+print("host cores: %d (the reference runs one region per core; %d cores would need %.1f ms)" % (os.cpu_count(), os.cpu_count(), t_total * 1e3 / os.cpu_count()))

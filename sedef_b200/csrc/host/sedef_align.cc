@@ -220,41 +220,115 @@ static void append_cigar(std::deque<std::pair<char, int>> &cigar, const std::deq
 	} else cigar.insert(cigar.end(), app.begin(), app.end());
 }
 
+// Requests given as WINDOWS of the region strings: the strings go up once (one flat buffer per side, every distinct region
+// string copied once), a request is four numbers, and the results are read straight out of the arena -- no std::string, no
+// Alignment object and no deque per request.  A region's chain wave is hundreds of gap fills of a few bases each (SURVEY 3.2:
+// the median call is <= 32 bp), so the per-request host cost is what the wave costs.
+namespace {
+struct WindowBatch {
+	std::vector<const std::string *> qstrs, tstrs;       // distinct region strings, in order of first use
+	std::vector<int64_t> qbase, tbase;                   // their offsets in the flat buffers
+	std::string qbuf, tbuf;
+	std::vector<int> ql, tl;
+	std::vector<int64_t> qo, to;
+	ksw_b200_result_t *res = nullptr;
+	const ksw_extz_t *ez = nullptr;
+	~WindowBatch() { if (res) ksw_b200_result_free(res); }
+	// base offset of a region string (registering it on first use); call serially
+	int64_t base_of(const std::string *s, std::vector<const std::string *> &strs, std::vector<int64_t> &bases, std::string &buf, const std::string *&last, int64_t &last_base)
+	{
+		if (s == last) return last_base;
+		for (size_t k = strs.size(); k-- > 0;) if (strs[k] == s) { last = s; return last_base = bases[k]; }
+		strs.push_back(s); bases.push_back((int64_t)buf.size()); buf += *s;
+		last = s; return last_base = bases.back();
+	}
+	void run(const AlignParams &p)
+	{
+		const int8_t a = (int8_t)p.match, b = p.mismatch < 0 ? (int8_t)p.mismatch : (int8_t)(-p.mismatch);
+		const int8_t mat[25] = {a, b, b, b, 0, b, a, b, b, 0, b, b, a, b, 0, b, b, b, a, 0, 0, 0, 0, 0, 0};
+		qbuf.push_back('\0'); tbuf.push_back('\0');
+		const double t0 = wall_ms();
+		int rc = ksw_extz2_batch_arena((int)ql.size(), ql.data(), qo.data(), nullptr, tl.data(), to.data(), nullptr, 5, mat,
+		                               (int8_t)p.gap_open, (int8_t)p.gap_extend, p.bandwidth, -1, 0, 0, (const uint8_t *)qbuf.data(), (const uint8_t *)tbuf.data(), &res);
+		if (rc) throw std::runtime_error(std::string("ksw_extz2_batch_arena: ") + ksw_b200_strerror(rc) + " -- " + ksw_b200_last_error());
+		if (region_trace()) fprintf(stderr, "[regions]     ksw_extz2_batch_arena (windows): %zu pairs, %.1f ms\n", ql.size(), wall_ms() - t0);
+		ez = ksw_b200_result_ez(res);
+	}
+};
+// append the raw ksw CIGAR of one result in SEDEF's alphabet (src/align.cc:58-63), merging equal neighbours like append_cigar
+inline void append_raw(std::deque<std::pair<char, int>> &cigar, const ksw_extz_t &z)
+{
+	for (int64_t c = 0; c < z.n_cigar; ++c) {
+		const int idx = z.cigar[c] & 0xf, len = (int)(z.cigar[c] >> 4);
+		if (idx >= 3) continue;
+		const char op = "MDI"[idx];
+		if (c == 0 && !cigar.empty() && cigar.back().first == op) cigar.back().second += len;
+		else cigar.push_back({op, len});
+	}
+}
+} // namespace
+
 std::vector<GuidedAlignment> align_chains_batch(const std::vector<ChainGuide> &chains, const AlignParams &p)
 {
-	// pass 1: walk every chain, queue its gap fills
-	struct Fill { size_t chain; size_t step; char tail_op; int tail_len; };   // fill result is spliced in at `step`
-	std::vector<std::pair<std::string, std::string>> reqs;
-	std::vector<Fill> fills;
-	std::vector<size_t> fill_first(chains.size() + 1, 0);                       // first fill of every chain: the stitch pass runs in parallel
-	for (size_t ci = 0; ci < chains.size(); ++ci) {
+	const long nc = (long)chains.size();
+	// pass 1a: how many gap fills does every chain need?  (a fill is needed where both sequences have bases between two anchors)
+	std::vector<size_t> fill_first(nc + 1, 0);
+#pragma omp parallel for schedule(static) if (nc >= 64)
+	for (long ci = 0; ci < nc; ++ci) {
 		const ChainGuide &cg = chains[ci];
 		const std::vector<Anchor> &g = *cg.anchors;
-		fill_first[ci] = fills.size();
+		size_t cnt = 0;
 		for (size_t k = 1; k < cg.guide_idx.size(); ++k) {
 			const Anchor &pv = g[cg.guide_idx[k - 1]], &cu = g[cg.guide_idx[k]];
-			const int qpe = pv.q + pv.l, rpe = pv.r + pv.l, qs = cu.q, rs = cu.r;
-			const int qgap = qs - qpe, rgap = rs - rpe;
-			if (qgap && rgap) {
-				if (qgap <= 1000 && rgap <= 1000) {                                     // "close" hits, src/align.cc:233-236
-					reqs.emplace_back(cg.qstr->substr(qpe, qgap), cg.rstr->substr(rpe, rgap));
-					fills.push_back({ci, k, 0, 0});
-				} else {                                                                // src/align.cc:237-246: ma1 is always taken
-					const int ma = std::max(qgap, rgap), mi = std::min(qgap, rgap);
-					reqs.emplace_back(cg.qstr->substr(qpe, mi), cg.rstr->substr(rpe, mi));
-					fills.push_back({ci, k, qgap == mi ? 'I' : 'D', ma - mi});
-				}
-			}
+			cnt += (cu.q - (pv.q + pv.l)) != 0 && (cu.r - (pv.r + pv.l)) != 0;
+		}
+		fill_first[ci + 1] = cnt;
+	}
+	for (long ci = 0; ci < nc; ++ci) fill_first[ci + 1] += fill_first[ci];
+	// the region strings, once each
+	WindowBatch wb;
+	std::vector<int64_t> cq(nc), ct(nc);
+	{
+		const std::string *lq = nullptr, *lt = nullptr; int64_t lqb = 0, ltb = 0;
+		for (long ci = 0; ci < nc; ++ci) {
+			cq[ci] = wb.base_of(chains[ci].qstr, wb.qstrs, wb.qbase, wb.qbuf, lq, lqb);
+			ct[ci] = wb.base_of(chains[ci].rstr, wb.tstrs, wb.tbase, wb.tbuf, lt, ltb);
 		}
 	}
-	fill_first[chains.size()] = fills.size();
-	std::vector<Alignment> filled = align_batch(reqs, p);                              // ONE batched ksw_extz2 call
+	// pass 1b: the requests, as windows
+	const size_t nf = fill_first[nc];
+	wb.ql.resize(nf); wb.tl.resize(nf); wb.qo.resize(nf); wb.to.resize(nf);
+	std::vector<int> tail_len(nf, 0);                                            // > 0: the fill covers mi x mi and a gap of this length follows
+	std::vector<char> tail_op(nf, 0);
+#pragma omp parallel for schedule(static) if (nc >= 64)
+	for (long ci = 0; ci < nc; ++ci) {
+		const ChainGuide &cg = chains[ci];
+		const std::vector<Anchor> &g = *cg.anchors;
+		size_t f = fill_first[ci];
+		for (size_t k = 1; k < cg.guide_idx.size(); ++k) {
+			const Anchor &pv = g[cg.guide_idx[k - 1]], &cu = g[cg.guide_idx[k]];
+			const int qpe = pv.q + pv.l, rpe = pv.r + pv.l;
+			const int qgap = cu.q - qpe, rgap = cu.r - rpe;
+			if (!(qgap && rgap)) continue;
+			int la = qgap, lb = rgap;
+			if (!(qgap <= 1000 && rgap <= 1000)) {                                  // src/align.cc:237-246: ma1 (mi x mi, then the rest as a gap) is always taken
+				const int ma = std::max(qgap, rgap), mi = std::min(qgap, rgap);
+				la = lb = mi; tail_op[f] = qgap == mi ? 'I' : 'D'; tail_len[f] = ma - mi;
+			}
+			wb.ql[f] = la; wb.tl[f] = lb; wb.qo[f] = cq[ci] + qpe; wb.to[f] = ct[ci] + rpe;
+			++f;
+		}
+	}
+	bool chunked = false;
+	for (size_t f = 0; f < nf && !chunked; ++f) chunked = wb.ql[f] > kMaxKswSeqLen || wb.tl[f] > kMaxKswSeqLen;
+	if (chunked) throw std::runtime_error("align_chains_batch: a gap fill longer than MAX_KSW_SEQ_LEN (chains come with gaps of at most MAX_CHAIN_GAP)");
+	wb.run(p);                                                                   // ONE batched ksw_extz2 call
 	// pass 2: stitch (chains are independent)
-	std::vector<GuidedAlignment> out(chains.size());
-	std::vector<StrPair> finals(chains.size());
-	std::vector<const std::deque<std::pair<char, int>> *> final_cigars(chains.size());
-#pragma omp parallel for schedule(dynamic, 16) if (chains.size() >= 64)
-	for (long ci = 0; ci < (long)chains.size(); ++ci) {
+	std::vector<GuidedAlignment> out(nc);
+	std::vector<StrPair> finals(nc);
+	std::vector<const std::deque<std::pair<char, int>> *> final_cigars(nc);
+#pragma omp parallel for schedule(dynamic, 16) if (nc >= 64)
+	for (long ci = 0; ci < nc; ++ci) {
 		const ChainGuide &cg = chains[ci];
 		GuidedAlignment &al = out[ci];
 		size_t fpos = fill_first[ci];
@@ -266,14 +340,14 @@ std::vector<GuidedAlignment> align_chains_batch(const std::vector<ChainGuide> &c
 		al.cigar = {{'M', a0.l}};
 		for (size_t k = 1; k < cg.guide_idx.size(); ++k) {
 			const Anchor &pv = g[cg.guide_idx[k - 1]], &cu = g[cg.guide_idx[k]];
-			const int qpe = pv.q + pv.l, rpe = pv.r + pv.l, qs = cu.q, rs = cu.r;
-			const int qgap = qs - qpe, rgap = rs - rpe;
+			const int qgap = cu.q - (pv.q + pv.l), rgap = cu.r - (pv.r + pv.l);
 			al.end_a = cu.q + cu.l; al.end_b = cu.r + cu.l;
 			if (qgap && rgap) {
-				const Fill &f = fills[fpos];
-				std::deque<std::pair<char, int>> gc = filled[fpos].cigar;
-				if (f.tail_op) gc.push_back({f.tail_op, f.tail_len});
-				append_cigar(al.cigar, gc);
+				// append_cigar(cigar, fill [+ tail]) (src/align.cc:468-477): only the FIRST appended run may merge
+				if (wb.ez[fpos].n_cigar > 0) {
+					append_raw(al.cigar, wb.ez[fpos]);
+					if (tail_op[fpos]) al.cigar.push_back({tail_op[fpos], tail_len[fpos]});
+				} else if (tail_op[fpos]) append_cigar(al.cigar, {{tail_op[fpos], tail_len[fpos]}});
 				++fpos;
 			} else if (qgap) append_cigar(al.cigar, {{'D', qgap}});
 			else if (rgap) append_cigar(al.cigar, {{'I', rgap}});
@@ -284,7 +358,7 @@ std::vector<GuidedAlignment> align_chains_batch(const std::vector<ChainGuide> &c
 	}
 	// populate_nice_alignment for every stitched alignment: one statistics-from-CIGAR call
 	std::vector<sd_stats_t> st = stats_of(finals, final_cigars);
-	for (size_t ci = 0; ci < chains.size(); ++ci) out[ci].stats = st[ci];
+	for (long ci = 0; ci < nc; ++ci) out[ci].stats = st[ci];
 	return out;
 }
 
@@ -974,6 +1048,9 @@ std::vector<std::vector<GuidedAlignment>> fast_align_batch(const std::vector<Reg
 		t.guides = chain_anchors(anchors[ri]);
 	}
 	if (region_trace()) fprintf(stderr, "[regions] anchors %.1f ms, chaining %.1f ms\n", t1 - t0, wall_ms() - t1);
+	// (Cutting large region sets into groups whose wave sequences run concurrently from several host threads was tried and is
+	// SLOWER -- 4000 regions: 2300 ms in 8 groups against 1322 ms in one -- the groups' persistent DP grids and their host
+	// threads get in each other's way; profiles/r02_tuning.md.)
 	return refine_regions_batch(tasks, p, stats);
 }
 

@@ -16,6 +16,7 @@
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 #include "../../include/ksw2_b200.h"
@@ -135,10 +136,26 @@ __global__ void __launch_bounds__(256) anchor_find_kernel(AnchorLaunch L)
 	}
 }
 
+// scratch buffers persist between calls (cudaMalloc / cudaFree of tens of MB cost more than the kernels): slot k of the
+// per-process scratch grows on demand; one call at a time (mutex)
+struct Scratch {
+	void *p[12] = {nullptr}; size_t cap[12] = {0}; int dev = -1;
+	void *get(int k, size_t bytes)
+	{
+		int cur = 0; cudaGetDevice(&cur);
+		if (cur != dev) { for (int i = 0; i < 12; ++i) { if (p[i]) cudaFree(p[i]); p[i] = nullptr; cap[i] = 0; } dev = cur; }
+		if (bytes <= cap[k]) return p[k];
+		if (p[k]) cudaFree(p[k]);
+		const size_t want = bytes + bytes / 4 + 256;
+		if (cudaMalloc(&p[k], want) != cudaSuccess) { cudaGetLastError(); p[k] = nullptr; cap[k] = 0; return nullptr; }
+		cap[k] = want; return p[k];
+	}
+};
+Scratch g_scratch;
+std::mutex g_scratch_mu;
 struct Dev {
-	void *p = nullptr;
-	~Dev() { if (p) cudaFree(p); }
-	bool alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 16) == cudaSuccess; }
+	void *p = nullptr; int slot = 0;
+	bool alloc(size_t bytes) { p = g_scratch.get(slot, bytes ? bytes : 16); return p != nullptr; }
 };
 
 } // namespace
@@ -168,7 +185,9 @@ extern "C" int sedef_anchors_batch(int n, const int *qlen, const int64_t *qoff, 
 		tbl_cap[i] = cap; tbl_off[i] = ttot; ttot += cap;
 	}
 	const int64_t ntot = rbase[n - 1] + rlen[n - 1];
+	std::lock_guard<std::mutex> lk(g_scratch_mu);
 	Dev dq, dr, dmeta, dkeys, dcount, dhead, dnext, dna, dout;
+	dq.slot = 0; dr.slot = 1; dmeta.slot = 2; dkeys.slot = 3; dcount.slot = 4; dhead.slot = 5; dnext.slot = 6; dna.slot = 7; dout.slot = 8;
 	const size_t meta_bytes = (size_t)n * (8 * 6 + 4 * 3 + 1) + 256;
 	if (!dq.alloc(qtot + 16) || !dr.alloc(rtot + 16) || !dmeta.alloc(meta_bytes) || !dkeys.alloc(ttot * 4) || !dcount.alloc(ttot * 4) ||
 	    !dhead.alloc(ttot * 4) || !dnext.alloc(ntot * 4) || !dna.alloc((size_t)n * 8)) { cudaGetLastError(); return KSW_B200_ERR_NOMEM; }
@@ -203,7 +222,7 @@ extern "C" int sedef_anchors_batch(int n, const int *qlen, const int64_t *qoff, 
 	const int64_t total = anchor_off[n];
 	sedef_anchor_t *host = (sedef_anchor_t *)malloc(std::max<int64_t>(1, total) * sizeof(sedef_anchor_t));
 	if (!host) return KSW_B200_ERR_NOMEM;
-	Dev doff;
+	Dev doff; doff.slot = 9;
 	if (!dout.alloc((size_t)std::max<int64_t>(1, total) * sizeof(sedef_anchor_t)) || !doff.alloc((size_t)(n + 1) * 8)) { free(host); cudaGetLastError(); return KSW_B200_ERR_NOMEM; }
 	ok = cudaMemcpy(doff.p, anchor_off, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice) == cudaSuccess && cudaMemset(dna.p, 0, (size_t)n * 8) == cudaSuccess;
 	L.out = (sedef_anchor_t *)dout.p; L.out_off = (const int64_t *)doff.p; L.pass = 1;

@@ -10,8 +10,10 @@
 // what src/chain.cc, src/refine.cc and src/align.cc call sites do once they collect pairs per wave.
 #pragma once
 #include <stdint.h>
+#include <stdio.h>
 #include <deque>
 #include <string>
+#include <unordered_map>
 #include <utility>
 #include <vector>
 #include "ksw2_b200.h"
@@ -128,6 +130,44 @@ std::vector<std::vector<int>> chain_anchors(const std::vector<Anchor> &anchors);
 std::vector<std::vector<GuidedAlignment>> fast_align_batch(const std::vector<RegionSeed> &regions, int kmer_size = 11,
                                                            const AlignParams &p = AlignParams(), RefineStats *stats = nullptr);
 
+// ---- the align stage's driver: `sedef align generate` (BASELINE.json configs 1/4/5) ------------------
+// FastaIndex + FastaReference::get_sequence (src/fasta.cc:25-143): .fai index, memory-mapped FASTA
+class FastaFile {
+public:
+	explicit FastaFile(const std::string &filename);     // throws "Cannot open file ...", "Index file ... is malformed at line ..."
+	~FastaFile();
+	FastaFile(const FastaFile &) = delete;
+	FastaFile &operator=(const FastaFile &) = delete;
+	// bases [start, *end) of chromosome `name`; *end is clamped to the chromosome length.  Throws "Chromosome ... does not exist".
+	std::string get_sequence(const std::string &name, int start, int *end = nullptr) const;
+private:
+	struct Entry { int length = 0; long long offset = 0; int line_blen = 0, line_len = 0; };
+	std::unordered_map<std::string, Entry> index_;
+	int fd_ = -1; void *map_ = nullptr; size_t size_ = 0;
+};
+// Hit (src/hit.h:22-53) as far as the BED text needs it
+struct BedHit {
+	std::string query_name, ref_name, name, comment;
+	int query_start = 0, query_end = 0, ref_start = 0, ref_end = 0, jaccard = 0;
+	bool query_rc = false, ref_rc = false;
+	static BedHit from_bed(const std::string &bed);      // Hit::from_bed(bed), src/hit.cc:29-60
+	// Hit::to_bed(false, with_cigar) (src/hit.cc:134-196); aln == nullptr: a hit without an alignment (span 0)
+	std::string to_bed(const Alignment *aln, bool with_cigar = true) const;
+};
+std::string reverse_complement(const std::string &s);   // rc, src/util.cc:43-48
+std::vector<BedHit> read_schedule(const std::string &bed_path);     // bucket_alignments(path, 1, "", false), src/align_main.cc:211-283
+struct GenerateStats {
+	long long regions = 0, hits = 0, groups = 0, rounds = 0, batch_calls = 0, ksw_requests = 0, region_bytes = 0;
+	double ms_total = 0, ms_align = 0, ms_io = 0;
+};
+// generate_alignments (src/align_main.cc:285-337): every seed hit of `bed_path` (a bucket file or a directory of *.bed) -> regions
+// out of the FASTA -> fast_align_batch on ALL of them together (groups of <= group_bytes of sequence; 0 = default) -> one line
+// per refined hit, "<hit.to_bed>\t<seed.to_bed>", byte-identical to the reference binary's output.  With shard_count > 1 only the
+// seed hits shard_index, shard_index + shard_count, ... of the schedule are processed (one process per GPU; outputs are merged by
+// the caller, as `sedef.sh` merges its per-bucket outputs with sort).
+GenerateStats align_generate(const std::string &ref_path, const std::string &bed_path, int kmer_size, FILE *out,
+                             const AlignParams &p = AlignParams(), int shard_index = 0, int shard_count = 1, size_t group_bytes = 0);
+
 // Deferred-alignment queue: call sites push requests, the driver flushes a whole wave at once.
 class AlignQueue {
 public:
@@ -146,3 +186,14 @@ private:
 // The ksw_extz2 calls align_helper makes for one Alignment(fa, fb) with |fa| = alen, |fb| = blen (src/align.cc:46-53):
 // call k aligns (fa + sp[k], qlen[k]) against (fb + sp[k], tlen[k]).  Returns the number of calls (fills at most `cap`).
 extern "C" int sedef_b200_chunk_plan(int64_t alen, int64_t blen, int cap, int64_t *sp, int *qlen, int *tlen);
+// `sedef align generate -k kmer_size ref_path bed_path > out_path` (src/align_main.cc:285-337,368-373) through fast_align_batch.
+// out_path NULL or "-": stdout.  stats[7] (may be NULL): regions, hits, groups, rounds, batch_calls, ksw_requests, region_bytes;
+// ms[3] (may be NULL): total, align, io.  Returns 0, or -1 with the message in sedef_b200_align_generate_error().
+extern "C" int sedef_b200_align_generate(const char *ref_path, const char *bed_path, int kmer_size, const char *out_path,
+                                         int shard_index, int shard_count, long long *stats, double *ms);
+extern "C" const char *sedef_b200_align_generate_error(void);
+// host-only pieces of the same driver (no device needed): FastaReference::get_sequence; the seed hits of a bucket file / directory
+// in processing order, one Hit::to_bed(false) line each (returns the bytes needed, text truncated to cap); rc() of n bytes
+extern "C" long long sedef_b200_fasta_fetch(const char *ref_path, const char *name, int start, int *end_io, char *out, long long cap);
+extern "C" long long sedef_b200_bed_schedule(const char *bed_path, char *out, long long cap);
+extern "C" void sedef_b200_reverse_complement(const char *in, long long n, char *out);

@@ -66,7 +66,9 @@ EXPORTS = ["ksw_b200_strerror", "ksw_b200_last_error", "ksw_b200_init", "ksw_b20
            "ksw_b200_host_alloc", "ksw_b200_host_free", "ksw_b200_host_register", "ksw_b200_host_unregister",
            "ksw_b200_set_fatal_handler", "ksw_extz2_batch_arena", "ksw_b200_result_ez", "ksw_b200_result_stats",
            "ksw_b200_result_count", "ksw_b200_result_io", "ksw_b200_result_free", "ksw_b200_batch_fetch_arena",
-           "ksw_b200_result_export", "ksw_b200_result_trims", "sedef_anchors_batch"]
+           "ksw_b200_result_export", "ksw_b200_result_trims", "sedef_anchors_batch", "sedef_b200_chain_anchors",
+           "sedef_b200_chunk_plan", "sedef_b200_align_generate", "sedef_b200_align_generate_error",
+           "sedef_b200_fasta_fetch", "sedef_b200_bed_schedule", "sedef_b200_reverse_complement"]
 
 
 def load():
@@ -140,6 +142,14 @@ def load():
     lib.ksw_b200_result_export.restype = i64
     lib.sedef_anchors_batch.argtypes = [i32, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, C.POINTER(vp), vp]
     lib.sedef_anchors_batch.restype = i32
+    lib.sedef_b200_align_generate.argtypes = [C.c_char_p, C.c_char_p, i32, C.c_char_p, i32, i32, vp, vp]
+    lib.sedef_b200_align_generate.restype = i32
+    lib.sedef_b200_align_generate_error.restype = C.c_char_p
+    lib.sedef_b200_fasta_fetch.argtypes = [C.c_char_p, C.c_char_p, i32, C.POINTER(i32), C.c_char_p, C.c_longlong]
+    lib.sedef_b200_fasta_fetch.restype = C.c_longlong
+    lib.sedef_b200_bed_schedule.argtypes = [C.c_char_p, C.c_char_p, C.c_longlong]
+    lib.sedef_b200_bed_schedule.restype = C.c_longlong
+    lib.sedef_b200_reverse_complement.argtypes = [C.c_char_p, C.c_longlong, C.c_char_p]
     lib.sd_stats_derive_fp.argtypes = [C.POINTER(SdStats), C.POINTER(SdStatsFp)]
     lib.free = C.CDLL(None).free
     lib.free.argtypes = [vp]
@@ -447,6 +457,50 @@ def anchors_batch(regions, kmer_size: int = 11, same_chr=None, orig_query_start=
     if out.value:
         lib.free(out.value)
     return [flat[int(off[i]):int(off[i + 1])] for i in range(n)]
+
+
+def align_generate(ref_path: str, bed_path: str, out_path: str, kmer_size: int = 11, shard_index: int = 0, shard_count: int = 1) -> dict:
+    """`sedef align generate -k kmer_size ref_path bed_path > out_path` (src/align_main.cc:285-337) through `fast_align_batch`:
+    every seed hit of the bucket file(s) at once.  Returns the run's counters and phase times."""
+    lib = load()
+    st = np.zeros(7, np.int64); ms = np.zeros(3, np.float64)
+    rc = lib.sedef_b200_align_generate(os.fsencode(ref_path), os.fsencode(bed_path), int(kmer_size), os.fsencode(out_path),
+                                       int(shard_index), int(shard_count), _ptr(st), _ptr(ms))
+    if rc != 0:
+        raise EngineError(rc, lib.sedef_b200_align_generate_error().decode())
+    keys = ["regions", "hits", "groups", "rounds", "batch_calls", "ksw_requests", "region_bytes"]
+    out = {k: int(v) for k, v in zip(keys, st)}
+    out.update(ms_total=float(ms[0]), ms_align=float(ms[1]), ms_io=float(ms[2]))
+    return out
+
+
+def fasta_fetch(ref_path: str, name: str, start: int, end: int):
+    """FastaReference::get_sequence (src/fasta.cc:106-143): (bases, clamped end)."""
+    lib = load()
+    e = C.c_int(end)
+    cap = max(0, end - max(start, 0)) + 16
+    buf = C.create_string_buffer(cap)
+    n = lib.sedef_b200_fasta_fetch(os.fsencode(ref_path), name.encode(), int(start), C.byref(e), buf, cap)
+    if n < 0:
+        raise EngineError(-1, lib.sedef_b200_align_generate_error().decode())
+    return buf.raw[:n], e.value
+
+
+def bed_schedule(bed_path: str) -> str:
+    """The seed hits of a bucket file / directory in the order `align generate` processes them (src/align_main.cc:211-283)."""
+    lib = load()
+    n = lib.sedef_b200_bed_schedule(os.fsencode(bed_path), None, 0)
+    if n < 0:
+        raise EngineError(-1, lib.sedef_b200_align_generate_error().decode())
+    buf = C.create_string_buffer(int(n) + 1)
+    lib.sedef_b200_bed_schedule(os.fsencode(bed_path), buf, n)
+    return buf.raw[:n].decode()
+
+
+def reverse_complement(s: bytes) -> bytes:
+    out = C.create_string_buffer(len(s) + 1)
+    load().sedef_b200_reverse_complement(s, len(s), out)
+    return out.raw[:len(s)]
 
 
 def derive_fp(stats_row) -> dict:

@@ -1,0 +1,161 @@
+"""The align stage's driver (`sedef align generate`, src/align_main.cc:285-337) against the reference BINARY: byte-level
+comparison of *.aligned.bed text (SURVEY.md section 8d "Configs 1/4/5", section 8 f2).
+
+CPU tests: the text / FASTA layer of the driver (get_sequence, BED parse / print, schedule order, rc) against the golden fixture
+written by the reference binary and against plain slicing.  GPU tests: whole bucket files through `sedef_b200_align_generate`
+(anchors on the GPU, chaining on the host, every alignment wave one batched ksw_extz2 call) -- output bytes must equal the
+reference binary's, from the committed fixture and, where oracle/_ref/sedef_ref travelled to the box, from a live run on the
+BASELINE.json configs[0] genome (2 Mbp, 40 planted duplications)."""
+import hashlib
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from helpers import load_json
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "sedef_ref")
+
+
+@pytest.fixture(scope="module")
+def small_stage(built, golden_dir, tmp_path_factory):
+    """The fixture's genome regenerated from its seed (sha1 pinned) + its bucket files on disk."""
+    from sedef_b200 import genome
+    g = load_json(golden_dir, "align_stage_golden.json")
+    wd = str(tmp_path_factory.mktemp("align_stage"))
+    fa, bed, _ = genome.write_align_stage_input(wd, **g["config"])
+    assert hashlib.sha1(open(fa, "rb").read()).hexdigest() == g["genome_sha1"], "generator drifted: regenerate the fixture"
+    assert open(bed).read() == g["seeds"]
+    bdir = os.path.join(wd, "buckets")
+    os.makedirs(bdir)
+    for name, text in g["buckets"].items():
+        with open(os.path.join(bdir, name + ".bed"), "w") as f:
+            f.write(text)
+    return dict(golden=g, fasta=fa, bdir=bdir, wd=wd)
+
+
+def test_fasta_fetch_matches_slicing(built, tmp_path):
+    """FastaReference::get_sequence (src/fasta.cc:106-143): ranges across line ends, clamping of start < 0 and end > length."""
+    from sedef_b200 import engine, genome
+    rng = np.random.default_rng(5)
+    chroms = {"c1": genome.synth.ASCII[rng.integers(0, 4, 1234)], "c2 extra words": genome.synth.ASCII_LOWER[rng.integers(0, 4, 61)],
+              "c3": genome.synth.ASCII[rng.integers(0, 4, 60)]}
+    fa = str(tmp_path / "t.fa")
+    genome.write_fasta(fa, chroms, line=60)
+    # the index is keyed by the first token of the name (src/fasta.cc:40)
+    for key, name in (("c1", "c1"), ("c2", "c2 extra words"), ("c3", "c3")):
+        seq = chroms[name].tobytes()
+        n = len(seq)
+        cases = [(0, n), (0, 1), (59, 61), (60, 120), (-5, 10), (n - 3, n + 50), (17, 17), (1, n - 1)]
+        cases += [tuple(sorted(rng.integers(0, n + 1, 2).tolist())) for _ in range(60)]
+        for s, e in cases:
+            got, end = engine.fasta_fetch(fa, key, s, e)
+            assert got == seq[max(s, 0):min(e, n)], (key, s, e)
+            assert end == min(e, n)
+    with pytest.raises(engine.EngineError, match="Chromosome nope does not exist"):
+        engine.fasta_fetch(fa, "nope", 0, 10)
+
+
+def test_reverse_complement(built):
+    from sedef_b200 import engine
+    assert engine.reverse_complement(b"ACGTacgtNnXx-") == b"NNNNNacgtACGT"      # rev_dna: everything else -> 'N' (src/common.h:72-86)
+    assert engine.reverse_complement(b"") == b""
+
+
+def test_schedule_and_bed_text(small_stage):
+    """Hit::from_bed -> Hit::to_bed(false) round trip and the processing order of generate_alignments: the seed columns the reference
+    binary printed behind each hit (h.to_bed(0)) appear in the product's schedule in the same order, with identical text up to the
+    clamped end coordinates (those are clamped while the regions are cut)."""
+    from sedef_b200 import engine
+    g = small_stage["golden"]
+    for name, text in g["buckets"].items():
+        path = os.path.join(small_stage["bdir"], name + ".bed")
+        sched = [ln for ln in engine.bed_schedule(path).split("\n") if ln]
+        # bucket lines were written by the reference's own to_bed(false): parse + print must reproduce them
+        lines = [ln for ln in text.split("\n") if ln]
+        assert sorted(sched) == sorted(lines)
+        # order: by complexity bin (sqrt(span_q * span_r) / 1000), stable inside a bin
+        def cplx(ln):
+            f = ln.split("\t")
+            return int((float(int(f[2]) - int(f[1])) * float(int(f[5]) - int(f[4]))) ** 0.5) // 1000
+        want = [ln for _, _, ln in sorted((cplx(ln), i, ln) for i, ln in enumerate(lines))]
+        assert sched == want
+        seen = []
+        for ln in g["aligned"][name].split("\n"):
+            if ln:
+                seed_name = ln.split("\t")[14 + 6]
+                if not seen or seen[-1] != seed_name:
+                    seen.append(seed_name)
+        order = [ln.split("\t")[6] for ln in sched]
+        it = iter(order)
+        assert all(s in it for s in seen), (seen, order)        # subsequence, same relative order
+    # a directory of *.bed files is read as one schedule
+    assert len([ln for ln in engine.bed_schedule(small_stage["bdir"]).split("\n") if ln]) == sum(t.count("\n") for t in g["buckets"].values())
+    with pytest.raises(engine.EngineError, match="neither file nor directory"):
+        engine.bed_schedule(os.path.join(small_stage["wd"], "missing"))
+
+
+@pytest.mark.gpu
+def test_align_generate_matches_reference_binary_golden(small_stage):
+    """Whole bucket files: output bytes == the reference binary's *.aligned.bed (tests/golden/align_stage_golden.json: two
+    chromosomes, both strands, regions clamped at chromosome ends, same- and different-chromosome seeds)."""
+    from sedef_b200 import engine
+    g = small_stage["golden"]
+    total = 0
+    for name in sorted(g["buckets"]):
+        out = os.path.join(small_stage["wd"], name + ".aligned.bed")
+        st = engine.align_generate(small_stage["fasta"], os.path.join(small_stage["bdir"], name + ".bed"), out)
+        got = open(out).read()
+        assert got == g["aligned"][name], name
+        assert st["regions"] == g["buckets"][name].count("\n") and st["hits"] == got.count("\n")
+        total += st["hits"]
+    assert total == g["n_lines"]
+    # one process per GPU: the shards' outputs together are the same lines
+    parts = []
+    for k in range(2):
+        out = os.path.join(small_stage["wd"], "shard%d.bed" % k)
+        engine.align_generate(small_stage["fasta"], small_stage["bdir"], out, shard_index=k, shard_count=2)
+        parts += [ln for ln in open(out).read().split("\n") if ln]
+    want = [ln for t in g["aligned"].values() for ln in t.split("\n") if ln]
+    assert sorted(parts) == sorted(want)
+    with pytest.raises(engine.EngineError, match="Chromosome"):
+        bad = os.path.join(small_stage["wd"], "bad.bed")
+        with open(bad, "w") as f:
+            f.write("chrZ\t0\t5000\tchrA\t0\t5000\tx\t\t+\t+\n")
+        engine.align_generate(small_stage["fasta"], bad, os.path.join(small_stage["wd"], "bad.out"))
+
+
+@pytest.mark.gpu
+def test_align_generate_config1_live_reference(built, tmp_path):
+    """BASELINE.json configs[0] at the align stage, end to end at the file level: 2 Mbp soft-masked chromosome, 40 planted 5-20 kbp
+    duplications at 2-10 % -> seed BED -> the reference binary's `align bucket` -> per bucket `align generate -k 11` with the
+    reference binary (live, on the host) and with the product: identical bytes.  Also recovers the planted catalog."""
+    if not os.path.exists(REF_BIN):
+        pytest.skip("oracle/_ref/sedef_ref not built")
+    from sedef_b200 import engine, genome
+    wd = str(tmp_path)
+    fa, bed, catalog = genome.write_align_stage_input(wd, **genome.CONFIGS[1])
+    bdir = os.path.join(wd, "buckets")
+    os.makedirs(bdir)
+    subprocess.run([REF_BIN, "align", "bucket", "-n", "4", bed, bdir, fa], check=True, capture_output=True, timeout=600)
+    lines = []
+    for b in sorted(os.listdir(bdir)):
+        ref = subprocess.run([REF_BIN, "align", "generate", "-k", "11", fa, os.path.join(bdir, b)], check=True, capture_output=True,
+                             text=True, timeout=1800).stdout
+        out = os.path.join(wd, b + ".aligned.bed")
+        engine.align_generate(fa, os.path.join(bdir, b), out)
+        assert open(out).read() == ref, b
+        lines += [ln for ln in ref.split("\n") if ln]
+    recovered = 0
+    for c in catalog:
+        for ln in lines:
+            f = ln.split("\t")
+            q0, q1, r0, r1 = int(f[1]), int(f[2]), int(f[4]), int(f[5])
+            a = (c["s0"], c["s1"], c["d0"], c["d1"])
+            if (q0 <= a[0] + 60 and q1 >= a[1] - 60 and r0 <= a[2] + 60 and r1 >= a[3] - 60) or \
+               (r0 <= a[0] + 60 and r1 >= a[1] - 60 and q0 <= a[2] + 60 and q1 >= a[3] - 60):
+                recovered += 1
+                break
+    assert recovered >= 36, recovered

@@ -91,7 +91,15 @@ static inline bool class_packed_cluster(int c) { return class_packed(c) && class
 static inline int class_cluster(int c) { return class_packed(c) ? (class_ns(c) > 8192 ? class_ns(c) / 8192 : 0) : kClasses[c].cluster; }
 static inline bool class_packed_wide(int c) { return class_packed(c) && class_ns(c) > 1024 && class_ns(c) <= 8192; }    // one CTA of NS/32 lanes per pair
 // one-slot lanes with S == 32 switch whole-lane (two 16-blocks at once), which costs 16 slots of window (extz_dp.cuh)
-static inline int class_capacity(int c) { return (kClasses[c].S > 16 && !class_packed(c)) ? class_ns(c) - 16 : class_ns(c); }
+// the packed 16-lane class (512 slots in registers) holds a 33rd block spread over its lanes (extz_dp16.cuh Spare16) -- not in the
+// KSW_EZ_APPROX_MAX variant
+static inline bool class_spare(int c, bool approx) { return class_packed(c) && class_ns(c) == 512 && !approx; }
+static inline int class_capacity(int c, bool approx)
+{
+	if (class_spare(c, approx)) return class_ns(c) + 16;
+	return (kClasses[c].S > 16 && !class_packed(c)) ? class_ns(c) - 16 : class_ns(c);
+}
+static inline size_t class_row_bytes(int c, bool approx) { return (size_t)class_ns(c) / 2 + (class_spare(c, approx) ? 16 : 0); }
 static inline int class_pairs_per_block(int c)
 {
 	if (class_packed(c)) return class_ns(c) > 1024 ? 1 : 128 * 32 / class_ns(c);
@@ -221,7 +229,7 @@ static bool is_pinned(const void *p)
 	if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
 	return a.type == cudaMemoryTypeHost;
 }
-extern "C" int ksw_b200_max_slots(void) { return class_capacity(kNumSizedClasses - 1); }
+extern "C" int ksw_b200_max_slots(void) { return class_capacity(kNumSizedClasses - 1, false); }
 
 static int ensure_init()
 {
@@ -566,6 +574,7 @@ extern "C" ksw_b200_batch_t *ksw_b200_batch_upload(int n, const int *qlen, const
 	struct Item { int cls; int64_t work; };
 	std::vector<Item> items(n);
 	const bool skip_s32 = getenv("KSW_B200_SKIP_S32") != nullptr;                       // A/B: 32 lanes x 32 slots vs 64-lane CTA
+	const bool approx_batch = (flag & KSW_EZ_APPROX_MAX) != 0;
 	int too_wide = -1;
 #pragma omp parallel for num_threads(threads_for(n, 32768)) schedule(static)
 	for (int i = 0; i < n; ++i) {
@@ -574,7 +583,7 @@ extern "C" ksw_b200_batch_t *ksw_b200_batch_upload(int n, const int *qlen, const
 		int wi = w < 0 ? std::max(qlen[i], tlen[i]) : std::min(w, std::max(qlen[i], tlen[i]));
 		int need = slots_needed(qlen[i], tlen[i], wi);
 		int c = 0;
-		while (c < kNumSizedClasses && class_capacity(c) < need) ++c;
+		while (c < kNumSizedClasses && class_capacity(c, approx_batch) < need) ++c;
 		if (c == 5 && skip_s32) c = 6;
 		if (c == kNumSizedClasses) {
 #pragma omp critical
@@ -588,7 +597,7 @@ extern "C" ksw_b200_batch_t *ksw_b200_batch_upload(int n, const int *qlen, const
 		int wi = w < 0 ? std::max(qlen[i], tlen[i]) : std::min(w, std::max(qlen[i], tlen[i]));
 		delete B;
 		return bail(fail(KSW_B200_ERR_TOO_WIDE, "pair " + std::to_string(i) + " needs " + std::to_string(slots_needed(qlen[i], tlen[i], wi)) +
-		                 " live slots; widest kernel holds " + std::to_string(class_capacity(kNumSizedClasses - 1))));
+		                 " live slots; widest kernel holds " + std::to_string(class_capacity(kNumSizedClasses - 1, false))));
 	}
 	std::vector<int> order; order.reserve(n);
 	for (int i = 0; i < n; ++i) { if (items[i].cls < 0) { B->is_empty[i] = 1; ++B->n_empty; } else order.push_back(i); }
@@ -767,7 +776,7 @@ static int plan_waves(ksw_b200_batch &B, SubBatch &sb, bool cigar)
 	for (int c = 0; c < kNumClasses; ++c) {
 		int first = sb.class_first[c], last = sb.class_first[c + 1];
 		if (first >= last) continue;
-		const size_t rowB = (size_t)class_ns(c) / 2;
+		const size_t rowB = class_row_bytes(c, (B.flag & KSW_EZ_APPROX_MAX) != 0);
 		int k = first;
 		while (k < last) {
 			Wave wv{c, k, 0, 0};
@@ -877,6 +886,7 @@ static int launch_sub(ksw_b200_batch &B, SubBatch &sb)
 			TL.t_match = B.mat[0]; TL.t_mismatch = B.mat[1]; TL.t_gapo = B.q; TL.t_gape = B.e;
 			TL.overflow = d_overflow;
 			TL.n = wv.count; TL.NS = class_ns(c); TL.flag = B.flag; TL.packed = class_packed(c) ? 1 : 0;
+			TL.spare = class_spare(c, approx) ? 1 : 0;
 			cudaStream_t tbs = sb.dc->tb_stream;
 			CUDA_TRY(cudaStreamWaitEvent(tbs, b2, 0));
 			// long walks are latency chains: one warp per pair with staged row tiles; short ones: one thread per pair

@@ -184,12 +184,19 @@ EXTZ_HD int64_t tb_row_bytes(int NS) { return NS >> 1; }
 //
 // Packed kernel (extz_dp16.cuh): same row size; a lane owns 16 bytes, byte i of lane L holds slot 32L + i in its
 // low nibble (block A) and slot 32L + 16 + i in its high nibble (block B).
-EXTZ_HD uint32_t tb_fetch(const uint8_t *tb_pair, int NS, int64_t r, int t, bool packed = false)
+// Classes with a spare block (extz_dp16.cuh Spare16): rows are NS/2 + 16 bytes; on anti-diagonals whose rounded range spans
+// NS/16 + 1 blocks the top block's codes sit behind the packed part, slot st + NS + 2k in the low nibble of byte NS/2 + k.
+EXTZ_HD uint32_t tb_fetch(const uint8_t *tb_pair, int NS, int64_t r, int t, bool packed = false, int spare = 0, int st = 0)
 {
+	const int64_t rowB = (NS >> 1) + (spare ? 16 : 0);
+	if (spare && t >= st + NS) {
+		uint8_t byte = tb_pair[r * rowB + (NS >> 1) + ((t & 15) >> 1)];
+		return (byte >> ((t & 1) * 4)) & 0xfu;
+	}
 	int c = t & (NS - 1);
 	int byte_idx = packed ? (((c >> 5) << 4) | (c & 15)) : (c >> 1);
 	int nib = packed ? ((c >> 4) & 1) : (c & 1);
-	uint8_t byte = tb_pair[r * (int64_t)(NS >> 1) + byte_idx];
+	uint8_t byte = tb_pair[r * rowB + byte_idx];
 	return (byte >> (nib * 4)) & 0xfu;
 }
 

@@ -361,6 +361,20 @@ struct PackedRows {
 #ifndef EXTZ_MIN_BLOCKS_P
 #define EXTZ_MIN_BLOCKS_P 3
 #endif
+// The SPARE block of the 16-lane class: a 33rd 16-slot block for the anti-diagonals on which the rounded range [st, max(en, fe)]
+// spans 33 blocks -- the block ENTERING at the top while the block congruent to it (same lane, same half) at the bottom is still
+// live.  Group lane j holds slot t0 + j of it in the LOW halves of five registers (same int8 << 8 form as Lane16) and its lazy H in
+// a register; the slot below is the previous lane's (one shuffle each for x, v, H) or, for lane 0, the top slot of the block below
+// the spare.  The cell is the same cell2<>.  When the bottom block leaves the band, the lane that owns the position takes the 16
+// slots over into its registers and rows (96 shuffles, once per 32 anti-diagonals), and the block lives on as an ordinary one.
+// Its traceback codes go to 8 extra bytes per row (row = NS/2 + 16 bytes).
+struct Spare16 {
+	uint32_t U, V, X, Y, Z;      // low half: the slot's value; high half: unused
+	uint32_t TW;                 // 32 * target[t0 + j]
+	int32_t H;                   // lazy H of the slot
+	int t0;                      // first slot of the block, -1 while there is none
+};
+template <int G, bool kApprox> struct kSpareClass { static constexpr bool value = (G == 16) && !kApprox; };
 template <int G, bool kCigar, bool kRight, bool kApprox = false>
 __global__ void __launch_bounds__(128, EXTZ_MIN_BLOCKS_P)
 extz_dp16_kernel(DpLaunch L)
@@ -369,6 +383,11 @@ extz_dp16_kernel(DpLaunch L)
 	constexpr int PPW = 32 / G;                          // pairs per warp
 	constexpr unsigned FULL = 0xffffffffu;
 	static_assert(G >= 1 && G <= 32 && (G & (G - 1)) == 0, "G must be a power of two");
+	// The 16-lane class holds 33 blocks: its 32 in the lanes' registers plus a SPARE block spread over the 16 lanes, one slot each
+	// (see Spare16).  A band of w = 496..511 (BASELINE.json configs[2]: w = 500) needs 33 blocks for a quarter of the anti-diagonals
+	// and would otherwise run in the 64-block class with half of the lane work outside the band.
+	constexpr bool kSpare = kSpareClass<G, kApprox>::value;
+	constexpr int ROWB = (NS >> 1) + (kSpare ? 16 : 0);  // bytes per traceback row
 
 	__shared__ int4 sH[8][128];                          // lazy H: H + (q+e)*r, row k of thread x at sH[k][x]
 	__shared__ uint4 sU[4][128];                         // u' of the current diagonal (for H[en0], :228), packed
@@ -389,38 +408,65 @@ extz_dp16_kernel(DpLaunch L)
 	const int qe = sc.qe;
 	const bool generic = (sc.flag & kFlagGenericSc) != 0;
 
+	// Per-GROUP state: every lane of a group holds the same values.  The 32/G groups of a warp advance INDEPENDENTLY -- each at
+	// its own anti-diagonal r of its own pair; a group whose pair is finished (end of the DP, z-drop, band exhausted) hands in the
+	// result and takes the next pair from the queue (pairs sorted by descending work) while the others carry on.  (Until round 2
+	// the pairs of a warp ran in lock-step from a common start, and a warp was busy until its longest pair had finished: 37 % of
+	// BASELINE.json configs[2]'s pairs z-drop somewhere along the way.)
+	int pi = -1, qlen = 0, tlen = 0, w = 0, T = 0, R = 0, r = 0;
+	const uint8_t *qseq = L.seq, *tseq = L.seq;
+	uint8_t *tbp = nullptr, *tb_sp = nullptr;
+	bool alive = false, exhausted = false;
+	Lane16 ls;
+	ls.t0[0] = ls.t0[1] = 0;
+#pragma unroll
+	for (int i = 0; i < 16; ++i) ls.U[i] = ls.V[i] = ls.X[i] = ls.Y[i] = ls.Z[i] = 0u;
+#pragma unroll
+	for (int i = 0; i < 8; ++i) ls.TW[i] = ls.QW[i] = 0u;
+	Leader ld; ld.reset();
+	int last_st = -1, last_en = -1, n_diag = 0, zdropped_band = 0;
+	Spare16 sp;
+	sp.U = sp.V = sp.X = sp.Y = sp.Z = sp.TW = 0u; sp.H = kNegInf; sp.t0 = -1;
+
 	for (;;) {
-		int base = 0;
-		if (lane_w == 0) base = atomicAdd(L.work_counter, PPW);      // dynamic work queue, pairs sorted by descending work
-		base = __shfl_sync(FULL, base, 0);
-		if (base >= L.n) break;
-		const int pi = base + lane_w / G;
-		bool alive = pi < L.n;
-		const PairDesc pd = L.pairs[alive ? pi : base];
-		const int qlen = pd.qlen, tlen = pd.tlen, w = pd.w;
-		const int T = (tlen + 15) & ~15;
-		const uint8_t *qseq = L.seq + pd.q_off;                      // qseq[j], j in [0, qlen + 15] is read
-		const uint8_t *tseq = L.seq + pd.t_off;
-		uint8_t *tbp = kCigar ? L.tb + pd.tb_off + gl * 16 : nullptr;
-		const int R = alive ? qlen + tlen - 1 : 0;
-		int maxR = R;
+		{
+			const bool done = !exhausted && !(alive && r < R);
+			if (__any_sync(FULL, done)) {
+				int nxt = L.n;
+				if (done && gl == 0) {
+					if (pi >= 0) { if (zdropped_band) ld.ez.zdropped = 1; ld.store(&L.results[pi], n_diag); }
+					nxt = atomicAdd(L.work_counter, 1);                  // dynamic work queue
+				}
+				nxt = __shfl_sync(FULL, nxt, 0, G);
+				if (done) {
+					pi = nxt < L.n ? nxt : -1;
+					alive = pi >= 0; exhausted = !alive; r = 0; R = 0;
+					if (alive) {
+						const PairDesc pd = L.pairs[pi];
+						qlen = pd.qlen; tlen = pd.tlen; w = pd.w;
+						T = (tlen + 15) & ~15;
+						qseq = L.seq + pd.q_off;                         // qseq[j], j in [0, qlen + 15] is read
+						tseq = L.seq + pd.t_off;
+						tbp = kCigar ? L.tb + pd.tb_off + gl * 16 : nullptr;
+						tb_sp = kCigar ? L.tb + pd.tb_off + (NS >> 1) : nullptr;     // the spare block's codes (kSpare)
+						R = qlen + tlen - 1;
+						ls.t0[0] = gl * 32; ls.t0[1] = gl * 32 + 16;
 #pragma unroll
-		for (int d = G; d < 32; d <<= 1) { int o = __shfl_xor_sync(FULL, maxR, d); maxR = maxR > o ? maxR : o; }
-
-		Lane16 ls;
-		ls.t0[0] = gl * 32; ls.t0[1] = gl * 32 + 16;
+						for (int i = 0; i < 16; ++i) { ls.U[i] = ls.V[i] = ls.X[i] = ls.Y[i] = 0u; ls.Z[i] = sc16.s0_2; }   // calloc'ed arrays (:83)
+						lane16_load_seq<0>(ls, tseq, tlen, qseq, 0);
+						lane16_load_seq<1>(ls, tseq, tlen, qseq, 0);
 #pragma unroll
-		for (int i = 0; i < 16; ++i) { ls.U[i] = ls.V[i] = ls.X[i] = ls.Y[i] = 0u; ls.Z[i] = sc16.s0_2; }   // calloc'ed arrays (:83)
-		lane16_load_seq<0>(ls, tseq, tlen, qseq, 0);
-		lane16_load_seq<1>(ls, tseq, tlen, qseq, 0);
-#pragma unroll
-		for (int k = 0; k < 8; ++k) Hrow[k * 128] = make_int4(kNegInf, kNegInf, kNegInf, kNegInf);           // :86-89
-		__syncwarp();
-
-		Leader ld; ld.reset();                                       // meaningful in the leader lane only
-		int last_st = -1, last_en = -1, n_diag = 0, zdropped_band = 0;
-
-		for (int r = 0; r < maxR; ++r) {
+						for (int k = 0; k < 8; ++k) Hrow[k * 128] = make_int4(kNegInf, kNegInf, kNegInf, kNegInf);       // :86-89
+						ld.reset();
+						last_st = -1; last_en = -1; n_diag = 0; zdropped_band = 0;
+						sp.U = sp.V = sp.X = sp.Y = sp.Z = sp.TW = 0u; sp.H = kNegInf; sp.t0 = -1;
+					}
+				}
+				__syncwarp();
+				if (!__any_sync(FULL, alive)) break;
+			}
+		}
+		{
 			bool act = alive && r < R;
 			Band b;
 			const bool okb = band_of(r, qlen, tlen, w, T, generic, b);
@@ -443,11 +489,10 @@ extz_dp16_kernel(DpLaunch L)
 				int stop = 0;
 				if (act && gl == 0) stop = ld.approx(rows, b, r, qe, ls.V[0] << 16, qlen, tlen, sc.zdrop, sc.e, (sc.flag & kFlagApproxDrop) != 0);
 				stop = __shfl_sync(FULL, stop, 0, G);
-				if (act) { n_diag = r + 1; last_st = b.st; last_en = b.en; if (stop) alive = false; }
+				if (act) { n_diag = r + 1; last_st = b.st; last_en = b.en; if (stop) alive = false; ++r; }
 				__syncwarp();            // the leader read the dumps; the next diagonal overwrites them
 				continue;
 			}
-#ifndef EXTZ_NARROW_LEADER
 			// ---- exact maximum, LEADERLESS ----------------------------------------------------------------------------------
 			// The scalar bookkeeping of a pair (ez, the special H entries) is not done by one leader lane reaching into the
 			// other lanes' shared-memory rows between __syncwarp()s: every lane of the group keeps an IDENTICAL copy of the scalar
@@ -469,46 +514,127 @@ extz_dp16_kernel(DpLaunch L)
 			}
 			const int32_t hcar = G == 1 ? htop : __shfl_sync(FULL, htop, pred_lane, G);
 			int32_t Hen0 = kNegInf;
-			int32_t lane_max = kNegInf;
+			int32_t lane_max = kNegInf;                                     // maximum over this lane's H ROWS (the spare's H is a register)
+			auto hptr = [&](int t) -> int32_t * {                           // lazy-H entry of a slot THIS lane owns
+				const int i = t & 15, half = (t >> 4) & 1;
+				return reinterpret_cast<int32_t *>(Hrow) + ((((((i >> 2) << 1) | half) * 128) << 2) | (i & 3));
+			};
+			auto owns = [&](int t) { return G == 1 || ((t & (NS - 1)) >> 5) == gl; };
+			// slot st0-1 left the band: freeze its TRUE H, drop it from the max.  (First of all: with a spare block the rows of the
+			// leaving block are overwritten below.)
+			if (act && r > 0 && b.st0 > ld.st0_prev) {
+				const int xs = b.st0 - 1;
+				ld.exit_slot = xs;
+				if (owns(xs)) { int32_t *px = hptr(xs); ld.exit_H = *px - qe * (r - 1); *px = kNegInf; }
+			}
+			// ---- the spare block, part 1: its position in the ring has become free -> the owning lane takes it over ----------
+			bool sp_on = false, sp_in = false;                              // spare in use on this diagonal / en0 lies in it
+			uint32_t sxin = 0u, svin = 0u, scw = 0u; int32_t shprev = kNegInf;
+			if (kSpare) {
+				const bool adopt = act && sp.t0 >= 0 && sp.t0 - NS + 15 < b.st;
+				if (__any_sync(FULL, adopt)) {
+					const int La = (sp.t0 & (NS - 1)) >> 5, ha = (sp.t0 >> 4) & 1;
+					const bool me = adopt && gl == La;
+					int32_t *hr = reinterpret_cast<int32_t *>(Hrow);
+#pragma unroll
+					for (int i = 0; i < 16; ++i) {
+						const uint32_t u = __shfl_sync(FULL, sp.U, i, 16), v = __shfl_sync(FULL, sp.V, i, 16);
+						const uint32_t x = __shfl_sync(FULL, sp.X, i, 16), y = __shfl_sync(FULL, sp.Y, i, 16);
+						const uint32_t z = __shfl_sync(FULL, sp.Z, i, 16);
+						const int32_t h = __shfl_sync(FULL, sp.H, i, 16);
+						if (me) {
+							if (ha) {
+								ls.U[i] = __byte_perm(ls.U[i], u, 0x5410); ls.V[i] = __byte_perm(ls.V[i], v, 0x5410);
+								ls.X[i] = __byte_perm(ls.X[i], x, 0x5410); ls.Y[i] = __byte_perm(ls.Y[i], y, 0x5410);
+								ls.Z[i] = __byte_perm(ls.Z[i], z, 0x5410);
+							} else {
+								ls.U[i] = __byte_perm(ls.U[i], u, 0x3254); ls.V[i] = __byte_perm(ls.V[i], v, 0x3254);
+								ls.X[i] = __byte_perm(ls.X[i], x, 0x3254); ls.Y[i] = __byte_perm(ls.Y[i], y, 0x3254);
+								ls.Z[i] = __byte_perm(ls.Z[i], z, 0x3254);
+							}
+							hr[((((((i >> 2) << 1) | ha) * 128) << 2) | (i & 3))] = h;
+						}
+					}
+					if (me) {
+						if (ha) { ls.t0[1] = sp.t0; lane16_load_seq<1>(ls, tseq, tlen, qseq, r); }
+						else { ls.t0[0] = sp.t0; lane16_load_seq<0>(ls, tseq, tlen, qseq, r); }
+					}
+					if (adopt) sp.t0 = -1;
+				}
+			}
+			if (act) lane16_prepare<NS>(ls, b, r, last_en, qseq, tseq, tlen, table_saddr, sc16);
+			// ---- the spare block, part 2: activation, band entry, carries from its neighbours, top row, score fill -----------
+			if (kSpare) {
+				const int top = b.en > b.fe ? b.en : b.fe;                  // the score fill can run ahead of the rounded range (:125)
+				if (act && sp.t0 < 0 && top >= b.st + NS) {
+					sp.t0 = b.st + NS;
+					sp.U = sp.V = sp.X = sp.Y = 0u; sp.Z = sc16.s0_2; sp.H = kNegInf;          // calloc'ed state (:83-89)
+					const int t = sp.t0 + gl;
+					sp.TW = t < tlen ? ld_u8(tseq + t) << 5 : 0u;
+				}
+				sp_on = act && sp.t0 >= 0;
+				if (__any_sync(FULL, sp_on)) {
+					if (sp_on && sp.t0 <= b.en && sp.t0 > last_en) sp.U = sp.V = sp.X = sp.Y = 0u;   // enters the rounded band
+					// OLD x, v, H of slot t-1: the previous spare lane, or (lane 0) the top slot of the block below the spare
+					const uint32_t xn = __shfl_up_sync(FULL, sp.X, 1, 16), vn = __shfl_up_sync(FULL, sp.V, 1, 16);
+					const int32_t hn = __shfl_up_sync(FULL, sp.H, 1, 16);
+					const int tp = sp.t0 - 16;
+					const int Lp = (tp & (NS - 1)) >> 5, hp = (tp >> 4) & 1;
+					const uint32_t cx = __shfl_sync(FULL, ls.X[15], Lp, 16), cv = __shfl_sync(FULL, ls.V[15], Lp, 16);
+					const int32_t h15 = reinterpret_cast<const int32_t *>(Hrow)[(((hp ? 7 : 6) * 128) << 2) | 3];
+					const int32_t ch = __shfl_sync(FULL, h15, Lp, 16);
+					sxin = gl ? xn : (hp ? cx >> 16 : cx & 0xffffu);
+					svin = gl ? vn : (hp ? cv >> 16 : cv & 0xffffu);
+					shprev = gl ? hn : ch;
+					const int t = sp.t0 + gl;
+					if (sp_on && b.en >= r && t == r) { sp.Y = 0u; sp.U = r ? sc16.q16 : 0u; }   // top-row boundary (:122)
+					if (sp_on && t >= b.st0 && t <= b.fe) sp.Z = lds_u32(table_saddr + sp.TW + qbyte4(qseq, r - t));   // score fill (:124-141)
+				}
+				sp_in = sp_on && b.en0 >= sp.t0;
+			}
+			int32_t tot_max = kNegInf;
 			if (act) {
-				auto hptr = [&](int t) -> int32_t * {                       // lazy-H entry of a slot THIS lane owns
-					const int i = t & 15, half = (t >> 4) & 1;
-					return reinterpret_cast<int32_t *>(Hrow) + ((((((i >> 2) << 1) | half) * 128) << 2) | (i & 3));
-				};
-				auto owns = [&](int t) { return G == 1 || ((t & (NS - 1)) >> 5) == gl; };
-				lane16_prepare<NS>(ls, b, r, last_en, qseq, tseq, tlen, table_saddr, sc16);
 				// (written branch-free where it can be: the owner-only steps are predicated loads / stores on the lane's own rows)
-				const bool own_en = en_owner == gl;
+				const bool own_en = (kSpare && sp_in) ? (gl == (b.en0 & 15)) : (en_owner == gl);
 				const int ps = b.en0 - 1;
 				int32_t hprev = hcar;                                       // en0 starts my block A: en0-1 is the predecessor lane's top slot
-				if (r > 0) {
-					if (b.st0 > ld.st0_prev) {                              // slot st0-1 left the band: freeze its TRUE H, drop it from the max
-						const int xs = b.st0 - 1;
-						ld.exit_slot = xs;
-						if (owns(xs)) { int32_t *px = hptr(xs); ld.exit_H = *px - qe * (r - 1); *px = kNegInf; }
-					}
-					if (own_en && b.en0 > 0) {                              // H[en0] is recomputed from the OLD H[en0-1] (:228)
-						if ((en_c & 31) != 0) hprev = (ps == ld.exit_slot) ? ld.exit_H + qe * (r - 1) : *hptr(ps);
-						*hptr(b.en0) = kNegInf;                             // the regular update below must not count for slot en0
-					}
+				if (kSpare && sp_in) hprev = shprev;
+				else if (r > 0 && own_en && b.en0 > 0) {                    // H[en0] is recomputed from the OLD H[en0-1] (:228)
+					if ((en_c & 31) != 0) hprev = (ps == ld.exit_slot) ? ld.exit_H + qe * (r - 1) : *hptr(ps);
+					*hptr(b.en0) = kNegInf;                                 // the regular update below must not count for slot en0
 				}
-				lane_max = lane16_cells<kCigar, kRight>(ls, b, r, last_st, xin, vin, (uint4 *)(tbp + (int64_t)r * (NS >> 1)), Hrow, Urow, sc16);
+				lane_max = lane16_cells<kCigar, kRight>(ls, b, r, last_st, xin, vin, (uint4 *)(tbp + (int64_t)r * ROWB), Hrow, Urow, sc16);
+				if (kSpare && sp_on) {
+					cell2<kRight, kCigar, 0>(sp.Z, sxin, svin, sp.U, sp.V, sp.X, sp.Y, sc16, scw);
+					sp.H = (int32_t)__dp4a(sp.V, 0x00000100u, (uint32_t)sp.H);
+				}
 				{
 					const int i = b.en0 & 15;
 					const uint32_t uw = reinterpret_cast<const uint32_t *>(Urow)[(((i >> 2) * 128) << 2) | (i & 3)];       // my own u' dump
-					const int32_t ub = (int32_t)(((b.en0 >> 4) & 1) ? (uw >> 24) : ((uw >> 8) & 0xffu));
+					int32_t ub = (int32_t)(((b.en0 >> 4) & 1) ? (uw >> 24) : ((uw >> 8) & 0xffu));
+					if (kSpare && sp_in) ub = (int32_t)((sp.U >> 8) & 0xffu);
 					int32_t hen = hprev + ub;                                                              // :228 in the lazy domain
 					if (r == 0) hen = (int32_t)((ls.V[0] >> 8) & 0xffu) - 2 * qe;                          // :259
 					else if (b.en0 == 0) hen = *hptr(0);                    // en0 == 0: the regular update (:228 else-arm)
 					if (own_en) {
-						*hptr(b.en0) = hen;
 						Hen0 = hen;
-						lane_max = lane_max > hen ? lane_max : hen;
+						if (kSpare && sp_in) sp.H = hen;
+						else { *hptr(b.en0) = hen; lane_max = lane_max > hen ? lane_max : hen; }
 					}
 				}
+				tot_max = lane_max;
+				if (kSpare && sp_on) tot_max = tot_max > sp.H ? tot_max : sp.H;
 			}
-			ld.gmax = group_max<G>(lane_max);
-			ld.Hen0_lazy = G == 1 ? Hen0 : __shfl_sync(FULL, Hen0, en_owner, G);
+			if (kSpare && kCigar) {
+				// the 16 codes of the spare block: 8 bytes behind the packed part of the row (slot 2k low nibble, 2k+1 high nibble)
+				if (__any_sync(FULL, sp_on)) {
+					const uint32_t nib = scw & 0xfu;
+					const uint32_t o = __shfl_down_sync(FULL, nib, 1, 16);
+					if (sp_on && !(gl & 1)) tb_sp[(int64_t)r * ROWB + (gl >> 1)] = (uint8_t)(nib | (o << 4));
+				}
+			}
+			ld.gmax = group_max<G>(tot_max);
+			ld.Hen0_lazy = G == 1 ? Hen0 : __shfl_sync(FULL, Hen0, (kSpare && sp_in) ? (b.en0 & 15) : en_owner, G);
 			int need = 0;
 			if (act) {
 				const int32_t maxH_true = ld.gmax - qe * r;
@@ -530,9 +656,10 @@ extz_dp16_kernel(DpLaunch L)
 					const int wt0a = __shfl_sync(FULL, ls.t0[0], wl, G), wt0b = __shfl_sync(FULL, ls.t0[1], wl, G);
 					if (need) {
 						if (__popc(gmask) == 1) cnt = group_argmax_count<G>(Hrow - gl, wl, wt0a, wt0b, gl, gm);
-						else cnt = lane16_argmax_count(ls, Hrow, gm);
+						else if (gmask) cnt = lane16_argmax_count(ls, Hrow, gm);
 					}
 				}
+				if (kSpare && need && sp_on && sp.H == gm) cnt += (1u << 24) + (uint32_t)(sp.t0 + gl);
 				cnt = group_sum_u<G>(cnt);
 				max_t = (int)(cnt & 0x00ffffffu);
 				const int tie = need && (cnt >> 24) != 1u;
@@ -540,6 +667,10 @@ extz_dp16_kernel(DpLaunch L)
 					uint32_t key = 0xffffffffu;
 					if (tie) {
 						key = lane16_argmax_key(b, Hrow, gm, ls.t0[0], ls.t0[1]);
+						if (kSpare && sp_on && sp.H == gm) {
+							const int t = sp.t0 + gl;
+							if (t >= b.st0 && t <= b.en0 && !(t == b.en0 && b.en0 > 0)) { const uint32_t kk = tie_key(t, b.st0, b.en0); key = kk < key ? kk : key; }
+						}
 						if (gl == 0) { uint32_t k0 = ld.en0_key(b, r); key = k0 < key ? k0 : key; }
 					}
 					key = group_min_u<G>(key);
@@ -563,69 +694,9 @@ extz_dp16_kernel(DpLaunch L)
 				const int stop = ld.fin_local(b, r, qe, max_t, Hst0_lazy, qlen, tlen, sc.zdrop, sc.e);
 				n_diag = r + 1; last_st = b.st; last_en = b.en;
 				if (stop) alive = false;
+				++r;
 			}
-#else
-			// ---- exact maximum, one LEADER lane per group (the round-1 formulation; -DEXTZ_NARROW_LEADER for A/B builds) ----
-			if (act) {
-				lane16_prepare<NS>(ls, b, r, last_en, qseq, tseq, tlen, table_saddr, sc16);
-				if (gl == 0) ld.pre(rows, b, r, qe);
-			}
-			__syncwarp();
-			int32_t lane_max = kNegInf;
-			if (act) lane_max = lane16_cells<kCigar, kRight>(ls, b, r, last_st, xin, vin, (uint4 *)(tbp + (int64_t)r * (NS >> 1)), Hrow, Urow, sc16);
-			__syncwarp();
-			const int32_t red = group_max<G>(lane_max);
-			int need = 0;
-			if (act && gl == 0) {
-				need = ld.mid(rows, b, r, qe, red, ls.V[0] << 16, sc.zdrop);
-				need |= (int)(ld.Hen0_lazy == ld.gmax) << 1;             // bit 1: the leader's H[en0] reaches the maximum
-			}
-			__syncwarp();
-			// the leader's answers travel together (independent shuffles overlap their latency)
-			need = __shfl_sync(FULL, need, 0, G);
-			const int32_t gm = __shfl_sync(FULL, ld.gmax, 0, G);
-			const int en0_max = need >> 1;
-			need &= 1;
-			int max_t = b.en0;
-			if (__any_sync(FULL, need)) {
-				uint32_t cnt = 0;
-				if (G == 1) { if (need) cnt = lane16_argmax_count(ls, Hrow, gm); }
-				else {
-					// Only a lane whose own maximum reaches gm, or the owner of slot en0 when the leader's H[en0] does, can
-					// hold the arg-max.  With ONE such lane (the rule) the G lanes of the group split ITS 8 rows between
-					// them instead of every lane scanning its own 32 entries.
-					const bool cand = need && (lane_max == gm || (en0_max && ((b.en0 & (NS - 1)) >> 5) == gl));
-					const unsigned bal = __ballot_sync(FULL, cand);
-					const unsigned gmask = G == 32 ? bal : ((bal >> (lane_w & ~(G - 1))) & ((1u << (G & 31)) - 1u));
-					const int wl = gmask ? __ffs(gmask) - 1 : 0;
-					const int wt0a = __shfl_sync(FULL, ls.t0[0], wl, G), wt0b = __shfl_sync(FULL, ls.t0[1], wl, G);
-					if (need) {
-						if (__popc(gmask) == 1) cnt = group_argmax_count<G>(Hrow - gl, wl, wt0a, wt0b, gl, gm);
-						else cnt = lane16_argmax_count(ls, Hrow, gm);
-					}
-				}
-				cnt = group_sum_u<G>(cnt);
-				max_t = (int)(cnt & 0x00ffffffu);
-				const int tie = need && (cnt >> 24) != 1u;
-				if (__any_sync(FULL, tie)) {                                                      // real ties: exact 4-lane rule
-					uint32_t key = 0xffffffffu;
-					if (tie) {
-						key = lane16_argmax_key(b, Hrow, gm, ls.t0[0], ls.t0[1]);
-						if (gl == 0) { uint32_t k0 = ld.en0_key(b, r); key = k0 < key ? k0 : key; }
-					}
-					key = group_min_u<G>(key);
-					if (tie) max_t = tie_key_slot(key, b.en0);
-				}
-			}
-			int stop = 0;
-			if (act && gl == 0) stop = ld.fin(rows, b, r, qe, max_t, qlen, tlen, sc.zdrop, sc.e);
-			stop = __shfl_sync(FULL, stop, 0, G);
-			if (act) { n_diag = r + 1; last_st = b.st; last_en = b.en; if (stop) alive = false; }
-			__syncwarp();            // the arg-max passes read H; the next diagonal's leader writes it
-#endif
 		}
-		if (pi < L.n && gl == 0) { if (zdropped_band) ld.ez.zdropped = 1; ld.store(&L.results[pi], n_diag); }
-		__syncwarp();
 	}
 }
 

@@ -34,7 +34,7 @@ extz_traceback_kernel(TbLaunch L)
 	PairResult pr = L.results[pi];
 	const int qlen = pd.qlen, tlen = pd.tlen, w = pd.w, NS = L.NS;
 	const int T = (tlen + 15) & ~15;
-	const int rowB = NS >> 1;
+	const int rowB = (NS >> 1) + (L.spare ? 16 : 0);
 
 	StatAcc sa;
 	sa.span = sa.gap_bases = sa.matches = sa.mismatches = sa.indel_a = sa.indel_b = sa.alnB = sa.matchB = 0;
@@ -77,7 +77,7 @@ extz_traceback_kernel(TbLaunch L)
 			if (i < b.st) force = 2;
 			if (i > b.en) force = 1;
 			uint32_t tmp = 0;
-			if (force < 0) tmp = tb_fetch(tbp, NS, r, i, L.packed != 0);
+			if (force < 0) tmp = tb_fetch(tbp, NS, r, i, L.packed != 0, L.spare, b.st);
 			int hstate = (tmp & 2u) ? 2 : (int)(tmp & 1u);          // which of H/E/F gave the max
 			if (state == 0) state = hstate;
 			else if (!((tmp >> (state + 1)) & 1u)) state = 0;       // continuation bits: E -> bit2, F -> bit3
@@ -148,7 +148,7 @@ template <bool kStats>
 __global__ void __launch_bounds__(128)
 extz_traceback_warp_kernel(TbLaunch L)
 {
-	__shared__ __align__(16) uint8_t sTile[4][32][32];
+	__shared__ __align__(16) uint8_t sTile[4][32][48];             // per row: the two 16-byte chunks around the column + the spare block's codes
 	const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const int pi = blockIdx.x * 4 + wid;
 	if (pi >= L.n) return;                                         // whole warps leave together
@@ -156,7 +156,7 @@ extz_traceback_warp_kernel(TbLaunch L)
 	const PairResult pr = L.results[pi];
 	const int qlen = pd.qlen, tlen = pd.tlen, w = pd.w, NS = L.NS;
 	const int T = (tlen + 15) & ~15;
-	const int rowB = NS >> 1;
+	const int rowB = (NS >> 1) + (L.spare ? 16 : 0);
 	const bool packed = L.packed != 0;
 
 	StatAcc sa;
@@ -190,6 +190,7 @@ extz_traceback_warp_kernel(TbLaunch L)
 			const uint4 *row = (const uint4 *)(tbp + (int64_t)(r_top - lane) * rowB);
 			*(uint4 *)&sTile[wid][lane][0] = row[g_lo];
 			*(uint4 *)&sTile[wid][lane][16] = row[g_hi];
+			if (L.spare) *(uint4 *)&sTile[wid][lane][32] = row[NS >> 5];
 		}
 		__syncwarp();
 		if (lane == 0) {
@@ -202,8 +203,9 @@ extz_traceback_warp_kernel(TbLaunch L)
 				uint32_t tmp = 0;
 				if (force < 0) {
 					const int c = i & (NS - 1);
-					const int off = ((c >> 5) == g_hi ? 16 : 0) + (packed ? (c & 15) : ((c >> 1) & 15));
-					const int nib = packed ? ((c >> 4) & 1) : (c & 1);
+					int off = ((c >> 5) == g_hi ? 16 : 0) + (packed ? (c & 15) : ((c >> 1) & 15));
+					int nib = packed ? ((c >> 4) & 1) : (c & 1);
+					if (L.spare && i >= b.st + NS) { off = 32 + ((i & 15) >> 1); nib = i & 1; }      // the class's spare block
 					tmp = (sTile[wid][r_top - r][off] >> (nib * 4)) & 0xfu;
 				}
 				int hstate = (tmp & 2u) ? 2 : (int)(tmp & 1u);

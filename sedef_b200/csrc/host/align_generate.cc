@@ -123,8 +123,14 @@ std::string FastaFile::get_sequence(const std::string &name, int start, int *end
 	std::string s;
 	s.reserve((size_t)length);
 	const char *p = (const char *)map_;
-	for (long long i = from; i < to; ++i)
-		if (p[i] != '\n' && p[i] != '\0') s.push_back(p[i]);    // std::remove of '\n' and '\0' (src/fasta.cc:137-138)
+	for (long long i = from; i < to;) {                            // line by line; std::remove of '\n' and '\0' (src/fasta.cc:137-138)
+		const char *nl = (const char *)memchr(p + i, '\n', (size_t)(to - i));
+		const long long stop = nl ? (long long)(nl - p) : to;
+		if (memchr(p + i, '\0', (size_t)(stop - i))) {
+			for (long long k = i; k < stop; ++k) if (p[k] != '\0') s.push_back(p[k]);
+		} else s.append(p + i, (size_t)(stop - i));
+		i = stop + 1;
+	}
 	return s;
 }
 
@@ -240,14 +246,28 @@ GenerateStats align_generate(const std::string &ref_path, const std::string &bed
 		std::vector<std::string> fa, fb;
 		size_t bytes = 0, end = at;
 		const double t0 = now_ms();
-		while (end < schedule.size() && (end == at || bytes < group_bytes)) {
-			BedHit &h = schedule[end];
-			fa.push_back(fr.get_sequence(h.query_name, h.query_start, &h.query_end));
-			std::string b = fr.get_sequence(h.ref_name, h.ref_start, &h.ref_end);
-			fb.push_back(h.ref_rc ? reverse_complement(b) : std::move(b));
-			bytes += fa.back().size() + fb.back().size();
+		while (end < schedule.size() && (end == at || bytes < group_bytes)) {      // the group: by the (unclamped) spans
+			const BedHit &h = schedule[end];
+			bytes += (size_t)std::max(0, h.query_end - h.query_start) + (size_t)std::max(0, h.ref_end - h.ref_start);
 			++end;
 		}
+		fa.resize(end - at); fb.resize(end - at);
+		std::string cut_error;
+#pragma omp parallel for schedule(dynamic, 4)
+		for (long i = (long)at; i < (long)end; ++i) {
+			try {
+				BedHit &h = schedule[i];
+				fa[i - at] = fr.get_sequence(h.query_name, h.query_start, &h.query_end);
+				std::string b = fr.get_sequence(h.ref_name, h.ref_start, &h.ref_end);
+				fb[i - at] = h.ref_rc ? reverse_complement(b) : std::move(b);
+			} catch (const std::exception &e) {
+#pragma omp critical
+				if (cut_error.empty()) cut_error = e.what();
+			}
+		}
+		if (!cut_error.empty()) throw std::runtime_error(cut_error);
+		bytes = 0;
+		for (size_t i = 0; i < fa.size(); ++i) bytes += fa[i].size() + fb[i].size();
 		std::vector<RegionSeed> seeds(end - at);
 		for (size_t i = at; i < end; ++i) {
 			const BedHit &h = schedule[i];
@@ -261,10 +281,12 @@ GenerateStats align_generate(const std::string &ref_path, const std::string &bed
 		std::vector<std::vector<GuidedAlignment>> hits = fast_align_batch(seeds, kmer_size, p, &rs);
 		const double t2 = now_ms();
 		gs.rounds += rs.rounds; gs.batch_calls += rs.batch_calls; gs.ksw_requests += rs.ksw_requests;
-		std::string text;
-		for (size_t i = at; i < end; ++i) {
+		std::vector<std::string> texts(end - at);
+#pragma omp parallel for schedule(dynamic, 4)
+		for (long i = (long)at; i < (long)end; ++i) {
 			const BedHit &h = schedule[i];
 			const std::string orig_text = h.to_bed(nullptr, true);
+			std::string &text = texts[i - at];
 			for (const GuidedAlignment &g : hits[i - at]) {
 				BedHit hh;                                       // the refined hit in genome coordinates (src/align_main.cc:314-329)
 				hh.query_name = h.query_name; hh.ref_name = h.ref_name;
@@ -274,9 +296,10 @@ GenerateStats align_generate(const std::string &ref_path, const std::string &bed
 				if (h.ref_rc) { hh.ref_start = h.ref_end - g.end_b; hh.ref_end = h.ref_end - g.start_b; }
 				else { hh.ref_start = g.start_b + h.ref_start; hh.ref_end = g.end_b + h.ref_start; }
 				text += hh.to_bed(&g, true); text += '\t'; text += orig_text; text += '\n';
-				++gs.hits;
 			}
 		}
+		std::string text;
+		for (size_t i = 0; i < texts.size(); ++i) { text += texts[i]; gs.hits += (long long)hits[i].size(); }
 		if (out && !text.empty() && fwrite(text.data(), 1, text.size(), out) != text.size())
 			throw std::runtime_error(std::string("write failed: ") + strerror(errno));
 		gs.regions += (long long)(end - at); gs.region_bytes += (long long)bytes; ++gs.groups;

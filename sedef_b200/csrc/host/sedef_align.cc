@@ -862,22 +862,29 @@ std::vector<std::vector<Anchor>> anchors_batch(const std::vector<RegionSeed> &re
 	std::vector<int> ql(n), rl(n);
 	std::vector<int64_t> qo(n), ro(n), oq(n), orr(n);
 	std::vector<uint8_t> same(n);
-	std::string qbuf, rbuf;
+	int64_t qtot = 0, rtot = 0;
 	for (int i = 0; i < n; ++i) {
 		ql[i] = (int)regions[i].qstr->size(); rl[i] = (int)regions[i].rstr->size();
-		qo[i] = (int64_t)qbuf.size(); ro[i] = (int64_t)rbuf.size();
-		qbuf += *regions[i].qstr; rbuf += *regions[i].rstr;
+		qo[i] = qtot; ro[i] = rtot; qtot += ql[i]; rtot += rl[i];
 		same[i] = regions[i].same_chr; oq[i] = regions[i].orig_query_start; orr[i] = regions[i].orig_ref_start;
 	}
-	qbuf.push_back('\0'); rbuf.push_back('\0');
+	std::string qbuf((size_t)qtot + 1, '\0'), rbuf((size_t)rtot + 1, '\0');
+#pragma omp parallel for schedule(dynamic, 16)
+	for (int i = 0; i < n; ++i) {
+		memcpy(&qbuf[(size_t)qo[i]], regions[i].qstr->data(), (size_t)ql[i]);
+		memcpy(&rbuf[(size_t)ro[i]], regions[i].rstr->data(), (size_t)rl[i]);
+	}
 	sedef_anchor_t *flat = nullptr;
 	std::vector<int64_t> off(n + 1, 0);
 	int rc = sedef_anchors_batch(n, ql.data(), qo.data(), (const uint8_t *)qbuf.data(), rl.data(), ro.data(), (const uint8_t *)rbuf.data(), kmer_size,
 	                             same.data(), oq.data(), orr.data(), &flat, off.data());
 	if (rc) throw std::runtime_error(std::string("sedef_anchors_batch: ") + ksw_b200_strerror(rc) + " -- " + ksw_b200_last_error());
 	std::vector<std::vector<Anchor>> out(n);
-	for (int i = 0; i < n; ++i)
+#pragma omp parallel for schedule(dynamic, 16)
+	for (int i = 0; i < n; ++i) {
+		out[i].reserve((size_t)(off[i + 1] - off[i]));
 		for (int64_t k = off[i]; k < off[i + 1]; ++k) out[i].push_back(Anchor{flat[k].q, flat[k].r, flat[k].l, flat[k].has_u});
+	}
 	free(flat);
 	return out;
 }

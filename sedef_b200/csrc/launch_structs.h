@@ -32,6 +32,7 @@ struct TbLaunch {
 	int *overflow;               // set to 1 when the compact arena is too small
 	int n, NS, flag;
 	int packed;                  // traceback rows written by the packed kernel (extz_dp16.cuh layout)
+	int spare;                   // rows carry 16 extra bytes: the codes of the class's SPARE block (extz_dp16.cuh Spare16) at [NS/2, NS/2 + 8)
 	int32_t *trims;              // per pair {trim_front max_i | -1, trim_back kept columns | -1} (extz_core.cuh TrimAcc), indexed like
 	                             // stats; nullptr: not wanted
 	int t_match, t_mismatch, t_gapo, t_gape;   // alignment scoring of the trim scans (Globals::Align, src/align.cc:343-456)

@@ -225,6 +225,43 @@ def test_packed_class_boundaries(checker, mat):
         compare(ps, mat, checker, L // 2, 60, 0)
 
 
+@pytest.mark.parametrize("w,zdrop,flag,kw", [
+    (500, 400, 0, dict(min_len=900, max_len=2600, div=0.15, burst=200)),       # BASELINE.json configs[2]'s band: 33 blocks on 1/4 of the diagonals
+    (500, -1, 0, dict(min_len=1100, max_len=1800, div=0.05)),
+    (496, 300, 0, dict(min_len=900, max_len=2000, div=0.2, burst=150)),        # w % 16 == 0: block entry and block exit on the SAME diagonal
+    (511, -1, 0, dict(min_len=520, max_len=1600, div=0.1)),                    # widest band of the class; the top row reaches the spare block
+    (505, 200, 0x02, dict(min_len=700, max_len=1500, div=0.2)),                # right-aligned gaps
+    (500, 250, 0x01, dict(min_len=700, max_len=1500, div=0.2)),                # score only
+    (503, 150, 0xc0, dict(min_len=700, max_len=1500, div=0.25, burst=120)),    # EXTZ_ONLY + REV_CIGAR: traceback from (max_t, max_q)
+    (500, 100, 0x04, dict(min_len=700, max_len=1500, div=0.2)),                # GENERIC_SC: the score fill stops at en0
+    (-1, -1, 0, dict(min_len=513, max_len=528, div=0.1)),                      # unbanded, 16 * ceil(tlen / 16) in (512, 528]
+    (-1, 200, 0, dict(min_len=505, max_len=528, div=0.3, burst=100)),
+])
+def test_spare_block_class(checker, mat, w, zdrop, flag, kw):
+    """The 16-lane packed class holds 33 blocks: 32 in registers + a SPARE block spread over its lanes (extz_dp16.cuh Spare16),
+    so pairs needing 513..528 live slots -- every band of w = 496..511 -- no longer fall into the 1024-slot class.  Activation
+    (also ahead of the rounded range, by the score fill), band entry, the carries from the block below, H[en0] inside the spare
+    block, the arg-max in it, its traceback codes, the hand-over to the owning lane and two spare blocks in a row."""
+    ps = synth.make_pairs_mixed(120, seed=7700 + 3 * (w + 2) + flag, **kw)
+    compare(ps, mat, checker, w, zdrop, flag)
+
+
+def test_spare_block_long_lived(checker, mat):
+    """Target of 513..528 bases against a much longer query, unbanded: block 0 stays live for thousands of anti-diagonals, and so
+    does the spare block (never handed over until the very end)."""
+    rng = np.random.default_rng(77)
+    pairs = []
+    for _ in range(12):
+        tl = int(rng.integers(513, 529)); ql = int(rng.integers(900, 2500))
+        t = "".join("ACGT"[k] for k in rng.integers(0, 4, tl))
+        q = "".join("ACGT"[k] for k in rng.integers(0, 4, ql))
+        k = int(rng.integers(0, ql - 300)); q = q[:k] + t[100:400] + q[k + 300:]       # a shared stretch somewhere
+        pairs.append((q, t))
+    ps = synth.pairs_from_strings(pairs)
+    compare(ps, mat, checker, -1, -1, 0)
+    compare(ps, mat, checker, -1, 300, 0x40)
+
+
 def test_maximum_in_the_block_that_leaves_the_band(checker, mat):
     """The arg-max of a diagonal can sit in the lowest 16-slot block, which leaves the band on the next diagonal (a
     maximum on the last query row is at slot st0).  The pipelined CTA-wide / cluster kernels run prepare(r+1) -- which

@@ -5,9 +5,14 @@ rep, ksub, diag = sys.argv[1], sys.argv[2], float(sys.argv[3])
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(root, "sedef_b200", "libsedef_b200.so")], cwd=tmp, capture_output=True)
-cubin = glob.glob(os.path.join(tmp, "*sm_100a*.cubin"))[0]
-dis = subprocess.run(["nvdisasm", "-g", "-c", cubin], capture_output=True, text=True).stdout.split("\n")
-start = [i for i, l in enumerate(dis) if l.startswith(".text.") and ksub in l][0]
+dis, start = None, None
+for cubin in sorted(glob.glob(os.path.join(tmp, "*sm_100a*.cubin"))):      # one cubin per translation unit: find the kernel's
+    d = subprocess.run(["nvdisasm", "-g", "-c", cubin], capture_output=True, text=True).stdout.split("\n")
+    hit = [i for i, l in enumerate(d) if l.startswith(".text.") and ksub in l]
+    if hit:
+        dis, start = d, hit[0]
+        break
+assert dis is not None, "kernel not found in any cubin of libsedef_b200.so"
 cur, insts = None, []
 for l in dis[start + 1:]:
     if (l.startswith(".text.") or l.startswith(".section")) and insts:

@@ -47,7 +47,7 @@ CONFIGS = {
     3: dict(name="BASELINE.json configs[2]: 10k pairs of 10-50 kbp per GPU, w=500, z-drop 400, 15% divergence with indels, flag=0 "
                  "(CIGAR + exact max + fused SD stats), SEDEF scoring 5/-4/40/1",
             pairs=10000, w=500, zdrop=400, flag=0, seed=0x5EDEF003,
-            kernel="extz_dp16_kernel<32,cigar,left> (packed: 32 lanes x 32 slots = 1024 live slots for the 528-slot band, 1 pair per warp)"),
+            kernel="extz_dp16_kernel<16,cigar,left> (packed: 16 lanes x 32 slots + a spare block spread over the lanes = 528 live slots, 2 pairs per warp)"),
 }
 
 

@@ -186,7 +186,11 @@ extern "C" int ksw_b200_init(int first_dev, int ndev)
 		CUDA_TRY(cudaStreamCreateWithPriority(&d.tb_stream, cudaStreamNonBlocking, prio_greatest));
 		size_t fr = 0, tot = 0; CUDA_TRY(cudaMemGetInfo(&fr, &tot));
 		const char *env = getenv("KSW_B200_TB_BUDGET_MB");
-		d.tb_budget = env ? (size_t)atoll(env) << 20 : std::min<size_t>(fr / 2, (size_t)48 << 30);
+		// A wave must hold enough pairs to fill the machine with SIMILAR work (3 CTAs x 4 warps per SM, up to 32 pairs per warp) --
+		// with 10-50 kbp pairs (16 MB of rows each) a 48 GB wave was 2000 pairs for 3552 resident groups and ran at 1.7 warps per
+		// scheduler; three quarters of the free memory (137 GB on a 180 GB B200) brought BASELINE configs[2] from 333 to 448 GCUPS
+		// (profiles/r02_tuning.md).  Memory is only taken as far as a wave needs it.
+		d.tb_budget = env ? (size_t)atoll(env) << 20 : std::min<size_t>(fr / 4 * 3, (size_t)140 << 30);
 		g_devs.push_back(d);
 	}
 	return ndev;

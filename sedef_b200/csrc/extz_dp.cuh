@@ -346,9 +346,16 @@ struct Leader {
 };
 
 // ---- group collectives (all 32 lanes of the warp execute them; groups are G-aligned lane ranges) ----
+// (G == 16: two full-warp REDUX with the other half masked to the identity -- two independent instructions instead of a chain of
+// four dependent shuffle + op steps)
 template <int G> __device__ __forceinline__ int32_t group_max(int32_t v)
 {
 	if (G == 32) return __reduce_max_sync(0xffffffffu, v);
+	if (G == 16) {
+		const bool hi = (threadIdx.x & 16) != 0;
+		const int32_t a = __reduce_max_sync(0xffffffffu, hi ? (int32_t)0x80000000 : v), b = __reduce_max_sync(0xffffffffu, hi ? v : (int32_t)0x80000000);
+		return hi ? b : a;
+	}
 #pragma unroll
 	for (int d = 1; d < G; d <<= 1) { int32_t o = __shfl_xor_sync(0xffffffffu, v, d); v = v > o ? v : o; }
 	return v;
@@ -356,6 +363,11 @@ template <int G> __device__ __forceinline__ int32_t group_max(int32_t v)
 template <int G> __device__ __forceinline__ uint32_t group_min_u(uint32_t v)
 {
 	if (G == 32) return __reduce_min_sync(0xffffffffu, v);
+	if (G == 16) {
+		const bool hi = (threadIdx.x & 16) != 0;
+		const uint32_t a = __reduce_min_sync(0xffffffffu, hi ? 0xffffffffu : v), b = __reduce_min_sync(0xffffffffu, hi ? v : 0xffffffffu);
+		return hi ? b : a;
+	}
 #pragma unroll
 	for (int d = 1; d < G; d <<= 1) { uint32_t o = __shfl_xor_sync(0xffffffffu, v, d); v = v < o ? v : o; }
 	return v;
@@ -363,6 +375,11 @@ template <int G> __device__ __forceinline__ uint32_t group_min_u(uint32_t v)
 template <int G> __device__ __forceinline__ uint32_t group_sum_u(uint32_t v)
 {
 	if (G == 32) return __reduce_add_sync(0xffffffffu, v);
+	if (G == 16) {
+		const bool hi = (threadIdx.x & 16) != 0;
+		const uint32_t a = __reduce_add_sync(0xffffffffu, hi ? 0u : v), b = __reduce_add_sync(0xffffffffu, hi ? v : 0u);
+		return hi ? b : a;
+	}
 #pragma unroll
 	for (int d = 1; d < G; d <<= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
 	return v;

@@ -168,6 +168,22 @@ struct GenerateStats {
 GenerateStats align_generate(const std::string &ref_path, const std::string &bed_path, int kmer_size, FILE *out,
                              const AlignParams &p = AlignParams(), int shard_index = 0, int shard_count = 1, size_t group_bytes = 0);
 
+// ---- the SD report: `sedef stats generate` (src/stats_main.cc:213-395,513-537) ---------------------------------------------------
+// populate_nice_alignment's counters + the BEDPE stat loop of many finished alignments (SEDEF-alphabet run lists over their own
+// original-case strings) in ONE statistics-from-CIGAR call on the GPU
+std::vector<sd_stats_t> stats_of_alignments(const std::vector<const GuidedAlignment *> &alns);
+struct StatsParams {                                   // Globals::Stats (src/globals.cc:36-39), the command's --max-ok-gap / --min-split / --uppercase / --max-error
+	int max_ok_gap = -1, min_split_size = 1000, min_uppercase = 100;
+	double max_scaled_error = 0.5;
+};
+struct StatsGenerateCounts { long long hits = 0, pieces = 0, lines = 0; };
+const char *stats_header();                            // the "#chr1\tstart1..." line (src/stats_main.cc:379-386)
+// stats() (src/stats_main.cc:338-395): the aligned hits of `bed_path` (28-column lines of `align generate`, after sedef.sh's
+// sort | uniq) -> Alignment(fa, fb, cigar) -> pieces at assembly gaps / large gaps, re-trimmed -> statistics of ALL pieces in one
+// GPU call -> filters -> the header and one 35-column line per piece, in the reference's (sequential) order.
+StatsGenerateCounts stats_generate(const std::string &ref_path, const std::string &bed_path, FILE *out,
+                                   const StatsParams &sp = StatsParams(), const AlignParams &p = AlignParams());
+
 // Deferred-alignment queue: call sites push requests, the driver flushes a whole wave at once.
 class AlignQueue {
 public:
@@ -186,12 +202,20 @@ private:
 // The ksw_extz2 calls align_helper makes for one Alignment(fa, fb) with |fa| = alen, |fb| = blen (src/align.cc:46-53):
 // call k aligns (fa + sp[k], qlen[k]) against (fb + sp[k], tlen[k]).  Returns the number of calls (fills at most `cap`).
 extern "C" int sedef_b200_chunk_plan(int64_t alen, int64_t blen, int cap, int64_t *sp, int *qlen, int *tlen);
+// chain_anchors (src/chain.cc:103-199 + the filter of :222-247) for callers without C++: anchors as (q, r, l, has_u) rows; chain k
+// holds chain_len[k] anchor indices (query order), concatenated in chain_idx.  Returns the number of chains (fills at most cap_*).
+extern "C" int sedef_b200_chain_anchors(int n, const int32_t *anchors4, int cap_chains, int *chain_len, int cap_idx, int *chain_idx);
 // `sedef align generate -k kmer_size ref_path bed_path > out_path` (src/align_main.cc:285-337,368-373) through fast_align_batch.
 // out_path NULL or "-": stdout.  stats[7] (may be NULL): regions, hits, groups, rounds, batch_calls, ksw_requests, region_bytes;
 // ms[3] (may be NULL): total, align, io.  Returns 0, or -1 with the message in sedef_b200_align_generate_error().
 extern "C" int sedef_b200_align_generate(const char *ref_path, const char *bed_path, int kmer_size, const char *out_path,
                                          int shard_index, int shard_count, long long *stats, double *ms);
 extern "C" const char *sedef_b200_align_generate_error(void);
+// `sedef stats generate [--max-ok-gap G] [--min-split S] [--uppercase U] [--max-error E] ref_path bed_path > out_path`
+// (reference defaults: -1, 1000, 100, 0.5).  counts[3] (may be NULL): hits read, pieces measured, lines written.
+extern "C" int sedef_b200_stats_generate(const char *ref_path, const char *bed_path, const char *out_path, int max_ok_gap, int min_split,
+                                         int min_uppercase, double max_scaled_error, long long *counts);
+extern "C" const char *sedef_b200_stats_generate_error(void);
 // host-only pieces of the same driver (no device needed): FastaReference::get_sequence; the seed hits of a bucket file / directory
 // in processing order, one Hit::to_bed(false) line each (returns the bytes needed, text truncated to cap); rc() of n bytes
 extern "C" long long sedef_b200_fasta_fetch(const char *ref_path, const char *name, int start, int *end_io, char *out, long long cap);

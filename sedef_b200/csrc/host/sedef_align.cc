@@ -210,6 +210,15 @@ std::vector<Alignment> from_cigar_batch(const std::vector<std::pair<std::string,
 	return out;
 }
 
+std::vector<sd_stats_t> stats_of_alignments(const std::vector<const GuidedAlignment *> &alns)
+{
+	std::vector<StrPair> sp(alns.size());
+	std::vector<const std::deque<std::pair<char, int>> *> cp(alns.size());
+	for (size_t i = 0; i < alns.size(); ++i) { sp[i] = {&alns[i]->a, &alns[i]->b}; cp[i] = &alns[i]->cigar; }
+	if (alns.empty()) return {};
+	return stats_of(sp, cp);
+}
+
 // append_cigar (src/align.cc:468-477): merge the first appended run into the last one when the ops are equal
 static void append_cigar(std::deque<std::pair<char, int>> &cigar, const std::deque<std::pair<char, int>> &app)
 {

@@ -68,7 +68,8 @@ EXPORTS = ["ksw_b200_strerror", "ksw_b200_last_error", "ksw_b200_init", "ksw_b20
            "ksw_b200_result_count", "ksw_b200_result_io", "ksw_b200_result_free", "ksw_b200_batch_fetch_arena",
            "ksw_b200_result_export", "ksw_b200_result_trims", "sedef_anchors_batch", "sedef_b200_chain_anchors",
            "sedef_b200_chunk_plan", "sedef_b200_align_generate", "sedef_b200_align_generate_error",
-           "sedef_b200_fasta_fetch", "sedef_b200_bed_schedule", "sedef_b200_reverse_complement"]
+           "sedef_b200_fasta_fetch", "sedef_b200_bed_schedule", "sedef_b200_reverse_complement",
+           "sedef_b200_stats_generate", "sedef_b200_stats_generate_error"]
 
 
 def load():
@@ -145,6 +146,9 @@ def load():
     lib.sedef_b200_align_generate.argtypes = [C.c_char_p, C.c_char_p, i32, C.c_char_p, i32, i32, vp, vp]
     lib.sedef_b200_align_generate.restype = i32
     lib.sedef_b200_align_generate_error.restype = C.c_char_p
+    lib.sedef_b200_stats_generate.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, i32, i32, i32, C.c_double, vp]
+    lib.sedef_b200_stats_generate.restype = i32
+    lib.sedef_b200_stats_generate_error.restype = C.c_char_p
     lib.sedef_b200_fasta_fetch.argtypes = [C.c_char_p, C.c_char_p, i32, C.POINTER(i32), C.c_char_p, C.c_longlong]
     lib.sedef_b200_fasta_fetch.restype = C.c_longlong
     lib.sedef_b200_bed_schedule.argtypes = [C.c_char_p, C.c_char_p, C.c_longlong]
@@ -472,6 +476,19 @@ def align_generate(ref_path: str, bed_path: str, out_path: str, kmer_size: int =
     out = {k: int(v) for k, v in zip(keys, st)}
     out.update(ms_total=float(ms[0]), ms_align=float(ms[1]), ms_io=float(ms[2]))
     return out
+
+
+def stats_generate(ref_path: str, bed_path: str, out_path: str, max_ok_gap: int = -1, min_split: int = 1000, min_uppercase: int = 100,
+                   max_scaled_error: float = 0.5) -> dict:
+    """`sedef stats generate` (src/stats_main.cc:338-395,513-537): the SD report of an aligned.bed; statistics of all pieces in one
+    GPU call."""
+    lib = load()
+    cnt = np.zeros(3, np.int64)
+    rc = lib.sedef_b200_stats_generate(os.fsencode(ref_path), os.fsencode(bed_path), os.fsencode(out_path), int(max_ok_gap), int(min_split),
+                                       int(min_uppercase), float(max_scaled_error), _ptr(cnt))
+    if rc != 0:
+        raise EngineError(rc, lib.sedef_b200_stats_generate_error().decode())
+    return dict(hits=int(cnt[0]), pieces=int(cnt[1]), lines=int(cnt[2]))
 
 
 def fasta_fetch(ref_path: str, name: str, start: int, end: int):

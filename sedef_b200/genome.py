@@ -22,7 +22,7 @@ def revcomp(a: np.ndarray) -> np.ndarray:
 
 
 def make_genome(chrom_lengths: Dict[str, int], n_dups: int, min_len: int = 5000, max_len: int = 20000, min_div: float = 0.02,
-                max_div: float = 0.10, seed: int = 0x5EDEF001, rc_frac: float = 0.3, large_indels: int = 2):
+                max_div: float = 0.10, seed: int = 0x5EDEF001, rc_frac: float = 0.3, large_indels: int = 2, assembly_gaps: int = 0):
     """Returns ({name: np.uint8 ASCII}, catalog); catalog rows are dicts with src/dst chromosome and [start, end), divergence and
     strand (rc = True: the copy is the reverse complement of the mutated source)."""
     rng = np.random.Generator(np.random.PCG64(seed))
@@ -53,6 +53,8 @@ def make_genome(chrom_lengths: Dict[str, int], n_dups: int, min_len: int = 5000,
             copy = (np.concatenate([copy[:p], copy[p + kk:]]) if rng.random() < 0.5
                     else np.concatenate([copy[:p], synth.ASCII[rng.integers(0, 4, kk)], copy[p:]]))
         copy = copy[:max_len + 400]
+        if k < assembly_gaps:                                    # an assembly gap inside the copy: a run of N (`sedef stats` splits there)
+            p = len(copy) // 2 + int(rng.integers(-200, 200)); copy = copy.copy(); copy[p:p + int(rng.integers(120, 260))] = ord("N")
         is_rc = bool(rng.random() < rc_frac)
         chroms[dc][d0:d0 + len(copy)] = revcomp(copy) if is_rc else copy
         catalog.append(dict(src_chr=sc, s0=s0, s1=s0 + L, dst_chr=dc, d0=d0, d1=d0 + len(copy), div=div, rc=is_rc))
@@ -100,6 +102,20 @@ def write_align_stage_input(workdir: str, chrom_lengths: Dict[str, int], n_dups:
     with open(bed, "w") as f:
         f.write("\n".join(seed_bed_lines(catalog)) + "\n")
     return fa, bed, catalog
+
+
+# hg38 chromosome lengths (Mbp, rounded): the shape of BASELINE.json configs[4]
+HG38_MBP = dict(chr1=248, chr2=242, chr3=198, chr4=190, chr5=182, chr6=171, chr7=159, chr8=145, chr9=138, chr10=134, chr11=135,
+                chr12=133, chr13=114, chr14=107, chr15=102, chr16=90, chr17=83, chr18=80, chr19=59, chr20=64, chr21=47, chr22=51,
+                chrX=156, chrY=57)
+
+
+def config5(scale: float = 1.0, dups_per_mbp: float = 8.0):
+    """configs[4]: 24 chromosomes with hg38's proportions (3.1 Gbp at scale 1), planted SD catalog up to 30 % divergence."""
+    lengths = {k: max(200_000, int(v * 1_000_000 * scale)) for k, v in HG38_MBP.items()}
+    total = sum(lengths.values())
+    return dict(chrom_lengths=lengths, n_dups=int(total / 1e6 * dups_per_mbp), min_len=2000, max_len=20000, min_div=0.02,
+                max_div=0.30, seed=0x5EDEF005, rc_frac=0.4)
 
 
 CONFIGS = {

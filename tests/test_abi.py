@@ -16,6 +16,9 @@ def declared_functions():
     src = open(os.path.join(ROOT, "include", "ksw2_b200.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     names = re.findall(r"\b(ksw_[a-z0-9_]+|sd_stats_[a-z0-9_]+|sedef_[a-z0-9_]+)\s*\(", src)
+    # the extern "C" entry points of the C++ host layer (include/sedef_align.hpp)
+    hpp = open(os.path.join(ROOT, "include", "sedef_align.hpp")).read()
+    names += re.findall(r'extern "C"[^;(]*?\b(sedef_b200_[a-z0-9_]+)\s*\(', hpp)
     return sorted(set(n for n in names if not n.endswith("_t")))
 
 

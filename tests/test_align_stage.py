@@ -159,3 +159,31 @@ def test_align_generate_config1_live_reference(built, tmp_path):
                 recovered += 1
                 break
     assert recovered >= 36, recovered
+
+
+@pytest.mark.gpu
+def test_stats_generate_matches_reference_binary_golden(built, golden_dir, tmp_path):
+    """`sedef stats generate` (src/stats_main.cc:213-395): the 35-column SD report of an aligned.bed -- Alignment(fa, fb, cigar), the
+    split at assembly gaps (runs of >= 100 N) with re-trimmed pieces, the BEDPE stat loop and populate_nice_alignment's counters of
+    ALL pieces in one GPU call, the floating-point columns in the reference's "%g" text, the filters -- against the reference
+    binary's own output (tests/golden/stats_golden.json), with the default parameters and with gap splitting switched on
+    (--max-ok-gap 1 --min-split 500: recursive cuts at the largest gaps)."""
+    from sedef_b200 import engine, genome
+    g = load_json(golden_dir, "stats_golden.json")
+    wd = str(tmp_path)
+    fa, _, _ = genome.write_align_stage_input(wd, **g["config"])
+    assert hashlib.sha1(open(fa, "rb").read()).hexdigest() == g["genome_sha1"], "generator drifted: regenerate the fixture"
+    ab = os.path.join(wd, "aligned.bed")
+    with open(ab, "w") as f:
+        f.write(g["aligned"])
+    for name, extra in g["variants"].items():
+        kw = {}
+        for k, v in zip(extra[::2], extra[1::2]):
+            kw[{"--max-ok-gap": "max_ok_gap", "--min-split": "min_split", "--uppercase": "min_uppercase"}[k]] = int(v)
+        out = os.path.join(wd, name + ".final.bed")
+        cnt = engine.stats_generate(fa, ab, out, **kw)
+        got = open(out).read()
+        assert got == g["reports"][name], name
+        assert cnt["hits"] == g["aligned"].count("\n") and cnt["lines"] == got.count("\n") - 1
+    assert g["reports"]["default"].count("\n") - 1 > g["aligned"].count("\n")          # the assembly gaps did split hits
+    assert g["reports"]["gap_split"].count("\n") > g["reports"]["default"].count("\n")

@@ -24,7 +24,8 @@ REF_BIN = os.path.join(ROOT, "oracle", "_ref", "sedef_ref")
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--config", type=int, default=1, choices=[1, 4])
+    ap.add_argument("--config", type=int, default=1, choices=[1, 4, 5])
+    ap.add_argument("--scale", type=float, default=0.02, help="config 5 only: fraction of hg38's 3.1 Gbp (24 chromosomes)")
     ap.add_argument("--dups", type=int, default=0, help="planted duplications (default: the config's own count)")
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--buckets", type=int, default=0, help="bucket files (default: host cores)")
@@ -36,7 +37,7 @@ def main():
 
     cores = len(os.sched_getaffinity(0))
     nb = args.buckets or cores
-    cfg = dict(genome.CONFIGS[args.config])
+    cfg = dict(genome.config5(args.scale) if args.config == 5 else genome.CONFIGS[args.config])
     if args.dups:
         cfg["n_dups"] = args.dups
     wd = args.keep or tempfile.mkdtemp(prefix="align_stage_")
@@ -72,7 +73,8 @@ def main():
     ours_s, st = best
     ours_lines = sorted(ln for ln in open(out).read().split("\n") if ln)
 
-    line = dict(metric="align-stage regions/s (sedef align generate, all buckets)", config="configs[%d]" % (args.config - 1),
+    line = dict(metric="align-stage regions/s (sedef align generate, all buckets)",
+                config="configs[%d]" % (args.config - 1) + (" at scale %g" % args.scale if args.config == 5 else ""),
                 genome_bp=sum(cfg["chrom_lengths"].values()), planted=len(catalog), regions=n_regions, region_bases=region_bases,
                 buckets=len(buckets), n_gpus=args.gpus, hits=st["hits"], seconds=round(ours_s, 3),
                 value=round(n_regions / ours_s, 1), unit="regions/s", hits_per_s=round(st["hits"] / ours_s, 1),

@@ -10,7 +10,9 @@ sets = [
     (synth.make_pairs_mixed(24, seed=2, min_len=40, max_len=120, div=0.1), -1, 50, 0),     # packed, 2-4 lanes
     (synth.make_pairs_small(12, length=400, div=0.05, seed=3), 100, -1, 0),                # packed, 4 lanes, banded
     (synth.make_pairs_small(6, length=500, div=0.1, seed=4), -1, -1, 2),                   # packed, 16 lanes, right-aligned arm
-    (synth.make_pairs_large(2, min_len=1500, max_len=2500, seed=5), 500, 400, 0),          # packed, 32 lanes (1024 slots)
+    (synth.make_pairs_large(2, min_len=1500, max_len=2500, seed=5), 500, 400, 0),          # packed, 16 lanes + the spare block (528 slots)
+    (synth.make_pairs_large(2, min_len=1500, max_len=2500, seed=10), 700, 400, 0),         # packed, 32 lanes (1024 slots)
+    (synth.make_pairs_mixed(6, seed=11, min_len=513, max_len=528, div=0.1), -1, -1, 0),    # packed, 16 lanes, spare block unbanded
     (synth.make_pairs_small(2, length=1500, div=0.1, seed=6), -1, -1, 0),                  # packed CTA-wide, 64 lanes
     (synth.make_pairs_small(1, length=4500, div=0.1, seed=7), -1, -1, 0),                  # packed CTA-wide, 256 lanes (dynamic smem)
     (synth.make_pairs_small(1, length=8500, div=0.1, seed=8), -1, -1, 0),                  # packed cluster of 2 CTAs (DSMEM)

@@ -24,7 +24,7 @@ FLAGS = [0, 0, 0, 0, 0x02, 0x01, 0x40, 0x80, 0x42, 0xc2, 0x04, 0x08, 0x18, 0x1a,
 tot = bad = 0
 t0 = time.time()
 for ci in range(ncfg):
-    kind = rng.choice(["mixed", "mixed", "mixed", "small", "lastrow", "boundary", "large"])
+    kind = rng.choice(["mixed", "mixed", "mixed", "small", "lastrow", "boundary", "large", "spare"])
     w = int(rng.choice([-1, -1, -1, 0, 1, 3, 7, 16, 31, 64, 100, 250, 500, 1000]))
     zd = int(rng.choice([-1, -1, 10, 40, 100, 300, 1000]))
     flag = int(rng.choice(FLAGS))
@@ -65,6 +65,14 @@ for ci in range(ncfg):
         ps = synth.make_pairs_small(10 if L <= 1024 else 4, length=L + 40, div=0.08, seed=s)
         ps.tlen[:] = np.minimum(ps.tlen, L + rng.integers(-17, 18, ps.n).astype(np.int32)).clip(1)
         ps.qlen[:] = np.minimum(ps.qlen, L + rng.integers(-17, 40, ps.n).astype(np.int32)).clip(1)
+    elif kind == "spare":                              # 513..528 live slots: the 16-lane class with its spare block (extz_dp16.cuh Spare16)
+        if rng.random() < 0.7:
+            w = int(rng.integers(496, 512))
+            ps = synth.make_pairs_mixed(int(rng.integers(8, 40)), seed=s, min_len=int(rng.choice([520, 800, 1200])), max_len=int(rng.choice([1300, 2500, 4000])),
+                                        div=float(rng.choice([0.03, 0.1, 0.2])), **({"burst": int(rng.integers(20, 250))} if rng.random() < 0.4 else {}))
+        else:
+            w = -1
+            ps = synth.make_pairs_mixed(int(rng.integers(8, 40)), seed=s, min_len=500, max_len=int(rng.choice([528, 540, 1500])), div=float(rng.choice([0.05, 0.2])))
     else:
         ps = synth.make_pairs_large(int(rng.integers(2, 6)), min_len=2000, max_len=int(rng.choice([5000, 9000, 14000])), seed=s)
         if w < 0 or w > 1000:

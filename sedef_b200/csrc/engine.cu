@@ -139,6 +139,7 @@ struct DevCtx {
 	cudaStream_t stream = nullptr;
 	cudaStream_t tb_stream = nullptr;   // highest priority: a finished chunk's traceback must not queue behind the persistent
 	                                    // DP CTAs of the chunks launched after it (one-shot pipeline)
+	cudaStream_t wave_streams[8] = {};  // kernel classes of one batch run side by side (launch_sub)
 	size_t tb_budget = 0;          // bytes of traceback memory one wave may use
 	int occ[kNumClasses][6];       // cached occupancy per (class, {score-only, cigar-left, cigar-right} x {exact, approx max}); -1 = not asked yet
 	DevCtx() { for (auto &row : occ) for (int &v : row) v = -1; }
@@ -173,7 +174,7 @@ extern "C" int ksw_b200_init(int first_dev, int ndev)
 	if (ndev <= 0 || first_dev + ndev > count) ndev = count - first_dev;
 	if (ndev <= 0) return fail(KSW_B200_ERR_NO_DEVICE, "no device in the requested range");
 	if ((int)g_devs.size() == ndev && g_devs[0].dev == first_dev) return ndev;
-	for (auto &d : g_devs) { cudaSetDevice(d.dev); if (d.stream) cudaStreamDestroy(d.stream); if (d.tb_stream) cudaStreamDestroy(d.tb_stream); }
+	for (auto &d : g_devs) { cudaSetDevice(d.dev); if (d.stream) cudaStreamDestroy(d.stream); if (d.tb_stream) cudaStreamDestroy(d.tb_stream); for (auto &ws : d.wave_streams) if (ws) cudaStreamDestroy(ws); }
 	g_devs.clear();
 	for (int i = 0; i < ndev; ++i) {
 		DevCtx d; d.dev = first_dev + i;
@@ -184,6 +185,7 @@ extern "C" int ksw_b200_init(int first_dev, int ndev)
 		int prio_least = 0, prio_greatest = 0;
 		CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
 		CUDA_TRY(cudaStreamCreateWithPriority(&d.tb_stream, cudaStreamNonBlocking, prio_greatest));
+		for (auto &ws : d.wave_streams) CUDA_TRY(cudaStreamCreateWithFlags(&ws, cudaStreamNonBlocking));
 		size_t fr = 0, tot = 0; CUDA_TRY(cudaMemGetInfo(&fr, &tot));
 		const char *env = getenv("KSW_B200_TB_BUDGET_MB");
 		// A wave must hold enough pairs to fill the machine with SIMILAR work (3 CTAs x 4 warps per SM, up to 32 pairs per warp) --
@@ -200,7 +202,7 @@ extern "C" void ksw_b200_destroy(void)
 {
 	pool_clear();
 	std::lock_guard<std::mutex> lk(g_mu);
-	for (auto &d : g_devs) { cudaSetDevice(d.dev); if (d.stream) cudaStreamDestroy(d.stream); if (d.tb_stream) cudaStreamDestroy(d.tb_stream); }
+	for (auto &d : g_devs) { cudaSetDevice(d.dev); if (d.stream) cudaStreamDestroy(d.stream); if (d.tb_stream) cudaStreamDestroy(d.tb_stream); for (auto &ws : d.wave_streams) if (ws) cudaStreamDestroy(ws); }
 	g_devs.clear();
 }
 extern "C" int ksw_b200_num_devices(void) { return (int)g_devs.size(); }
@@ -328,7 +330,7 @@ struct PinBuf {
 	void release() { if (p) pool_give(p, cap, 0, true); p = nullptr; cap = 0; }
 };
 
-struct Wave { int cls; int first, count; size_t tb_bytes; };
+struct Wave { int cls; int first, count; size_t tb_bytes; size_t tb_base = 0; };   // tb_base: offset of the wave's rows in the arena (concurrent waves)
 
 // one device's share of a batch
 struct SubBatch {
@@ -349,6 +351,8 @@ struct SubBatch {
 	size_t h2d_seq_bytes = 0, h2d_desc_bytes = 0, d2h_bytes = 0;
 	std::vector<std::pair<cudaEvent_t, cudaEvent_t>> dp_ev, tb_ev;   // per-wave kernel timing events of the last launch
 	bool launched = false, touched = false;
+	bool concurrent = false;            // the waves of this launch run side by side, each on its own stream and arena slice
+	std::vector<int> ev_wave;           // wave index of every dp_ev / tb_ev entry
 	void drop_events()
 	{
 		for (auto &p : dp_ev) cudaEventDestroy(p.first);
@@ -359,6 +363,7 @@ struct SubBatch {
 		// kernels and copies of this batch may still be in flight on an error path: the buffers go back to a process-wide pool,
 		// so wait for the stream first (the traceback stream's work is ordered before it by events)
 		if (stream && touched) cudaStreamSynchronize(stream);
+		if (dc && touched && concurrent) for (auto &ws : dc->wave_streams) if (ws) cudaStreamSynchronize(ws);   // (joined into `stream` unless a launch failed half-way)
 		drop_events();
 		for (auto &b : h_stage) b.release();
 		h_recs.release(); h_stats.release(); h_trims.release(); h_pairs.release();
@@ -799,6 +804,19 @@ static int plan_waves(ksw_b200_batch &B, SubBatch &sb, bool cigar)
 			sb.waves.push_back(wv);
 		}
 	}
+	// Waves of different classes are independent.  When all of them fit the budget together they get disjoint slices of the arena
+	// and run SIDE BY SIDE (launch_sub): a mixed batch -- SEDEF's waves hold everything from 30-base gap fills to a few multi-kbp
+	// unbanded fills that keep one CTA or cluster busy for tens of milliseconds -- then takes as long as its slowest class instead
+	// of the sum of all classes.
+	size_t total_tb = 0;
+	for (Wave &wv : sb.waves) { wv.tb_base = 0; total_tb += align_up(wv.tb_bytes, 256); }
+	static const bool no_conc = getenv("KSW_B200_SERIAL_WAVES") != nullptr;                // A/B aid
+	sb.concurrent = !no_conc && sb.waves.size() > 1 && sb.waves.size() <= 32 && total_tb <= budget;
+	if (sb.concurrent) {
+		size_t base = 0;
+		for (Wave &wv : sb.waves) { wv.tb_base = base; base += align_up(wv.tb_bytes, 256); }
+		max_tb = total_tb;
+	}
 	if (cigar) {
 		if (sb.d_tb.ensure(max_tb + 256)) return fail(KSW_B200_ERR_NOMEM, "traceback arena allocation failed");
 		// compact CIGAR arena: offsets are int32 in PairResult
@@ -855,14 +873,23 @@ static int launch_sub(ksw_b200_batch &B, SubBatch &sb)
 	CUDA_TRY(cudaEventRecord(sb.ev[0], st));
 	sb.drop_events();
 	auto &dp_ev = sb.dp_ev; auto &tb_ev = sb.tb_ev;
-	int wave_no = 0;
-	for (const Wave &wv : sb.waves) {
+	sb.ev_wave.clear();
+	const bool conc = sb.concurrent;
+	cudaEvent_t ev_fork = nullptr;
+	if (conc) { CUDA_TRY(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming)); CUDA_TRY(cudaEventRecord(ev_fork, st)); }
+	const int nw = (int)sb.waves.size();
+	for (int wi = 0; wi < nw; ++wi) {
+		// concurrent waves: the widest classes first -- their pairs are the latency-bound ones, they should own their SMs from the start
+		const int wave_no = conc ? nw - 1 - wi : wi;
+		const Wave &wv = sb.waves[wave_no];
+		cudaStream_t ws = conc ? sb.dc->wave_streams[wi % 8] : st;
+		if (conc) CUDA_TRY(cudaStreamWaitEvent(ws, ev_fork, 0));
 		const int c = wv.cls;
 		DpLaunch L;
 		L.pairs = (const PairDesc *)sb.d_pairs.p + wv.first;
 		L.results = (PairResult *)sb.d_results.p + wv.first;
 		L.seq = (const uint8_t *)sb.d_arena.p;
-		L.tb = (uint8_t *)sb.d_tb.p;
+		L.tb = (uint8_t *)sb.d_tb.p + wv.tb_base;
 		L.table = (const uint32_t *)sb.d_table.p;
 		L.work_counter = d_counters + wave_no;
 		L.n = wv.count; L.sc = B.sc;
@@ -873,10 +900,10 @@ static int launch_sub(ksw_b200_batch &B, SubBatch &sb)
 		                               : std::min((wv.count + groups_per_block - 1) / groups_per_block, sb.dc->sms * occ);
 		cudaEvent_t a, b2, c2;
 		CUDA_TRY(cudaEventCreate(&a)); CUDA_TRY(cudaEventCreate(&b2)); CUDA_TRY(cudaEventCreate(&c2));
-		dp_ev.push_back({a, b2}); tb_ev.push_back({b2, c2});
-		CUDA_TRY(cudaEventRecord(a, st));
-		CUDA_TRY(launch_dp(c, L, cigar, right, approx, grid, st));
-		CUDA_TRY(cudaEventRecord(b2, st));
+		dp_ev.push_back({a, b2}); tb_ev.push_back({b2, c2}); sb.ev_wave.push_back(wave_no);
+		CUDA_TRY(cudaEventRecord(a, ws));
+		CUDA_TRY(launch_dp(c, L, cigar, right, approx, grid, ws));
+		CUDA_TRY(cudaEventRecord(b2, ws));
 		++sb.launches;
 		if (cigar) {
 			TbLaunch TL;
@@ -891,8 +918,8 @@ static int launch_sub(ksw_b200_batch &B, SubBatch &sb)
 			TL.overflow = d_overflow;
 			TL.n = wv.count; TL.NS = class_ns(c); TL.flag = B.flag; TL.packed = class_packed(c) ? 1 : 0;
 			TL.spare = class_spare(c, approx) ? 1 : 0;
-			cudaStream_t tbs = sb.dc->tb_stream;
-			CUDA_TRY(cudaStreamWaitEvent(tbs, b2, 0));
+			cudaStream_t tbs = conc ? ws : sb.dc->tb_stream;
+			if (!conc) CUDA_TRY(cudaStreamWaitEvent(tbs, b2, 0));
 			// long walks are latency chains: one warp per pair with staged row tiles; short ones: one thread per pair
 			int64_t steps = 0;
 			for (int k = wv.first; k < wv.first + wv.count; ++k) steps += (int64_t)sb.pairs[k].qlen + sb.pairs[k].tlen;
@@ -900,11 +927,13 @@ static int launch_sub(ksw_b200_batch &B, SubBatch &sb)
 			CUDA_TRY(k_traceback_launch(TL, steps / std::max(1, wv.count) >= warp_min_steps, stats_on, tbs));
 			++sb.launches;
 			CUDA_TRY(cudaEventRecord(c2, tbs));
-			CUDA_TRY(cudaStreamWaitEvent(st, c2, 0));             // the next wave reuses the traceback arena
-		} else
-		CUDA_TRY(cudaEventRecord(c2, st));
-		++wave_no;
+			CUDA_TRY(cudaStreamWaitEvent(st, c2, 0));             // serial: the next wave reuses the traceback arena; concurrent: the join
+		} else {
+			CUDA_TRY(cudaEventRecord(c2, ws));
+			if (conc) CUDA_TRY(cudaStreamWaitEvent(st, c2, 0));
+		}
 	}
+	if (ev_fork) cudaEventDestroy(ev_fork);
 	CUDA_TRY(cudaEventRecord(sb.ev[1], st));
 	sb.launched = true;
 	return 0;
@@ -925,8 +954,17 @@ static int finish_sub(ksw_b200_batch &B, SubBatch &sb)
 	CUDA_TRY(cudaStreamSynchronize(st));
 	memcpy(&tail, sb.h_pairs.p, sizeof(Tail));
 	CUDA_TRY(cudaEventElapsedTime(&sb.total_ms, sb.ev[0], sb.ev[1]));
-	for (auto &p : sb.dp_ev) { float ms = 0; cudaEventElapsedTime(&ms, p.first, p.second); sb.dp_ms += ms; }
-	for (auto &p : sb.tb_ev) { float ms = 0; cudaEventElapsedTime(&ms, p.first, p.second); sb.tb_ms += ms; }
+	static const bool wave_trace = [] { const char *e = getenv("KSW_B200_TRACE"); return e && atoi(e) >= 2; }();   // developer aid
+	for (size_t k = 0; k < sb.dp_ev.size(); ++k) {
+		float ms = 0, ms2 = 0;
+		cudaEventElapsedTime(&ms, sb.dp_ev[k].first, sb.dp_ev[k].second); sb.dp_ms += ms;
+		if (k < sb.tb_ev.size()) { cudaEventElapsedTime(&ms2, sb.tb_ev[k].first, sb.tb_ev[k].second); sb.tb_ms += ms2; }
+		if (wave_trace && k < sb.ev_wave.size()) {
+			const Wave &wv = sb.waves[sb.ev_wave[k]];
+			fprintf(stderr, "[ksw_b200]   wave %d%s: class of %d slots, %d pairs, DP %.2f ms, traceback %.2f ms\n", sb.ev_wave[k], sb.concurrent ? " (concurrent)" : "",
+			        class_ns(wv.cls), wv.count, ms, ms2);
+		}
+	}
 	sb.drop_events();
 	sb.cigar_used = tail.cursor;
 	if (tail.badsym) return fail(KSW_B200_ERR_ARG, (B.flag & KSW_EZ_GENERIC_SC) ? "sequence symbol >= m" : "sequence symbol >= 8");

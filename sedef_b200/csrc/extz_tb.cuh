@@ -275,45 +275,60 @@ extz_traceback_warp_kernel(TbLaunch L)
 	}
 }
 
-// ---- Alignment(fa, fb, cigar): SD statistics from an EXISTING CIGAR (src/align.cc:90-105,274-315; the consumer is
-// `sedef stats generate`, src/stats_main.cc:224).  One thread per alignment, forward walk over the raw ksw ops. ----
+// ---- Alignment(fa, fb, cigar): SD statistics from an EXISTING CIGAR (src/align.cc:90-105,274-315; the consumers are
+// `sedef stats generate`, src/stats_main.cc:224, and the finished alignments of every wave of the region driver).  One WARP per
+// alignment: every counter is a sum over columns, and the position of a column in the two strings is the run's start plus an
+// offset -- so the lanes split the columns of each CIGAR run (coalesced reads of 32 consecutive bases per side) and the 14
+// counters are warp-reduced at the end.  (One thread per alignment walked 10^4 columns serially: 3 ms for a single 20 kbp
+// alignment, a fifth of the region driver's time, profiles/r02_tuning.md.) ----
 __global__ void __launch_bounds__(128)
 sd_stats_from_cigar_kernel(CigarStatsLaunch L)
 {
-	int k = blockIdx.x * blockDim.x + threadIdx.x;
-	if (k >= L.n) return;
+	const int k = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+	if (k >= L.n) return;                                            // whole warps leave together
 	StatAcc sa;
 	sa.span = sa.gap_bases = sa.matches = sa.mismatches = sa.indel_a = sa.indel_b = sa.alnB = sa.matchB = 0;
 	sa.mismatchB = sa.transitionsB = sa.transversionsB = sa.uppercaseA = sa.uppercaseB = sa.uppercaseMatches = 0;
 	const uint32_t *c = L.cig + L.cig_off[k];
 	const uint8_t *a = L.a + L.a_off[k], *b = L.b + L.b_off[k];
 	const int alen = L.alen[k], blen = L.blen[k];
-	int ia = 0, ib = 0, gaps = 0, bad = 0;
-	for (int64_t x = 0; x < L.n_cig[k] && !bad; ++x) {
-		const uint32_t op = c[x] & 0xfu; const int len = (int)(c[x] >> 4);
-		if (op != 0) ++gaps;                                          // every non-M run counts, zero-length ones too (src/align.cc:300-305)
-		for (int y = 0; y < len; ++y) {
-			if (op == 0) {
-				if (ia >= alen || ib >= blen) { bad = 1; break; }     // the reference asserts (src/align.cc:281-282)
-				stat_match_col(sa, a[ia++], b[ib++]);
-			} else if (op == 1) { stat_qonly_col(sa, ia < alen ? a[ia] : 0); ++ia; }
-			else if (op == 2) { stat_tonly_col(sa, ib < blen ? b[ib] : 0); ++ib; }
-			else {
-				// any other op letter: populate_nice_alignment (src/align.cc:283-297) consumes BOTH strings ("not D", "not I"), so
-				// the column is gap-free for the match / mismatch and BEDPE counters, while the run still counts as a gap run
-				if (ia >= alen || ib >= blen) { bad = 1; break; }     // (the reference reads past the string here: undefined)
-				stat_match_col(sa, a[ia++], b[ib++]);
-				sa.gap_bases++;
-			}
+	const int64_t nc = L.n_cig[k];
+	int64_t ia = 0, ib = 0;                                          // warp-uniform
+	int gaps = 0, bad = 0;
+	for (int64_t x = 0; x < nc && !bad; ++x) {
+		const uint32_t w = c[x];
+		const uint32_t op = w & 0xfu; const int len = (int)(w >> 4);
+		if (op != 0) ++gaps;                                         // every non-M run counts, zero-length ones too (src/align.cc:300-305)
+		if (op == 0 || op >= 3) {
+			// M -- or any other op letter: populate_nice_alignment (src/align.cc:283-297) consumes BOTH strings ("not D", "not I"), so
+			// the column is gap-free for the match / mismatch and BEDPE counters, while the run still counts as a gap run
+			int64_t ok = len;
+			if (ok > alen - ia) ok = alen - ia;
+			if (ok > blen - ib) ok = blen - ib;
+			if (ok < 0) ok = 0;
+			if (ok < len) bad = 1;                                   // the reference asserts (src/align.cc:281-282) / reads past the string
+			for (int64_t y = lane; y < ok; y += 32) { stat_match_col(sa, a[ia + y], b[ib + y]); if (op != 0) sa.gap_bases++; }
+			ia += len; ib += len;
+		} else if (op == 1) {
+			for (int64_t y = lane; y < len; y += 32) stat_qonly_col(sa, ia + y < alen ? a[ia + y] : 0);
+			ia += len;
+		} else {
+			for (int64_t y = lane; y < len; y += 32) stat_tonly_col(sa, ib + y < blen ? b[ib + y] : 0);
+			ib += len;
 		}
 	}
-	sd_stats_t s;
-	s.span = sa.span; s.gaps = gaps; s.gap_bases = sa.gap_bases; s.matches = sa.matches; s.mismatches = sa.mismatches;
-	s.indel_a = sa.indel_a; s.indel_b = sa.indel_b; s.alnB = sa.alnB; s.matchB = sa.matchB; s.mismatchB = sa.mismatchB;
-	s.transitionsB = sa.transitionsB; s.transversionsB = sa.transversionsB;
-	s.uppercaseA = sa.uppercaseA; s.uppercaseB = sa.uppercaseB; s.uppercaseMatches = sa.uppercaseMatches; s.reserved = 0;
-	L.out[k] = s;
-	L.status[k] = bad ? -1 : 0;
+	int32_t *f = &sa.span;                                           // 14 consecutive int32 counters
+#pragma unroll
+	for (int i = 0; i < 14; ++i) f[i] = (int32_t)__reduce_add_sync(0xffffffffu, (uint32_t)f[i]);
+	if (lane == 0) {
+		sd_stats_t s;
+		s.span = sa.span; s.gaps = gaps; s.gap_bases = sa.gap_bases; s.matches = sa.matches; s.mismatches = sa.mismatches;
+		s.indel_a = sa.indel_a; s.indel_b = sa.indel_b; s.alnB = sa.alnB; s.matchB = sa.matchB; s.mismatchB = sa.mismatchB;
+		s.transitionsB = sa.transitionsB; s.transversionsB = sa.transversionsB;
+		s.uppercaseA = sa.uppercaseA; s.uppercaseB = sa.uppercaseB; s.uppercaseMatches = sa.uppercaseMatches; s.reserved = 0;
+		L.out[k] = s;
+		L.status[k] = bad ? -1 : 0;
+	}
 }
 
 } // namespace extz

@@ -153,6 +153,7 @@ static std::vector<Alignment> align_batch_impl(const std::vector<std::pair<std::
 static std::vector<sd_stats_t> stats_of(const std::vector<StrPair> &pairs, const std::vector<const std::deque<std::pair<char, int>> *> &cigars)
 {
 	const int n = (int)pairs.size();
+	const double t_pack = wall_ms();
 	std::vector<int64_t> coff(n), cn(n), ao(n), bo(n);
 	std::vector<int> al(n), bl(n);
 	int64_t ctot = 0, atot = 0, btot = 0;
@@ -177,8 +178,11 @@ static std::vector<sd_stats_t> stats_of(const std::vector<StrPair> &pairs, const
 	}
 	std::vector<sd_stats_t> st(n);
 	std::vector<int> status(n);
+	const double t_call = wall_ms();
 	int rc = sd_stats_from_cigar_batch_flat(n, coff.data(), cn.data(), cbuf.data(), al.data(), ao.data(), abuf.data(),
 	                                       bl.data(), bo.data(), bbuf.data(), st.data(), status.data());
+	if (region_trace()) fprintf(stderr, "[regions]     sd_stats_from_cigar: %d alignments, %.1f MB, pack %.1f ms, call %.1f ms\n", n, (atot + btot) / 1e6,
+	                            t_call - t_pack, wall_ms() - t_call);
 	if (rc) throw std::runtime_error(std::string("sd_stats_from_cigar_batch_flat: ") + ksw_b200_strerror(rc) + " -- " + ksw_b200_last_error());
 	for (int i = 0; i < n; ++i)
 		if (status[i]) throw std::runtime_error("CIGAR " + std::to_string(i) + " overruns a sequence (the reference asserts, src/align.cc:281-282)");
@@ -243,19 +247,28 @@ struct WindowBatch {
 	ksw_b200_result_t *res = nullptr;
 	const ksw_extz_t *ez = nullptr;
 	~WindowBatch() { if (res) ksw_b200_result_free(res); }
-	// base offset of a region string (registering it on first use); call serially
-	int64_t base_of(const std::string *s, std::vector<const std::string *> &strs, std::vector<int64_t> &bases, std::string &buf, const std::string *&last, int64_t &last_base)
+	// base offset of a region string (registering it on first use); call serially.  The bytes are copied by fill() afterwards.
+	int64_t base_of(const std::string *s, std::vector<const std::string *> &strs, std::vector<int64_t> &bases, int64_t &total, const std::string *&last, int64_t &last_base)
 	{
 		if (s == last) return last_base;
 		for (size_t k = strs.size(); k-- > 0;) if (strs[k] == s) { last = s; return last_base = bases[k]; }
-		strs.push_back(s); bases.push_back((int64_t)buf.size()); buf += *s;
+		strs.push_back(s); bases.push_back(total); total += (int64_t)s->size();
 		last = s; return last_base = bases.back();
+	}
+	int64_t qtotal = 0, ttotal = 0;
+	void fill()                                          // one allocation per side, the region strings copied in parallel
+	{
+		qbuf.assign((size_t)qtotal + 1, '\0'); tbuf.assign((size_t)ttotal + 1, '\0');
+#pragma omp parallel for schedule(dynamic, 8)
+		for (long k = 0; k < (long)(qstrs.size() + tstrs.size()); ++k) {
+			if (k < (long)qstrs.size()) memcpy(&qbuf[(size_t)qbase[k]], qstrs[k]->data(), qstrs[k]->size());
+			else { const size_t j = (size_t)k - qstrs.size(); memcpy(&tbuf[(size_t)tbase[j]], tstrs[j]->data(), tstrs[j]->size()); }
+		}
 	}
 	void run(const AlignParams &p)
 	{
 		const int8_t a = (int8_t)p.match, b = p.mismatch < 0 ? (int8_t)p.mismatch : (int8_t)(-p.mismatch);
 		const int8_t mat[25] = {a, b, b, b, 0, b, a, b, b, 0, b, b, a, b, 0, b, b, b, a, 0, 0, 0, 0, 0, 0};
-		qbuf.push_back('\0'); tbuf.push_back('\0');
 		const double t0 = wall_ms();
 		int rc = ksw_extz2_batch_arena((int)ql.size(), ql.data(), qo.data(), nullptr, tl.data(), to.data(), nullptr, 5, mat,
 		                               (int8_t)p.gap_open, (int8_t)p.gap_extend, p.bandwidth, -1, 0, 0, (const uint8_t *)qbuf.data(), (const uint8_t *)tbuf.data(), &res);
@@ -300,9 +313,10 @@ std::vector<GuidedAlignment> align_chains_batch(const std::vector<ChainGuide> &c
 	{
 		const std::string *lq = nullptr, *lt = nullptr; int64_t lqb = 0, ltb = 0;
 		for (long ci = 0; ci < nc; ++ci) {
-			cq[ci] = wb.base_of(chains[ci].qstr, wb.qstrs, wb.qbase, wb.qbuf, lq, lqb);
-			ct[ci] = wb.base_of(chains[ci].rstr, wb.tstrs, wb.tbase, wb.tbuf, lt, ltb);
+			cq[ci] = wb.base_of(chains[ci].qstr, wb.qstrs, wb.qbase, wb.qtotal, lq, lqb);
+			ct[ci] = wb.base_of(chains[ci].rstr, wb.tstrs, wb.tbase, wb.ttotal, lt, ltb);
 		}
+		wb.fill();
 	}
 	// pass 1b: the requests, as windows
 	const size_t nf = fill_first[nc];

@@ -22,7 +22,7 @@ cudaError_t k_traceback_launch(const TbLaunch &L, bool warp_per_pair, bool stats
 cudaError_t k_stats_from_cigar_launch(const CigarStatsLaunch &L, cudaStream_t st)
 {
 	if (L.n <= 0) return cudaSuccess;
-	sd_stats_from_cigar_kernel<<<(L.n + 127) / 128, 128, 0, st>>>(L);
+	sd_stats_from_cigar_kernel<<<(L.n + 3) / 4, 128, 0, st>>>(L);                // one warp per alignment
 	return cudaGetLastError();
 }
 static inline int io_grid(size_t nvec)

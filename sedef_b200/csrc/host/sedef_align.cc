@@ -2,6 +2,7 @@
 #include "../../../include/sedef_align.hpp"
 #include <algorithm>
 #include <functional>
+#include <memory>
 #include <tuple>
 #include <chrono>
 #include <climits>
@@ -163,9 +164,10 @@ static std::vector<sd_stats_t> stats_of(const std::vector<StrPair> &pairs, const
 		al[i] = (int)pairs[i].a->size(); bl[i] = (int)pairs[i].b->size();
 		atot += al[i]; btot += bl[i];
 	}
-	std::vector<uint32_t> cbuf(ctot + 1);
-	std::vector<uint8_t> abuf(atot + 1), bbuf(btot + 1);
-#pragma omp parallel for schedule(static) if (n >= 256)
+	// (uninitialised: the parallel copies below are the first touch of the pages)
+	std::unique_ptr<uint32_t[]> cbuf(new uint32_t[ctot + 1]);
+	std::unique_ptr<uint8_t[]> abuf(new uint8_t[atot + 1]), bbuf(new uint8_t[btot + 1]);
+#pragma omp parallel for schedule(dynamic, 16) if (n >= 64)
 	for (int i = 0; i < n; ++i) {
 		int64_t c = coff[i];
 		for (auto &run : *cigars[i]) {
@@ -179,8 +181,8 @@ static std::vector<sd_stats_t> stats_of(const std::vector<StrPair> &pairs, const
 	std::vector<sd_stats_t> st(n);
 	std::vector<int> status(n);
 	const double t_call = wall_ms();
-	int rc = sd_stats_from_cigar_batch_flat(n, coff.data(), cn.data(), cbuf.data(), al.data(), ao.data(), abuf.data(),
-	                                       bl.data(), bo.data(), bbuf.data(), st.data(), status.data());
+	int rc = sd_stats_from_cigar_batch_flat(n, coff.data(), cn.data(), cbuf.get(), al.data(), ao.data(), abuf.get(),
+	                                       bl.data(), bo.data(), bbuf.get(), st.data(), status.data());
 	if (region_trace()) fprintf(stderr, "[regions]     sd_stats_from_cigar: %d alignments, %.1f MB, pack %.1f ms, call %.1f ms\n", n, (atot + btot) / 1e6,
 	                            t_call - t_pack, wall_ms() - t_call);
 	if (rc) throw std::runtime_error(std::string("sd_stats_from_cigar_batch_flat: ") + ksw_b200_strerror(rc) + " -- " + ksw_b200_last_error());
@@ -241,7 +243,7 @@ namespace {
 struct WindowBatch {
 	std::vector<const std::string *> qstrs, tstrs;       // distinct region strings, in order of first use
 	std::vector<int64_t> qbase, tbase;                   // their offsets in the flat buffers
-	std::string qbuf, tbuf;
+	std::unique_ptr<char[]> qbuf, tbuf;                  // uninitialised; fill() copies the region strings in (first touch in parallel)
 	std::vector<int> ql, tl;
 	std::vector<int64_t> qo, to;
 	ksw_b200_result_t *res = nullptr;
@@ -258,7 +260,8 @@ struct WindowBatch {
 	int64_t qtotal = 0, ttotal = 0;
 	void fill()                                          // one allocation per side, the region strings copied in parallel
 	{
-		qbuf.assign((size_t)qtotal + 1, '\0'); tbuf.assign((size_t)ttotal + 1, '\0');
+		qbuf.reset(new char[(size_t)qtotal + 1]); tbuf.reset(new char[(size_t)ttotal + 1]);
+		qbuf[(size_t)qtotal] = tbuf[(size_t)ttotal] = '\0';
 #pragma omp parallel for schedule(dynamic, 8)
 		for (long k = 0; k < (long)(qstrs.size() + tstrs.size()); ++k) {
 			if (k < (long)qstrs.size()) memcpy(&qbuf[(size_t)qbase[k]], qstrs[k]->data(), qstrs[k]->size());
@@ -271,7 +274,7 @@ struct WindowBatch {
 		const int8_t mat[25] = {a, b, b, b, 0, b, a, b, b, 0, b, b, a, b, 0, b, b, b, a, 0, 0, 0, 0, 0, 0};
 		const double t0 = wall_ms();
 		int rc = ksw_extz2_batch_arena((int)ql.size(), ql.data(), qo.data(), nullptr, tl.data(), to.data(), nullptr, 5, mat,
-		                               (int8_t)p.gap_open, (int8_t)p.gap_extend, p.bandwidth, -1, 0, 0, (const uint8_t *)qbuf.data(), (const uint8_t *)tbuf.data(), &res);
+		                               (int8_t)p.gap_open, (int8_t)p.gap_extend, p.bandwidth, -1, 0, 0, (const uint8_t *)qbuf.get(), (const uint8_t *)tbuf.get(), &res);
 		if (rc) throw std::runtime_error(std::string("ksw_extz2_batch_arena: ") + ksw_b200_strerror(rc) + " -- " + ksw_b200_last_error());
 		if (region_trace()) fprintf(stderr, "[regions]     ksw_extz2_batch_arena (windows): %zu pairs, %.1f ms\n", ql.size(), wall_ms() - t0);
 		ez = ksw_b200_result_ez(res);
@@ -891,7 +894,8 @@ std::vector<std::vector<Anchor>> anchors_batch(const std::vector<RegionSeed> &re
 		qo[i] = qtot; ro[i] = rtot; qtot += ql[i]; rtot += rl[i];
 		same[i] = regions[i].same_chr; oq[i] = regions[i].orig_query_start; orr[i] = regions[i].orig_ref_start;
 	}
-	std::string qbuf((size_t)qtot + 1, '\0'), rbuf((size_t)rtot + 1, '\0');
+	std::unique_ptr<char[]> qbuf(new char[(size_t)qtot + 1]), rbuf(new char[(size_t)rtot + 1]);     // uninitialised: first touch in parallel
+	qbuf[(size_t)qtot] = rbuf[(size_t)rtot] = '\0';
 #pragma omp parallel for schedule(dynamic, 16)
 	for (int i = 0; i < n; ++i) {
 		memcpy(&qbuf[(size_t)qo[i]], regions[i].qstr->data(), (size_t)ql[i]);
@@ -899,7 +903,7 @@ std::vector<std::vector<Anchor>> anchors_batch(const std::vector<RegionSeed> &re
 	}
 	sedef_anchor_t *flat = nullptr;
 	std::vector<int64_t> off(n + 1, 0);
-	int rc = sedef_anchors_batch(n, ql.data(), qo.data(), (const uint8_t *)qbuf.data(), rl.data(), ro.data(), (const uint8_t *)rbuf.data(), kmer_size,
+	int rc = sedef_anchors_batch(n, ql.data(), qo.data(), (const uint8_t *)qbuf.get(), rl.data(), ro.data(), (const uint8_t *)rbuf.get(), kmer_size,
 	                             same.data(), oq.data(), orr.data(), &flat, off.data());
 	if (rc) throw std::runtime_error(std::string("sedef_anchors_batch: ") + ksw_b200_strerror(rc) + " -- " + ksw_b200_last_error());
 	std::vector<std::vector<Anchor>> out(n);

@@ -180,7 +180,7 @@ struct StatsGenerateCounts { long long hits = 0, pieces = 0, lines = 0; };
 const char *stats_header();                            // the "#chr1\tstart1..." line (src/stats_main.cc:379-386)
 // stats() (src/stats_main.cc:338-395): the aligned hits of `bed_path` (28-column lines of `align generate`, after sedef.sh's
 // sort | uniq) -> Alignment(fa, fb, cigar) -> pieces at assembly gaps / large gaps, re-trimmed -> statistics of ALL pieces in one
-// GPU call -> filters -> the header and one 35-column line per piece, in the reference's (sequential) order.
+// GPU call -> filters -> the header and one 34-column line per piece, in the reference's (sequential) order.
 StatsGenerateCounts stats_generate(const std::string &ref_path, const std::string &bed_path, FILE *out,
                                    const StatsParams &sp = StatsParams(), const AlignParams &p = AlignParams());
 

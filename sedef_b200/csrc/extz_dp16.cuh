@@ -432,12 +432,14 @@ extz_dp16_kernel(DpLaunch L)
 		{
 			const bool done = !exhausted && !(alive && r < R);
 			if (__any_sync(FULL, done)) {
-				int nxt = L.n;
-				if (done && gl == 0) {
-					if (pi >= 0) { if (zdropped_band) ld.ez.zdropped = 1; ld.store(&L.results[pi], n_diag); }
-					nxt = atomicAdd(L.work_counter, 1);                  // dynamic work queue
-				}
-				nxt = __shfl_sync(FULL, nxt, 0, G);
+				if (done && gl == 0 && pi >= 0) { if (zdropped_band) ld.ez.zdropped = 1; ld.store(&L.results[pi], n_diag); }
+				// dynamic work queue: ONE atomic per warp for all of its waiting groups (with one lane per pair that is up to 32 at once)
+				const unsigned dmask = __ballot_sync(FULL, done && gl == 0);
+				const int first = __ffs(dmask) - 1;
+				int base = 0;
+				if (lane_w == first) base = atomicAdd(L.work_counter, __popc(dmask));
+				base = __shfl_sync(FULL, base, first);
+				const int nxt = base + __popc(dmask & ((1u << (lane_w - gl)) - 1u));   // my group's rank among the waiting ones
 				if (done) {
 					pi = nxt < L.n ? nxt : -1;
 					alive = pi >= 0; exhausted = !alive; r = 0; R = 0;

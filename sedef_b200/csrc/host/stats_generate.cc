@@ -3,7 +3,7 @@
 // Mirrors (argument meaning, results, text format; not code) of the reference:
 //   stats                      src/stats_main.cc:338-395   read the aligned hits, order them, header, process() each
 //   process                    src/stats_main.cc:213-336   Alignment(fa, fb, cigar), split, the BEDPE stat loop, the
-//                                                           floating-point columns, the filters, one 35-column line per piece
+//                                                           floating-point columns, the filters, one 34-column line per piece
 //   split_alignment / subhit   src/stats_main.cc:32-211    pieces at assembly gaps (>= 100 N columns) and, with --max-ok-gap, at
 //                              / gap_split                  large gaps; each piece is re-trimmed (trim_back, trim_front)
 // The shape of the work changes: every piece of every hit goes through ONE statistics-from-CIGAR call on the GPU

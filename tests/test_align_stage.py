@@ -97,6 +97,36 @@ def test_schedule_and_bed_text(small_stage):
         engine.bed_schedule(os.path.join(small_stage["wd"], "missing"))
 
 
+def test_driver_error_paths_and_empty_inputs(built, tmp_path):
+    """What the two drivers do before any alignment is needed (no device involved): an empty bucket file gives an empty
+    *.aligned.bed / a header-only report, like the reference's loops over zero hits; unreadable inputs fail with the reference's
+    messages (src/fasta.cc:70-72, src/align_main.cc:228-230, src/hit.cc:31)."""
+    from sedef_b200 import engine, genome
+    rng = np.random.default_rng(3)
+    fa = str(tmp_path / "g.fa")
+    genome.write_fasta(fa, {"c1": genome.synth.ASCII[rng.integers(0, 4, 5000)]})
+    empty = str(tmp_path / "empty.bed")
+    open(empty, "w").close()
+    out = str(tmp_path / "o.bed")
+    st = engine.align_generate(fa, empty, out)
+    assert st["regions"] == 0 and st["hits"] == 0 and open(out).read() == ""
+    cnt = engine.stats_generate(fa, empty, out)
+    assert cnt == dict(hits=0, pieces=0, lines=0)
+    text = open(out).read()
+    assert text.startswith("#chr1\tstart1\tend1\tchr2") and text.count("\n") == 1 and text.rstrip("\n").count("\t") == 33
+    with pytest.raises(engine.EngineError, match="Cannot open file"):
+        engine.align_generate(str(tmp_path / "missing.fa"), empty, out)
+    with pytest.raises(engine.EngineError, match="neither file nor directory"):
+        engine.align_generate(fa, str(tmp_path / "missing.bed"), out)
+    short = str(tmp_path / "short.bed")
+    with open(short, "w") as f:
+        f.write("c1\t0\t100\tc1\t200\t300\n")
+    with pytest.raises(engine.EngineError, match="fewer than 10 columns"):
+        engine.align_generate(fa, short, out)
+    with pytest.raises(engine.EngineError, match="does not exist"):
+        engine.stats_generate(fa, str(tmp_path / "missing.bed"), out)
+
+
 @pytest.mark.gpu
 def test_align_generate_matches_reference_binary_golden(small_stage):
     """Whole bucket files: output bytes == the reference binary's *.aligned.bed (tests/golden/align_stage_golden.json: two
@@ -163,7 +193,7 @@ def test_align_generate_config1_live_reference(built, tmp_path):
 
 @pytest.mark.gpu
 def test_stats_generate_matches_reference_binary_golden(built, golden_dir, tmp_path):
-    """`sedef stats generate` (src/stats_main.cc:213-395): the 35-column SD report of an aligned.bed -- Alignment(fa, fb, cigar), the
+    """`sedef stats generate` (src/stats_main.cc:213-395): the 34-column SD report of an aligned.bed -- Alignment(fa, fb, cigar), the
     split at assembly gaps (runs of >= 100 N) with re-trimmed pieces, the BEDPE stat loop and populate_nice_alignment's counters of
     ALL pieces in one GPU call, the floating-point columns in the reference's "%g" text, the filters -- against the reference
     binary's own output (tests/golden/stats_golden.json), with the default parameters and with gap splitting switched on

@@ -22,12 +22,55 @@ sys.path.insert(0, ROOT)
 REF_BIN = os.path.join(ROOT, "oracle", "_ref", "sedef_ref")
 
 
+def worker(k: int, n: int, fa: str, bdir: str, wd: str):
+    """One process per GPU (the caller set CUDA_VISIBLE_DEVICES): seed hits k, k + n, ... of the schedule.  A warm-up run, then the
+    timed run starts when the parent creates the go-file; start / end wall-clock times go to a JSON file."""
+    from sedef_b200 import engine
+    engine.init(0, 1)
+    out = os.path.join(wd, "shard_%d_of_%d.bed" % (k, n))
+    engine.align_generate(fa, bdir, out, shard_index=k, shard_count=n)
+    open(os.path.join(wd, "ready_%d_of_%d" % (k, n)), "w").close()
+    go = os.path.join(wd, "go_%d" % n)
+    while not os.path.exists(go):
+        time.sleep(0.001)
+    t0 = time.time()
+    st = engine.align_generate(fa, bdir, out, shard_index=k, shard_count=n)
+    t1 = time.time()
+    with open(os.path.join(wd, "done_%d_of_%d.json" % (k, n)), "w") as f:
+        json.dump(dict(start=t0, end=t1, **st), f)
+
+
+def run_procs(n: int, fa: str, bdir: str, wd: str, cores: int):
+    """n worker processes, one GPU each; returns (makespan seconds, sorted output lines, per-worker seconds)."""
+    procs = []
+    for k in range(n):
+        env = dict(os.environ, CUDA_VISIBLE_DEVICES=str(k), OMP_NUM_THREADS=str(max(1, cores // n)))
+        procs.append(subprocess.Popen([sys.executable, os.path.abspath(__file__), "--worker", str(k), str(n), fa, bdir, wd], env=env))
+    while not all(os.path.exists(os.path.join(wd, "ready_%d_of_%d" % (k, n))) for k in range(n)):
+        if any(p.poll() not in (None, 0) for p in procs):
+            raise SystemExit("a worker failed")
+        time.sleep(0.01)
+    open(os.path.join(wd, "go_%d" % n), "w").close()
+    for p in procs:
+        if p.wait() != 0:
+            raise SystemExit("a worker failed")
+    recs = [json.load(open(os.path.join(wd, "done_%d_of_%d.json" % (k, n)))) for k in range(n)]
+    lines = []
+    for k in range(n):
+        lines += [ln for ln in open(os.path.join(wd, "shard_%d_of_%d.bed" % (k, n))).read().split("\n") if ln]
+    return max(r["end"] for r in recs) - min(r["start"] for r in recs), sorted(lines), [round(r["end"] - r["start"], 3) for r in recs]
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "--worker":
+        return worker(int(sys.argv[2]), int(sys.argv[3]), sys.argv[4], sys.argv[5], sys.argv[6])
     ap = argparse.ArgumentParser()
     ap.add_argument("--config", type=int, default=1, choices=[1, 4, 5])
     ap.add_argument("--scale", type=float, default=0.02, help="config 5 only: fraction of hg38's 3.1 Gbp (24 chromosomes)")
     ap.add_argument("--dups", type=int, default=0, help="planted duplications (default: the config's own count)")
     ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--procs", default="", help="comma-separated process counts, one GPU per process (e.g. 1,2,4,8): every process takes the "
+                    "seed hits k mod n of the schedule (align_generate's shard arguments), the outputs are concatenated and sorted")
     ap.add_argument("--buckets", type=int, default=0, help="bucket files (default: host cores)")
     ap.add_argument("--repeat", type=int, default=2, help="timed product runs (best is reported; the first also warms the pools)")
     ap.add_argument("--no-ref", action="store_true")
@@ -81,6 +124,13 @@ def main():
                 region_mbp_per_s=round(region_bases / ours_s / 1e6, 2),
                 phases_ms=dict(total=round(st["ms_total"], 1), align=round(st["ms_align"], 1), io=round(st["ms_io"], 1)),
                 rounds=st["rounds"], batch_calls=st["batch_calls"], ksw_requests=st["ksw_requests"], genome_gen_s=round(t_gen, 1))
+    if args.procs:
+        scaling = []
+        for n in [int(x) for x in args.procs.split(",")]:
+            sec, lines_n, per = run_procs(n, fa, bdir, wd, cores)
+            scaling.append(dict(processes=n, seconds=round(sec, 3), regions_per_s=round(n_regions / sec, 1), per_worker_seconds=per,
+                                identical_to_one_process=lines_n == ours_lines))
+        line["one_process_per_gpu"] = scaling
     if not args.no_ref:
         def one(b):
             t = time.time()

@@ -186,14 +186,6 @@ extern "C" int ksw_b200_init(int first_dev, int ndev)
 		CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
 		CUDA_TRY(cudaStreamCreateWithPriority(&d.tb_stream, cudaStreamNonBlocking, prio_greatest));
 		for (auto &ws : d.wave_streams) CUDA_TRY(cudaStreamCreateWithFlags(&ws, cudaStreamNonBlocking));
-		// The traceback walk reads ONE byte per row (rows are 64 B and more apart): with the default L2 fetch granularity every miss
-		// pulls the neighbouring sector in as well and the walk of config 2 reads the whole 12.8 GB arena at 5.2 TB/s
-		// (profiles/r02_tb_kernel_ncu.json).  32-byte fetches halve that traffic; nothing else in the engine streams from DRAM.
-		{
-			const char *g = getenv("KSW_B200_L2_FETCH");
-			cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, g ? (size_t)atoi(g) : 32);       // a hint; failure is not an error
-			cudaGetLastError();
-		}
 		size_t fr = 0, tot = 0; CUDA_TRY(cudaMemGetInfo(&fr, &tot));
 		const char *env = getenv("KSW_B200_TB_BUDGET_MB");
 		// A wave must hold enough pairs to fill the machine with SIMILAR work (3 CTAs x 4 warps per SM, up to 32 pairs per warp) --

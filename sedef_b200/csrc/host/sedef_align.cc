@@ -3,7 +3,9 @@
 #include <algorithm>
 #include <functional>
 #include <memory>
+#include <mutex>
 #include <tuple>
+#include <unordered_map>
 #include <chrono>
 #include <climits>
 #include <cstdio>
@@ -240,10 +242,36 @@ static void append_cigar(std::deque<std::pair<char, int>> &cigar, const std::deq
 // Alignment object and no deque per request.  A region's chain wave is hundreds of gap fills of a few bases each (SURVEY 3.2:
 // the median call is <= 32 bp), so the per-request host cost is what the wave costs.
 namespace {
+// The region strings of the fast_align_batch call in flight on this thread, copied ONCE into two page-locked flat buffers: the
+// anchors kernel reads them from there, and the chain wave's window requests reference them by offset instead of concatenating
+// the strings a second time.  The buffers are grow-only and reused from call to call (cudaHostAlloc of a gigabyte costs more than
+// the stage); one call at a time owns them, a concurrent caller simply works without.
+struct RegionArena {
+	char *q = nullptr, *r = nullptr;
+	size_t qcap = 0, rcap = 0;
+	int64_t qtot = 0, rtot = 0;
+	std::unordered_map<const std::string *, int64_t> qoff, roff;
+	std::mutex mu;
+	bool reserve(char *&buf, size_t &cap, size_t need)
+	{
+		if (need <= cap) return true;
+		if (buf) ksw_b200_host_free(buf);
+		cap = need + need / 4 + 4096;
+		buf = (char *)ksw_b200_host_alloc(cap);
+		if (!buf) cap = 0;
+		return buf != nullptr;
+	}
+};
+RegionArena g_region_arena;
+thread_local RegionArena *tl_arena = nullptr;
+} // namespace
+
+namespace {
 struct WindowBatch {
 	std::vector<const std::string *> qstrs, tstrs;       // distinct region strings, in order of first use
 	std::vector<int64_t> qbase, tbase;                   // their offsets in the flat buffers
 	std::unique_ptr<char[]> qbuf, tbuf;                  // uninitialised; fill() copies the region strings in (first touch in parallel)
+	const char *qptr = nullptr, *tptr = nullptr;         // the flat buffers the requests refer to: qbuf / tbuf, or the call's RegionArena
 	std::vector<int> ql, tl;
 	std::vector<int64_t> qo, to;
 	ksw_b200_result_t *res = nullptr;
@@ -262,6 +290,7 @@ struct WindowBatch {
 	{
 		qbuf.reset(new char[(size_t)qtotal + 1]); tbuf.reset(new char[(size_t)ttotal + 1]);
 		qbuf[(size_t)qtotal] = tbuf[(size_t)ttotal] = '\0';
+		qptr = qbuf.get(); tptr = tbuf.get();
 #pragma omp parallel for schedule(dynamic, 8)
 		for (long k = 0; k < (long)(qstrs.size() + tstrs.size()); ++k) {
 			if (k < (long)qstrs.size()) memcpy(&qbuf[(size_t)qbase[k]], qstrs[k]->data(), qstrs[k]->size());
@@ -274,7 +303,7 @@ struct WindowBatch {
 		const int8_t mat[25] = {a, b, b, b, 0, b, a, b, b, 0, b, b, a, b, 0, b, b, b, a, 0, 0, 0, 0, 0, 0};
 		const double t0 = wall_ms();
 		int rc = ksw_extz2_batch_arena((int)ql.size(), ql.data(), qo.data(), nullptr, tl.data(), to.data(), nullptr, 5, mat,
-		                               (int8_t)p.gap_open, (int8_t)p.gap_extend, p.bandwidth, -1, 0, 0, (const uint8_t *)qbuf.get(), (const uint8_t *)tbuf.get(), &res);
+		                               (int8_t)p.gap_open, (int8_t)p.gap_extend, p.bandwidth, -1, 0, 0, (const uint8_t *)qptr, (const uint8_t *)tptr, &res);
 		if (rc) throw std::runtime_error(std::string("ksw_extz2_batch_arena: ") + ksw_b200_strerror(rc) + " -- " + ksw_b200_last_error());
 		if (region_trace()) fprintf(stderr, "[regions]     ksw_extz2_batch_arena (windows): %zu pairs, %.1f ms\n", ql.size(), wall_ms() - t0);
 		ez = ksw_b200_result_ez(res);
@@ -313,7 +342,17 @@ std::vector<GuidedAlignment> align_chains_batch(const std::vector<ChainGuide> &c
 	// the region strings, once each
 	WindowBatch wb;
 	std::vector<int64_t> cq(nc), ct(nc);
-	{
+	bool in_arena = tl_arena != nullptr;
+	if (in_arena) {
+		const std::string *lq = nullptr, *lt = nullptr; int64_t lqb = 0, ltb = 0;
+		for (long ci = 0; ci < nc && in_arena; ++ci) {
+			if (chains[ci].qstr != lq) { auto it = tl_arena->qoff.find(chains[ci].qstr); if (it == tl_arena->qoff.end()) in_arena = false; else { lq = chains[ci].qstr; lqb = it->second; } }
+			if (chains[ci].rstr != lt) { auto it = tl_arena->roff.find(chains[ci].rstr); if (it == tl_arena->roff.end()) in_arena = false; else { lt = chains[ci].rstr; ltb = it->second; } }
+			cq[ci] = lqb; ct[ci] = ltb;
+		}
+		if (in_arena) { wb.qptr = tl_arena->q; wb.tptr = tl_arena->r; }
+	}
+	if (!in_arena) {
 		const std::string *lq = nullptr, *lt = nullptr; int64_t lqb = 0, ltb = 0;
 		for (long ci = 0; ci < nc; ++ci) {
 			cq[ci] = wb.base_of(chains[ci].qstr, wb.qstrs, wb.qbase, wb.qtotal, lq, lqb);
@@ -894,16 +933,29 @@ std::vector<std::vector<Anchor>> anchors_batch(const std::vector<RegionSeed> &re
 		qo[i] = qtot; ro[i] = rtot; qtot += ql[i]; rtot += rl[i];
 		same[i] = regions[i].same_chr; oq[i] = regions[i].orig_query_start; orr[i] = regions[i].orig_ref_start;
 	}
-	std::unique_ptr<char[]> qbuf(new char[(size_t)qtot + 1]), rbuf(new char[(size_t)rtot + 1]);     // uninitialised: first touch in parallel
+	// the flat buffers: the call's page-locked RegionArena (fast_align_batch), or two plain ones
+	std::unique_ptr<char[]> qown, rown;
+	char *qbuf = nullptr, *rbuf = nullptr;
+	RegionArena *ar = tl_arena;
+	if (ar && ar->reserve(ar->q, ar->qcap, (size_t)qtot + 16) && ar->reserve(ar->r, ar->rcap, (size_t)rtot + 16)) {
+		qbuf = ar->q; rbuf = ar->r; ar->qtot = qtot; ar->rtot = rtot;
+		ar->qoff.clear(); ar->roff.clear();
+		ar->qoff.reserve((size_t)n * 2); ar->roff.reserve((size_t)n * 2);
+		for (int i = 0; i < n; ++i) { ar->qoff.emplace(regions[i].qstr, qo[i]); ar->roff.emplace(regions[i].rstr, ro[i]); }   // (a string used twice: its first copy)
+	} else {
+		if (ar) { ar->qoff.clear(); ar->roff.clear(); }
+		qown.reset(new char[(size_t)qtot + 1]); rown.reset(new char[(size_t)rtot + 1]);              // uninitialised: first touch in parallel
+		qbuf = qown.get(); rbuf = rown.get();
+	}
 	qbuf[(size_t)qtot] = rbuf[(size_t)rtot] = '\0';
 #pragma omp parallel for schedule(dynamic, 16)
 	for (int i = 0; i < n; ++i) {
-		memcpy(&qbuf[(size_t)qo[i]], regions[i].qstr->data(), (size_t)ql[i]);
-		memcpy(&rbuf[(size_t)ro[i]], regions[i].rstr->data(), (size_t)rl[i]);
+		memcpy(qbuf + qo[i], regions[i].qstr->data(), (size_t)ql[i]);
+		memcpy(rbuf + ro[i], regions[i].rstr->data(), (size_t)rl[i]);
 	}
 	sedef_anchor_t *flat = nullptr;
 	std::vector<int64_t> off(n + 1, 0);
-	int rc = sedef_anchors_batch(n, ql.data(), qo.data(), (const uint8_t *)qbuf.get(), rl.data(), ro.data(), (const uint8_t *)rbuf.get(), kmer_size,
+	int rc = sedef_anchors_batch(n, ql.data(), qo.data(), (const uint8_t *)qbuf, rl.data(), ro.data(), (const uint8_t *)rbuf, kmer_size,
 	                             same.data(), oq.data(), orr.data(), &flat, off.data());
 	if (rc) throw std::runtime_error(std::string("sedef_anchors_batch: ") + ksw_b200_strerror(rc) + " -- " + ksw_b200_last_error());
 	std::vector<std::vector<Anchor>> out(n);
@@ -1071,6 +1123,12 @@ std::vector<std::vector<GuidedAlignment>> fast_align_batch(const std::vector<Reg
                                                            RefineStats *stats)
 {
 	const double t0 = wall_ms();
+	// the call's region arena (page-locked flat copies of the region strings, shared by the anchors kernel and the chain wave)
+	struct ArenaGuard {
+		bool own = false;
+		ArenaGuard() { if (!tl_arena && g_region_arena.mu.try_lock()) { own = true; tl_arena = &g_region_arena; g_region_arena.qoff.clear(); g_region_arena.roff.clear(); } }
+		~ArenaGuard() { if (own) { g_region_arena.qoff.clear(); g_region_arena.roff.clear(); tl_arena = nullptr; g_region_arena.mu.unlock(); } }
+	} arena_guard;
 	std::vector<std::vector<Anchor>> anchors = anchors_batch(regions, kmer_size);
 	const double t1 = wall_ms();
 	std::vector<RegionTask> tasks(regions.size());

@@ -413,9 +413,10 @@ extz_dp16_kernel(DpLaunch L)
 	// result and takes the next pair from the queue (pairs sorted by descending work) while the others carry on.  (Until round 2
 	// the pairs of a warp ran in lock-step from a common start, and a warp was busy until its longest pair had finished: 37 % of
 	// BASELINE.json configs[2]'s pairs z-drop somewhere along the way.)
-	int pi = -1, qlen = 0, tlen = 0, w = 0, T = 0, R = 0, r = 0;
+	int pi = -1, qlen = 0, tlen = 0, w = 0, r = 0;        // (R = qlen + tlen - 1, T = tlen rounded up to 16 and the number of processed
+	                                                      // anti-diagonals = r are recomputed where they are needed: registers are scarce here)
 	const uint8_t *qseq = L.seq, *tseq = L.seq;
-	uint8_t *tbp = nullptr, *tb_sp = nullptr;
+	uint8_t *tbp = nullptr;
 	bool alive = false, exhausted = false;
 	Lane16 ls;
 	ls.t0[0] = ls.t0[1] = 0;
@@ -424,15 +425,15 @@ extz_dp16_kernel(DpLaunch L)
 #pragma unroll
 	for (int i = 0; i < 8; ++i) ls.TW[i] = ls.QW[i] = 0u;
 	Leader ld; ld.reset();
-	int last_st = -1, last_en = -1, n_diag = 0, zdropped_band = 0;
+	int last_st = -1, last_en = -1;
 	Spare16 sp;
 	sp.U = sp.V = sp.X = sp.Y = sp.Z = sp.TW = 0u; sp.H = kNegInf; sp.t0 = -1;
 
 	for (;;) {
 		{
-			const bool done = !exhausted && !(alive && r < R);
+			const bool done = !exhausted && !(alive && r < qlen + tlen - 1);
 			if (__any_sync(FULL, done)) {
-				if (done && gl == 0 && pi >= 0) { if (zdropped_band) ld.ez.zdropped = 1; ld.store(&L.results[pi], n_diag); }
+				if (done && gl == 0 && pi >= 0) ld.store(&L.results[pi], r);     // r = anti-diagonals processed
 				// dynamic work queue: ONE atomic per warp for all of its waiting groups (with one lane per pair that is up to 32 at once)
 				const unsigned dmask = __ballot_sync(FULL, done && gl == 0);
 				const int first = __ffs(dmask) - 1;
@@ -442,16 +443,14 @@ extz_dp16_kernel(DpLaunch L)
 				const int nxt = base + __popc(dmask & ((1u << (lane_w - gl)) - 1u));   // my group's rank among the waiting ones
 				if (done) {
 					pi = nxt < L.n ? nxt : -1;
-					alive = pi >= 0; exhausted = !alive; r = 0; R = 0;
+					alive = pi >= 0; exhausted = !alive; r = 0;
+					if (!alive) { qlen = 0; tlen = 0; }
 					if (alive) {
 						const PairDesc pd = L.pairs[pi];
 						qlen = pd.qlen; tlen = pd.tlen; w = pd.w;
-						T = (tlen + 15) & ~15;
 						qseq = L.seq + pd.q_off;                         // qseq[j], j in [0, qlen + 15] is read
 						tseq = L.seq + pd.t_off;
 						tbp = kCigar ? L.tb + pd.tb_off + gl * 16 : nullptr;
-						tb_sp = kCigar ? L.tb + pd.tb_off + (NS >> 1) : nullptr;     // the spare block's codes (kSpare)
-						R = qlen + tlen - 1;
 						ls.t0[0] = gl * 32; ls.t0[1] = gl * 32 + 16;
 #pragma unroll
 						for (int i = 0; i < 16; ++i) { ls.U[i] = ls.V[i] = ls.X[i] = ls.Y[i] = 0u; ls.Z[i] = sc16.s0_2; }   // calloc'ed arrays (:83)
@@ -460,7 +459,7 @@ extz_dp16_kernel(DpLaunch L)
 #pragma unroll
 						for (int k = 0; k < 8; ++k) Hrow[k * 128] = make_int4(kNegInf, kNegInf, kNegInf, kNegInf);       // :86-89
 						ld.reset();
-						last_st = -1; last_en = -1; n_diag = 0; zdropped_band = 0;
+						last_st = -1; last_en = -1;
 						sp.U = sp.V = sp.X = sp.Y = sp.Z = sp.TW = 0u; sp.H = kNegInf; sp.t0 = -1;
 					}
 				}
@@ -469,10 +468,11 @@ extz_dp16_kernel(DpLaunch L)
 			}
 		}
 		{
-			bool act = alive && r < R;
+			bool act = alive && r < qlen + tlen - 1;
+			const int T = (tlen + 15) & ~15;
 			Band b;
 			const bool okb = band_of(r, qlen, tlen, w, T, generic, b);
-			if (act && !okb) { zdropped_band = 1; alive = false; act = false; }                // :110-113
+			if (act && !okb) { ld.ez.zdropped = 1; alive = false; act = false; }               // :110-113 (nothing reads the flag before the store)
 
 			// carries: OLD x,v of the slot below each block (:28-35)
 			uint32_t xin, vin;
@@ -491,7 +491,7 @@ extz_dp16_kernel(DpLaunch L)
 				int stop = 0;
 				if (act && gl == 0) stop = ld.approx(rows, b, r, qe, ls.V[0] << 16, qlen, tlen, sc.zdrop, sc.e, (sc.flag & kFlagApproxDrop) != 0);
 				stop = __shfl_sync(FULL, stop, 0, G);
-				if (act) { n_diag = r + 1; last_st = b.st; last_en = b.en; if (stop) alive = false; ++r; }
+				if (act) { last_st = b.st; last_en = b.en; if (stop) alive = false; ++r; }
 				__syncwarp();            // the leader read the dumps; the next diagonal overwrites them
 				continue;
 			}
@@ -632,7 +632,7 @@ extz_dp16_kernel(DpLaunch L)
 				if (__any_sync(FULL, sp_on)) {
 					const uint32_t nib = scw & 0xfu;
 					const uint32_t o = __shfl_down_sync(FULL, nib, 1, 16);
-					if (sp_on && !(gl & 1)) tb_sp[(int64_t)r * ROWB + (gl >> 1)] = (uint8_t)(nib | (o << 4));
+					if (sp_on && !(gl & 1)) (tbp - gl * 16 + (NS >> 1))[(int64_t)r * ROWB + (gl >> 1)] = (uint8_t)(nib | (o << 4));   // behind the packed part of the row
 				}
 			}
 			ld.gmax = group_max<G>(tot_max);
@@ -694,7 +694,7 @@ extz_dp16_kernel(DpLaunch L)
 			}
 			if (act) {
 				const int stop = ld.fin_local(b, r, qe, max_t, Hst0_lazy, qlen, tlen, sc.zdrop, sc.e);
-				n_diag = r + 1; last_st = b.st; last_en = b.en;
+				last_st = b.st; last_en = b.en;
 				if (stop) alive = false;
 				++r;
 			}

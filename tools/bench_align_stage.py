@@ -3,8 +3,10 @@ planted SD catalog): the product's `sedef_b200_align_generate` (all regions thro
 BINARY's own `align generate` (oracle/_ref/sedef_ref, one process per bucket, as many processes at a time as the host has cores --
 the way sedef.sh runs it, sedef.sh:190), on the same bucket files, with a byte-level comparison of the outputs.
 
-    python tools/bench_align_stage.py --config 1            # 2 Mbp, 40 duplications
-    python tools/bench_align_stage.py --config 4 --dups 600 # 50 Mbp chromosome, planted catalog
+    python tools/bench_align_stage.py --config 1                      # configs[0]: 2 Mbp, 40 duplications
+    python tools/bench_align_stage.py --config 4                      # configs[3]: 50 Mbp chromosome, 1000 duplications
+    python tools/bench_align_stage.py --config 5 --scale 1.0          # configs[4]: 24 chromosomes, 3.085 Gbp, 24 680 duplications up to 30 %
+    python tools/bench_align_stage.py --config 5 --scale 1.0 --procs 1,2,4,8   # ... and one process per GPU
 Prints one JSON line.  `--gpus N`: N in-process devices (ksw_b200_init(0, N); every batched call is LPT-sharded over them)."""
 from __future__ import annotations
 

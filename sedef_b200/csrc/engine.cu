@@ -64,7 +64,8 @@ extern "C" const char *ksw_b200_last_error(void) { return g_last_error.c_str(); 
 // A class is a live-slot capacity: 32, 64, ..., 16384 (a pair needs min(16*ceil(tlen/16), 16*n_col_) slots).  Every class has
 // two implementations:
 //   * packed (default, extz_dp16.cuh; two slots per register, NS / 32 lanes per pair):
-//       NS <= 1024           extz_dp16_kernel<NS/32>          128-thread CTAs, 32 / (NS/32) pairs per warp in lock-step
+//       NS <= 1024           extz_dp16_kernel<NS/32>          128-thread CTAs, 32 / (NS/32) pairs per warp, each group at its own anti-diagonal;
+//                                                             the 512-slot class holds 528 (a spare block spread over its 16 lanes)
 //       NS = 2048/4096/8192  extz_dp16_wide_kernel<NS/32>     one CTA of 64 / 128 / 256 lanes per pair
 //       NS = 16384 ... 65536 extz_dp16_cluster_kernel<C>      one cluster of C = 2 / 4 / 8 CTAs x 256 lanes per pair (DSMEM); 65536
 //                                                             live slots hold the largest call the reference makes (60 000 per chunk)

@@ -356,7 +356,8 @@ struct PackedRows {
 };
 
 // =====================================================================================================
-// packed narrow kernel: G <= 32 lanes x 32 slots per pair, the 32/G pairs of a warp advance in lock-step
+// packed narrow kernel: G <= 32 lanes x 32 slots per pair; the 32/G groups of a warp each run their own pair at their own
+// anti-diagonal (independent groups, see below)
 // =====================================================================================================
 #ifndef EXTZ_MIN_BLOCKS_P
 #define EXTZ_MIN_BLOCKS_P 3

@@ -216,6 +216,9 @@ extern "C" const char *sedef_b200_align_generate_error(void);
 extern "C" int sedef_b200_stats_generate(const char *ref_path, const char *bed_path, const char *out_path, int max_ok_gap, int min_split,
                                          int min_uppercase, double max_scaled_error, long long *counts);
 extern "C" const char *sedef_b200_stats_generate_error(void);
+// host-only half of the report (no device needed): the pieces it would measure, one "qname qs qe rname rs re strand strand span cigar"
+// line each (returns the bytes needed, text truncated to cap; -1 on error)
+extern "C" long long sedef_b200_stats_pieces(const char *ref_path, const char *bed_path, int max_ok_gap, int min_split, char *out, long long cap);
 // host-only pieces of the same driver (no device needed): FastaReference::get_sequence; the seed hits of a bucket file / directory
 // in processing order, one Hit::to_bed(false) line each (returns the bytes needed, text truncated to cap); rc() of n bytes
 extern "C" long long sedef_b200_fasta_fetch(const char *ref_path, const char *name, int start, int *end_io, char *out, long long cap);

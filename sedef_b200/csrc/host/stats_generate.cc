@@ -249,9 +249,12 @@ const char *stats_header()
 	       "aln_gaps\tuppercaseA\tuppercaseB\tuppercaseMatches\taln_matches\taln_mismatches\taln_gaps\taln_gap_bases\tcigar\tfilter_score";
 }
 
-StatsGenerateCounts stats_generate(const std::string &ref_path, const std::string &bed_path, FILE *out, const StatsParams &sp, const AlignParams &p)
+namespace {
+// the first half of stats() / process() (src/stats_main.cc:213-231,338-374): read and order the aligned hits, cut the sequences,
+// Alignment(fa, fb, cigar), split -- the pieces of every hit that are long enough to be measured.  Host control logic only.
+std::vector<std::vector<SHit>> stats_pieces(const std::string &ref_path, const std::string &bed_path, const StatsParams &sp, const AlignParams &p,
+                                            long long *n_hits)
 {
-	StatsGenerateCounts cnt;
 	FastaFile fr(ref_path);
 	std::ifstream fin(bed_path.c_str());
 	if (!fin.is_open()) throw std::runtime_error("BED file " + bed_path + " does not exist");
@@ -279,8 +282,8 @@ StatsGenerateCounts stats_generate(const std::string &ref_path, const std::strin
 		return std::tie(x.h.ref_rc, x.h.query_name, x.h.ref_name, x.h.query_start, x.h.ref_start) <
 		       std::tie(y.h.ref_rc, y.h.query_name, y.h.ref_name, y.h.query_start, y.h.ref_start);
 	});
-	cnt.hits = (long long)hits.size();
-	// ---- per hit: the two sequences, Alignment(fa, fb, cigar), the pieces (host control logic, one hit per thread) ----
+	if (n_hits) *n_hits = (long long)hits.size();
+	// ---- per hit: the two sequences, Alignment(fa, fb, cigar), the pieces (one hit per thread) ----
 	std::vector<std::vector<SHit>> pieces(hits.size());
 	std::string err;
 #pragma omp parallel for schedule(dynamic, 8)
@@ -309,10 +312,18 @@ StatsGenerateCounts stats_generate(const std::string &ref_path, const std::strin
 		}
 	}
 	if (!err.empty()) throw std::runtime_error(err);
+	return pieces;
+}
+} // namespace
+
+StatsGenerateCounts stats_generate(const std::string &ref_path, const std::string &bed_path, FILE *out, const StatsParams &sp, const AlignParams &p)
+{
+	StatsGenerateCounts cnt;
+	const std::vector<std::vector<SHit>> pieces = stats_pieces(ref_path, bed_path, sp, p, &cnt.hits);
 	// ---- ONE statistics call for all pieces: the pieces' own columns as (CIGAR, a, b) ----
 	std::vector<GuidedAlignment> flat;
-	for (auto &v : pieces)
-		for (auto &x : v) {
+	for (const auto &v : pieces)
+		for (const auto &x : v) {
 			GuidedAlignment g;
 			// (from the column strings, which is what process() walks -- for an ordinary piece they are the piece's a / b / cigar)
 			for (char c : x.aln.col_a) if (c != '-') g.a.push_back(c);
@@ -330,7 +341,7 @@ StatsGenerateCounts stats_generate(const std::string &ref_path, const std::strin
 	text += '\n';
 	size_t k = 0;
 	for (size_t i = 0; i < pieces.size(); ++i)
-		for (auto &x : pieces[i]) {
+		for (const auto &x : pieces[i]) {
 			const sd_stats_t &t = st[k++];
 			sd_stats_t own = t;                                       // AlignmentError of the piece: the counters its last populate() left
 			own.matches = x.aln.matches; own.mismatches = x.aln.mismatches; own.gaps = x.aln.gaps; own.gap_bases = x.aln.gap_bases;
@@ -367,6 +378,29 @@ StatsGenerateCounts stats_generate(const std::string &ref_path, const std::strin
 } // namespace sedef_b200
 
 static thread_local std::string g_stats_error;
+
+// Host-only half of the report (no device needed; callers without C++ and the CPU tests): the pieces `stats generate` would measure,
+// one line each: "query_name qs qe ref_name rs re strand_q strand_r span cigar" (coordinates, strands and CIGAR as the report prints
+// them).  Returns the bytes needed (text truncated to cap), -1 on error.
+extern "C" long long sedef_b200_stats_pieces(const char *ref_path, const char *bed_path, int max_ok_gap, int min_split, char *out, long long cap)
+{
+	try {
+		sedef_b200::StatsParams sp;
+		sp.max_ok_gap = max_ok_gap; sp.min_split_size = min_split;
+		const auto pieces = sedef_b200::stats_pieces(ref_path, bed_path, sp, sedef_b200::AlignParams(), nullptr);
+		std::string text;
+		for (const auto &v : pieces)
+			for (const auto &x : v) {
+				sedef_b200::Alignment al; al.cigar = x.aln.cigar;
+				text += x.h.query_name + "\t" + std::to_string(x.h.query_start) + "\t" + std::to_string(x.h.query_end) + "\t" + x.h.ref_name + "\t" +
+				        std::to_string(x.h.ref_start) + "\t" + std::to_string(x.h.ref_end) + "\t" + (x.h.query_rc ? "-" : "+") + "\t" + (x.h.ref_rc ? "-" : "+") +
+				        "\t" + std::to_string(x.aln.span()) + "\t" + al.cigar_string() + "\n";
+			}
+		const long long n = std::min<long long>((long long)text.size(), cap);
+		if (out && n > 0) memcpy(out, text.data(), (size_t)n);
+		return (long long)text.size();
+	} catch (const std::exception &e) { g_stats_error = e.what(); return -1; }
+}
 extern "C" const char *sedef_b200_stats_generate_error(void) { return g_stats_error.c_str(); }
 
 // `sedef stats generate [--max-ok-gap G] [--min-split S] [--uppercase U] [--max-error E] ref_path bed_path > out_path`

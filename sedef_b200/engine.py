@@ -69,7 +69,7 @@ EXPORTS = ["ksw_b200_strerror", "ksw_b200_last_error", "ksw_b200_init", "ksw_b20
            "ksw_b200_result_export", "ksw_b200_result_trims", "sedef_anchors_batch", "sedef_b200_chain_anchors",
            "sedef_b200_chunk_plan", "sedef_b200_align_generate", "sedef_b200_align_generate_error",
            "sedef_b200_fasta_fetch", "sedef_b200_bed_schedule", "sedef_b200_reverse_complement",
-           "sedef_b200_stats_generate", "sedef_b200_stats_generate_error"]
+           "sedef_b200_stats_generate", "sedef_b200_stats_generate_error", "sedef_b200_stats_pieces"]
 
 
 def load():
@@ -149,6 +149,8 @@ def load():
     lib.sedef_b200_stats_generate.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, i32, i32, i32, C.c_double, vp]
     lib.sedef_b200_stats_generate.restype = i32
     lib.sedef_b200_stats_generate_error.restype = C.c_char_p
+    lib.sedef_b200_stats_pieces.argtypes = [C.c_char_p, C.c_char_p, i32, i32, C.c_char_p, C.c_longlong]
+    lib.sedef_b200_stats_pieces.restype = C.c_longlong
     lib.sedef_b200_fasta_fetch.argtypes = [C.c_char_p, C.c_char_p, i32, C.POINTER(i32), C.c_char_p, C.c_longlong]
     lib.sedef_b200_fasta_fetch.restype = C.c_longlong
     lib.sedef_b200_bed_schedule.argtypes = [C.c_char_p, C.c_char_p, C.c_longlong]
@@ -489,6 +491,23 @@ def stats_generate(ref_path: str, bed_path: str, out_path: str, max_ok_gap: int 
     if rc != 0:
         raise EngineError(rc, lib.sedef_b200_stats_generate_error().decode())
     return dict(hits=int(cnt[0]), pieces=int(cnt[1]), lines=int(cnt[2]))
+
+
+def stats_pieces(ref_path: str, bed_path: str, max_ok_gap: int = -1, min_split: int = 1000):
+    """Host-only half of `stats generate`: the pieces it would measure, as (qname, qs, qe, rname, rs, re, strand_q, strand_r, span,
+    cigar) tuples."""
+    lib = load()
+    n = lib.sedef_b200_stats_pieces(os.fsencode(ref_path), os.fsencode(bed_path), int(max_ok_gap), int(min_split), None, 0)
+    if n < 0:
+        raise EngineError(-1, lib.sedef_b200_stats_generate_error().decode())
+    buf = C.create_string_buffer(int(n) + 1)
+    lib.sedef_b200_stats_pieces(os.fsencode(ref_path), os.fsencode(bed_path), int(max_ok_gap), int(min_split), buf, n)
+    out = []
+    for ln in buf.raw[:n].decode().split("\n"):
+        if ln:
+            f = ln.split("\t")
+            out.append((f[0], int(f[1]), int(f[2]), f[3], int(f[4]), int(f[5]), f[6], f[7], int(f[8]), f[9] if len(f) > 9 else ""))
+    return out
 
 
 def fasta_fetch(ref_path: str, name: str, start: int, end: int):

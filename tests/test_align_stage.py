@@ -127,6 +127,37 @@ def test_driver_error_paths_and_empty_inputs(built, tmp_path):
         engine.stats_generate(fa, str(tmp_path / "missing.bed"), out)
 
 
+def test_stats_pieces_match_reference_report(built, golden_dir, tmp_path):
+    """The host-only half of `stats generate` (no device): Alignment(fa, fb, cigar), the split at assembly gaps -- and, with
+    --max-ok-gap, the recursive split at large gaps -- and the re-trimming of every piece (subhit: cigar_from_alignment, trim_back,
+    trim_front, src/stats_main.cc:32-211).  Every line of the reference binary's report must be one of the pieces: same
+    coordinates, strands, alignment length and CIGAR (tests/golden/stats_golden.json; the pieces the report leaves out are the ones
+    its filters reject)."""
+    from sedef_b200 import engine, genome
+    g = load_json(golden_dir, "stats_golden.json")
+    wd = str(tmp_path)
+    fa, _, _ = genome.write_align_stage_input(wd, **g["config"])
+    assert hashlib.sha1(open(fa, "rb").read()).hexdigest() == g["genome_sha1"], "generator drifted: regenerate the fixture"
+    ab = os.path.join(wd, "aligned.bed")
+    with open(ab, "w") as f:
+        f.write(g["aligned"])
+    n_split = 0
+    for name, extra in g["variants"].items():
+        kw = {}
+        for k, v in zip(extra[::2], extra[1::2]):
+            kw[{"--max-ok-gap": "max_ok_gap", "--min-split": "min_split"}[k]] = int(v)
+        pieces = engine.stats_pieces(fa, ab, **kw)
+        have = set(pieces)
+        lines = [ln.split("\t") for ln in g["reports"][name].split("\n")[1:] if ln]
+        assert lines
+        for f in lines:
+            key = (f[0], int(f[1]), int(f[2]), f[3], int(f[4]), int(f[5]), f[8], f[9], int(f[11]), f[32])
+            assert key in have, (name, key[:9])
+        assert len(pieces) >= len(lines)
+        n_split += len(pieces) - g["aligned"].count("\n")
+    assert n_split > 0                                              # the fixture does split hits
+
+
 @pytest.mark.gpu
 def test_align_generate_matches_reference_binary_golden(small_stage):
     """Whole bucket files: output bytes == the reference binary's *.aligned.bed (tests/golden/align_stage_golden.json: two

@@ -189,6 +189,41 @@ def test_align_generate_matches_reference_binary_golden(small_stage):
 
 
 @pytest.mark.gpu
+def test_align_generate_degenerate_regions(built, tmp_path):
+    """Seed hits whose regions are shorter than a k-mer, all N, or unrelated sequence: no hits and no output for them, like the
+    reference's fast_align on such regions, next to an ordinary region that does align.  (Coordinates past the chromosome end are not
+    in the comparison: the reference binary crashes on them, this driver cuts an empty region and finds nothing.)"""
+    from sedef_b200 import engine, genome
+    rng = np.random.default_rng(11)
+    core = genome.synth.ASCII[rng.integers(0, 4, 6000)]
+    c1 = np.concatenate([genome.synth.ASCII[rng.integers(0, 4, 3000)], core, genome.synth.ASCII[rng.integers(0, 4, 3000)]])
+    c2 = np.concatenate([genome.synth.ASCII[rng.integers(0, 4, 2000)], core, genome.synth.ASCII[rng.integers(0, 4, 2000)], np.full(3000, ord("N"), np.uint8)])
+    fa = str(tmp_path / "d.fa")
+    genome.write_fasta(fa, {"c1": c1, "c2": c2})
+    bed = str(tmp_path / "d.bed")
+    with open(bed, "w") as f:
+        f.write("c1\t2500\t9500\tc2\t1500\t8500\tgood\t\t+\t+\n")          # the shared 6 kbp core
+        f.write("c1\t100\t105\tc2\t100\t105\ttiny\t\t+\t+\n")               # shorter than k = 11
+        f.write("c1\t100\t3000\tc2\t10000\t13000\tall_n\t\t+\t+\n")          # reference region of N only
+        f.write("c1\t0\t2900\tc2\t0\t1900\tunrelated\t\t+\t-\n")              # random against random, reverse strand
+    out = str(tmp_path / "d.out")
+    st = engine.align_generate(fa, bed, out)
+    lines = [ln for ln in open(out).read().split("\n") if ln]
+    assert st["regions"] == 4
+    assert len(lines) >= 1 and all(ln.split("\t")[20] == "good" for ln in lines), [ln.split("\t")[20] for ln in lines]
+    f = lines[0].split("\t")
+    assert int(f[1]) <= 3050 and int(f[2]) >= 8950 and int(f[4]) <= 2050 and int(f[5]) >= 7950      # the planted core, in genome coordinates
+    if os.path.exists(REF_BIN):
+        ref = subprocess.run([REF_BIN, "align", "generate", "-k", "11", fa, bed], check=True, capture_output=True, text=True, timeout=600).stdout
+        assert open(out).read() == ref
+    past = str(tmp_path / "past.bed")
+    with open(past, "w") as f:
+        f.write("c1\t50000\t60000\tc2\t100\t5000\tpast_the_end\t\t+\t+\n")
+    st = engine.align_generate(fa, past, out)
+    assert st["regions"] == 1 and st["hits"] == 0 and open(out).read() == ""
+
+
+@pytest.mark.gpu
 def test_align_generate_config1_live_reference(built, tmp_path):
     """BASELINE.json configs[0] at the align stage, end to end at the file level: 2 Mbp soft-masked chromosome, 40 planted 5-20 kbp
     duplications at 2-10 % -> seed BED -> the reference binary's `align bucket` -> per bucket `align generate -k 11` with the

@@ -109,7 +109,10 @@ struct RegionTask {
 	bool same_chr = false;                              // orig.query->name == orig.ref->name && same strand (src/refine.cc:29-30)
 	int orig_query_start = 0, orig_ref_start = 0;       // of the seed hit the region was cut from
 };
-struct RefineStats { int rounds = 0; long long batch_calls = 0, ksw_requests = 0; };
+struct RefineStats {
+	int rounds = 0; long long batch_calls = 0, ksw_requests = 0;      // requests: chains / merges / guide constructors
+	long long ksw_pairs = 0, ksw_cells = 0;                            // ksw_extz2 pairs of the batched calls and their DP cells (unbanded: qlen x tlen)
+};
 std::vector<std::vector<GuidedAlignment>> refine_regions_batch(const std::vector<RegionTask> &regions, const AlignParams &p = AlignParams(),
                                                               RefineStats *stats = nullptr);
 
@@ -158,6 +161,7 @@ std::string reverse_complement(const std::string &s);   // rc, src/util.cc:43-48
 std::vector<BedHit> read_schedule(const std::string &bed_path);     // bucket_alignments(path, 1, "", false), src/align_main.cc:211-283
 struct GenerateStats {
 	long long regions = 0, hits = 0, groups = 0, rounds = 0, batch_calls = 0, ksw_requests = 0, region_bytes = 0;
+	long long ksw_pairs = 0, ksw_cells = 0;
 	double ms_total = 0, ms_align = 0, ms_io = 0;
 };
 // generate_alignments (src/align_main.cc:285-337): every seed hit of `bed_path` (a bucket file or a directory of *.bed) -> regions
@@ -206,7 +210,8 @@ extern "C" int sedef_b200_chunk_plan(int64_t alen, int64_t blen, int cap, int64_
 // holds chain_len[k] anchor indices (query order), concatenated in chain_idx.  Returns the number of chains (fills at most cap_*).
 extern "C" int sedef_b200_chain_anchors(int n, const int32_t *anchors4, int cap_chains, int *chain_len, int cap_idx, int *chain_idx);
 // `sedef align generate -k kmer_size ref_path bed_path > out_path` (src/align_main.cc:285-337,368-373) through fast_align_batch.
-// out_path NULL or "-": stdout.  stats[7] (may be NULL): regions, hits, groups, rounds, batch_calls, ksw_requests, region_bytes;
+// out_path NULL or "-": stdout.  stats[9] (may be NULL): regions, hits, groups, rounds, batch_calls, ksw_requests, region_bytes,
+// ksw_pairs, ksw_cells;
 // ms[3] (may be NULL): total, align, io.  Returns 0, or -1 with the message in sedef_b200_align_generate_error().
 extern "C" int sedef_b200_align_generate(const char *ref_path, const char *bed_path, int kmer_size, const char *out_path,
                                          int shard_index, int shard_count, long long *stats, double *ms);

@@ -281,6 +281,7 @@ GenerateStats align_generate(const std::string &ref_path, const std::string &bed
 		std::vector<std::vector<GuidedAlignment>> hits = fast_align_batch(seeds, kmer_size, p, &rs);
 		const double t2 = now_ms();
 		gs.rounds += rs.rounds; gs.batch_calls += rs.batch_calls; gs.ksw_requests += rs.ksw_requests;
+		gs.ksw_pairs += rs.ksw_pairs; gs.ksw_cells += rs.ksw_cells;
 		std::vector<std::string> texts(end - at);
 #pragma omp parallel for schedule(dynamic, 4)
 		for (long i = (long)at; i < (long)end; ++i) {
@@ -319,7 +320,7 @@ static thread_local std::string g_generate_error;
 extern "C" const char *sedef_b200_align_generate_error(void) { return g_generate_error.c_str(); }
 
 // `sedef align generate -k kmer_size ref_path bed_path > out_path` (src/align_main.cc:285-337, 368-373).  out_path NULL or "-":
-// stdout.  stats (may be NULL): regions, hits, groups, rounds, batch_calls, ksw_requests, region_bytes.  Returns 0, or -1 with
+// stdout.  stats[9] (may be NULL): regions, hits, groups, rounds, batch_calls, ksw_requests, region_bytes, ksw_pairs, ksw_cells.  Returns 0, or -1 with
 // the message in sedef_b200_align_generate_error() (the reference throws its message and exits).
 extern "C" int sedef_b200_align_generate(const char *ref_path, const char *bed_path, int kmer_size, const char *out_path,
                                          int shard_index, int shard_count, long long *stats, double *ms)
@@ -337,6 +338,7 @@ extern "C" int sedef_b200_align_generate(const char *ref_path, const char *bed_p
 		if (stats) {
 			stats[0] = gs.regions; stats[1] = gs.hits; stats[2] = gs.groups; stats[3] = gs.rounds;
 			stats[4] = gs.batch_calls; stats[5] = gs.ksw_requests; stats[6] = gs.region_bytes;
+			stats[7] = gs.ksw_pairs; stats[8] = gs.ksw_cells;
 		}
 		if (ms) { ms[0] = gs.ms_total; ms[1] = gs.ms_align; ms[2] = gs.ms_io; }
 		return 0;

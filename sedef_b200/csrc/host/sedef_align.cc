@@ -40,6 +40,8 @@ sd_stats_fp_t Alignment::bedpe_fp() const
 }
 
 static inline double wall_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+// ksw_extz2 pairs and in-band cells of the batched calls issued on this thread (every SEDEF call is unbanded: cells = qlen x tlen)
+static thread_local long long tl_ksw_pairs = 0, tl_ksw_cells = 0;
 static inline bool region_trace() { static const bool on = getenv("SEDEF_B200_TRACE") != nullptr; return on; }   // developer aid: phase times on stderr
 
 static void add_stats(sd_stats_t &d, const sd_stats_t &s)
@@ -101,6 +103,11 @@ static std::vector<Alignment> align_batch_impl(const std::vector<std::pair<std::
 		memcpy(&traw[to[k]], pairs[owner[k]].second.data() + chunks[k].sp, tl[k]);
 	}
 	const int n = (int)owner.size();
+	{
+		long long cells = 0;
+		for (int k = 0; k < n; ++k) cells += (long long)ql[k] * tl[k];
+		tl_ksw_pairs += n; tl_ksw_cells += cells;
+	}
 	ksw_b200_result_t *res = nullptr;
 	const double t_call = wall_ms();
 	int rc = ksw_extz2_batch_arena(n, ql.data(), qo.data(), nullptr, tl.data(), to.data(), nullptr, 5, mat,
@@ -302,6 +309,11 @@ struct WindowBatch {
 		const int8_t a = (int8_t)p.match, b = p.mismatch < 0 ? (int8_t)p.mismatch : (int8_t)(-p.mismatch);
 		const int8_t mat[25] = {a, b, b, b, 0, b, a, b, b, 0, b, b, a, b, 0, b, b, b, a, 0, 0, 0, 0, 0, 0};
 		const double t0 = wall_ms();
+		{
+			long long cells = 0;
+			for (size_t k = 0; k < ql.size(); ++k) cells += (long long)ql[k] * tl[k];
+			tl_ksw_pairs += (long long)ql.size(); tl_ksw_cells += cells;
+		}
 		int rc = ksw_extz2_batch_arena((int)ql.size(), ql.data(), qo.data(), nullptr, tl.data(), to.data(), nullptr, 5, mat,
 		                               (int8_t)p.gap_open, (int8_t)p.gap_extend, p.bandwidth, -1, 0, 0, (const uint8_t *)qptr, (const uint8_t *)tptr, &res);
 		if (rc) throw std::runtime_error(std::string("ksw_extz2_batch_arena: ") + ksw_b200_strerror(rc) + " -- " + ksw_b200_last_error());
@@ -864,6 +876,7 @@ bool advance(const RegionTask &t, RegionState &st, Request &rq)
 std::vector<std::vector<GuidedAlignment>> refine_regions_batch(const std::vector<RegionTask> &regions, const AlignParams &p, RefineStats *stats)
 {
 	RefineStats rs;
+	const long long pairs0 = tl_ksw_pairs, cells0 = tl_ksw_cells;
 	const double t_begin = wall_ms();
 	// wave 0: every chain of every region through one batched call
 	std::vector<ChainGuide> chains;
@@ -916,6 +929,7 @@ std::vector<std::vector<GuidedAlignment>> refine_regions_batch(const std::vector
 	}
 	std::vector<std::vector<GuidedAlignment>> out(regions.size());
 	for (size_t ri = 0; ri < regions.size(); ++ri) out[ri] = std::move(st[ri].accepted);
+	rs.ksw_pairs = tl_ksw_pairs - pairs0; rs.ksw_cells = tl_ksw_cells - cells0;
 	if (stats) *stats = rs;
 	return out;
 }

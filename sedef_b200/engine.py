@@ -469,12 +469,12 @@ def align_generate(ref_path: str, bed_path: str, out_path: str, kmer_size: int =
     """`sedef align generate -k kmer_size ref_path bed_path > out_path` (src/align_main.cc:285-337) through `fast_align_batch`:
     every seed hit of the bucket file(s) at once.  Returns the run's counters and phase times."""
     lib = load()
-    st = np.zeros(7, np.int64); ms = np.zeros(3, np.float64)
+    st = np.zeros(9, np.int64); ms = np.zeros(3, np.float64)
     rc = lib.sedef_b200_align_generate(os.fsencode(ref_path), os.fsencode(bed_path), int(kmer_size), os.fsencode(out_path),
                                        int(shard_index), int(shard_count), _ptr(st), _ptr(ms))
     if rc != 0:
         raise EngineError(rc, lib.sedef_b200_align_generate_error().decode())
-    keys = ["regions", "hits", "groups", "rounds", "batch_calls", "ksw_requests", "region_bytes"]
+    keys = ["regions", "hits", "groups", "rounds", "batch_calls", "ksw_requests", "region_bytes", "ksw_pairs", "ksw_cells"]
     out = {k: int(v) for k, v in zip(keys, st)}
     out.update(ms_total=float(ms[0]), ms_align=float(ms[1]), ms_io=float(ms[2]))
     return out

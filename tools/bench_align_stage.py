@@ -125,7 +125,9 @@ def main():
                 value=round(n_regions / ours_s, 1), unit="regions/s", hits_per_s=round(st["hits"] / ours_s, 1),
                 region_mbp_per_s=round(region_bases / ours_s / 1e6, 2),
                 phases_ms=dict(total=round(st["ms_total"], 1), align=round(st["ms_align"], 1), io=round(st["ms_io"], 1)),
-                rounds=st["rounds"], batch_calls=st["batch_calls"], ksw_requests=st["ksw_requests"], genome_gen_s=round(t_gen, 1))
+                rounds=st["rounds"], batch_calls=st["batch_calls"], ksw_requests=st["ksw_requests"],
+                ksw_pairs=st["ksw_pairs"], ksw_cells=st["ksw_cells"], ksw_pairs_per_s=round(st["ksw_pairs"] / ours_s, 1),
+                ksw_gcups_over_the_stage=round(st["ksw_cells"] / ours_s / 1e9, 2), genome_gen_s=round(t_gen, 1))
     if args.procs:
         scaling = []
         for n in [int(x) for x in args.procs.split(",")]:
